@@ -1,0 +1,137 @@
+/*
+ * libotb200 -- B200 (sm_100a) hot path for the OpenTransformer speech transformer, C ABI.
+ *
+ * The reference has no FFI / operator API: its boundary is the Python nn.Module surface
+ * (SURVEY.md 8b).  Every entry point below therefore names the reference *module method* whose
+ * per-call compute it replaces (file:line under the reference tree); the Python classes in
+ * opentransformer_b200/ keep the reference's constructor kwargs / state_dict keys and call these
+ * functions through ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; "bf16" buffers are uint16 bfloat16, row-major
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - functions return 0 on success, non-zero on error; otb_last_error() gives the message
+ *     (thread-local).  Nothing aborts; kernels are asynchronous on `stream`.
+ *   - the library keeps no global mutable state besides the per-thread error string and lazily
+ *     set function attributes, so one thread per GPU (nn.DataParallel, trainer.py:65) is safe.
+ */
+#ifndef OTB200_H_
+#define OTB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTB_VERSION 1
+
+/* GEMM epilogues (otb_linear) */
+enum {
+    OTB_EPI_BIAS = 0,     /* y = x W^T + b                                   nn.Linear                          */
+    OTB_EPI_RELU = 1,     /* relu(.)                                          ffn.py:16, conv.py:64              */
+    OTB_EPI_GLU = 2,      /* W has 2N rows: (a + b_a) * sigmoid(g + b_g)      ffn.py:18 F.glu, conformer.py:45   */
+    OTB_EPI_TABLE = 3,    /* (.) * alpha + table[row % period]                pos.py:56  x*sqrt(d)+PE            */
+    OTB_EPI_RESID = 4,    /* resid + alpha * (.)                              encoder/conformer.py:53,72         */
+    OTB_EPI_RESID_LN = 5, /* LayerNorm(resid + (.)) * gamma + beta            encoder/transformer.py:54-56,61-63 */
+    OTB_EPI_SWISH = 6,    /* v * sigmoid(v)                                   ffn.py:20                          */
+    OTB_EPI_GELU = 7,     /* F.gelu                                           ffn.py:17                          */
+    OTB_EPI_TANH = 8      /* tanh                                             ffn.py:19                          */
+};
+
+const char* otb_last_error(void);
+int otb_version(void);
+int otb_num_sms(void);
+
+/* Conv2dLayer output geometry, kernel 3, stride 2, padding (0,1)  (frontend/conv.py:10-11,27):
+ * T1 = (T-3)/2+1, F1 = (F-1)/2+1, T2 = (T1-3)/2+1, F2 = (F1-1)/2+1.  The conv1 activation buffer is
+ * NHWC bf16 [B, 2*(T2+1), 2*F2, C1]. */
+int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2);
+
+/* Conv2dLayer.forward #1 (frontend/conv.py:50-76; C_in = 1): relu(conv2d(x, w) + b).
+ * x f32 [B,T,F]; w f32 [C1,1,3,3]; bias f32 [C1]; out bf16 NHWC [B, 2*(T2+1), 2*F2, C1]. */
+int otb_conv1_relu(const float* x, const float* w, const float* bias, void* out, int B, int T, int F, int C1,
+                   void* stream);
+
+/* Conv2dLayer.forward #2 + the transpose/reshape of ConvFrontEnd.forward (frontend/conv.py:63-64,145)
+ * as a tcgen05 implicit GEMM.  in = conv1 buffer; w bf16 [C2, 9*C1] with k = (kh*3+kw)*C1 + c;
+ * out bf16 [B*T2, F2*C2] with feature index f*C2 + c (the caller permutes output_layer.weight columns
+ * from the reference's c*F2 + f order once at load time). */
+int otb_conv2_relu(const void* in, const void* w, const float* bias, void* out, int B, int T, int F, int C1, int C2,
+                   void* stream);
+
+/* nn.Linear with a fused epilogue on tcgen05 tensor cores: out[M,N] = epi(a[M,K] w[N(,2N),K]^T + bias).
+ * a, w bf16 (lda, ldw in elements, multiples of 8); out bf16 or f32 (out_f32); unused pointers NULL.
+ * row_len/row_period: optional key-padding mask, rows with (m % row_period) >= row_len[m / row_period]
+ * produce 0 before the residual is added (conformer.py:46,55 masked_fill).
+ * Replaces attention.py:68,128-129,44; ffn.py:39-41; frontend/conv.py:146; decoder/transformer.py:181. */
+int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldc, int M, int N,
+               int K, int epilogue, int out_f32, const void* resid, int ldr, const float* gamma, const float* beta,
+               float eps, float alpha, const float* table, int period, const int* row_len, int row_period,
+               void* stream);
+
+/* Fused masked multi-head attention, d_k = 64 (attention.py:80,34-41): for batch b, head h
+ *   out[b*Tq+i, h*64:(h+1)*64] = softmax_j((q_i . k_j + bd) / 8, j < kv_len[b], causal: j <= i) V
+ * q/k/v are row-major bf16 matrices; batch b owns rows [b*Tq, (b+1)*Tq) of q and [b*Tk, (b+1)*Tk) of k,v;
+ * head h starts at column q_col0/k_col0/v_col0 + 64*h.  bd (optional, f32 [B,H,Tq,ldbd]) holds
+ * relative-position scores, bias(i,j) = bd[b,h,i, j-i+Tq-1] (attention.py:196-215). */
+int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                  void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
+                  int k_col0, int v_col0, const float* bd, int ldbd, void* stream);
+
+/* nn.LayerNorm (eps as given), optionally two in a row (encoder/conformer.py:87-89). g2/b2 may be NULL. */
+int otb_layernorm(const void* x, int ldx, void* out, int ldo, int out_f32, const float* g1, const float* b1,
+                  const float* g2, const float* b2, float eps, int M, int N, void* stream);
+
+/* PositionalEncoding.forward stand-alone (module/pos.py:56): out bf16 = x * alpha + table[row % period];
+ * x is f32 (x_f32 != 0) or bf16; table may be NULL (pure scale / dtype conversion). */
+int otb_scale_add_table(const void* x, int ldx, int x_f32, void* out, int ldo, float alpha, const float* table,
+                        int period, int M, int N, void* stream);
+
+/* PositionalEncoding._embedding_from_positions (module/pos.py:30-42): out f32 [n_pos, d] for positions
+ * first_pos .. first_pos + n_pos - 1 (negative allowed). */
+int otb_sinusoid_table(float* out, int n_pos, int d, int first_pos, void* stream);
+
+/* embedding + PositionalEncoding.forward (decoder/transformer.py:163,169; pos.py:56):
+ * out[n] = emb[tok[n*tok_stride]] * sqrt(d) + table[pos], pos = step_ptr ? *step_ptr : n % period. */
+int otb_embed_posenc(const int64_t* tok, int tok_stride, const void* emb, const float* table, void* out, int N,
+                     int d, int period, const int* step_ptr, int vocab, void* stream);
+
+/* F.log_softmax over the last dim, fp32 (decoder/transformer.py:206). */
+int otb_log_softmax(const float* x, int ldx, float* out, int ldo, int rows, int V, void* stream);
+
+/* Decode-step self-attention over a per-hypothesis KV cache (the cache API the reference left as a
+ * stub, decoder/transformer.py:92-126,188-203): qkv bf16 [N,3d] of the newest token; kc/vc bf16
+ * [Lmax,N,d]; anc i32 [2,N,Lmax]; *step_ptr = 0-based position; out bf16 [N,d]. */
+int otb_decode_self_attn(const void* qkv, void* kc, void* vc, const int* anc, const int* step_ptr, void* out, int N,
+                         int H, int Lmax, void* stream);
+
+/* Device-resident beam-search state, N = B*beam hypotheses (all device pointers). */
+typedef struct {
+    int32_t* tok_hist;  /* [Lmax, N] */
+    int32_t* par_hist;  /* [Lmax, N] */
+    int64_t* last_tok;  /* [N]       */
+    float* scores;      /* [N]       */
+    uint8_t* flag;      /* [N]       */
+    int32_t* anc;       /* [2, N, Lmax] */
+    int32_t* ctrl;      /* [4] = {step, done, ended_now, -} */
+    int32_t N, beam, Lmax;
+} otb_beam_state;
+
+/* recognize() initial state (recognize/speech2text.py:54-58). */
+int otb_beam_init(const otb_beam_state* st, void* stream);
+/* SpeechToTextRecognizer.decode_step after the decoder call (recognize/speech2text.py:102-153,156-192).
+ * logp f32 [N, ldl] log-probs; lm_logp optional (shallow fusion, :102-105).  dbg_ktok i64 [N,beam] and
+ * dbg_offs i32 [N] (optional) receive last_k_preds / offset_k_indices for parity traces. */
+int otb_beam_step(const float* logp, int ldl, int V, const float* lm_logp, int ld_lm, float lm_weight,
+                  const otb_beam_state* st, int64_t* dbg_ktok, int32_t* dbg_offs, void* stream);
+/* Materialise preds i64 [N, ld] (column 0 = BOS) after `steps` steps from the back-pointers. */
+int otb_beam_reconstruct(const otb_beam_state* st, int64_t* preds, int ld, int steps, void* stream);
+/* Tail of recognize() (recognize/speech2text.py:70-91). out_preds i64 [B,nbest,Lmax], out_scores f32 [B,nbest]. */
+int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int nbest, int64_t* out_preds,
+                      float* out_scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTB200_H_ */

@@ -1,0 +1,72 @@
+"""ctypes binding of libotb200.so (C ABI declared in include/otb200.h).
+
+The product path fails loudly when the CUDA library is missing: there is NO CPU / PyTorch fallback.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libotb200.so')
+
+_lib = None
+
+
+class BeamStateC(ctypes.Structure):
+    """otb_beam_state (include/otb200.h)."""
+    _fields_ = [('tok_hist', c_void_p), ('par_hist', c_void_p), ('last_tok', c_void_p), ('scores', c_void_p),
+                ('flag', c_void_p), ('anc', c_void_p), ('ctrl', c_void_p),
+                ('N', c_int32), ('beam', c_int32), ('Lmax', c_int32)]
+
+
+_P = c_void_p
+_SIGS = {
+    'otb_last_error': (c_char_p, []),
+    'otb_version': (c_int, []),
+    'otb_num_sms': (c_int, []),
+    'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'otb_conv2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'otb_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P,
+                           c_float, c_float, _P, c_int, _P, c_int, _P]),
+    'otb_attention': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int,
+                              _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'otb_layernorm': (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_int, c_int, _P]),
+    'otb_scale_add_table': (c_int, [_P, c_int, c_int, _P, c_int, c_float, _P, c_int, c_int, c_int, _P]),
+    'otb_sinusoid_table': (c_int, [_P, c_int, c_int, c_int, _P]),
+    'otb_embed_posenc': (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),
+    'otb_log_softmax': (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
+    'otb_decode_self_attn': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    'otb_beam_init': (c_int, [POINTER(BeamStateC), _P]),
+    'otb_beam_step': (c_int, [_P, c_int, c_int, _P, c_int, c_float, POINTER(BeamStateC), _P, _P, _P]),
+    'otb_beam_reconstruct': (c_int, [POINTER(BeamStateC), _P, c_int, c_int, _P]),
+    'otb_beam_finalize': (c_int, [POINTER(BeamStateC), c_float, c_float, c_int, _P, _P, _P]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by tests/test_capi_symbols.py)."""
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m opentransformer_b200.build` '
+                '(there is no CPU fallback for the B200 hot path)')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().otb_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'libotb200 {what} failed: {msg}')

@@ -1,0 +1,209 @@
+// extern "C" boundary of libotb200.so (declared in include/otb200.h).  Argument checking, error
+// reporting (thread-local string, integer status, no aborts) and dispatch to the kernel launchers.
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/otb200.h"
+#include "otb_internal.h"
+
+namespace otb {
+
+
+static thread_local char g_err[512] = "";
+void set_error(const char* msg) {
+    strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+    g_err[sizeof(g_err) - 1] = 0;
+}
+static int fail(const char* where, const char* msg) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", where, msg);
+    set_error(buf);
+    return 1;
+}
+static BeamState to_state(const otb_beam_state* s) {
+    BeamState b;
+    b.tok_hist = s->tok_hist; b.par_hist = s->par_hist; b.last_tok = (long long*)s->last_tok;
+    b.scores = s->scores; b.flag = s->flag; b.anc = s->anc; b.ctrl = s->ctrl;
+    b.N = s->N; b.beam = s->beam; b.Lmax = s->Lmax;
+    return b;
+}
+
+}  // namespace otb
+
+using namespace otb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define RET(where, expr)                      \
+    do {                                      \
+        const char* _e = (expr);              \
+        if (_e) return fail(where, _e);       \
+        return 0;                             \
+    } while (0)
+
+extern "C" {
+
+const char* otb_last_error(void) { return g_err; }
+int otb_version(void) { return OTB_VERSION; }
+int otb_num_sms(void) { return num_sms(); }
+
+int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2) {
+    if (T < 7 || F < 1) return fail("otb_conv_geometry", "need T >= 7 and F >= 1");
+    const int t1 = (T - 3) / 2 + 1, f1 = (F - 1) / 2 + 1;
+    const int t2 = (t1 - 3) / 2 + 1, f2 = (f1 - 1) / 2 + 1;
+    if (T1) *T1 = t1;
+    if (F1) *F1 = f1;
+    if (T2) *T2 = t2;
+    if (F2) *F2 = f2;
+    return 0;
+}
+
+int otb_conv1_relu(const float* x, const float* w, const float* bias, void* out, int B, int T, int F, int C1,
+                   void* stream) {
+    int T1, F1, T2, F2;
+    if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;
+    if (!x || !w || !bias || !out || B < 1) return fail("otb_conv1_relu", "null pointer or empty batch");
+    RET("otb_conv1_relu",
+        conv1_launch(ST(stream), x, w, bias, reinterpret_cast<bf16*>(out), B, T, F, T1, F1, 2 * (T2 + 1), 2 * F2, C1));
+}
+
+int otb_conv2_relu(const void* in, const void* w, const float* bias, void* out, int B, int T, int F, int C1, int C2,
+                   void* stream) {
+    int T1, F1, T2, F2;
+    if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;
+    if (!in || !w || !bias || !out || B < 1) return fail("otb_conv2_relu", "null pointer or empty batch");
+    if (C1 % 64) return fail("otb_conv2_relu", "C1 must be a multiple of 64 (one 128-byte tap per k-block)");
+    if (C2 % 8) return fail("otb_conv2_relu", "C2 must be a multiple of 8");
+    if (F2 > 128) return fail("otb_conv2_relu", "F2 > 128 not supported");
+    const int T1h = T2 + 1;
+    int R = 128 / F2;
+    if (R > T1h) R = T1h;
+    if (R > 256) R = 256;
+    CUtensorMap cmap;
+    const char* e = encode_tmap_conv5d(&cmap, in, C1, F2, B * T1h, (uint32_t)F2, (uint32_t)R);
+    if (e) return fail("otb_conv2_relu", e);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = B * T2 * F2;
+    p.N = C2;
+    p.K = 9 * C1;
+    p.bias = bias;
+    p.out = out;
+    p.ldc = C2;
+    p.alpha = 1.f;
+    p.conv = 1;
+    p.conv_F2 = F2;
+    p.conv_R = R;
+    p.conv_T1h = T1h;
+    p.conv_T2 = T2;
+    p.conv_B = B;
+    p.conv_cchunks = C1 / 64;
+    RET("otb_conv2_relu", gemm_launch(ST(stream), nullptr, 0, w, 9 * C1, C2, EPI_RELU, p, &cmap));
+}
+
+int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldc, int M, int N,
+               int K, int epilogue, int out_f32, const void* resid, int ldr, const float* gamma, const float* beta,
+               float eps, float alpha, const float* table, int period, const int* row_len, int row_period,
+               void* stream) {
+    if (!a || !w || !out) return fail("otb_linear", "null operand");
+    if (epilogue < 0 || epilogue > EPI_TANH) return fail("otb_linear", "unknown epilogue");
+    if ((epilogue == EPI_RESID || epilogue == EPI_RESID_LN) && !resid) return fail("otb_linear", "residual epilogue without resid");
+    if (epilogue == EPI_RESID_LN && (!gamma || !beta)) return fail("otb_linear", "LayerNorm epilogue without gamma/beta");
+    if (epilogue == EPI_TABLE && (!table || period < 1)) return fail("otb_linear", "table epilogue without table/period");
+    if (row_len && row_period < 1) return fail("otb_linear", "row_len without row_period");
+    if (out_f32 ? (ldc < N) : (ldc < N)) return fail("otb_linear", "ldc < N");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.bias = bias;
+    p.out = out; p.ldc = ldc; p.out_f32 = out_f32;
+    p.resid = reinterpret_cast<const bf16*>(resid); p.ldr = ldr;
+    p.gamma = gamma; p.beta = beta; p.eps = eps; p.alpha = alpha;
+    p.table = table; p.period = period;
+    p.row_len = row_len; p.row_period = row_period;
+    const int w_rows = (epilogue == EPI_GLU) ? 2 * N : N;
+    RET("otb_linear", gemm_launch(ST(stream), a, lda, w, ldw, w_rows, epilogue, p, nullptr));
+}
+
+int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                  void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
+                  int k_col0, int v_col0, const float* bd, int ldbd, void* stream) {
+    if (!q || !k || !v || !out) return fail("otb_attention", "null operand");
+    if (q_col0 % 8 || k_col0 % 8 || v_col0 % 8 || ldo % 8) return fail("otb_attention", "column offsets / ldo must be multiples of 8");
+    AttnParams p;
+    p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk;
+    p.kv_len = kv_len; p.causal = causal;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.out = reinterpret_cast<bf16*>(out); p.ldo = ldo;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.bd = bd; p.ldbd = ldbd;
+    RET("otb_attention", attn_launch(ST(stream), q, ldq, q_rows, k, ldk, k_rows, v, ldv, p));
+}
+
+int otb_layernorm(const void* x, int ldx, void* out, int ldo, int out_f32, const float* g1, const float* b1,
+                  const float* g2, const float* b2, float eps, int M, int N, void* stream) {
+    if (!x || !out || !g1 || !b1) return fail("otb_layernorm", "null operand");
+    if ((g2 == nullptr) != (b2 == nullptr)) return fail("otb_layernorm", "g2/b2 must both be given");
+    RET("otb_layernorm", layernorm_launch(ST(stream), reinterpret_cast<const bf16*>(x), ldx, out, ldo, out_f32, g1, b1,
+                                          g2, b2, eps, M, N));
+}
+
+int otb_scale_add_table(const void* x, int ldx, int x_f32, void* out, int ldo, float alpha, const float* table,
+                        int period, int M, int N, void* stream) {
+    if (!x || !out || M < 1 || N < 1) return fail("otb_scale_add_table", "bad arguments");
+    if (table && period < 1) return fail("otb_scale_add_table", "table without period");
+    RET("otb_scale_add_table", scale_add_table_launch(ST(stream), x, ldx, x_f32, reinterpret_cast<bf16*>(out), ldo, alpha,
+                                                      table, period, M, N));
+}
+
+int otb_sinusoid_table(float* out, int n_pos, int d, int first_pos, void* stream) {
+    if (!out || n_pos < 1 || d < 2 || (d & 1)) return fail("otb_sinusoid_table", "bad arguments");
+    RET("otb_sinusoid_table", sinusoid_table_launch(ST(stream), out, n_pos, d, first_pos));
+}
+
+int otb_embed_posenc(const int64_t* tok, int tok_stride, const void* emb, const float* table, void* out, int N,
+                     int d, int period, const int* step_ptr, int vocab, void* stream) {
+    if (!tok || !emb || !table || !out) return fail("otb_embed_posenc", "null operand");
+    if (!step_ptr && period < 1) return fail("otb_embed_posenc", "need period or step_ptr");
+    RET("otb_embed_posenc",
+        embed_posenc_launch(ST(stream), reinterpret_cast<const long long*>(tok), tok_stride,
+                            reinterpret_cast<const bf16*>(emb), table, reinterpret_cast<bf16*>(out), N, d, period,
+                            step_ptr, vocab));
+}
+
+int otb_log_softmax(const float* x, int ldx, float* out, int ldo, int rows, int V, void* stream) {
+    if (!x || !out || rows < 1 || V < 1) return fail("otb_log_softmax", "bad arguments");
+    RET("otb_log_softmax", log_softmax_launch(ST(stream), x, ldx, out, ldo, rows, V));
+}
+
+int otb_decode_self_attn(const void* qkv, void* kc, void* vc, const int* anc, const int* step_ptr, void* out, int N,
+                         int H, int Lmax, void* stream) {
+    if (!qkv || !kc || !vc || !anc || !step_ptr || !out) return fail("otb_decode_self_attn", "null operand");
+    RET("otb_decode_self_attn",
+        decode_self_attn_launch(ST(stream), reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(kc),
+                                reinterpret_cast<bf16*>(vc), anc, step_ptr, reinterpret_cast<bf16*>(out), N, H, Lmax));
+}
+
+int otb_beam_init(const otb_beam_state* st, void* stream) {
+    if (!st) return fail("otb_beam_init", "null state");
+    RET("otb_beam_init", beam_init_launch(ST(stream), to_state(st)));
+}
+
+int otb_beam_step(const float* logp, int ldl, int V, const float* lm_logp, int ld_lm, float lm_weight,
+                  const otb_beam_state* st, int64_t* dbg_ktok, int32_t* dbg_offs, void* stream) {
+    if (!st || !logp) return fail("otb_beam_step", "null operand");
+    RET("otb_beam_step", beam_step_launch(ST(stream), logp, ldl, V, lm_logp, ld_lm, lm_weight, to_state(st),
+                                          reinterpret_cast<long long*>(dbg_ktok), dbg_offs));
+}
+
+int otb_beam_reconstruct(const otb_beam_state* st, int64_t* preds, int ld, int steps, void* stream) {
+    if (!st || !preds) return fail("otb_beam_reconstruct", "null operand");
+    RET("otb_beam_reconstruct", beam_reconstruct_launch(ST(stream), to_state(st), reinterpret_cast<long long*>(preds), ld, steps));
+}
+
+int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int nbest, int64_t* out_preds,
+                      float* out_scores, void* stream) {
+    if (!st || !out_preds || !out_scores) return fail("otb_beam_finalize", "null operand");
+    RET("otb_beam_finalize", beam_finalize_launch(ST(stream), to_state(st), penalty, lamda, nbest,
+                                                  reinterpret_cast<long long*>(out_preds), out_scores));
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// HBM-bound / latency-bound kernels of the hot path (no tensor cores): coalesced, vectorised,
+// warp-shuffle reductions.  Each kernel cites the reference lines it replaces.
+#include <math.h>
+
+#include "otb_internal.h"
+#include "ptx.cuh"
+
+namespace otb {
+
+// ------------------------------------------------------------------------------------------------
+// conv1: Conv2d(1 -> C1, 3x3, stride 2, padding (0,1)) + ReLU      otrans/frontend/conv.py:63-64
+// in : x f32 [B, T, F]
+// out: bf16 NHWC [B, 2*T1h, 2*F1h, C1]; columns f >= F1 are written as zero (they are the right
+//      frequency padding of conv2); rows t >= T1 are never read for valid outputs and left untouched.
+// One CTA per output row (b, t1); 3 input rows + the 9xC1 filter staged in smem; each thread
+// produces 8 channels of one (f1) -> one 16-byte store, fully coalesced along (f1, c).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1_relu_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, bf16* __restrict__ out,
+                                                              int B, int T, int F, int T1, int F1, int T1pad,
+                                                              int F1pad, int C1) {
+    extern __shared__ float sm[];
+    float* sx = sm;                    // [3][F + 2]  (one zero column each side)
+    float* sw = sm + 3 * (F + 2);      // [9][C1]  tap-major
+    float* sb = sw + 9 * C1;           // [C1]
+    const int row = blockIdx.x;        // b * T1 + t1
+    const int b = row / T1, t1 = row % T1;
+    for (int i = threadIdx.x; i < 3 * (F + 2); i += blockDim.x) {
+        const int r = i / (F + 2), f = i % (F + 2) - 1;
+        sx[i] = (f >= 0 && f < F) ? x[((size_t)b * T + 2 * t1 + r) * F + f] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 9 * C1; i += blockDim.x) {
+        const int tap = i / C1, c = i % C1;
+        sw[i] = w[c * 9 + tap];
+    }
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int cg = C1 / 8;
+    bf16* orow = out + ((size_t)b * T1pad + t1) * F1pad * C1;
+    for (int i = threadIdx.x; i < F1pad * cg; i += blockDim.x) {
+        const int f1 = i / cg, c0 = (i % cg) * 8;
+        float v[8];
+        if (f1 < F1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sb[c0 + j];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float xv = sx[kh * (F + 2) + 2 * f1 + kw];  // input col 2*f1 + kw - 1, +1 for the halo
+                    const float* wt = sw + (kh * 3 + kw) * C1 + c0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, wt[j], v[j]);
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]);
+        u.y = pack_bf16(v[2], v[3]);
+        u.z = pack_bf16(v[4], v[5]);
+        u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(orow + (size_t)f1 * C1 + c0) = u;
+    }
+}
+
+const char* conv1_launch(cudaStream_t st, const float* x, const float* w, const float* bias, bf16* out, int B, int T,
+                         int F, int T1, int F1, int T1pad, int F1pad, int C1) {
+    if (C1 % 8) return "conv1: C1 must be a multiple of 8";
+    size_t smem = (3 * (F + 2) + 10 * C1) * sizeof(float);
+    if (smem > 48 * 1024) return "conv1: F or C1 too large";
+    conv1_relu_nhwc_kernel<<<B * T1, 256, smem, st>>>(x, w, bias, out, B, T, F, T1, F1, T1pad, F1pad, C1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (nn.LayerNorm, eps 1e-5): otrans/encoder/conformer.py:52,57,62,67,87,89
+// bf16 in -> bf16 (or f32) out, fp32 statistics, warp per row, 16-byte loads.  An optional second
+// affine LayerNorm is applied back to back (Conformer post_ffn_norm -> final_norm, conformer.py:87-89).
+// ------------------------------------------------------------------------------------------------
+template <int CH>  // CH = 16-byte chunks per lane (N = CH * 256)
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int ldx, void* __restrict__ out,
+                                                        int ldo, int out_f32, const float* __restrict__ g1,
+                                                        const float* __restrict__ b1, const float* __restrict__ g2,
+                                                        const float* __restrict__ b2, float eps, int M, int N) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float v[CH * 8];
+    const bf16* xr = x + (size_t)row * ldx;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < N) {
+            uint4 u = *reinterpret_cast<const uint4*>(xr + col);
+            float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+            v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = b.x; v[c * 8 + 3] = b.y;
+            v[c * 8 + 4] = cc.x; v[c * 8 + 5] = cc.y; v[c * 8 + 6] = d.x; v[c * 8 + 7] = d.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c * 8 + j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c * 8 + j];
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* g = pass ? g2 : g1;
+        const float* bb = pass ? b2 : b1;
+        if (pass == 1) {
+            if (g2 == nullptr) break;
+            s = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH * 8; ++i) s += v[i];
+        }
+        const float mean = warp_sum(s) / N;
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int col = (c * 32 + lane) * 8;
+            if (col < N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[c * 8 + j] - mean; q += d * d; }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / N + eps);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int col = (c * 32 + lane) * 8;
+            if (col < N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[c * 8 + j] = (v[c * 8 + j] - mean) * rstd * g[col + j] + bb[col + j];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < N) {
+            if (out_f32) {
+                float* o = reinterpret_cast<float*>(out) + (size_t)row * ldo + col;
+                *reinterpret_cast<float4*>(o) = make_float4(v[c * 8], v[c * 8 + 1], v[c * 8 + 2], v[c * 8 + 3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[c * 8 + 4], v[c * 8 + 5], v[c * 8 + 6], v[c * 8 + 7]);
+            } else {
+                uint4 u;
+                u.x = pack_bf16(v[c * 8], v[c * 8 + 1]);
+                u.y = pack_bf16(v[c * 8 + 2], v[c * 8 + 3]);
+                u.z = pack_bf16(v[c * 8 + 4], v[c * 8 + 5]);
+                u.w = pack_bf16(v[c * 8 + 6], v[c * 8 + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + (size_t)row * ldo + col) = u;
+            }
+        }
+    }
+}
+
+const char* layernorm_launch(cudaStream_t st, const bf16* x, int ldx, void* out, int ldo, int out_f32, const float* g1,
+                             const float* b1, const float* g2, const float* b2, float eps, int M, int N) {
+    if (N % 8 || ldx % 8 || N > 1024) return "layernorm: N must be a multiple of 8 and <= 1024";
+    if ((out_f32 && ldo % 4) || (!out_f32 && ldo % 8)) return "layernorm: bad output stride";
+    const int rows_per_block = 8;
+    dim3 grid((M + rows_per_block - 1) / rows_per_block);
+    const int ch = (N + 255) / 256;
+    switch (ch) {
+        case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        default: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sinusoidal table: PE[p,2i] = sin(p*w_i), PE[p,2i+1] = cos(p*w_i), w_i = exp(-2i*ln(1e4)/d)
+// otrans/module/pos.py:30-42 (recomputed on every call there; computed once per (first_pos, n, d) here)
+// ------------------------------------------------------------------------------------------------
+__global__ void sinusoid_table_kernel(float* __restrict__ out, int n_pos, int d, int first_pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pos * d) return;
+    const int p = i / d + first_pos, c = i % d;
+    const float w = expf((float)(c & ~1) * -(logf(10000.0f) / (float)d));
+    const float a = (float)p * w;
+    out[i] = (c & 1) ? cosf(a) : sinf(a);
+}
+
+const char* sinusoid_table_launch(cudaStream_t st, float* out, int n_pos, int d, int first_pos) {
+    const int n = n_pos * d;
+    sinusoid_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, n_pos, d, first_pos);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding gather + positional encoding:  out[n] = emb[tok[n]] * sqrt(d) + PE[pos(n)]
+// otrans/decoder/transformer.py:163,169  (+ module/pos.py:56)
+// tok index:  tok[n * tok_stride + tok_off]; position: step_ptr ? *step_ptr : n % period
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_posenc_kernel(const long long* __restrict__ tok, int tok_stride, const bf16* __restrict__ emb,
+                                    const float* __restrict__ table, bf16* __restrict__ out, int N, int d, int period,
+                                    const int* __restrict__ step_ptr, float xscale, int vocab) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int pos = step_ptr ? *step_ptr : (n % period);
+    long long t = tok[(size_t)n * tok_stride];
+    if (t < 0 || t >= vocab) t = 0;
+    const bf16* e = emb + (size_t)t * d;
+    const float* pe = table + (size_t)pos * d;
+    for (int col = lane * 8; col < d; col += 256) {
+        uint4 u = *reinterpret_cast<const uint4*>(e + col);
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), dd = unpack_bf16(u.w);
+        const float4 p0 = *reinterpret_cast<const float4*>(pe + col);
+        const float4 p1 = *reinterpret_cast<const float4*>(pe + col + 4);
+        uint4 o;
+        o.x = pack_bf16(a.x * xscale + p0.x, a.y * xscale + p0.y);
+        o.y = pack_bf16(b.x * xscale + p0.z, b.y * xscale + p0.w);
+        o.z = pack_bf16(c.x * xscale + p1.x, c.y * xscale + p1.y);
+        o.w = pack_bf16(dd.x * xscale + p1.z, dd.y * xscale + p1.w);
+        *reinterpret_cast<uint4*>(out + (size_t)n * d + col) = o;
+    }
+}
+
+const char* embed_posenc_launch(cudaStream_t st, const long long* tok, int tok_stride, const bf16* emb,
+                                const float* table, bf16* out, int N, int d, int period, const int* step_ptr,
+                                int vocab) {
+    if (d % 8) return "embed: d must be a multiple of 8";
+    embed_posenc_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, tok_stride, emb, table, out, N, d, period, step_ptr,
+                                                     sqrtf((float)d), vocab);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row log-softmax, fp32 (F.log_softmax of the last position's logits, decoder/transformer.py:206)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out,
+                                                          int ldo, int V) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const float* xr = x + (size_t)blockIdx.x * ldx;
+    float* orow = out + (size_t)blockIdx.x * ldo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += 256) m = fmaxf(m, xr[i]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+        bc = t;
+    }
+    __syncthreads();
+    m = bc;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += 256) s += expf(xr[i] - m);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        bc = m + logf(t);
+    }
+    __syncthreads();
+    const float lse = bc;
+    for (int i = threadIdx.x; i < V; i += 256) orow[i] = xr[i] - lse;
+}
+
+const char* log_softmax_launch(cudaStream_t st, const float* x, int ldx, float* out, int ldo, int rows, int V) {
+    log_softmax_kernel<<<rows, 256, 0, st>>>(x, ldx, out, ldo, V);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode-time self-attention with a per-hypothesis KV cache (the `cache` the reference stubbed out,
+// decoder/transformer.py:92-126,188-203).  One query (the newest token) per hypothesis; the prefix
+// K/V of hypothesis n at position s' < step live in slot anc[n][s'] of step s' (beam reordering
+// moves 4-byte ancestry entries, never K/V rows).  Warp = (hypothesis, head), d_k = 64, lane owns
+// two dims.  Also appends the current K/V to the cache.
+//   qkv   bf16 [N, 3d] (Q | K | V of the current token, attention.py:73 split order)
+//   kc,vc bf16 [Lmax, N, d]
+//   anc   int32 [2, N, Lmax]  (ping-pong, buffer (step & 1) is current)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
+                                                               bf16* __restrict__ vc, const int* __restrict__ anc,
+                                                               const int* __restrict__ step_ptr, bf16* __restrict__ out,
+                                                               int N, int H, int Lmax, float scale) {
+    extern __shared__ float sc[];  // [warps][Lmax + 1]
+    const int n = blockIdx.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const int d = H * 64;
+    const int step = *step_ptr;
+    const int* an = anc + ((size_t)(step & 1) * N + n) * Lmax;
+    for (int h = wib; h < H; h += nw) {
+        float* s_row = sc + wib * (Lmax + 1);
+        const bf16* base = qkv + (size_t)n * 3 * d + h * 64 + 2 * lane;
+        const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(base));
+        const uint32_t kcur = *reinterpret_cast<const uint32_t*>(base + d);
+        const uint32_t vcur = *reinterpret_cast<const uint32_t*>(base + 2 * d);
+        const size_t cur_off = ((size_t)step * N + n) * d + h * 64 + 2 * lane;
+        *reinterpret_cast<uint32_t*>(kc + cur_off) = kcur;
+        *reinterpret_cast<uint32_t*>(vc + cur_off) = vcur;
+        // scores
+        float mx = -INFINITY;
+        for (int s0 = 0; s0 <= step; s0 += 4) {
+            float part[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = s0 + j;
+                float dot = 0.f;
+                if (s <= step) {
+                    uint32_t kk;
+                    if (s == step) kk = kcur;
+                    else kk = *reinterpret_cast<const uint32_t*>(kc + ((size_t)s * N + an[s]) * d + h * 64 + 2 * lane);
+                    const float2 kf = unpack_bf16(kk);
+                    dot = q.x * kf.x + q.y * kf.y;
+                }
+                part[j] = dot;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t = warp_sum(part[j]) * scale;
+                if (s0 + j <= step) {
+                    if (lane == 0) s_row[s0 + j] = t;
+                    mx = fmaxf(mx, t);
+                }
+            }
+        }
+        __syncwarp();
+        float l = 0.f, ax = 0.f, ay = 0.f;
+        for (int s = 0; s <= step; ++s) {
+            const float pw = __expf(s_row[s] - mx);
+            uint32_t vv;
+            if (s == step) vv = vcur;
+            else vv = *reinterpret_cast<const uint32_t*>(vc + ((size_t)s * N + an[s]) * d + h * 64 + 2 * lane);
+            const float2 vf = unpack_bf16(vv);
+            l += pw;
+            ax += pw * vf.x;
+            ay += pw * vf.y;
+        }
+        const float inv = 1.0f / l;
+        *reinterpret_cast<uint32_t*>(out + (size_t)n * d + h * 64 + 2 * lane) = pack_bf16(ax * inv, ay * inv);
+        __syncwarp();
+    }
+}
+
+const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, bf16* vc, const int* anc,
+                                    const int* step_ptr, bf16* out, int N, int H, int Lmax) {
+    const int warps = H < 4 ? H : 4;
+    size_t smem = (size_t)warps * (Lmax + 1) * sizeof(float);
+    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone PositionalEncoding.forward: out = x * alpha + table[row % period]   (module/pos.py:56)
+// (the fused path does this in the front-end Linear's epilogue; this kernel serves the module-level
+// drop-in API where frontend and encoder are called separately).  x f32 or bf16 -> bf16.
+// ------------------------------------------------------------------------------------------------
+__global__ void scale_add_table_kernel(const void* __restrict__ x, int ldx, int x_f32, bf16* __restrict__ out, int ldo,
+                                       float alpha, const float* __restrict__ table, int period, int M, int N) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(i / N), col = (int)(i % N);
+    if (row >= M) return;
+    const float v = x_f32 ? reinterpret_cast<const float*>(x)[(size_t)row * ldx + col]
+                          : __bfloat162float(reinterpret_cast<const bf16*>(x)[(size_t)row * ldx + col]);
+    const float t = table ? table[(size_t)(row % period) * N + col] : 0.f;
+    out[(size_t)row * ldo + col] = __float2bfloat16(v * alpha + t);
+}
+
+const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int x_f32, bf16* out, int ldo, float alpha,
+                                   const float* table, int period, int M, int N) {
+    const size_t n = (size_t)M * N;
+    scale_add_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, x_f32, out, ldo, alpha, table, period, M, N);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace otb

@@ -1,0 +1,108 @@
+// Internal declarations shared by the .cu translation units of libotb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace otb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- epilogues of the tcgen05 GEMM (C = A[M,K] * W[N,K]^T, fp32 accumulate in TMEM) ----
+enum Epilogue : int {
+    EPI_BIAS = 0,      // out = acc + bias
+    EPI_RELU = 1,      // out = relu(acc + bias)
+    EPI_GLU = 2,       // W has 2*Nh rows; out[:, j] = (acc_j + b_j) * sigmoid(acc_{Nh+j} + b_{Nh+j})
+    EPI_TABLE = 3,     // out = (acc + bias) * alpha + table[(row % period) * N + col]     (x*sqrt(d)+PE)
+    EPI_RESID = 4,     // out = resid + alpha * (acc + bias)
+    EPI_RESID_LN = 5,  // out = LayerNorm(resid + acc + bias) * gamma + beta   (tile spans the whole row)
+    EPI_SWISH = 6,     // out = v * sigmoid(v), v = acc + bias
+    EPI_GELU = 7,      // out = gelu(v) (erf form, as F.gelu)
+    EPI_TANH = 8,      // out = tanh(v)
+};
+
+struct GemmParams {
+    int M, N, K;  // N = number of output columns (for GLU: Nh); K multiple of 8
+    const float* bias;
+    void* out;
+    int ldc;
+    int out_f32;
+    const bf16* resid;
+    int ldr;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    float alpha;
+    const float* table;
+    int period;
+    const int* row_len;  // optional: rows with (m % row_period) >= row_len[m / row_period] produce 0 (before resid)
+    int row_period;
+    // implicit-GEMM 3x3/stride-2 convolution mode (A operand gathered by a 5-D TMA map)
+    int conv;
+    int conv_F2;       // output frequency bins
+    int conv_R;        // output time rows per M tile (R * F2 <= 128)
+    int conv_T1h;      // (padded input time rows) / 2
+    int conv_T2;       // valid output time rows per utterance
+    int conv_B;        // batch
+    int conv_cchunks;  // C_in / 64
+};
+
+const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, int ldw, int w_rows, int epi,
+                        GemmParams p, const CUtensorMap* conv_map);
+
+// encode helpers (driver entry point fetched at runtime; libcuda is not a link-time dependency)
+const char* encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+                           uint32_t box_cols, uint32_t box_rows);
+const char* encode_tmap_conv5d(CUtensorMap* m, const void* base, int C, int F1h, int T1h_total, uint32_t boxF,
+                               uint32_t boxR);
+
+struct AttnParams {
+    int B, H, Tq, Tk;
+    const int* kv_len;  // [B] or null
+    int causal;
+    float scale_log2;   // (1/sqrt(dk)) * log2(e)
+    bf16* out;
+    int ldo;
+    int q_col0, k_col0, v_col0;
+    const float* bd;    // optional relative-position scores, [B,H,Tq,ldbd]; bias(i,j) = bd[.., i, j - i + Tq - 1]
+    int ldbd;
+};
+
+struct BeamState {
+    int* tok_hist;
+    int* par_hist;
+    long long* last_tok;
+    float* scores;
+    unsigned char* flag;
+    int* anc;
+    int* ctrl;
+    int N, beam, Lmax;
+};
+
+const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,
+                        const void* v, int ldv, const AttnParams& p);
+const char* conv1_launch(cudaStream_t st, const float* x, const float* w, const float* bias, bf16* out, int B, int T,
+                         int F, int T1, int F1, int T1pad, int F1pad, int C1);
+const char* layernorm_launch(cudaStream_t st, const bf16* x, int ldx, void* out, int ldo, int out_f32, const float* g1,
+                             const float* b1, const float* g2, const float* b2, float eps, int M, int N);
+const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int x_f32, bf16* out, int ldo, float alpha,
+                                   const float* table, int period, int M, int N);
+const char* sinusoid_table_launch(cudaStream_t st, float* out, int n_pos, int d, int first_pos);
+const char* embed_posenc_launch(cudaStream_t st, const long long* tok, int tok_stride, const bf16* emb,
+                                const float* table, bf16* out, int N, int d, int period, const int* step_ptr,
+                                int vocab);
+const char* log_softmax_launch(cudaStream_t st, const float* x, int ldx, float* out, int ldo, int rows, int V);
+const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, bf16* vc, const int* anc,
+                                    const int* step_ptr, bf16* out, int N, int H, int Lmax);
+const char* beam_init_launch(cudaStream_t stream, BeamState st);
+const char* beam_step_launch(cudaStream_t stream, const float* logp, int ldl, int V, const float* lm_logp, int ld_lm,
+                             float lm_weight, BeamState st, long long* dbg_ktok, int* dbg_offs);
+const char* beam_reconstruct_launch(cudaStream_t stream, BeamState st, long long* preds, int ld, int steps);
+const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalty, float lamda, int nbest,
+                                 long long* out_preds, float* out_scores);
+
+int num_sms();
+void set_error(const char* msg);
+
+}  // namespace otb

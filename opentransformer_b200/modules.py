@@ -1,0 +1,445 @@
+"""Host-side mirror of the reference's nn.Module surface for the hot path.
+
+Same class names, constructor kwargs (the YAML sub-dicts verbatim) and ``state_dict()`` key names /
+shapes as the reference so existing checkpoints load unchanged:
+
+    ConvFrontEnd        <- otrans/frontend/conv.py:86-159
+    TransformerEncoder  <- otrans/encoder/transformer.py:93-134
+    TransformerDecoder  <- otrans/decoder/transformer.py:129-208
+
+The nn.Linear / nn.LayerNorm / nn.Conv2d / nn.Embedding objects below are *parameter holders*
+only (they give identical key names and default init); their ``forward`` is never called.  All
+compute goes through ``ops`` -> libotb200.so (hand-written sm_100a kernels).  There is no CPU path:
+calling a module with CPU tensors raises.
+
+Numerics: GEMM operands / activations are bf16, accumulation fp32, LayerNorm / softmax statistics
+fp32 (DESIGN.md "rounding points").  Inference only in round 1 (no backward kernels yet).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import BF16, EPI_BIAS, EPI_GLU, EPI_RELU, EPI_RESID, EPI_RESID_LN, EPI_TABLE, ACT_EPILOGUE
+
+
+def _lengths(mask):
+    """bool [B,T] prefix mask -> int32 [B] lengths (masks are contiguous prefixes)."""
+    return mask.sum(dim=1).to(torch.int32).contiguous()
+
+
+class _Packed:
+    """bf16 shadow copies of fp32 master parameters, refreshed when any parameter changes
+    (load_state_dict / optimizer steps bump ``Tensor._version``)."""
+
+    def __init__(self, module, builder):
+        self._module, self._builder, self._sig, self._val = module, builder, None, None
+
+    def get(self):
+        sig = tuple((p.data_ptr(), p._version) for p in self._module.parameters())
+        if self._val is None or sig != self._sig:
+            with torch.no_grad():
+                self._val = self._builder()
+            self._sig = sig
+        return self._val
+
+
+def _w(lin):
+    return lin.weight.detach().to(BF16).contiguous()
+
+
+def _b(lin):
+    return lin.bias.detach().float().contiguous() if lin.bias is not None else None
+
+
+def _ln(norm):
+    return norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous()
+
+
+def _no_train(module):
+    if module.training and torch.is_grad_enabled():
+        raise NotImplementedError('opentransformer_b200 round 1 implements the forward hot path only; '
+                                  'call under model.eval() / torch.no_grad()')
+
+
+# ------------------------------------------------------------------------------------------------
+# front end
+# ------------------------------------------------------------------------------------------------
+class Conv2dLayer(nn.Module):
+    """Parameter holder with the reference's key names (frontend/conv.py:15-48)."""
+
+    def __init__(self, input_size, in_channel, out_channel, kernel_size, stride, dropout=0.1, batch_norm=False,
+                 residual=False, act_func_type='relu'):
+        super().__init__()
+        ks = kernel_size if isinstance(kernel_size, (list, tuple)) else [kernel_size, kernel_size]
+        if list(ks) != [3, 3] or stride != 2 or batch_norm or residual or act_func_type != 'relu':
+            raise NotImplementedError('B200 ConvFrontEnd supports the shipped configuration only: '
+                                      '3x3 kernels, stride 2, relu, no batch_norm / residual')
+        self.conv_layer = nn.Conv2d(in_channel, out_channel, (3, 3), stride=2, padding=(0, 1))
+        self.output_size = (input_size + 2 - 3) // 2 + 1
+        self.out_channel = out_channel
+
+
+class ConvFrontEnd(nn.Module):
+    """forward(x f32 [B,T,F], mask bool [B,T]) -> (f32 [B,T',D], bool [B,T'])   (frontend/conv.py:131-153)."""
+
+    def __init__(self, input_size, output_size, in_channel=1, mid_channel=32, out_channel=128,
+                 kernel_size=[[3, 3], [3, 3]], stride=[2, 2], dropout=0.0, act_func_type='relu',
+                 front_end_layer_norm=False):
+        super().__init__()
+        assert isinstance(kernel_size, list) and len(kernel_size) == 2
+        assert isinstance(stride, list) and len(stride) == 2
+        if in_channel != 1:
+            raise NotImplementedError('in_channel must be 1 (log-fbank input)')
+        if dropout:
+            raise NotImplementedError('frontend dropout > 0 is a training feature (round 2)')
+        self.input_size, self.output_size = input_size, output_size
+        self.front_end_layer_norm = front_end_layer_norm
+        self.conv1 = Conv2dLayer(input_size, in_channel, mid_channel, kernel_size[0], stride[0], dropout)
+        self.conv2 = Conv2dLayer(self.conv1.output_size, mid_channel, out_channel, kernel_size[1], stride[1], dropout)
+        self.conv_output_size = self.conv2.output_size * out_channel
+        self.output_layer = nn.Linear(self.conv_output_size, output_size)
+        if front_end_layer_norm:
+            self.layer_norm = nn.LayerNorm(output_size)
+        self._pack = _Packed(self, self._build_pack)
+
+    def _build_pack(self):
+        c1 = self.conv1.conv_layer
+        c2 = self.conv2.conv_layer
+        C1, C2 = c1.out_channels, c2.out_channels
+        F2 = self.conv2.output_size
+        C1p = (C1 + 63) // 64 * 64          # one 128-byte tap per k-block needs 64-channel multiples
+        w1 = torch.zeros(C1p, 1, 3, 3, device=c1.weight.device)
+        w1[:C1] = c1.weight.detach().float()
+        b1 = torch.zeros(C1p, device=c1.weight.device)
+        b1[:C1] = c1.bias.detach().float()
+        w2 = torch.zeros(C2, 3, 3, C1p, device=c1.weight.device)
+        w2[..., :C1] = c2.weight.detach().float().permute(0, 2, 3, 1)   # [C2,kh,kw,C1]: k = (kh*3+kw)*C1 + c
+        # reference feature index is c*F2 + f (conv.py:145); conv2 kernel emits f*C2 + c -> permute columns once
+        wo = self.output_layer.weight.detach().float().view(self.output_size, C2, F2).permute(0, 2, 1)
+        pk = {'w1': w1.contiguous(), 'b1': b1.contiguous(), 'C1p': C1p,
+              'w2': w2.reshape(C2, 9 * C1p).to(BF16).contiguous(), 'b2': c2.bias.detach().float().contiguous(),
+              'wo': wo.reshape(self.output_size, F2 * C2).to(BF16).contiguous(), 'bo': _b(self.output_layer)}
+        if self.front_end_layer_norm:
+            pk['ln'] = _ln(self.layer_norm)
+        return pk
+
+    def output_mask(self, mask):
+        # Conv2dLayer.return_output_mask twice (frontend/conv.py:78-83): mask[:, 1::2][:, :t]
+        _, _, t2, _ = ops.conv_geometry(mask.shape[1], self.input_size)
+        t1 = (mask.shape[1] - 3) // 2 + 1
+        m = mask[:, 1::2][:, :t1]
+        return m[:, 1::2][:, :t2]
+
+    def forward_bf16(self, x, posenc_scale=None, posenc_table=None):
+        """x f32 [B,T,F] -> bf16 [B*T', D].  When posenc_* are given, x*scale+PE is fused into the Linear
+        epilogue (pos.py:56) so the encoder can skip its own positional-encoding pass."""
+        _no_train(self)
+        pk = self._pack.get()
+        B, T, F = x.shape
+        if F != self.input_size:
+            raise ValueError(f'expected {self.input_size} features, got {F}')
+        x = x.contiguous().float()
+        _, _, T2, F2 = ops.conv_geometry(T, F)
+        h1 = ops.conv1_relu(x, pk['w1'], pk['b1'])
+        h2 = ops.conv2_relu(h1, pk['w2'], pk['b2'], B, T, F)
+        if posenc_table is not None and not self.front_end_layer_norm:
+            y = ops.linear(h2, pk['wo'], pk['bo'], EPI_TABLE, alpha=posenc_scale, table=posenc_table, period=T2)
+        else:
+            y = ops.linear(h2, pk['wo'], pk['bo'], EPI_BIAS)
+            if self.front_end_layer_norm:
+                y = ops.layernorm(y, *pk['ln'])
+            if posenc_table is not None:
+                y = ops.scale_add_table(y, posenc_scale, posenc_table, T2)
+        return y, T2
+
+    def forward(self, x, mask):
+        y, T2 = self.forward_bf16(x)
+        return y.float().view(x.shape[0], T2, self.output_size), self.output_mask(mask)
+
+    def inference(self, x, mask, cache):
+        y, m = self.forward(x, mask)
+        return y, m, cache
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders shared by encoder / decoder layers
+# ------------------------------------------------------------------------------------------------
+class MultiHeadedSelfAttention(nn.Module):
+    """Keys: qvk_proj.{weight,bias} [3d,d] (split order Q,K,V -- attention.py:73), output_proj.*"""
+
+    def __init__(self, n_heads, d_model, dropout_rate=0.0, share_qvk_proj=False):
+        super().__init__()
+        if share_qvk_proj:
+            raise NotImplementedError('share_qvk_proj')
+        if d_model != n_heads * 64:
+            raise NotImplementedError('the sm_100a attention kernel is specialised for d_k = 64')
+        self.qvk_proj = nn.Linear(d_model, d_model * 3)
+        self.output_proj = nn.Linear(d_model, d_model)
+
+
+class MultiHeadedCrossAttention(nn.Module):
+    """Keys: q_proj.*, vk_proj.* [2d,mem] (split order K,V -- attention.py:134), output_proj.*"""
+
+    def __init__(self, n_heads, d_model, memory_dim, dropout_rate=0.0, share_vk_proj=False):
+        super().__init__()
+        if share_vk_proj:
+            raise NotImplementedError('share_vk_proj')
+        if d_model != n_heads * 64:
+            raise NotImplementedError('the sm_100a attention kernel is specialised for d_k = 64')
+        self.q_proj = nn.Linear(d_model, d_model)
+        self.vk_proj = nn.Linear(memory_dim, d_model * 2)
+        self.output_proj = nn.Linear(d_model, d_model)
+
+
+class PositionwiseFeedForward(nn.Module):
+    """Keys: w_1.* [d_ff or 2*d_ff, d], w_2.* [d, d_ff]   (module/ffn.py:24-41)"""
+
+    def __init__(self, d_model, d_ff, dropout, activation='relu'):
+        super().__init__()
+        assert activation in ['relu', 'gelu', 'glu', 'tanh', 'swish']
+        self.activation = activation
+        self.w_1 = nn.Linear(d_model, d_ff * 2 if activation == 'glu' else d_ff)
+        self.w_2 = nn.Linear(d_ff, d_model)
+
+
+class PositionalEncoding(nn.Module):
+    """module/pos.py:11-28.  Quirk kept: callers pass pos_dropout into the
+    ``scale_learnable`` slot, so a non-zero pos_dropout creates ``alpha`` and switches to x + alpha*PE."""
+
+    def __init__(self, emb_dim, scale_learnable=False, dropout=0.0):
+        super().__init__()
+        self.emb_dim = emb_dim
+        self.xscale = math.sqrt(emb_dim)
+        self.scale_learnable = bool(scale_learnable)
+        if self.scale_learnable:
+            self.alpha = nn.Parameter(torch.tensor(1.0))
+
+    def scale_and_table(self, n_pos, device):
+        table = ops.sinusoid_table(n_pos, self.emb_dim, 0, device)
+        if self.scale_learnable:
+            return 1.0, table * self.alpha.detach().float()
+        return self.xscale, table
+
+
+def _ffn(x, pk, resid, ln=None, alpha=1.0):
+    """w_2(act(w_1(x))) with the residual (and post-LayerNorm) fused into the second GEMM."""
+    h = ops.linear(x, pk['w1'], pk['b1'], pk['act'])
+    if ln is not None and pk['w2'].shape[0] in (64, 128, 256):
+        return ops.linear(h, pk['w2'], pk['b2'], EPI_RESID_LN, resid=resid, gamma=ln[0], beta=ln[1])
+    y = ops.linear(h, pk['w2'], pk['b2'], EPI_RESID, resid=resid, alpha=alpha)
+    return ops.layernorm(y, *ln) if ln is not None else y
+
+
+def _proj_resid_ln(ctx, w, b, resid, ln):
+    """output_proj + residual (+ post-LayerNorm) in one GEMM when the row fits one tile."""
+    if ln is not None and w.shape[0] in (64, 128, 256):
+        return ops.linear(ctx, w, b, EPI_RESID_LN, resid=resid, gamma=ln[0], beta=ln[1])
+    y = ops.linear(ctx, w, b, EPI_RESID, resid=resid)
+    return ops.layernorm(y, *ln) if ln is not None else y
+
+
+def _ffn_pack(ff):
+    return {'w1': _w(ff.w_1), 'b1': _b(ff.w_1), 'w2': _w(ff.w_2), 'b2': _b(ff.w_2),
+            'act': ACT_EPILOGUE[ff.activation]}
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder
+# ------------------------------------------------------------------------------------------------
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, n_heads, d_model, d_ff, slf_attn_dropout, ffn_dropout, residual_dropout,
+                 normalize_before=False, concat_after=False, relative_positional=False, activation='relu'):
+        super().__init__()
+        if concat_after:
+            raise NotImplementedError('concat_after is not used by any shipped config')
+        if relative_positional:
+            raise NotImplementedError('relative_positional TransformerEncoder: use the Conformer encoder path')
+        self.n_heads = n_heads
+        self.normalize_before = normalize_before
+        self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
+        self.feed_forward = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def pack(self):
+        a = self.slf_attn
+        return {'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj),
+                'ffn': _ffn_pack(self.feed_forward), 'ln1': _ln(self.norm1), 'ln2': _ln(self.norm2)}
+
+    def run(self, x, pk, B, T, lengths):
+        """x bf16 [B*T, d] -> bf16 [B*T, d]   (encoder/transformer.py:41-65)"""
+        d, H = x.shape[1], self.n_heads
+        if self.normalize_before:
+            x = ops.layernorm(x, *pk['ln1'])          # residual is taken AFTER the norm (transformer.py:42-44)
+        qkv = ops.linear(x, pk['wqkv'], pk['bqkv'])
+        ctx = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
+        x = _proj_resid_ln(ctx, pk['wo'], pk['bo'], x, None if self.normalize_before else pk['ln1'])
+        if self.normalize_before:
+            x = ops.layernorm(x, *pk['ln2'])
+        return _ffn(x, pk['ffn'], x, None if self.normalize_before else pk['ln2'])
+
+
+class TransformerEncoder(nn.Module):
+    """forward(inputs f32 [B,T,D], mask bool [B,T]) -> (f32 [B,T,D], mask, attn_weights)
+
+    ``attn_weights`` maps 'enc_block_i' -> {'slf_attn_weights': None}: the reference materialises and
+    returns [B,h,T,T] weights that no caller reads; the fused kernel never forms them.
+    """
+
+    def __init__(self, d_model=256, n_heads=4, d_ff=2048, n_blocks=6, pos_dropout=0.0, slf_attn_dropout=0.0,
+                 ffn_dropout=0.0, residual_dropout=0.1, normalize_before=False, concat_after=False,
+                 relative_positional=False, activation='relu'):
+        super().__init__()
+        self.d_model = d_model
+        self.normalize_before = normalize_before
+        self.relative_positional = relative_positional
+        self.pos_emb = PositionalEncoding(d_model, pos_dropout)
+        self.blocks = nn.ModuleList([
+            TransformerEncoderLayer(n_heads, d_model, d_ff, slf_attn_dropout, ffn_dropout, residual_dropout,
+                                    normalize_before, concat_after, relative_positional, activation)
+            for _ in range(n_blocks)])
+        if normalize_before:
+            self.norm = nn.LayerNorm(d_model)
+        self._pack = _Packed(self, lambda: {'blocks': [b.pack() for b in self.blocks],
+                                            'norm': _ln(self.norm) if normalize_before else None})
+
+    def forward_bf16(self, x, B, T, lengths):
+        """x bf16 [B*T, d] with the positional encoding already applied."""
+        _no_train(self)
+        pk = self._pack.get()
+        for blk, bpk in zip(self.blocks, pk['blocks']):
+            x = blk.run(x, bpk, B, T, lengths)
+        if self.normalize_before:
+            x = ops.layernorm(x, *pk['norm'])
+        return x
+
+    def fuse_abs_posenc(self):
+        """True when x*sqrt(d)+PE may be fused into the front end's Linear epilogue."""
+        return not self.relative_positional
+
+    def apply_posenc_bf16(self, x, B, T):
+        scale, table = self.pos_emb.scale_and_table(T, x.device)
+        return ops.scale_add_table(x, scale, table, T)
+
+    def forward(self, inputs, mask):
+        B, T, D = inputs.shape
+        x = self.apply_posenc_bf16(inputs.contiguous().view(B * T, D), B, T)
+        y = self.forward_bf16(x, B, T, _lengths(mask))
+        attn = {'enc_block_%d' % i: {'slf_attn_weights': None} for i in range(len(self.blocks))}
+        return y.float().view(B, T, D), mask, attn
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------------
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, n_heads, d_model, d_ff, memory_dim, slf_attn_dropout=0.0, src_attn_dropout=0.0,
+                 ffn_dropout=0.0, residual_dropout=0.1, normalize_before=False, concat_after=False,
+                 relative_positional=False, activation='relu'):
+        super().__init__()
+        if concat_after or relative_positional:
+            raise NotImplementedError('concat_after / relative_positional decoder')
+        self.n_heads = n_heads
+        self.normalize_before = normalize_before
+        self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
+        self.src_attn = MultiHeadedCrossAttention(n_heads, d_model, memory_dim, src_attn_dropout)
+        self.feed_forward = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def pack(self):
+        a, c = self.slf_attn, self.src_attn
+        return {'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj),
+                'wq': _w(c.q_proj), 'bq': _b(c.q_proj), 'wkv': _w(c.vk_proj), 'bkv': _b(c.vk_proj),
+                'wo2': _w(c.output_proj), 'bo2': _b(c.output_proj), 'ffn': _ffn_pack(self.feed_forward),
+                'ln1': _ln(self.norm1), 'ln2': _ln(self.norm2), 'ln3': _ln(self.norm3)}
+
+
+class TransformerDecoder(nn.Module):
+    """forward(targets i64 [B,L], memory f32 [B,T,D], memory_mask bool [B,T]) -> (logits f32 [B,L,V], attn)
+    inference(preds i64 [N,l], memory, memory_mask, cache) -> (log_probs f32 [N,V], cache, attn)
+    (decoder/transformer.py:161-208).  `cache` is passed through untouched exactly like the reference;
+    the KV-cached incremental path lives in recognize.BeamDecoder."""
+
+    def __init__(self, vocab_size, d_model=256, n_heads=4, d_ff=2048, memory_dim=256, n_blocks=6, pos_dropout=0.0,
+                 slf_attn_dropout=0.0, src_attn_dropout=0.0, ffn_dropout=0.0, residual_dropout=0.1,
+                 activation='relu', normalize_before=True, concat_after=False, share_embedding=False):
+        super().__init__()
+        self.decoder_type = 'transformer'
+        self.normalize_before = normalize_before
+        self.relative_positional = False
+        self.d_model, self.n_heads, self.vocab_size = d_model, n_heads, vocab_size
+        self.embedding = nn.Embedding(vocab_size, d_model)
+        self.pos_emb = PositionalEncoding(d_model, pos_dropout)
+        self.blocks = nn.ModuleList([
+            TransformerDecoderLayer(n_heads, d_model, d_ff, memory_dim, slf_attn_dropout, src_attn_dropout,
+                                    ffn_dropout, residual_dropout, normalize_before, concat_after, False, activation)
+            for _ in range(n_blocks)])
+        if normalize_before:
+            self.after_norm = nn.LayerNorm(d_model)
+        self.output_layer = nn.Linear(d_model, vocab_size)
+        if share_embedding:
+            assert self.embedding.weight.size() == self.output_layer.weight.size()
+            self.output_layer.weight = self.embedding.weight   # tied (decoder/transformer.py:156-158)
+        self._pack = _Packed(self, self._build_pack)
+
+    def _build_pack(self):
+        emb = self.embedding.weight.detach().to(BF16).contiguous()
+        tied = self.output_layer.weight is self.embedding.weight
+        return {'emb': emb, 'wout': emb if tied else _w(self.output_layer), 'bout': _b(self.output_layer),
+                'blocks': [b.pack() for b in self.blocks],
+                'after': _ln(self.after_norm) if self.normalize_before else None}
+
+    def packed(self):
+        return self._pack.get()
+
+    @property
+    def ld_logits(self):
+        return (self.vocab_size + 7) // 8 * 8
+
+    def forward_bf16(self, targets, memory_bf16, mem_len, B, L, T):
+        """targets i64 [B,L]; memory bf16 [B*T, D] -> logits f32 [B*L, ld_logits] (first V columns valid)."""
+        _no_train(self)
+        pk = self._pack.get()
+        d, H = self.d_model, self.n_heads
+        scale, table = self.pos_emb.scale_and_table(L, memory_bf16.device)
+        if self.pos_emb.scale_learnable:
+            raise NotImplementedError('decoder with learnable positional scale')
+        x = ops.embed_posenc(targets.contiguous(), pk['emb'], table, B * L, d, period=L)
+        for blk, p in zip(self.blocks, pk['blocks']):
+            nb = blk.normalize_before
+            if nb:
+                x = ops.layernorm(x, *p['ln1'])
+            qkv = ops.linear(x, p['wqkv'], p['bqkv'])
+            ctx = ops.attention(qkv, qkv, qkv, B, H, L, L, causal=True, q_col0=0, k_col0=d, v_col0=2 * d)
+            x = _proj_resid_ln(ctx, p['wo'], p['bo'], x, None if nb else p['ln1'])
+            if nb:
+                x = ops.layernorm(x, *p['ln2'])
+            q = ops.linear(x, p['wq'], p['bq'])
+            kv = ops.linear(memory_bf16, p['wkv'], p['bkv'])
+            ctx = ops.attention(q, kv, kv, B, H, L, T, kv_len=mem_len, k_col0=0, v_col0=d)
+            x = _proj_resid_ln(ctx, p['wo2'], p['bo2'], x, None if nb else p['ln2'])
+            if nb:
+                x = ops.layernorm(x, *p['ln3'])
+            x = _ffn(x, p['ffn'], x, None if nb else p['ln3'])
+        if self.normalize_before:
+            x = ops.layernorm(x, *pk['after'])
+        return ops.linear(x, pk['wout'], pk['bout'], EPI_BIAS, out_f32=True, n_out=self.ld_logits)
+
+    def forward(self, targets, memory, memory_mask):
+        B, L = targets.shape
+        T, D = memory.shape[1], memory.shape[2]
+        mem = ops.scale_add_table(memory.contiguous().view(B * T, D))   # f32 -> bf16
+        logits = self.forward_bf16(targets, mem, _lengths(memory_mask), B, L, T)
+        attn = {'dec_block_%d' % i: {'slf_attn_weights': None, 'src_attn_weights': None}
+                for i in range(len(self.blocks))}
+        return logits.view(B, L, -1)[:, :, :self.vocab_size], attn
+
+    def inference(self, preds, memory, memory_mask=None, cache=None):
+        assert preds.dim() == 2
+        logits, attn = self.forward(preds, memory, memory_mask)       # full recompute, as transformer.py:204
+        last = logits[:, -1, :].contiguous()
+        return ops.log_softmax(last, self.vocab_size), cache, attn

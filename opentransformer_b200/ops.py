@@ -1,0 +1,209 @@
+"""torch.Tensor-level wrappers around the C ABI (include/otb200.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; all compute is in
+libotb200.so.  Every wrapper launches on ``torch.cuda.current_stream()`` so the calls can be
+captured into a CUDA graph (see graphs.py).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+EPI_BIAS, EPI_RELU, EPI_GLU, EPI_TABLE, EPI_RESID, EPI_RESID_LN, EPI_SWISH, EPI_GELU, EPI_TANH = range(9)
+ACT_EPILOGUE = {'relu': EPI_RELU, 'glu': EPI_GLU, 'swish': EPI_SWISH, 'gelu': EPI_GELU, 'tanh': EPI_TANH}
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: the B200 hot path has no CPU fallback')
+    if t.dtype != dtype:
+        raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+    return t
+
+
+def conv_geometry(T, F):
+    t1, f1, t2, f2 = (ctypes.c_int() for _ in range(4))
+    check(_lib.lib().otb_conv_geometry(T, F, t1, f1, t2, f2), 'otb_conv_geometry')
+    return t1.value, f1.value, t2.value, f2.value
+
+
+def conv1_relu(x, w, bias, out=None):
+    """x f32 [B,T,F]; w f32 [C1,1,3,3] -> bf16 NHWC [B, 2*(T2+1), 2*F2, C1]."""
+    _need(x, torch.float32, 'x'); _need(w, torch.float32, 'w'); _need(bias, torch.float32, 'bias')
+    B, T, F = x.shape
+    C1 = w.shape[0]
+    _, _, T2, F2 = conv_geometry(T, F)
+    if out is None:
+        out = torch.empty(B, 2 * (T2 + 1), 2 * F2, C1, dtype=BF16, device=x.device)
+    check(_lib.lib().otb_conv1_relu(_p(x), _p(w), _p(bias), _p(out), B, T, F, C1, _stream()), 'otb_conv1_relu')
+    return out
+
+
+def conv2_relu(h1, w, bias, B, T, F, out=None):
+    """h1 = conv1 buffer; w bf16 [C2, 9*C1] (kh,kw,c order) -> bf16 [B*T2, F2*C2] (feature = f*C2 + c)."""
+    _need(h1, BF16, 'h1'); _need(w, BF16, 'w'); _need(bias, torch.float32, 'bias')
+    C2, K = w.shape
+    C1 = K // 9
+    _, _, T2, F2 = conv_geometry(T, F)
+    if out is None:
+        out = torch.empty(B * T2, F2 * C2, dtype=BF16, device=h1.device)
+    check(_lib.lib().otb_conv2_relu(_p(h1), _p(w), _p(bias), _p(out), B, T, F, C1, C2, _stream()), 'otb_conv2_relu')
+    return out
+
+
+def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=None, gamma=None, beta=None,
+           eps=1e-5, alpha=1.0, table=None, period=0, row_len=None, row_period=0, n_out=None):
+    """out[M,N] = epi(a[M,K] @ w[N(,2N),K]^T + bias).  a, w bf16 2-D (row stride = shape[1])."""
+    _need(a, BF16, 'a'); _need(w, BF16, 'w')
+    M, K = a.shape
+    N = w.shape[0] // 2 if epilogue == EPI_GLU else w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f'linear: K mismatch {w.shape} vs {a.shape}')
+    if out is None:
+        ldc = n_out if n_out is not None else N
+        out = torch.empty(M, ldc, dtype=torch.float32 if out_f32 else BF16, device=a.device)
+    ldc = out.stride(0)
+    check(_lib.lib().otb_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), ldc, M, N, K, epilogue,
+                                1 if out.dtype == torch.float32 else 0, _p(resid),
+                                resid.stride(0) if resid is not None else 0, _p(gamma), _p(beta), eps, alpha,
+                                _p(table), period, _p(row_len), row_period, _stream()), 'otb_linear')
+    return out
+
+
+def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0=0, v_col0=0, out=None, bd=None):
+    """q/k/v: bf16 2-D matrices (may be the same [M,3d] buffer with different column offsets)."""
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _need(t, BF16, n)
+    d = H * 64
+    if out is None:
+        out = torch.empty(B * Tq, d, dtype=BF16, device=q.device)
+    if kv_len is not None:
+        _need(kv_len, torch.int32, 'kv_len')
+    check(_lib.lib().otb_attention(_p(q), q.stride(0), q.shape[0], _p(k), k.stride(0), k.shape[0], _p(v), v.stride(0),
+                                   _p(out), out.stride(0), B, H, Tq, Tk, _p(kv_len), 1 if causal else 0, q_col0,
+                                   k_col0, v_col0, _p(bd), bd.shape[-1] if bd is not None else 0, _stream()),
+          'otb_attention')
+    return out
+
+
+def layernorm(x, g1, b1, g2=None, b2=None, eps=1e-5, out=None, out_f32=False):
+    _need(x, BF16, 'x')
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=x.device)
+    check(_lib.lib().otb_layernorm(_p(x), x.stride(0), _p(out), out.stride(0), 1 if out.dtype == torch.float32 else 0,
+                                   _p(g1), _p(b1), _p(g2), _p(b2), eps, M, N, _stream()), 'otb_layernorm')
+    return out
+
+
+def scale_add_table(x, alpha=1.0, table=None, period=1, out=None):
+    """bf16 out = x * alpha + table[row % period]; x f32 or bf16 2-D."""
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(M, N, dtype=BF16, device=x.device)
+    check(_lib.lib().otb_scale_add_table(_p(x), x.stride(0), 1 if x.dtype == torch.float32 else 0, _p(out),
+                                         out.stride(0), alpha, _p(table), period, M, N, _stream()),
+          'otb_scale_add_table')
+    return out
+
+
+_TABLES = {}
+
+
+def sinusoid_table(n_pos, d, first_pos=0, device=None):
+    """Cached f32 [n_pos, d] sinusoid table (module/pos.py:30-42), computed once on the device."""
+    device = torch.device(device if device is not None else torch.cuda.current_device())
+    key = (n_pos, d, first_pos, device.index if device.index is not None else torch.cuda.current_device())
+    t = _TABLES.get(key)
+    if t is None:
+        t = torch.empty(n_pos, d, dtype=torch.float32, device=device)
+        check(_lib.lib().otb_sinusoid_table(_p(t), n_pos, d, first_pos, _stream()), 'otb_sinusoid_table')
+        _TABLES[key] = t
+    return t
+
+
+def embed_posenc(tok, emb, table, N, d, period=1, tok_stride=1, step_ptr=None, out=None):
+    _need(emb, BF16, 'emb')
+    if out is None:
+        out = torch.empty(N, d, dtype=BF16, device=emb.device)
+    check(_lib.lib().otb_embed_posenc(_p(tok), tok_stride, _p(emb), _p(table), _p(out), N, d, period, _p(step_ptr),
+                                      emb.shape[0], _stream()), 'otb_embed_posenc')
+    return out
+
+
+def log_softmax(x, V, out=None):
+    _need(x, torch.float32, 'x')
+    rows = x.shape[0]
+    if out is None:
+        out = torch.empty(rows, V, dtype=torch.float32, device=x.device)
+    check(_lib.lib().otb_log_softmax(_p(x), x.stride(0), _p(out), out.stride(0), rows, V, _stream()),
+          'otb_log_softmax')
+    return out
+
+
+def decode_self_attn(qkv, kc, vc, anc, step_ptr, N, H, Lmax, out=None):
+    if out is None:
+        out = torch.empty(N, H * 64, dtype=BF16, device=qkv.device)
+    check(_lib.lib().otb_decode_self_attn(_p(qkv), _p(kc), _p(vc), _p(anc), _p(step_ptr), _p(out), N, H, Lmax,
+                                          _stream()), 'otb_decode_self_attn')
+    return out
+
+
+class BeamState:
+    """Device-resident beam-search state (otb_beam_state)."""
+
+    def __init__(self, batch, beam, max_len, device):
+        self.B, self.beam, self.Lmax = batch, beam, max_len
+        self.N = N = batch * beam
+        kw = dict(device=device)
+        self.tok_hist = torch.zeros(max_len, N, dtype=torch.int32, **kw)
+        self.par_hist = torch.zeros(max_len, N, dtype=torch.int32, **kw)
+        self.last_tok = torch.ones(N, dtype=torch.int64, **kw)
+        self.scores = torch.zeros(N, dtype=torch.float32, **kw)
+        self.flag = torch.zeros(N, dtype=torch.uint8, **kw)
+        self.anc = torch.zeros(2, N, max_len, dtype=torch.int32, **kw)
+        self.ctrl = torch.zeros(4, dtype=torch.int32, **kw)
+        self.c = _lib.BeamStateC(self.tok_hist.data_ptr(), self.par_hist.data_ptr(), self.last_tok.data_ptr(),
+                                 self.scores.data_ptr(), self.flag.data_ptr(), self.anc.data_ptr(),
+                                 self.ctrl.data_ptr(), N, beam, max_len)
+
+    @property
+    def step_ptr(self):
+        return self.ctrl  # ctrl[0] is the step counter
+
+    def init(self):
+        check(_lib.lib().otb_beam_init(ctypes.byref(self.c), _stream()), 'otb_beam_init')
+
+    def step(self, logp, V, lm_logp=None, lm_weight=0.0, dbg_ktok=None, dbg_offs=None):
+        _need(logp, torch.float32, 'logp')
+        check(_lib.lib().otb_beam_step(_p(logp), logp.stride(0), V, _p(lm_logp),
+                                       lm_logp.stride(0) if lm_logp is not None else 0, lm_weight,
+                                       ctypes.byref(self.c), _p(dbg_ktok), _p(dbg_offs), _stream()), 'otb_beam_step')
+
+    def reconstruct(self, steps):
+        preds = torch.empty(self.N, steps + 1, dtype=torch.int64, device=self.scores.device)
+        check(_lib.lib().otb_beam_reconstruct(ctypes.byref(self.c), _p(preds), steps + 1, steps, _stream()),
+              'otb_beam_reconstruct')
+        return preds
+
+    def finalize(self, penalty, lamda, nbest):
+        k = min(nbest, self.beam)
+        out_preds = torch.empty(self.B, k, self.Lmax, dtype=torch.int64, device=self.scores.device)
+        out_scores = torch.empty(self.B, k, dtype=torch.float32, device=self.scores.device)
+        check(_lib.lib().otb_beam_finalize(ctypes.byref(self.c), float(penalty), float(lamda), k, _p(out_preds),
+                                           _p(out_scores), _stream()), 'otb_beam_finalize')
+        return out_preds, out_scores

@@ -1,0 +1,257 @@
+"""Batched beam-search recogniser on the B200 hot path.
+
+Mirror of otrans/recognize/speech2text.py (SpeechToTextRecognizer) and the bits of
+otrans/recognize/base.py it needs.  Same constructor, same ``recognize`` / ``encode`` / ``decode`` /
+``decode_step`` seams and return types.  What changes underneath:
+
+  * encode: conv front end + encoder run as hand-written sm_100a kernels (bf16 tensor cores);
+  * decode: the reference re-runs the whole decoder over the whole prefix -- and the cross-attention
+    K/V projection of the beam-tiled memory -- at every step (decoder/transformer.py:204,
+    attention.py:129).  Here cross K/V are projected ONCE per utterance (shared by the beams), self-attention
+    K/V live in a per-hypothesis cache addressed through a 4-byte ancestry table, and one step is
+    a fixed sequence of kernels captured in a CUDA graph and replayed;
+  * beam step: one kernel per step (top-k, finished masking, pruning, back-pointers), no host sync
+    inside the loop except a 4-byte "all ended" poll every few steps.
+"""
+import torch
+
+from . import ops
+from .modules import _lengths, _ffn, _proj_resid_ln
+
+PAD, BOS, EOS = 0, 1, 1   # otrans/data/__init__.py:7-10
+
+
+class Recognizer:
+    """otrans/recognize/base.py:5-24,91-119 (model holder + id -> string translation)."""
+
+    def __init__(self, model, idx2unit=None, lm=None, lm_weight=None, ngpu=1):
+        self.ngpu = ngpu
+        self.model = model
+        self.model.eval()
+        if self.ngpu > 0:
+            self.model.cuda()
+        self.lm = lm
+        if self.lm is not None:
+            self.lm.eval()
+        self.idx2unit = idx2unit
+        self.lm_weight = lm_weight
+
+    def translate(self, seqs):
+        results = []
+        for seq in seqs:
+            pred = []
+            for i in seq:
+                if int(i) == EOS:
+                    break
+                if int(i) == PAD:
+                    continue
+                pred.append(self.idx2unit[int(i)])
+            results.append(' '.join(pred))
+        return results
+
+    def nbest_translate(self, nbest_preds):
+        assert nbest_preds.dim() == 3
+        if self.idx2unit is None:          # ids requested (tests / benchmarks): keep the tensor
+            return nbest_preds
+        rows = nbest_preds.cpu().tolist()
+        results = []
+        for per_utt in rows:
+            nbest_list = []
+            for seq in per_utt:
+                pred = []
+                for token in seq:
+                    if token == EOS:
+                        break
+                    pred.append(self.idx2unit[token])
+                nbest_list.append(' '.join(pred))
+            results.append(nbest_list)
+        return results
+
+
+class BeamDecoder:
+    """KV-cached incremental decoder + device-side beam search for one (batch, beam, T, max_len) shape.
+
+    Buffers are allocated once; one decode step (decoder on the newest token -> log-softmax -> beam
+    kernel) is captured into a CUDA graph on first use and replayed for every step.
+    """
+
+    def __init__(self, decoder, batch, beam, T, max_len, device, use_graph=True):
+        self.dec = decoder
+        self.B, self.beam, self.T, self.Lmax = batch, beam, T, max_len
+        self.N = batch * beam
+        self.device = device
+        d, nl = decoder.d_model, len(decoder.blocks)
+        self.state = ops.BeamState(batch, beam, max_len, device)
+        self.kc = torch.zeros(nl, max_len, self.N, d, dtype=ops.BF16, device=device)
+        self.vc = torch.zeros(nl, max_len, self.N, d, dtype=ops.BF16, device=device)
+        self.kvx = torch.zeros(nl, batch * T, 2 * d, dtype=ops.BF16, device=device)  # cross K|V per utterance
+        self.mem_len = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.table = ops.sinusoid_table(max_len + 1, d, 0, device)
+        self.logits = torch.zeros(self.N, decoder.ld_logits, dtype=torch.float32, device=device)
+        self.logp = torch.zeros(self.N, decoder.vocab_size, dtype=torch.float32, device=device)
+        self.use_graph = use_graph
+        self.graph = None
+        self.lm_logp = None
+        self.lm_weight = 0.0
+        if decoder.pos_emb.scale_learnable:
+            raise NotImplementedError('decoder with learnable positional scale')
+
+    def setup(self, memory_bf16, mem_len):
+        """Project cross-attention K/V once per utterance and reset the search state."""
+        pk = self.dec.packed()
+        self.mem_len.copy_(mem_len)
+        for l, p in enumerate(pk['blocks']):
+            ops.linear(memory_bf16, p['wkv'], p['bkv'], out=self.kvx[l])
+        self.state.init()
+
+    def _step_kernels(self):
+        dec, st = self.dec, self.state
+        pk = dec.packed()
+        d, H, N = dec.d_model, dec.n_heads, self.N
+        x = ops.embed_posenc(st.last_tok, pk['emb'], self.table, N, d, step_ptr=st.step_ptr)
+        for l, (blk, p) in enumerate(zip(dec.blocks, pk['blocks'])):
+            nb = blk.normalize_before
+            if nb:
+                x = ops.layernorm(x, *p['ln1'])
+            qkv = ops.linear(x, p['wqkv'], p['bqkv'])
+            ctx = ops.decode_self_attn(qkv, self.kc[l], self.vc[l], st.anc, st.step_ptr, N, H, self.Lmax)
+            x = _proj_resid_ln(ctx, p['wo'], p['bo'], x, None if nb else p['ln1'])
+            if nb:
+                x = ops.layernorm(x, *p['ln2'])
+            q = ops.linear(x, p['wq'], p['bq'])
+            # the `beam` hypotheses of utterance b are the query rows [b*beam, (b+1)*beam) of one attention problem
+            ctx = ops.attention(q, self.kvx[l], self.kvx[l], self.B, H, self.beam, self.T, kv_len=self.mem_len,
+                                k_col0=0, v_col0=d)
+            x = _proj_resid_ln(ctx, p['wo2'], p['bo2'], x, None if nb else p['ln2'])
+            if nb:
+                x = ops.layernorm(x, *p['ln3'])
+            x = _ffn(x, p['ffn'], x, None if nb else p['ln3'])
+        if dec.normalize_before:
+            x = ops.layernorm(x, *pk['after'])
+        ops.linear(x, pk['wout'], pk['bout'], out=self.logits)
+        ops.log_softmax(self.logits, dec.vocab_size, out=self.logp)
+        st.step(self.logp, dec.vocab_size, self.lm_logp, self.lm_weight)
+
+    def step(self):
+        if not self.use_graph:
+            return self._step_kernels()
+        if self.graph is None:
+            # warm-up outside capture (lazy func attributes, caches), then restore the state it advanced
+            snap = [t.clone() for t in (self.state.tok_hist, self.state.par_hist, self.state.last_tok,
+                                        self.state.scores, self.state.flag, self.state.anc, self.state.ctrl)]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._step_kernels()
+            torch.cuda.current_stream().wait_stream(s)
+            for t, c in zip((self.state.tok_hist, self.state.par_hist, self.state.last_tok, self.state.scores,
+                             self.state.flag, self.state.anc, self.state.ctrl), snap):
+                t.copy_(c)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_kernels()
+            for t, c in zip((self.state.tok_hist, self.state.par_hist, self.state.last_tok, self.state.scores,
+                             self.state.flag, self.state.anc, self.state.ctrl), snap):
+                t.copy_(c)
+        self.graph.replay()
+
+    def run(self, max_steps, poll_every=8):
+        """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
+        (speech2text.py:66-67).  Steps launched after the end are no-ops on the search state."""
+        for i in range(max_steps):
+            self.step()
+            if (i + 1) % poll_every == 0 and i + 1 < max_steps:
+                if int(self.state.ctrl[1].item()):
+                    break
+        return int(self.state.ctrl[0].item())
+
+
+class SpeechToTextRecognizer(Recognizer):
+    """otrans/recognize/speech2text.py:6-93 on the B200 path."""
+
+    def __init__(self, model, lm=None, lm_weight=0.1, ctc_weight=0.0, beam_width=5, nbest=1, max_len=50,
+                 idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True):
+        super().__init__(model, idx2unit, lm, lm_weight, ngpu)
+        if lm is not None:
+            raise NotImplementedError('LM shallow fusion: the beam kernel takes lm_log_probs, but no B200 LM '
+                                      'is wired in yet (SURVEY.md 8f "next" row 2)')
+        self.beam_width, self.max_len, self.nbest = beam_width, max_len, nbest
+        self.penalty, self.lamda = penalty, lamda
+        self.ctc_weight, self.lm_weight = ctc_weight, lm_weight
+        self.attn_weights = {}
+        self.apply_cache = False
+        self.use_graph = use_graph
+        self._decoders = {}
+
+    # ---- reference-facing seams -------------------------------------------------------------
+    def encode(self, inputs, inputs_mask, cache=None):
+        mem, mem_len, B, T2 = self._encode_bf16(inputs, inputs_mask)
+        memory = mem.float().view(B, T2, -1)
+        return memory, self.model.frontend.output_mask(inputs_mask), {'frontend': None}, {}
+
+    def decode(self, preds, memory, memory_mask, cache=None):
+        return self.model.decoder.inference(preds, memory, memory_mask, cache)
+
+    def decode_step(self, preds, memory, memory_mask, cache, scores, flag):
+        """One reference-style step on caller-owned tensors (speech2text.py:95-153): full-prefix decoder
+        (as the reference) + the CUDA beam kernel.  The fast path used by recognize() is BeamDecoder."""
+        n = scores.size(0)
+        batch = n // self.beam_width
+        log_probs, _, _ = self.decode(preds, memory, memory_mask, cache['decoder'] if cache else None)
+        st = ops.BeamState(batch, self.beam_width, 1, scores.device)
+        st.init()
+        st.scores.copy_(scores.view(-1))
+        st.flag.copy_(flag.view(-1).to(torch.uint8))
+        st.step(log_probs.contiguous(), log_probs.shape[-1])
+        parent = st.par_hist[0].long()
+        tok = st.tok_hist[0].long()
+        preds_symbol = torch.cat((preds.index_select(0, parent), tok.view(-1, 1)), dim=1)
+        return preds_symbol, cache, st.scores.view(-1, 1).clone(), (tok == EOS).view(-1, 1)
+
+    # ---- fast path ------------------------------------------------------------------------------
+    def _encode_bf16(self, inputs, inputs_mask):
+        fe, enc = self.model.frontend, self.model.encoder
+        B, T, _ = inputs.shape
+        _, _, T2, _ = ops.conv_geometry(T, fe.input_size)
+        lengths = _lengths(fe.output_mask(inputs_mask))
+        fused = getattr(enc, 'fuse_abs_posenc', None)
+        if fused is not None and fused():
+            scale, table = enc.pos_emb.scale_and_table(T2, inputs.device)
+            x, _ = fe.forward_bf16(inputs, scale, table)
+        else:
+            x, _ = fe.forward_bf16(inputs)
+            x = enc.apply_posenc_bf16(x, B, T2)
+        mem = enc.forward_bf16(x, B, T2, lengths)
+        return mem, lengths, B, T2
+
+    def _decoder_for(self, B, T2, device):
+        key = (B, self.beam_width, T2, self.max_len, device.index)
+        bd = self._decoders.get(key)
+        if bd is None:
+            bd = BeamDecoder(self.model.decoder, B, self.beam_width, T2, self.max_len, device, self.use_graph)
+            self._decoders[key] = bd
+        return bd
+
+    def recognize_ids(self, inputs, inputs_mask):
+        """-> (nbest ids i64 [B,nbest,steps], scores f32 [B,nbest], steps)"""
+        with torch.no_grad():
+            mem, mem_len, B, T2 = self._encode_bf16(inputs, inputs_mask)
+            bd = self._decoder_for(B, T2, inputs.device)
+            bd.setup(mem, mem_len)
+            steps = bd.run(self.max_len)
+            preds, scores = bd.state.finalize(self.penalty, self.lamda, self.nbest)
+        return preds[:, :, :steps], scores, steps
+
+    def recognize(self, inputs, inputs_mask):
+        preds, scores, _ = self.recognize_ids(inputs, inputs_mask)
+        return self.nbest_translate(preds), scores
+
+
+def build_recognizer(model_type, model, lm, args, idx2unit):
+    """otrans/recognize/__init__.py:5-16 (speech2text only; CTC is out of scope)."""
+    if model_type == 'speech2text':
+        return SpeechToTextRecognizer(
+            model=model, lm=lm, lm_weight=args.lm_weight, ctc_weight=args.ctc_weight, beam_width=args.beam_width,
+            nbest=args.nbest, max_len=args.max_len, idx2unit=idx2unit, penalty=args.penalty, lamda=args.lamda,
+            ngpu=args.ngpu)
+    raise NotImplementedError(model_type)
