@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path (BASELINE.json metric): utterances/sec through frontend+encoder
+forward and batched beam-search decode, synthetic 80-dim fbank (1000 frames), random-init weights.
+
+    python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                      # the reference algorithm on host cores (oracle port)
+
+One "step" = one full recognize pass (frontend -> 12-layer encoder -> 60-step beam-10 decode ->
+n-best) over a batch of 32 utterances per GPU.  N > 1 shards utterance batches across ranks with no
+data-path collective (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, T_FRAMES, F_BINS, BEAM, MAX_LEN, PENALTY, LAMDA = 32, 1000, 80, 10, 60, 0.6, 5
+
+
+def model_params():
+    """egs/aishell/conf/transformer_baseline.yaml `model:` with input_size 80."""
+    return {'type': 'speech2text', 'frontend_type': 'conv', 'encoder_type': 'transformer',
+            'decoder_type': 'transformer',
+            'frontend': dict(input_size=F_BINS, output_size=256, in_channel=1, mid_channel=64, out_channel=128,
+                             kernel_size=[[3, 3], [3, 3]], stride=[2, 2], dropout=0.0, act_func_type='relu',
+                             front_end_layer_norm=False),
+            'encoder': dict(d_model=256, n_heads=4, d_ff=2048, n_blocks=12, pos_dropout=0.0, slf_attn_dropout=0.0,
+                            ffn_dropout=0.0, residual_dropout=0.1, normalize_before=False, concat_after=False,
+                            activation='glu', relative_positional=False),
+            'decoder': dict(vocab_size=4234, d_model=256, n_heads=4, d_ff=2048, memory_dim=256, n_blocks=6,
+                            pos_dropout=0.0, slf_attn_dropout=0.0, src_attn_dropout=0.0, ffn_dropout=0.0,
+                            residual_dropout=0.1, activation='glu', normalize_before=False, concat_after=False,
+                            share_embedding=True),
+            'ctc_weight': 0.0, 'smoothing': 0.1}
+
+
+def build_model():
+    from opentransformer_b200.model import SpeechToText
+    torch.manual_seed(1234)
+    model = SpeechToText(model_params()).eval()
+    with torch.no_grad():
+        model.decoder.output_layer.bias[1] = -1e4      # all 60 steps execute
+    return model
+
+
+def flat_state_dict(model):
+    sd = {}
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k, v in getattr(model, part).state_dict().items():
+            sd[f'{part}.{k}'] = v.detach().float().cpu().clone()
+    return sd
+
+
+def synthetic_batch(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, T_FRAMES, F_BINS, generator=g)
+    mask = torch.ones(batch, T_FRAMES, dtype=torch.bool)
+    return x, mask
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return p, 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(sd, params, x, mask):
+    """The reference algorithm (oracle port, fp32, all host threads): encode + 60-step beam-10 decode."""
+    from oracle import beam_search as obs
+    with torch.no_grad():
+        return obs.recognize(x, mask, sd, params, beam=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    sample = args.ref_sample
+    model = build_model()
+    sd, params = flat_state_dict(model), model_params()
+    x, mask = synthetic_batch(sample, 0)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_pass(sd, params, x, mask)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(sd, params, x, mask)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {'impl': 'reference', 'metric': 'utterances/sec (encoder-fwd + beam-10 decode, 60 steps)', 'value': val,
+            'unit': 'utt/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1),
+            'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, sample),
+            'cpu_baseline': {'value': val, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} utterances x {args.steps} passes of the full workload '
+                                       '(oracle/ = torch-CPU fp32 restatement of the reference; the Python reference '
+                                       'itself cannot travel to the GPU box)'},
+            'e2e': {'value': val, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, batch):
+    return {'workload': 'Speech-Transformer 12-enc/6-dec d_model=256 h=4 d_ff=2048(GLU) V=4234; '
+                        f'{batch} utt x {T_FRAMES} frames x {F_BINS}-dim fbank per GPU; frontend+encoder forward + '
+                        f'batch beam search (beam={BEAM}, max_len={MAX_LEN}, penalty={PENALTY}, lamda={LAMDA}, LM off, '
+                        'EOS bias -1e4 so all steps run)',
+            'batch_per_gpu': batch, 'frames': T_FRAMES, 'beam': BEAM, 'max_len': MAX_LEN,
+            'parallelism': f'dp{args.gpus} (utterance sharding, no data-path collective)',
+            'l2_policy': 'L2 flushed (256 MiB write) before every timed step'}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from opentransformer_b200 import ops
+    from opentransformer_b200.recognize import SpeechToTextRecognizer
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = build_model().to(dev)
+    rec = SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA, ngpu=1)
+    x_cpu, mask_cpu = synthetic_batch(B_PER_GPU, rank)
+    x_pin, mask_pin = x_cpu.pin_memory(), mask_cpu.pin_memory()
+    x_dev, mask_dev = x_cpu.to(dev), mask_cpu.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        return rec.recognize_ids(x_dev, mask_dev)
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)
+        md = mask_pin.to(dev, non_blocking=True)
+        out, scores = rec.recognize(xd, md)              # public API (ids because idx2unit is None)
+        return out.cpu(), scores.cpu()
+
+    def timed(fn, steps, profile=False):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+
+    # ---- phase breakdown (encoder-forward / beam decode), untimed-region diagnostics
+    def enc_only():
+        with torch.no_grad():
+            return rec._encode_bf16(x_dev, mask_dev)
+    ms_enc = timed(enc_only, 5) / 5
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.PROFILE = []
+    n0 = ops.COUNTERS['launches']
+    ms_total = timed(step_resident, args.steps)
+    launches = ops.COUNTERS['launches'] - n0
+    prof, ops.PROFILE = ops.PROFILE, None
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total, ms_e2e, ms_enc], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_enc = t.tolist()
+
+    if rank == 0:
+        peaks, src = measured_peaks()
+        gemm = [(k, f, a.elapsed_time(b)) for k, f, a, b in prof if k == 'gemm']
+        flops = sum(f for _, f, _ in gemm)
+        gms = sum(m for _, _, m in gemm)
+        ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        utt = B_PER_GPU * world * args.steps
+        value = utt / (ms_total * 1e-3)
+        e2e = utt / (ms_e2e * 1e-3)
+        line = {
+            'metric': 'utterances/sec (encoder-fwd + beam-10 decode, 60 steps)', 'value': value, 'unit': 'utt/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args, B_PER_GPU),
+            'e2e': {'value': e2e, 'unit': 'utt/s', 'h2d_bytes_per_step': x_cpu.numel() * 4 + mask_cpu.numel(),
+                    'd2h_bytes_per_step': B_PER_GPU * MAX_LEN * 8 + B_PER_GPU * 4},
+            'gpu_launches': launches,
+            'breakdown': {'encoder_fwd_ms': ms_enc, 'encoder_fwd_utt_per_s': B_PER_GPU * world / (ms_enc * 1e-3),
+                          'beam_decode_ms': ms_total / args.steps - ms_enc,
+                          'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_total / args.steps - ms_enc) * 1e-3)},
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': ach / peak if peak else None, 'traffic': None,
+                         'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all eager launches in the timed region: '
+                                   f'{len(gemm)} launches, {flops / 1e9:.1f} GFLOP algorithmic, {gms:.3f} ms by CUDA events)',
+                         'peak_source': f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'},
+            'clocks': clocks,
+        }
+        if args.cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sd, params = flat_state_dict(model), model_params()
+            xs, ms_ = synthetic_batch(args.ref_sample, 0)
+            t0 = time.perf_counter()
+            cpu_reference_pass(sd, params, xs, ms_)
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {'value': args.ref_sample / dt, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'{args.ref_sample} utterances, one full pass (encoder-fwd + 60-step '
+                                              f'beam-10 decode) of the oracle port in {dt:.1f} s'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--ref-sample', type=int, default=2, help='utterances per CPU reference pass')
+    ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)')
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

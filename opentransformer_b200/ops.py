@@ -17,6 +17,35 @@ ACT_EPILOGUE = {'relu': EPI_RELU, 'glu': EPI_GLU, 'swish': EPI_SWISH, 'gelu': EP
 BF16 = torch.bfloat16
 
 
+# ---- instrumentation (bench.py): kernel-launch counter and optional per-launch CUDA-event timing ----
+COUNTERS = {'launches': 0}
+PROFILE = None          # set to a list to collect (kind, algorithmic_flops, start_event, end_event) per GEMM launch
+
+
+def _count(n=1):
+    COUNTERS['launches'] += n
+
+
+class _Timed:
+    """Record CUDA events around one launch on the current stream when PROFILE is enabled."""
+
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None and not torch.cuda.is_current_stream_capturing():
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        else:
+            self.e0 = None
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -50,6 +79,7 @@ def conv1_relu(x, w, bias, out=None):
     if out is None:
         out = torch.empty(B, 2 * (T2 + 1), 2 * F2, C1, dtype=BF16, device=x.device)
     check(_lib.lib().otb_conv1_relu(_p(x), _p(w), _p(bias), _p(out), B, T, F, C1, _stream()), 'otb_conv1_relu')
+    _count()
     return out
 
 
@@ -61,7 +91,10 @@ def conv2_relu(h1, w, bias, B, T, F, out=None):
     _, _, T2, F2 = conv_geometry(T, F)
     if out is None:
         out = torch.empty(B * T2, F2 * C2, dtype=BF16, device=h1.device)
-    check(_lib.lib().otb_conv2_relu(_p(h1), _p(w), _p(bias), _p(out), B, T, F, C1, C2, _stream()), 'otb_conv2_relu')
+    with _Timed('conv2_gemm', 2.0 * B * T2 * F2 * C2 * K):
+        check(_lib.lib().otb_conv2_relu(_p(h1), _p(w), _p(bias), _p(out), B, T, F, C1, C2, _stream()),
+              'otb_conv2_relu')
+    _count()
     return out
 
 
@@ -77,10 +110,12 @@ def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=No
         ldc = n_out if n_out is not None else N
         out = torch.empty(M, ldc, dtype=torch.float32 if out_f32 else BF16, device=a.device)
     ldc = out.stride(0)
-    check(_lib.lib().otb_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), ldc, M, N, K, epilogue,
-                                1 if out.dtype == torch.float32 else 0, _p(resid),
-                                resid.stride(0) if resid is not None else 0, _p(gamma), _p(beta), eps, alpha,
-                                _p(table), period, _p(row_len), row_period, _stream()), 'otb_linear')
+    with _Timed('gemm', 2.0 * M * w.shape[0] * K):
+        check(_lib.lib().otb_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), ldc, M, N, K, epilogue,
+                                    1 if out.dtype == torch.float32 else 0, _p(resid),
+                                    resid.stride(0) if resid is not None else 0, _p(gamma), _p(beta), eps, alpha,
+                                    _p(table), period, _p(row_len), row_period, _stream()), 'otb_linear')
+    _count()
     return out
 
 
@@ -97,6 +132,7 @@ def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0
                                    _p(out), out.stride(0), B, H, Tq, Tk, _p(kv_len), 1 if causal else 0, q_col0,
                                    k_col0, v_col0, _p(bd), bd.shape[-1] if bd is not None else 0, _stream()),
           'otb_attention')
+    _count()
     return out
 
 
@@ -107,6 +143,7 @@ def layernorm(x, g1, b1, g2=None, b2=None, eps=1e-5, out=None, out_f32=False):
         out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=x.device)
     check(_lib.lib().otb_layernorm(_p(x), x.stride(0), _p(out), out.stride(0), 1 if out.dtype == torch.float32 else 0,
                                    _p(g1), _p(b1), _p(g2), _p(b2), eps, M, N, _stream()), 'otb_layernorm')
+    _count()
     return out
 
 
@@ -118,6 +155,7 @@ def scale_add_table(x, alpha=1.0, table=None, period=1, out=None):
     check(_lib.lib().otb_scale_add_table(_p(x), x.stride(0), 1 if x.dtype == torch.float32 else 0, _p(out),
                                          out.stride(0), alpha, _p(table), period, M, N, _stream()),
           'otb_scale_add_table')
+    _count()
     return out
 
 
@@ -132,6 +170,7 @@ def sinusoid_table(n_pos, d, first_pos=0, device=None):
     if t is None:
         t = torch.empty(n_pos, d, dtype=torch.float32, device=device)
         check(_lib.lib().otb_sinusoid_table(_p(t), n_pos, d, first_pos, _stream()), 'otb_sinusoid_table')
+        _count()
         _TABLES[key] = t
     return t
 
@@ -142,6 +181,7 @@ def embed_posenc(tok, emb, table, N, d, period=1, tok_stride=1, step_ptr=None, o
         out = torch.empty(N, d, dtype=BF16, device=emb.device)
     check(_lib.lib().otb_embed_posenc(_p(tok), tok_stride, _p(emb), _p(table), _p(out), N, d, period, _p(step_ptr),
                                       emb.shape[0], _stream()), 'otb_embed_posenc')
+    _count()
     return out
 
 
@@ -152,6 +192,7 @@ def log_softmax(x, V, out=None):
         out = torch.empty(rows, V, dtype=torch.float32, device=x.device)
     check(_lib.lib().otb_log_softmax(_p(x), x.stride(0), _p(out), out.stride(0), rows, V, _stream()),
           'otb_log_softmax')
+    _count()
     return out
 
 
@@ -160,6 +201,7 @@ def decode_self_attn(qkv, kc, vc, anc, step_ptr, N, H, Lmax, out=None):
         out = torch.empty(N, H * 64, dtype=BF16, device=qkv.device)
     check(_lib.lib().otb_decode_self_attn(_p(qkv), _p(kc), _p(vc), _p(anc), _p(step_ptr), _p(out), N, H, Lmax,
                                           _stream()), 'otb_decode_self_attn')
+    _count()
     return out
 
 
@@ -187,17 +229,20 @@ class BeamState:
 
     def init(self):
         check(_lib.lib().otb_beam_init(ctypes.byref(self.c), _stream()), 'otb_beam_init')
+        _count()
 
     def step(self, logp, V, lm_logp=None, lm_weight=0.0, dbg_ktok=None, dbg_offs=None):
         _need(logp, torch.float32, 'logp')
         check(_lib.lib().otb_beam_step(_p(logp), logp.stride(0), V, _p(lm_logp),
                                        lm_logp.stride(0) if lm_logp is not None else 0, lm_weight,
                                        ctypes.byref(self.c), _p(dbg_ktok), _p(dbg_offs), _stream()), 'otb_beam_step')
+        _count(2)   # beam_step_kernel + beam_advance_kernel
 
     def reconstruct(self, steps):
         preds = torch.empty(self.N, steps + 1, dtype=torch.int64, device=self.scores.device)
         check(_lib.lib().otb_beam_reconstruct(ctypes.byref(self.c), _p(preds), steps + 1, steps, _stream()),
               'otb_beam_reconstruct')
+        _count()
         return preds
 
     def finalize(self, penalty, lamda, nbest):
@@ -206,4 +251,5 @@ class BeamState:
         out_scores = torch.empty(self.B, k, dtype=torch.float32, device=self.scores.device)
         check(_lib.lib().otb_beam_finalize(ctypes.byref(self.c), float(penalty), float(lamda), k, _p(out_preds),
                                            _p(out_scores), _stream()), 'otb_beam_finalize')
+        _count()
         return out_preds, out_scores

@@ -148,12 +148,16 @@ class BeamDecoder:
                              self.state.flag, self.state.anc, self.state.ctrl), snap):
                 t.copy_(c)
             self.graph = torch.cuda.CUDAGraph()
+            n0 = ops.COUNTERS['launches']
             with torch.cuda.graph(self.graph):
                 self._step_kernels()
+            self.launches_per_step = ops.COUNTERS['launches'] - n0
+            ops.COUNTERS['launches'] = n0                      # capture records, it does not launch
             for t, c in zip((self.state.tok_hist, self.state.par_hist, self.state.last_tok, self.state.scores,
                              self.state.flag, self.state.anc, self.state.ctrl), snap):
                 t.copy_(c)
         self.graph.replay()
+        ops.COUNTERS['launches'] += self.launches_per_step
 
     def run(self, max_steps, poll_every=8):
         """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
