@@ -74,20 +74,20 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
                 self.rows.append([c.strip() for c in out.strip().split(',')])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
@@ -107,6 +107,45 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads():
+    """Give the CPU arm its best case: calibrate the intra-op thread count on a micro-workload shaped like
+    the decoder hot loop (torch's default of one thread per visible core was 60x slower on the 128-core
+    GPU box than 8 threads because the per-op work is small).  Returns (threads, visible_cores)."""
+    import torch.nn.functional as F
+    cores = usable_cpus()
+    a, w = torch.randn(320 * 8, 256), torch.randn(4096, 256)
+    xc, wc = torch.randn(2, 64, 499, 40), torch.randn(128, 64, 3, 3)
+    best, best_t = 1, float('inf')
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 128, cores) if c <= cores} | {min(cores, 4)})
+    for c in cands:
+        torch.set_num_threads(c)
+        F.glu(a @ w.t()); F.conv2d(xc, wc, stride=2, padding=(0, 1))      # warm the pool
+        t0 = time.perf_counter()
+        for _ in range(5):
+            F.glu(a @ w.t())
+            torch.softmax((a[:, :64] @ a[:, :64].t()), -1)
+        F.conv2d(xc, wc, stride=2, padding=(0, 1))
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        elif dt > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    return best, cores
+
+
 def cpu_reference_pass(sd, params, x, mask):
     """The reference algorithm (oracle port, fp32, all host threads): encode + 60-step beam-10 decode."""
     from oracle import beam_search as obs
@@ -118,8 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads, cores = pick_cpu_threads()
     torch.manual_seed(1234)
     sample = args.ref_sample
     model = build_model()
@@ -136,7 +174,7 @@ def run_reference(args):
             'unit': 'utt/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1),
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, sample),
-            'cpu_baseline': {'value': val, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+            'cpu_baseline': {'value': val, 'unit': 'utt/s', 'cores': threads, 'visible_cores': cores, 'kind': 'port',
                              'sample': f'{sample} utterances x {args.steps} passes of the full workload '
                                        '(oracle/ = torch-CPU fp32 restatement of the reference; the Python reference '
                                        'itself cannot travel to the GPU box)'},
@@ -259,14 +297,14 @@ def run_b200(args):
             'clocks': clocks,
         }
         if args.cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
+            threads, cores = pick_cpu_threads()
             sd, params = flat_state_dict(model), model_params()
             xs, ms_ = synthetic_batch(args.ref_sample, 0)
             t0 = time.perf_counter()
             cpu_reference_pass(sd, params, xs, ms_)
             dt = time.perf_counter() - t0
-            line['cpu_baseline'] = {'value': args.ref_sample / dt, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+            line['cpu_baseline'] = {'value': args.ref_sample / dt, 'unit': 'utt/s', 'cores': threads,
+                                    'visible_cores': cores, 'kind': 'port',
                                     'sample': f'{args.ref_sample} utterances, one full pass (encoder-fwd + 60-step '
                                               f'beam-10 decode) of the oracle port in {dt:.1f} s'}
         print(json.dumps(line))

@@ -125,6 +125,14 @@ int otb_beam_init(const otb_beam_state* st, void* stream);
  * dbg_offs i32 [N] (optional) receive last_k_preds / offset_k_indices for parity traces. */
 int otb_beam_step(const float* logp, int ldl, int V, const float* lm_logp, int ld_lm, float lm_weight,
                   const otb_beam_state* st, int64_t* dbg_ktok, int32_t* dbg_offs, void* stream);
+/* Fused log_softmax (+ lm_weight * lm_logp) + per-row top-k (decoder/transformer.py:206 + speech2text.py:102-112):
+ * logits f32 [rows, ldl] -> out_val f32 [rows,k] (log-prob values, descending), out_idx i32 [rows,k];
+ * out_logp (optional, f32 [rows, ld_logp]) additionally receives the full log-prob rows. */
+int otb_logsoftmax_topk(const float* logits, int ldl, int V, const float* lm_logp, int ld_lm, float lm_weight, int k,
+                        int rows, float* out_val, int32_t* out_idx, float* out_logp, int ld_logp, void* stream);
+/* otb_beam_step with the per-hypothesis top-k already computed by otb_logsoftmax_topk (k == beam). */
+int otb_beam_step_topk(const float* topk_val, const int32_t* topk_idx, const otb_beam_state* st, int64_t* dbg_ktok,
+                       int32_t* dbg_offs, void* stream);
 /* Materialise preds i64 [N, ld] (column 0 = BOS) after `steps` steps from the back-pointers. */
 int otb_beam_reconstruct(const otb_beam_state* st, int64_t* preds, int ld, int steps, void* stream);
 /* Tail of recognize() (recognize/speech2text.py:70-91). out_preds i64 [B,nbest,Lmax], out_scores f32 [B,nbest]. */

@@ -21,6 +21,13 @@ namespace otb {
 
 static constexpr int ATT_SMEM = 16384 * 3 + 32768 + 128 + 1024;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool HAS_BD>
 __global__ void __launch_bounds__(128, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -88,28 +95,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&bar[3], ph);
         tc_fence_after();
 
-        // ---- pass 1: row maximum of the masked, scaled scores
+        // ---- pass 1: row maximum of the visible raw scores (the positive scale is applied afterwards)
         const int lim = p.causal ? min(kv_len, qi + 1) : kv_len;  // keys [0, lim) are visible to this row
         const float* bd_row = nullptr;
-        if (p.bd) bd_row = p.bd + (((size_t)b * p.H + h) * p.Tq + min(qi, p.Tq - 1)) * p.ldbd + (p.Tq - 1 - min(qi, p.Tq - 1));
+        if (HAS_BD) {
+            const int qc = min(qi, p.Tq - 1);
+            bd_row = p.bd + (((size_t)b * p.H + h) * p.Tq + qc) * p.ldbd + (p.Tq - 1 - qc);
+        }
         float m_blk = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
             uint32_t r[32];
             tmem_ld32(t_row + c, r);
             tmem_ld_wait();
+            const int k0 = key0 + c;
+            if (k0 + 32 <= lim) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int key = key0 + c + i;
-                float s = __uint_as_float(r[i]);
-                if (bd_row && key < lim) s += bd_row[key];
-                s = (key < lim) ? s * p.scale_log2 : -INFINITY;
-                m_blk = fmaxf(m_blk, s);
+                for (int i = 0; i < 32; ++i) {
+                    float sv = __uint_as_float(r[i]);
+                    if (HAS_BD) sv += bd_row[k0 + i];
+                    m_blk = fmaxf(m_blk, sv);
+                }
+            } else if (k0 < lim) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float sv = __uint_as_float(r[i]);
+                    if (HAS_BD && k0 + i < lim) sv += bd_row[k0 + i];
+                    m_blk = fmaxf(m_blk, (k0 + i < lim) ? sv : -INFINITY);
+                }
             }
         }
+        m_blk *= p.scale_log2;  // -inf stays -inf
         const float m_new = fmaxf(m_run, m_blk);
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
+        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_use);
         float l_blk = 0.f;
         // ---- pass 2: probabilities -> bf16 -> smem (K-major, 128B swizzle)
 #pragma unroll 1
@@ -118,14 +137,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tmem_ld32(t_row + c, r);
             tmem_ld_wait();
             float pv[32];
+            const int k0 = key0 + c;
+            if (k0 + 32 <= lim) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int key = key0 + c + i;
-                float s = __uint_as_float(r[i]);
-                if (bd_row && key < lim) s += bd_row[key];
-                const float e = (key < lim) ? exp2f(s * p.scale_log2 - m_use) : 0.f;
-                pv[i] = e;
-                l_blk += e;
+                for (int i = 0; i < 32; ++i) {
+                    float sv = __uint_as_float(r[i]);
+                    if (HAS_BD) sv += bd_row[k0 + i];
+                    pv[i] = ex2_approx(fmaf(sv, p.scale_log2, -m_use));
+                    l_blk += pv[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float sv = __uint_as_float(r[i]);
+                    if (HAS_BD && k0 + i < lim) sv += bd_row[k0 + i];
+                    pv[i] = (k0 + i < lim) ? ex2_approx(fmaf(sv, p.scale_log2, -m_use)) : 0.f;
+                    l_blk += pv[i];
+                }
             }
             uint8_t* prow = sP + (c >> 6) * 16384 + tid * 128;
             const int chunk0 = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
@@ -200,12 +228,14 @@ const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, con
     if ((err = encode_tmap_2d(&tv, v, (uint64_t)ldv, (uint64_t)k_rows, (uint64_t)ldv, 64, 128))) return err;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM) != cudaSuccess)
             return "cudaFuncSetAttribute(attn smem) failed";
         attr_set = true;
     }
     dim3 grid((p.Tq + 127) / 128, p.H, p.B);
-    attn_tc_kernel<<<grid, 128, ATT_SMEM, st>>>(tq, tk, tv, p);
+    if (p.bd) attn_tc_kernel<true><<<grid, 128, ATT_SMEM, st>>>(tq, tk, tv, p);
+    else attn_tc_kernel<false><<<grid, 128, ATT_SMEM, st>>>(tq, tk, tv, p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -64,7 +64,14 @@ __device__ __forceinline__ void warp_topk(F get, int n, int k, float* out_v, int
     const int lane = threadIdx.x & 31;
     TopList tl;
     tl.init();
-    for (int idx = lane; idx < n; idx += 32) tl.push(get(idx), idx);
+    for (int idx = lane; idx < n; idx += 128) {   // 4 independent loads in flight, then the branchy insertions
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (idx + 32 * j < n) ? get(idx + 32 * j) : -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (idx + 32 * j < n) tl.push(v[j], idx + 32 * j);
+    }
     for (int r = 0; r < k; ++r) {
         float bv = tl.v[0];
         int bi = tl.i[0];
@@ -83,7 +90,8 @@ __device__ __forceinline__ void warp_topk(F get, int n, int k, float* out_v, int
 __global__ void __launch_bounds__(KMAX * 32) beam_step_kernel(const float* __restrict__ logp, int ldl, int V,
                                                               const float* __restrict__ lm_logp, int ld_lm,
                                                               float lm_weight, BeamState st, long long* dbg_ktok,
-                                                              int* dbg_offs) {
+                                                              int* dbg_offs, const float* __restrict__ pre_val,
+                                                              const int* __restrict__ pre_idx) {
     __shared__ float c_val[KMAX * KMAX];
     __shared__ int c_tok[KMAX * KMAX];
     __shared__ float sel_v[KMAX];
@@ -104,6 +112,11 @@ __global__ void __launch_bounds__(KMAX * 32) beam_step_kernel(const float* __res
             if (lane < beam) {
                 row_v[warp][lane] = (lane == 0) ? 0.f : -INFINITY;
                 row_i[warp][lane] = (int)EOS_ID;
+            }
+        } else if (pre_val != nullptr) {
+            if (lane < beam) {
+                row_v[warp][lane] = pre_val[(size_t)n * beam + lane];
+                row_i[warp][lane] = pre_idx[(size_t)n * beam + lane];
             }
         } else {
             const float* lp = logp + (size_t)n * ldl;
@@ -169,11 +182,14 @@ __global__ void beam_advance_kernel(int* ctrl, int N, int Lmax) {
 }
 
 const char* beam_step_launch(cudaStream_t stream, const float* logp, int ldl, int V, const float* lm_logp, int ld_lm,
-                             float lm_weight, BeamState st, long long* dbg_ktok, int* dbg_offs) {
+                             float lm_weight, BeamState st, long long* dbg_ktok, int* dbg_offs, const float* pre_val,
+                             const int* pre_idx) {
     if (st.beam < 1 || st.beam > KMAX) return "beam_step: beam must be in [1,16]";
     if (st.N % st.beam) return "beam_step: N must be a multiple of beam";
+    if (!logp && !pre_val) return "beam_step: need log-probs or a precomputed top-k";
+    if ((pre_val == nullptr) != (pre_idx == nullptr)) return "beam_step: pre_val / pre_idx must both be given";
     beam_step_kernel<<<st.N / st.beam, st.beam * 32, 0, stream>>>(logp, ldl, V, lm_logp, ld_lm, lm_weight, st,
-                                                                  dbg_ktok, dbg_offs);
+                                                                  dbg_ktok, dbg_offs, pre_val, pre_idx);
     beam_advance_kernel<<<1, 1, 0, stream>>>(st.ctrl, st.N, st.Lmax);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -267,6 +283,124 @@ __global__ void beam_init_kernel(BeamState st) {
 const char* beam_init_launch(cudaStream_t stream, BeamState st) {
     int n = st.N < 4 ? 4 : st.N;
     beam_init_kernel<<<(n + 127) / 128, 128, 0, stream>>>(st);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused  log_softmax(logits[row]) (+ lm_weight * lm_logp[row])  ->  top-k (values, vocabulary ids)
+// decoder/transformer.py:206 + recognize/speech2text.py:102-112 in ONE pass over the logits: the row is
+// staged in smem once (coalesced), so the [N,V] log-prob matrix is never written or re-read.  Values are
+// formed exactly as the stand-alone log-softmax kernel does (x - (max + log sum exp(x - max))) before the
+// top-k, so the selected ids equal top-k over the materialised log-probs (ties -> lower index).
+// One CTA per hypothesis row, 8 warps; per-warp top-k over a slice, then one warp merges 8*k candidates.
+// ------------------------------------------------------------------------------------------------
+static constexpr int TOPK_THREADS = 256;
+
+__global__ void __launch_bounds__(TOPK_THREADS) logsoftmax_topk_kernel(const float* __restrict__ logits, int ldl, int V,
+                                                                       const float* __restrict__ lm_logp, int ld_lm,
+                                                                       float lm_weight, int k, float* __restrict__ out_val,
+                                                                       int* __restrict__ out_idx,
+                                                                       float* __restrict__ out_logp, int ld_logp) {
+    extern __shared__ float srow[];   // [V]
+    __shared__ float red[8];
+    __shared__ float bc;
+    __shared__ float cand_v[8 * KMAX];
+    __shared__ int cand_i[8 * KMAX];
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* x = logits + (size_t)row * ldl;
+    float m = -INFINITY;
+    for (int i = tid; i < V; i += TOPK_THREADS) {
+        const float v = x[i];
+        srow[i] = v;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float t = red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+        bc = t;
+    }
+    __syncthreads();
+    m = bc;
+    float sum = 0.f;
+    for (int i = tid; i < V; i += TOPK_THREADS) sum += expf(srow[i] - m);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        bc = m + logf(t);
+    }
+    __syncthreads();
+    const float lse = bc;
+    const float* lm = lm_logp ? lm_logp + (size_t)row * ld_lm : nullptr;
+    for (int i = tid; i < V; i += TOPK_THREADS) {
+        float v = srow[i] - lse;
+        if (lm) v = v + lm_weight * lm[i];
+        srow[i] = v;
+        if (out_logp) out_logp[(size_t)row * ld_logp + i] = v;
+    }
+    __syncthreads();
+    // per-warp top-k over a contiguous slice
+    const int per = (V + 7) / 8;
+    const int lo = warp * per, hi = min(V, lo + per);
+    {
+        TopList tl;
+        tl.init();
+        for (int idx = lo + lane; idx < hi; idx += 32) tl.push(srow[idx], idx);
+        for (int r = 0; r < k; ++r) {
+            float bv = tl.v[0];
+            int bi = tl.i[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (tl.i[0] == bi && tl.v[0] == bv) tl.pop();
+            if (lane == 0) { cand_v[warp * KMAX + r] = bv; cand_i[warp * KMAX + r] = bi; }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // merge: 8 sorted lists of k -> global top-k (lane w < 8 walks list w)
+        int pos = 0;
+        for (int r = 0; r < k; ++r) {
+            float bv = (lane < 8 && pos < k) ? cand_v[lane * KMAX + pos] : -INFINITY;
+            int bi = (lane < 8 && pos < k) ? cand_i[lane * KMAX + pos] : 0x7fffffff;
+            const float mv = bv;
+            const int mi = bi;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (mi == bi && mv == bv && lane < 8) ++pos;
+            if (lane == 0) { out_val[(size_t)row * k + r] = bv; out_idx[(size_t)row * k + r] = bi; }
+        }
+    }
+}
+
+const char* logsoftmax_topk_launch(cudaStream_t stream, const float* logits, int ldl, int V, const float* lm_logp,
+                                   int ld_lm, float lm_weight, int k, int rows, float* out_val, int* out_idx,
+                                   float* out_logp, int ld_logp) {
+    if (k < 1 || k > KMAX) return "logsoftmax_topk: k must be in [1,16]";
+    if (V < 1 || V > 48 * 1024) return "logsoftmax_topk: vocabulary too large for one CTA's shared memory";
+    const size_t smem = (size_t)V * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 40 * 1024) {
+        if (cudaFuncSetAttribute(logsoftmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return "cudaFuncSetAttribute(logsoftmax_topk) failed";
+        attr_set = true;
+    }
+    logsoftmax_topk_kernel<<<rows, TOPK_THREADS, smem, stream>>>(logits, ldl, V, lm_logp, ld_lm, lm_weight, k, out_val,
+                                                                 out_idx, out_logp, ld_logp);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -191,7 +191,21 @@ int otb_beam_step(const float* logp, int ldl, int V, const float* lm_logp, int l
                   const otb_beam_state* st, int64_t* dbg_ktok, int32_t* dbg_offs, void* stream) {
     if (!st || !logp) return fail("otb_beam_step", "null operand");
     RET("otb_beam_step", beam_step_launch(ST(stream), logp, ldl, V, lm_logp, ld_lm, lm_weight, to_state(st),
-                                          reinterpret_cast<long long*>(dbg_ktok), dbg_offs));
+                                          reinterpret_cast<long long*>(dbg_ktok), dbg_offs, nullptr, nullptr));
+}
+
+int otb_beam_step_topk(const float* topk_val, const int32_t* topk_idx, const otb_beam_state* st, int64_t* dbg_ktok,
+                       int32_t* dbg_offs, void* stream) {
+    if (!st || !topk_val || !topk_idx) return fail("otb_beam_step_topk", "null operand");
+    RET("otb_beam_step_topk", beam_step_launch(ST(stream), nullptr, 0, 0, nullptr, 0, 0.f, to_state(st),
+                                               reinterpret_cast<long long*>(dbg_ktok), dbg_offs, topk_val, topk_idx));
+}
+
+int otb_logsoftmax_topk(const float* logits, int ldl, int V, const float* lm_logp, int ld_lm, float lm_weight, int k,
+                        int rows, float* out_val, int32_t* out_idx, float* out_logp, int ld_logp, void* stream) {
+    if (!logits || !out_val || !out_idx || rows < 1) return fail("otb_logsoftmax_topk", "bad arguments");
+    RET("otb_logsoftmax_topk", logsoftmax_topk_launch(ST(stream), logits, ldl, V, lm_logp, ld_lm, lm_weight, k, rows,
+                                                      out_val, out_idx, out_logp, ld_logp));
 }
 
 int otb_beam_reconstruct(const otb_beam_state* st, int64_t* preds, int ld, int steps, void* stream) {

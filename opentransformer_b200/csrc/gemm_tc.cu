@@ -7,11 +7,16 @@
 //   otrans/module/attention.py:68,128-129,44   otrans/module/ffn.py:39-41
 //   otrans/frontend/conv.py:63-64,146          otrans/decoder/transformer.py:181
 //
-// Structure (persistent, one CTA per SM, 256 threads):
+// Structure (persistent, one CTA per SM, 384 threads):
 //   warp 0 lane 0 : TMA producer   (A tile 128x64, B tile BNx64 per k-block, SWIZZLE_128B)
 //   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, 4 per k-block), tcgen05.commit -> mbarriers
 //   warp 2        : TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4..7    : epilogue: tcgen05.ld -> registers -> fused math -> vectorised global stores
+//   warps 4..11   : epilogue, two warpgroups: warp w reads TMEM lanes 32*(w%4).., warpgroup (w-4)/4 takes
+//                   one half of the tile's columns.  tcgen05.ld -> registers -> fused math (bias / LN
+//                   parameters broadcast from smem) -> staged in smem -> coalesced 16-byte global stores
+//                   (one full output row segment per warp instruction; the residual tile is fetched the
+//                   same way).  Round-1 profile: per-thread row stores were 32 sectors/request and the
+//                   epilogue, not the MMA, bounded every GEMM (profiles/r1_*).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "otb_internal.h"
@@ -21,67 +26,43 @@ namespace otb {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;
+static constexpr int kEpiThreads = 256;
+static constexpr int STG_PITCH_MAX = 512 + 16;          // bytes per staged row (+16 B pad: conflict-free 16 B accesses)
+static constexpr int STG_BYTES = BM * STG_PITCH_MAX;    // 67,584
+static constexpr int AUX_BYTES = 6144;                  // barriers, TMEM slot, bias / gamma / beta, row map, LN stats
 
 template <int BN>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+    static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+    static constexpr int TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// store 32 consecutive output columns of one row (col0 multiple of 32)
-__device__ __forceinline__ void store_row32(const GemmParams& p, int row, int col0, const float (&v)[32]) {
-    if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + col0;
-        if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) o[i] = v[i];
-        }
-    } else {
-        bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldc + col0;
-        if (col0 + 32 <= p.N && (p.ldc & 7) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint4 u;
-                u.x = pack_bf16(v[i], v[i + 1]);
-                u.y = pack_bf16(v[i + 2], v[i + 3]);
-                u.z = pack_bf16(v[i + 4], v[i + 5]);
-                u.w = pack_bf16(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(o + i) = u;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) o[i] = __float2bfloat16(v[i]);
-        }
-    }
-}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// load 32 consecutive bf16 of a residual row into fp32
-__device__ __forceinline__ void load_resid32(const GemmParams& p, int row, int col0, float (&r)[32]) {
-    const bf16* src = p.resid + (size_t)row * p.ldr + col0;
-    if (col0 + 32 <= p.N && (p.ldr & 7) == 0) {
+// 32 fp32 values -> staged row (bf16 or f32), 16-byte shared stores
+__device__ __forceinline__ void stage32(uint8_t* row_ptr, int col, int out_f32, const float (&v)[32]) {
+    if (out_f32) {
+        float4* d = reinterpret_cast<float4*>(row_ptr + col * 4);
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            uint4 u = *reinterpret_cast<const uint4*>(src + i);
-            float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-            r[i] = a.x; r[i + 1] = a.y; r[i + 2] = b.x; r[i + 3] = b.y;
-            r[i + 4] = c.x; r[i + 5] = c.y; r[i + 6] = d.x; r[i + 7] = d.y;
-        }
+        for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
+        uint4* d = reinterpret_cast<uint4*>(row_ptr + col * 2);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
+        for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+            u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+            d[i] = u;
+        }
     }
 }
 
@@ -91,14 +72,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BN_OUT = (EPI == EPI_GLU) ? BN / 2 : BN;  // output columns per tile
+    constexpr int HALF = BN_OUT / 2;                        // output columns per epilogue warpgroup
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* aux = stg + STG_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(aux + 256);   // [256]  (GLU: value half | gate half)
+    float* s_gamma = s_bias + 256;                          // [256]
+    float* s_beta = s_gamma + 256;                          // [256]
+    int* s_rowmap = reinterpret_cast<int*>(s_beta + 256);   // [128] output row of each tile row, -1 = skip
+    float2* s_stats = reinterpret_cast<float2*>(s_rowmap + 128);  // [2][128] partial (sum, sumsq)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tempty_bar[i], kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -188,124 +177,205 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (128 threads, thread = row)
-        const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-        const int row_in_tile = ew * 32 + lane;
+        // ------------------------------------------------------------------ epilogue (256 threads)
+        const int et = threadIdx.x - 128;       // 0..255
+        const int ewarp = warp - 4;             // 0..7
+        const int quad = ewarp & 3;             // TMEM lane quadrant == warp % 4
+        const int half = ewarp >> 2;            // column half handled by this warpgroup
+        const int row_in_tile = quad * 32 + lane;
+        const int esize = p.out_f32 ? 4 : 2;
+        const int pitch = BN_OUT * esize + 16;
+        uint8_t* my_row = stg + row_in_tile * pitch;
+
+        if (EPI == EPI_RESID_LN) {
+            for (int i = et; i < BN; i += kEpiThreads) {
+                s_gamma[i] = p.gamma[i];
+                s_beta[i] = p.beta[i];
+            }
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            mbar_wait(&tfull_bar[as], aph);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+            const int col_base = n_blk * BN_OUT;             // first output column of the tile
+            const int ncols = min(BN_OUT, p.N - col_base);   // valid output columns
 
-            // output row + validity
-            int out_row;
-            bool row_ok;
-            if (p.conv) {
-                const int r = row_in_tile / p.conv_F2, f = row_in_tile % p.conv_F2;
-                const int bt = m_blk * p.conv_R + r;
-                const int b = bt / p.conv_T1h, t = bt % p.conv_T1h;
-                row_ok = (r < p.conv_R) && (b < p.conv_B) && (t < p.conv_T2);
-                out_row = (b * p.conv_T2 + t) * p.conv_F2 + f;
-            } else {
-                out_row = m_blk * BM + row_in_tile;
-                row_ok = out_row < p.M;
+            // ---- (a) per-tile smem setup: bias slice, row map, residual tile (all coalesced)
+            for (int i = et; i < BN; i += kEpiThreads) {
+                int c;
+                if (EPI == EPI_GLU) c = (i < BN_OUT) ? col_base + i : p.N + col_base + (i - BN_OUT);
+                else c = col_base + i;
+                const bool ok = (EPI == EPI_GLU) ? ((i % BN_OUT) < ncols) : (i < ncols);
+                s_bias[i] = (p.bias != nullptr && ok) ? p.bias[c] : 0.f;
             }
-            bool row_live = true;  // false -> masked row: sub-layer output forced to zero
-            if (p.row_len != nullptr && row_ok) {
+            if (et < BM) {
+                int out_row;
+                bool ok;
+                if (p.conv) {
+                    const int r = et / p.conv_F2, f = et % p.conv_F2;
+                    const int bt = m_blk * p.conv_R + r;
+                    const int b = bt / p.conv_T1h, t = bt % p.conv_T1h;
+                    ok = (r < p.conv_R) && (b < p.conv_B) && (t < p.conv_T2);
+                    out_row = (b * p.conv_T2 + t) * p.conv_F2 + f;
+                } else {
+                    out_row = m_blk * BM + et;
+                    ok = out_row < p.M;
+                }
+                s_rowmap[et] = ok ? out_row : -1;
+            }
+            if (EPI == EPI_RESID || EPI == EPI_RESID_LN) {
+                // residual rows are contiguous (no conv mode): warp copies one row segment per instruction
+                for (int r = ewarp; r < BM; r += 8) {
+                    const int grow = m_blk * BM + r;
+                    if (grow >= p.M) continue;
+                    const bf16* src = p.resid + (size_t)grow * p.ldr + col_base;
+                    uint8_t* dst = stg + r * pitch;
+                    for (int c = lane * 8; c < ncols; c += 256) {
+                        if (c + 8 <= ncols) {
+                            *reinterpret_cast<uint4*>(dst + c * 2) = *reinterpret_cast<const uint4*>(src + c);
+                        } else {
+                            for (int j = c; j < ncols; ++j) reinterpret_cast<bf16*>(dst)[j] = src[j];
+                        }
+                    }
+                }
+            }
+            epi_bar();
+
+            // row validity / padding mask of this thread's row
+            const int out_row = s_rowmap[row_in_tile];
+            bool row_live = true;
+            if (p.row_len != nullptr && out_row >= 0) {
                 const int b = out_row / p.row_period, t = out_row % p.row_period;
                 row_live = t < p.row_len[b];
             }
-            const int safe_row = row_ok ? out_row : 0;
+
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
             if (EPI == EPI_RESID_LN) {
-                // pass 1: v = resid + acc + bias, parked back in TMEM; accumulate sum / sum of squares
+                // pass 1: v = resid + acc + bias parked back in TMEM; row statistics over both column halves
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
                     uint32_t r[32];
                     tmem_ld32(t_row + c, r);
                     tmem_ld_wait();
-                    float res[32];
-                    load_resid32(p, safe_row, c, res);
+                    const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float v = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + c + i) : 0.f);
-                        v = (row_live ? v : 0.f) + res[i];
-                        s1 += v;
-                        s2 += v * v;
-                        r[i] = __float_as_uint(v);
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 u = rs[i];
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack_bf16(w[j]);
+                            const int e = 8 * i + 2 * j;
+                            float v0 = __uint_as_float(r[e]) + s_bias[c + e];
+                            float v1 = __uint_as_float(r[e + 1]) + s_bias[c + e + 1];
+                            v0 = (row_live ? v0 : 0.f) + f.x;
+                            v1 = (row_live ? v1 : 0.f) + f.y;
+                            s1 += v0 + v1;
+                            s2 += v0 * v0 + v1 * v1;
+                            r[e] = __float_as_uint(v0);
+                            r[e + 1] = __float_as_uint(v1);
+                        }
                     }
                     tmem_st32(t_row + c, r);
                 }
                 tmem_st_wait();
-                const float mean = s1 * (1.0f / BN);
-                const float var = fmaxf(s2 * (1.0f / BN) - mean * mean, 0.f);
+                s_stats[half * BM + row_in_tile] = make_float2(s1, s2);
+                epi_bar();
+                const float2 o = s_stats[(half ^ 1) * BM + row_in_tile];
+                const float mean = (s1 + o.x) * (1.0f / BN);
+                const float var = fmaxf((s2 + o.y) * (1.0f / BN) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.eps);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
                     uint32_t r[32];
                     tmem_ld32(t_row + c, r);
                     tmem_ld_wait();
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        v[i] = (__uint_as_float(r[i]) - mean) * rstd * __ldg(p.gamma + c + i) + __ldg(p.beta + c + i);
-                    if (row_ok) store_row32(p, out_row, c, v);
+                        v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
+                    stage32(my_row, c, p.out_f32, v);
                 }
             } else if (EPI == EPI_GLU) {
 #pragma unroll 1
-                for (int c = 0; c < BN_OUT; c += 32) {
+                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
                     uint32_t ra[32], rg[32];
                     tmem_ld32(t_row + c, ra);
                     tmem_ld32(t_row + BN_OUT + c, rg);
                     tmem_ld_wait();
-                    const int col0 = n_blk * BN_OUT + c;
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int col = col0 + i;
-                        const float ba = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
-                        const float bg = (p.bias && col < p.N) ? __ldg(p.bias + p.N + col) : 0.f;
-                        const float a = __uint_as_float(ra[i]) + ba;
-                        const float g = __uint_as_float(rg[i]) + bg;
-                        v[i] = row_live ? a * sigmoidf_(g) : 0.f;
+                        const float a = __uint_as_float(ra[i]) + s_bias[c + i];
+                        const float g = __uint_as_float(rg[i]) + s_bias[BN_OUT + c + i];
+                        v[i] = row_live ? a * fast_sigmoid(g) : 0.f;
                     }
-                    if (row_ok && col0 < p.N) store_row32(p, out_row, col0, v);
+                    stage32(my_row, c, p.out_f32, v);
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
                     uint32_t r[32];
                     tmem_ld32(t_row + c, r);
                     tmem_ld_wait();
-                    const int col0 = n_blk * BN + c;
-                    if (col0 >= p.N) continue;  // warp-uniform
+                    if (c >= ncols) continue;  // warp-uniform
                     float v[32];
                     float res[32];
-                    if (EPI == EPI_RESID) load_resid32(p, safe_row, col0, res);
+                    if (EPI == EPI_RESID) {
+                        const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 u = rs[i];
+                            const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z),
+                                         f3 = unpack_bf16(u.w);
+                            res[8 * i] = f0.x; res[8 * i + 1] = f0.y; res[8 * i + 2] = f1.x; res[8 * i + 3] = f1.y;
+                            res[8 * i + 4] = f2.x; res[8 * i + 5] = f2.y; res[8 * i + 6] = f3.x; res[8 * i + 7] = f3.y;
+                        }
+                    }
+                    const float* trow = nullptr;
+                    if (EPI == EPI_TABLE)
+                        trow = p.table + (size_t)((out_row >= 0 ? out_row : 0) % p.period) * p.N + col_base + c;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int col = col0 + i;
-                        float x = __uint_as_float(r[i]) + ((p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f);
+                        float x = __uint_as_float(r[i]) + s_bias[c + i];
                         if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
-                        if (EPI == EPI_SWISH) x = x * sigmoidf_(x);
+                        if (EPI == EPI_SWISH) x = x * fast_sigmoid(x);
                         if (EPI == EPI_GELU) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
                         if (EPI == EPI_TANH) x = tanhf(x);
-                        if (EPI == EPI_TABLE)
-                            x = x * p.alpha +
-                                ((col < p.N) ? __ldg(p.table + (size_t)(safe_row % p.period) * p.N + col) : 0.f);
+                        if (EPI == EPI_TABLE) x = x * p.alpha + ((c + i < ncols) ? __ldg(trow + i) : 0.f);
                         if (!row_live) x = 0.f;
                         if (EPI == EPI_RESID) x = res[i] + p.alpha * x;
                         v[i] = x;
                     }
-                    if (row_ok) store_row32(p, out_row, col0, v);
+                    stage32(my_row, c, p.out_f32, v);
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);
+            mbar_arrive(&tempty_bar[as]);  // TMEM stage is free for the next tile's MMAs
+            epi_bar();
+
+            // ---- (e) coalesced copy-out: one output row segment per warp instruction
+            const int row_bytes = ncols * esize;
+            for (int r = ewarp; r < BM; r += 8) {
+                const int orow = s_rowmap[r];
+                if (orow < 0) continue;
+                const uint8_t* src = stg + r * pitch;
+                uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)orow * p.ldc + col_base) * esize;
+                for (int off = lane * 16; off < row_bytes; off += 512) {
+                    if (off + 16 <= row_bytes) {
+                        *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(src + off);
+                    } else {
+                        for (int j = off; j < row_bytes; j += 2)
+                            *reinterpret_cast<uint16_t*>(dst + j) = *reinterpret_cast<const uint16_t*>(src + j);
+                    }
+                }
+            }
+            epi_bar();  // staging / bias smem may be rewritten for the next tile
         }
     }
 
@@ -413,7 +483,7 @@ static const char* launch_bn(cudaStream_t st, const CUtensorMap& ta, const CUten
 }
 
 // Pick the N tile that wastes the fewest MMA cycles across the persistent grid.
-static int choose_bn(int m_tiles, int n_cols, int epi) {
+static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
     if (epi == EPI_RESID_LN) return n_cols;  // tile must span the row
     const int sms = num_sms();
     int best = 0;
@@ -422,7 +492,8 @@ static int choose_bn(int m_tiles, int n_cols, int epi) {
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const int bn_out = (epi == EPI_GLU) ? bn / 2 : bn;
-        if (epi == EPI_GLU && bn == 64) continue;  // GLU tile needs >= 32 output columns per half, keep 64+
+        if (bn_out * (out_f32 ? 4 : 2) > 512) continue;  // staged row must fit the staging pitch
+        if (bn_out < 64) continue;                       // each epilogue warpgroup needs >= 32 columns
         const int n_tiles = (n_cols + bn_out - 1) / bn_out;
         const long tiles = (long)m_tiles * n_tiles;
         const long waves = (tiles + sms - 1) / sms;
@@ -436,10 +507,16 @@ const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, 
                         GemmParams p, const CUtensorMap* conv_map) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
     if (p.K % 8) return "gemm: K must be a multiple of 8";
+    if (p.ldc % (p.out_f32 ? 4 : 8)) return "gemm: ldc must keep rows 16-byte aligned (ldc % 8 == 0 for bf16, % 4 for f32)";
+    if (reinterpret_cast<uintptr_t>(p.out) & 15) return "gemm: out must be 16-byte aligned";
+    if ((epi == EPI_RESID || epi == EPI_RESID_LN) && ((p.ldr % 8) || (reinterpret_cast<uintptr_t>(p.resid) & 15)))
+        return "gemm: residual must be 16-byte aligned with ldr % 8 == 0";
     const int m_tiles = p.conv ? (p.conv_B * p.conv_T1h + p.conv_R - 1) / p.conv_R : (p.M + BM - 1) / BM;
     if (epi == EPI_RESID_LN && !(p.N == 64 || p.N == 128 || p.N == 256))
         return "gemm: fused residual+LayerNorm epilogue needs N in {64,128,256}";
-    const int bn = choose_bn(m_tiles, p.N, epi);
+    if (epi == EPI_RESID_LN && p.out_f32) return "gemm: fused residual+LayerNorm epilogue writes bf16";
+    const int bn = choose_bn(m_tiles, p.N, epi, p.out_f32);
+    if (bn == 0) return "gemm: no tile configuration";
     const int bn_out = (epi == EPI_GLU) ? bn / 2 : bn;
     const int n_tiles = (p.N + bn_out - 1) / bn_out;
     const int num_tiles = m_tiles * n_tiles;

@@ -12,45 +12,53 @@ namespace otb {
 // in : x f32 [B, T, F]
 // out: bf16 NHWC [B, 2*T1h, 2*F1h, C1]; columns f >= F1 are written as zero (they are the right
 //      frequency padding of conv2); rows t >= T1 are never read for valid outputs and left untouched.
-// One CTA per output row (b, t1); 3 input rows + the 9xC1 filter staged in smem; each thread
-// produces 8 channels of one (f1) -> one 16-byte store, fully coalesced along (f1, c).
+// HBM-bound on the output write (82 MB at cfg 2).  One CTA = 8 consecutive output rows of one
+// utterance: the 17 input rows are staged in smem once, each thread keeps the 3x3 filters + bias of
+// its 8 channels in registers and walks over (row, f1) positions, one 16-byte store per position,
+// fully coalesced along (f1, c).
 // ------------------------------------------------------------------------------------------------
+static constexpr int CONV1_ROWS = 8;
+
 __global__ void __launch_bounds__(256) conv1_relu_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, bf16* __restrict__ out,
                                                               int B, int T, int F, int T1, int F1, int T1pad,
                                                               int F1pad, int C1) {
-    extern __shared__ float sm[];
-    float* sx = sm;                    // [3][F + 2]  (one zero column each side)
-    float* sw = sm + 3 * (F + 2);      // [9][C1]  tap-major
-    float* sb = sw + 9 * C1;           // [C1]
-    const int row = blockIdx.x;        // b * T1 + t1
-    const int b = row / T1, t1 = row % T1;
-    for (int i = threadIdx.x; i < 3 * (F + 2); i += blockDim.x) {
-        const int r = i / (F + 2), f = i % (F + 2) - 1;
-        sx[i] = (f >= 0 && f < F) ? x[((size_t)b * T + 2 * t1 + r) * F + f] : 0.f;
+    extern __shared__ float sx[];  // [2*CONV1_ROWS + 1][F + 2]  (one zero column each side)
+    const int chunks = (T1 + CONV1_ROWS - 1) / CONV1_ROWS;
+    const int b = blockIdx.x / chunks, t1_0 = (blockIdx.x % chunks) * CONV1_ROWS;
+    const int nrows = min(CONV1_ROWS, T1 - t1_0);
+    const int W2 = F + 2;
+    const int in_rows = 2 * nrows + 1;
+    for (int i = threadIdx.x; i < in_rows * W2; i += blockDim.x) {
+        const int r = i / W2, f = i % W2 - 1;
+        sx[i] = (f >= 0 && f < F) ? x[((size_t)b * T + 2 * t1_0 + r) * F + f] : 0.f;
     }
-    for (int i = threadIdx.x; i < 9 * C1; i += blockDim.x) {
-        const int tap = i / C1, c = i % C1;
-        sw[i] = w[c * 9 + tap];
+    const int cgs = C1 / 8;             // channel groups of 8
+    const int ppp = blockDim.x / cgs;   // positions per pass
+    const int cg = threadIdx.x % cgs, pos0 = threadIdx.x / cgs;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        br[j] = bias[cg * 8 + j];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) wr[tap][j] = w[(cg * 8 + j) * 9 + tap];
     }
-    for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = bias[i];
     __syncthreads();
-    const int cg = C1 / 8;
-    bf16* orow = out + ((size_t)b * T1pad + t1) * F1pad * C1;
-    for (int i = threadIdx.x; i < F1pad * cg; i += blockDim.x) {
-        const int f1 = i / cg, c0 = (i % cg) * 8;
+    if (pos0 >= ppp) return;
+    const int npos = nrows * F1pad;
+    for (int pos = pos0; pos < npos; pos += ppp) {
+        const int r = pos / F1pad, f1 = pos % F1pad;
         float v[8];
         if (f1 < F1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = sb[c0 + j];
+            for (int j = 0; j < 8; ++j) v[j] = br[j];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    const float xv = sx[kh * (F + 2) + 2 * f1 + kw];  // input col 2*f1 + kw - 1, +1 for the halo
-                    const float* wt = sw + (kh * 3 + kw) * C1 + c0;
+                    const float xv = sx[(2 * r + kh) * W2 + 2 * f1 + kw];  // input col 2*f1 + kw - 1, +1 for the halo
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, wt[j], v[j]);
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, wr[kh * 3 + kw][j], v[j]);
                 }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -63,16 +71,17 @@ __global__ void __launch_bounds__(256) conv1_relu_nhwc_kernel(const float* __res
         u.y = pack_bf16(v[2], v[3]);
         u.z = pack_bf16(v[4], v[5]);
         u.w = pack_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(orow + (size_t)f1 * C1 + c0) = u;
+        *reinterpret_cast<uint4*>(out + (((size_t)b * T1pad + t1_0 + r) * F1pad + f1) * C1 + cg * 8) = u;
     }
 }
 
 const char* conv1_launch(cudaStream_t st, const float* x, const float* w, const float* bias, bf16* out, int B, int T,
                          int F, int T1, int F1, int T1pad, int F1pad, int C1) {
-    if (C1 % 8) return "conv1: C1 must be a multiple of 8";
-    size_t smem = (3 * (F + 2) + 10 * C1) * sizeof(float);
-    if (smem > 48 * 1024) return "conv1: F or C1 too large";
-    conv1_relu_nhwc_kernel<<<B * T1, 256, smem, st>>>(x, w, bias, out, B, T, F, T1, F1, T1pad, F1pad, C1);
+    if (C1 % 8 || C1 > 2048) return "conv1: C1 must be a multiple of 8 (<= 2048)";
+    size_t smem = (size_t)(2 * CONV1_ROWS + 1) * (F + 2) * sizeof(float);
+    if (smem > 48 * 1024) return "conv1: F too large";
+    const int chunks = (T1 + CONV1_ROWS - 1) / CONV1_ROWS;
+    conv1_relu_nhwc_kernel<<<B * chunks, 256, smem, st>>>(x, w, bias, out, B, T, F, T1, F1, T1pad, F1pad, C1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -292,7 +301,9 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
                                                                bf16* __restrict__ vc, const int* __restrict__ anc,
                                                                const int* __restrict__ step_ptr, bf16* __restrict__ out,
                                                                int N, int H, int Lmax, float scale) {
-    extern __shared__ float sc[];  // [warps][Lmax + 1]
+    // Lanes run over KEYS for the scores (each lane owns up to KPL cached positions and reads whole 128-byte
+    // K rows with 16-byte loads: 8 independent loads in flight per key), then over the 64 head DIMS for P.V.
+    constexpr int KPL = 4;  // keys per lane -> up to 128 cached positions
     const int n = blockIdx.x;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
@@ -300,63 +311,87 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
     const int step = *step_ptr;
     const int* an = anc + ((size_t)(step & 1) * N + n) * Lmax;
     for (int h = wib; h < H; h += nw) {
-        float* s_row = sc + wib * (Lmax + 1);
-        const bf16* base = qkv + (size_t)n * 3 * d + h * 64 + 2 * lane;
-        const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(base));
-        const uint32_t kcur = *reinterpret_cast<const uint32_t*>(base + d);
-        const uint32_t vcur = *reinterpret_cast<const uint32_t*>(base + 2 * d);
+        const bf16* base = qkv + (size_t)n * 3 * d + h * 64;
+        // append the newest K/V to the cache (lane owns dims 2*lane, 2*lane+1)
+        const uint32_t kcur = *reinterpret_cast<const uint32_t*>(base + d + 2 * lane);
+        const uint32_t vcur = *reinterpret_cast<const uint32_t*>(base + 2 * d + 2 * lane);
         const size_t cur_off = ((size_t)step * N + n) * d + h * 64 + 2 * lane;
         *reinterpret_cast<uint32_t*>(kc + cur_off) = kcur;
         *reinterpret_cast<uint32_t*>(vc + cur_off) = vcur;
-        // scores
+        // q in registers (every lane needs all 64 dims)
+        float q[64];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = *reinterpret_cast<const uint4*>(base + 8 * i);
+            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+            q[8 * i] = a.x; q[8 * i + 1] = a.y; q[8 * i + 2] = b.x; q[8 * i + 3] = b.y;
+            q[8 * i + 4] = c.x; q[8 * i + 5] = c.y; q[8 * i + 6] = e.x; q[8 * i + 7] = e.y;
+        }
+        float sc[KPL];
+        int slot[KPL];
         float mx = -INFINITY;
-        for (int s0 = 0; s0 <= step; s0 += 4) {
-            float part[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int s = s0 + j;
+        for (int j = 0; j < KPL; ++j) {
+            const int s = lane + 32 * j;
+            sc[j] = -INFINITY;
+            slot[j] = n;
+            if (s <= step) {
+                const bf16* krow;
+                if (s == step) {
+                    krow = base + d;
+                } else {
+                    slot[j] = an[s];
+                    krow = kc + ((size_t)s * N + slot[j]) * d + h * 64;
+                }
                 float dot = 0.f;
-                if (s <= step) {
-                    uint32_t kk;
-                    if (s == step) kk = kcur;
-                    else kk = *reinterpret_cast<const uint32_t*>(kc + ((size_t)s * N + an[s]) * d + h * 64 + 2 * lane);
-                    const float2 kf = unpack_bf16(kk);
-                    dot = q.x * kf.x + q.y * kf.y;
-                }
-                part[j] = dot;
-            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float t = warp_sum(part[j]) * scale;
-                if (s0 + j <= step) {
-                    if (lane == 0) s_row[s0 + j] = t;
-                    mx = fmaxf(mx, t);
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(krow + 8 * i);
+                    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+                    dot += q[8 * i] * a.x + q[8 * i + 1] * a.y + q[8 * i + 2] * b.x + q[8 * i + 3] * b.y +
+                           q[8 * i + 4] * c.x + q[8 * i + 5] * c.y + q[8 * i + 6] * e.x + q[8 * i + 7] * e.y;
                 }
+                sc[j] = dot * scale;
+                mx = fmaxf(mx, sc[j]);
             }
         }
-        __syncwarp();
-        float l = 0.f, ax = 0.f, ay = 0.f;
-        for (int s = 0; s <= step; ++s) {
-            const float pw = __expf(s_row[s] - mx);
-            uint32_t vv;
-            if (s == step) vv = vcur;
-            else vv = *reinterpret_cast<const uint32_t*>(vc + ((size_t)s * N + an[s]) * d + h * 64 + 2 * lane);
-            const float2 vf = unpack_bf16(vv);
-            l += pw;
-            ax += pw * vf.x;
-            ay += pw * vf.y;
+        mx = warp_max(mx);
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            sc[j] = (lane + 32 * j <= step) ? __expf(sc[j] - mx) : 0.f;
+            l += sc[j];
+        }
+        l = warp_sum(l);
+        // P.V : lane owns output dims 2*lane, 2*lane+1; probabilities / slots broadcast by shuffle
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int s_hi = min(31, step - 32 * j);
+            if (s_hi < 0) break;   // warp-uniform
+#pragma unroll 8
+            for (int t = 0; t <= s_hi; ++t) {
+                const int s = t + 32 * j;
+                const float pw = __shfl_sync(0xffffffffu, sc[j], t);
+                const int sl = __shfl_sync(0xffffffffu, slot[j], t);
+                uint32_t vv;
+                if (s == step) vv = vcur;
+                else vv = *reinterpret_cast<const uint32_t*>(vc + ((size_t)s * N + sl) * d + h * 64 + 2 * lane);
+                const float2 vf = unpack_bf16(vv);
+                ax = fmaf(pw, vf.x, ax);
+                ay = fmaf(pw, vf.y, ay);
+            }
         }
         const float inv = 1.0f / l;
         *reinterpret_cast<uint32_t*>(out + (size_t)n * d + h * 64 + 2 * lane) = pack_bf16(ax * inv, ay * inv);
-        __syncwarp();
     }
 }
 
 const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, bf16* vc, const int* anc,
                                     const int* step_ptr, bf16* out, int N, int H, int Lmax) {
+    if (Lmax > 128) return "decode_self_attn: at most 128 cached positions (max_len <= 128)";
     const int warps = H < 4 ? H : 4;
-    size_t smem = (size_t)warps * (Lmax + 1) * sizeof(float);
-    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
+    decode_self_attn_kernel<<<N, warps * 32, 0, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -97,7 +97,11 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
                                     const int* step_ptr, bf16* out, int N, int H, int Lmax);
 const char* beam_init_launch(cudaStream_t stream, BeamState st);
 const char* beam_step_launch(cudaStream_t stream, const float* logp, int ldl, int V, const float* lm_logp, int ld_lm,
-                             float lm_weight, BeamState st, long long* dbg_ktok, int* dbg_offs);
+                             float lm_weight, BeamState st, long long* dbg_ktok, int* dbg_offs, const float* pre_val,
+                             const int* pre_idx);
+const char* logsoftmax_topk_launch(cudaStream_t stream, const float* logits, int ldl, int V, const float* lm_logp,
+                                   int ld_lm, float lm_weight, int k, int rows, float* out_val, int* out_idx,
+                                   float* out_logp, int ld_logp);
 const char* beam_reconstruct_launch(cudaStream_t stream, BeamState st, long long* preds, int ld, int steps);
 const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalty, float lamda, int nbest,
                                  long long* out_preds, float* out_scores);

@@ -196,6 +196,23 @@ def log_softmax(x, V, out=None):
     return out
 
 
+def logsoftmax_topk(logits, V, k, lm_logp=None, lm_weight=0.0, out_val=None, out_idx=None, out_logp=None):
+    """Fused log-softmax (+ LM shallow fusion) + per-row top-k.  logits f32 [rows, ld]."""
+    _need(logits, torch.float32, 'logits')
+    rows = logits.shape[0]
+    if out_val is None:
+        out_val = torch.empty(rows, k, dtype=torch.float32, device=logits.device)
+    if out_idx is None:
+        out_idx = torch.empty(rows, k, dtype=torch.int32, device=logits.device)
+    check(_lib.lib().otb_logsoftmax_topk(_p(logits), logits.stride(0), V, _p(lm_logp),
+                                         lm_logp.stride(0) if lm_logp is not None else 0, lm_weight, k, rows,
+                                         _p(out_val), _p(out_idx), _p(out_logp),
+                                         out_logp.stride(0) if out_logp is not None else 0, _stream()),
+          'otb_logsoftmax_topk')
+    _count()
+    return out_val, out_idx
+
+
 def decode_self_attn(qkv, kc, vc, anc, step_ptr, N, H, Lmax, out=None):
     if out is None:
         out = torch.empty(N, H * 64, dtype=BF16, device=qkv.device)
@@ -237,6 +254,11 @@ class BeamState:
                                        lm_logp.stride(0) if lm_logp is not None else 0, lm_weight,
                                        ctypes.byref(self.c), _p(dbg_ktok), _p(dbg_offs), _stream()), 'otb_beam_step')
         _count(2)   # beam_step_kernel + beam_advance_kernel
+
+    def step_topk(self, topk_val, topk_idx, dbg_ktok=None, dbg_offs=None):
+        check(_lib.lib().otb_beam_step_topk(_p(topk_val), _p(topk_idx), ctypes.byref(self.c), _p(dbg_ktok),
+                                            _p(dbg_offs), _stream()), 'otb_beam_step_topk')
+        _count(2)
 
     def reconstruct(self, steps):
         preds = torch.empty(self.N, steps + 1, dtype=torch.int64, device=self.scores.device)

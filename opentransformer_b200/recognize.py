@@ -89,6 +89,9 @@ class BeamDecoder:
         self.table = ops.sinusoid_table(max_len + 1, d, 0, device)
         self.logits = torch.zeros(self.N, decoder.ld_logits, dtype=torch.float32, device=device)
         self.logp = torch.zeros(self.N, decoder.vocab_size, dtype=torch.float32, device=device)
+        self.topk_val = torch.zeros(self.N, beam, dtype=torch.float32, device=device)
+        self.topk_idx = torch.zeros(self.N, beam, dtype=torch.int32, device=device)
+        self.keep_logp = not use_graph      # eager (test / debug) mode also materialises the full log-probs
         self.use_graph = use_graph
         self.graph = None
         self.lm_logp = None
@@ -129,8 +132,10 @@ class BeamDecoder:
         if dec.normalize_before:
             x = ops.layernorm(x, *pk['after'])
         ops.linear(x, pk['wout'], pk['bout'], out=self.logits)
-        ops.log_softmax(self.logits, dec.vocab_size, out=self.logp)
-        st.step(self.logp, dec.vocab_size, self.lm_logp, self.lm_weight)
+        ops.logsoftmax_topk(self.logits, dec.vocab_size, self.beam, self.lm_logp, self.lm_weight,
+                            out_val=self.topk_val, out_idx=self.topk_idx,
+                            out_logp=self.logp if self.keep_logp else None)
+        st.step_topk(self.topk_val, self.topk_idx)
 
     def step(self):
         if not self.use_graph:

@@ -245,8 +245,24 @@ def test_log_softmax_rows():
     print(_report('log_softmax', out, ref, 1e-6, 2e-5))
 
 
+@pytest.mark.parametrize('rows,V,k,lm', [(320, 4234, 10, False), (7, 100, 5, True), (3, 40, 16, False), (5, 9000, 1, True)])
+def test_logsoftmax_topk_fused(rows, V, k, lm):
+    ld = (V + 7) // 8 * 8
+    x = _rnd(rows, ld, scale=4.0, seed=1)
+    lm_lp = torch.log_softmax(_rnd(rows, V, seed=2), -1) if lm else None
+    lp = torch.empty(rows, V, device=DEV)
+    val, idx = ops.logsoftmax_topk(x, V, k, lm_lp, 0.3, out_logp=lp)
+    ref = torch.log_softmax(x[:, :V], -1) + (0.3 * lm_lp if lm else 0)
+    print(_report('fused log-probs', lp, ref, 1e-6, 3e-5))
+    tv, ti = torch.topk(lp, k, dim=-1)                   # top-k over the kernel's own log-probs must be identical
+    assert torch.equal(idx.long(), ti), 'fused top-k ids differ from topk(log_probs)'
+    assert torch.equal(val, tv)
+    val2, idx2 = ops.logsoftmax_topk(x, V, k, lm_lp, 0.3)          # without materialising log-probs
+    assert torch.equal(idx2, idx) and torch.equal(val2, val)
+
+
 def test_decode_self_attention_with_ancestry_cache():
-    N, H, Lmax, step = 12, 4, 9, 5
+    N, H, Lmax, step = 12, 4, 60, 45
     d = H * 64
     qkv = _rnd(N, 3 * d, seed=1).to(BF)
     kc = _rnd(Lmax, N, d, seed=2).to(BF)
@@ -294,6 +310,15 @@ def _run_beam_step(case):
     new_preds = torch.cat((case['preds'].to(DEV).index_select(0, st.par_hist[0].long()),
                            st.tok_hist[0].long().view(-1, 1)), 1)
     assert torch.equal(new_preds.cpu(), p)
+    # the fused path (top-k computed by otb_logsoftmax_topk from logits == log-probs up to the constant lse)
+    st2 = ops.BeamState(n // beam, beam, 4, DEV)
+    st2.init()
+    st2.scores.copy_(case['scores'].view(-1).to(DEV))
+    st2.flag.copy_(case['flag'].view(-1).to(torch.uint8).to(DEV))
+    tv, ti = torch.topk(lp, beam, dim=-1)
+    st2.step_topk(tv.contiguous(), ti.to(torch.int32).contiguous())
+    assert torch.equal(st2.tok_hist[0], st.tok_hist[0]) and torch.equal(st2.par_hist[0], st.par_hist[0])
+    assert torch.equal(st2.scores, st.scores) and torch.equal(st2.flag, st.flag)
     return st
 
 
