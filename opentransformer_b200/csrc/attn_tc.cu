@@ -47,24 +47,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (p.causal) kv_end = min(kv_end, q0 + 128);
     const int nblk = (kv_end + 127) / 128;
 
-    if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
-        fence_barrier_init();
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
+    if (warp == 0) {
+        if (tid == 0) {
+            for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1);
+            fence_barrier_init();
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            // Q and the first K/V block are requested before the TMEM allocation / CTA sync
+            mbar_arrive_expect_tx(&bar[0], 16384);
+            tma_load_2d(sQ, &tmQ, &bar[0], p.q_col0 + h * 64, b * p.Tq + q0);
+            if (nblk > 0) {
+                mbar_arrive_expect_tx(&bar[1], 16384);
+                tma_load_2d(sK, &tmK, &bar[1], p.k_col0 + h * 64, b * p.Tk);
+                mbar_arrive_expect_tx(&bar[2], 16384);
+                tma_load_2d(sV, &tmV, &bar[2], p.v_col0 + h * 64, b * p.Tk);
+            }
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
     }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&bar[0], 16384);
-        tma_load_2d(sQ, &tmQ, &bar[0], p.q_col0 + h * 64, b * p.Tq + q0);
-    }
 
     const int qi = q0 + tid;  // query index inside the utterance
     float m_run = -INFINITY, l_run = 0.f;
@@ -79,10 +86,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t ph = blk & 1;
         const int key0 = blk * 128;
         if (tid == 0) {
-            mbar_arrive_expect_tx(&bar[1], 16384);
-            tma_load_2d(sK, &tmK, &bar[1], p.k_col0 + h * 64, b * p.Tk + key0);
-            mbar_arrive_expect_tx(&bar[2], 16384);
-            tma_load_2d(sV, &tmV, &bar[2], p.v_col0 + h * 64, b * p.Tk + key0);
             if (blk == 0) mbar_wait(&bar[0], 0);
             mbar_wait(&bar[1], ph);
             tc_fence_after();
@@ -92,8 +95,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 umma_bf16(tmem_base, umma_desc_sw128(qa + k * 32), umma_desc_sw128(ka + k * 32), idesc_s, (uint32_t)(k != 0));
             umma_commit(&bar[3]);
         }
+        __syncwarp();
         mbar_wait(&bar[3], ph);
         tc_fence_after();
+        if (tid == 0 && blk + 1 < nblk) {   // S = QK^T has consumed the K block: prefetch the next one
+            mbar_arrive_expect_tx(&bar[1], 16384);
+            tma_load_2d(sK, &tmK, &bar[1], p.k_col0 + h * 64, b * p.Tk + key0 + 128);
+        }
+        __syncwarp();
 
         // ---- pass 1: row maximum of the visible raw scores (the positive scale is applied afterwards)
         const int lim = p.causal ? min(kv_len, qi + 1) : kv_len;  // keys [0, lim) are visible to this row
@@ -183,8 +192,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                           umma_desc_sw128(va + kk * 2048), idesc_o, (uint32_t)(kk != 0));
             umma_commit(&bar[4]);
         }
+        __syncwarp();
         mbar_wait(&bar[4], ph);
         tc_fence_after();
+        if (tid == 0 && blk + 1 < nblk) {   // PV has consumed the V block: prefetch the next one
+            mbar_arrive_expect_tx(&bar[2], 16384);
+            tma_load_2d(sV, &tmV, &bar[2], p.v_col0 + h * 64, b * p.Tk + key0 + 128);
+        }
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
             uint32_t r[32];

@@ -45,6 +45,12 @@ const char* otb_last_error(void) { return g_err; }
 int otb_version(void) { return OTB_VERSION; }
 int otb_num_sms(void) { return num_sms(); }
 
+/* debug / profiling aid: when buf != NULL every GEMM CTA writes 8 clock64 phase stamps to buf[cta*8 ..] */
+int otb_debug_gemm_timing(unsigned long long* buf) {
+    g_gemm_dbg = buf;
+    return 0;
+}
+
 int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2) {
     if (T < 7 || F < 1) return fail("otb_conv_geometry", "need T >= 7 and F >= 1");
     const int t1 = (T - 3) / 2 + 1, f1 = (F - 1) / 2 + 1;

@@ -17,12 +17,21 @@
 //                   (one full output row segment per warp instruction; the residual tile is fetched the
 //                   same way).  Round-1 profile: per-thread row stores were 32 sectors/request and the
 //                   epilogue, not the MMA, bounded every GEMM (profiles/r1_*).
+// Residual + LayerNorm epilogue (N = d_model <= 256): the output row is split over a thread-block CLUSTER
+// of N/64 CTAs (64 columns each); per-row partial (sum, sum of squares) are exchanged through distributed
+// shared memory (st.shared::cluster + remote mbarrier arrive), so the LN-fused GEMMs run on 4x more SMs
+// than a one-CTA-per-row-block tiling would (63 -> 252 CTAs at cfg 2, 3 -> 12 in the decode loop).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <string.h>
+
 #include "otb_internal.h"
 #include "ptx.cuh"
 
 namespace otb {
+
+unsigned long long* g_gemm_dbg = nullptr;
+#define DBG_STAMP(i) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (i)] = clock64(); } while (0)
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
@@ -82,15 +91,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* ln_bar = tempty_bar + 2;                     // cluster LayerNorm statistics exchange
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 1);
     float* s_bias = reinterpret_cast<float*>(aux + 256);   // [256]  (GLU: value half | gate half)
     float* s_gamma = s_bias + 256;                          // [256]
     float* s_beta = s_gamma + 256;                          // [256]
     int* s_rowmap = reinterpret_cast<int*>(s_beta + 256);   // [128] output row of each tile row, -1 = skip
-    float2* s_stats = reinterpret_cast<float2*>(s_rowmap + 128);  // [2][128] partial (sum, sumsq)
+    // LN partial statistics [2 tile parities][cluster ranks * 2 halves <= 8][128 rows] live in the upper part of
+    // the staging buffer (the LN kernels stage only 128 x 144 B there)
+    float2* s_stats = reinterpret_cast<float2*>(stg + 32768);
+    const uint32_t cl_rank = (EPI == EPI_RESID_LN) ? cluster_ctarank() : 0;
+    const uint32_t cl_size = (EPI == EPI_RESID_LN) ? cluster_nctarank() : 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) DBG_STAMP(0);
 
     const int m_tiles = p.conv ? (p.conv_B * p.conv_T1h + p.conv_R - 1) / p.conv_R : (p.M + BM - 1) / BM;
     const int n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
@@ -98,60 +113,81 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_kb = (p.K + BK - 1) / BK;
     const uint32_t a_tx = p.conv ? (uint32_t)(p.conv_R * p.conv_F2 * BK * 2) : (uint32_t)Cfg::A_BYTES;
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+    // One k-block load of the flat (tile, kb) sequence this CTA walks through.
+    auto issue_load = [&](int tile, int kb, int stage) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], a_tx + (uint32_t)Cfg::B_BYTES);
+        if (p.conv) {
+            // k-block -> (tap, channel chunk); tap (kh,kw): input row 2t'+kh, col 2f'+kw-1
+            const int tap = kb / p.conv_cchunks, cc = kb % p.conv_cchunks;
+            const int kh = tap / 3, kw = tap % 3;
+            const int par_f = (kw == 1) ? 0 : 1, f0 = (kw == 0) ? -1 : 0;
+            const int par_t = (kh == 1) ? 1 : 0, dt = (kh == 2) ? 1 : 0;
+            tma_load_5d(sa, &tmA, &full_bar[stage], cc * BK, par_f, f0, par_t, m_blk * p.conv_R + dt);
+        } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiThreads);
+        if (EPI == EPI_GLU) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN_OUT);
+            tma_load_2d(sb + Cfg::B_BYTES / 2, &tmB, &full_bar[stage], kb * BK, p.N + n_blk * BN_OUT);
+        } else {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
         }
-        fence_barrier_init();
+    };
+
+    // Producer state (meaningful in warp 0 lane 0 only): next load = (p_tile, p_kb) into p_stage.
+    int p_tile = blockIdx.x, p_kb = 0, p_stage = 0;
+    uint32_t p_phase = 0;
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tfull_bar[i], 1);
+                mbar_init(&tempty_bar[i], kEpiThreads);
+            }
+            mbar_init(ln_bar, kEpiThreads * cl_size);
+            fence_barrier_init();
+            // the first STAGES slots are free by construction: start the loads before the CTA-wide sync so
+            // their latency overlaps the TMEM allocation
+            for (int i = 0; i < STAGES && p_tile < num_tiles; ++i) {
+                issue_load(p_tile, p_kb, p_stage);
+                if (i == 0) DBG_STAMP(2);
+                if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
+                if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
+            }
+        }
+        __syncwarp();
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (EPI == EPI_RESID_LN && cl_size > 1) cluster_sync_all();  // peers' mbarriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG_STAMP(1);
 
-    if (warp == 0 && lane == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                uint8_t* sb = sa + Cfg::A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], a_tx + (uint32_t)Cfg::B_BYTES);
-                if (p.conv) {
-                    // k-block -> (tap, channel chunk); tap (kh,kw): input row 2t'+kh, col 2f'+kw-1
-                    const int tap = kb / p.conv_cchunks, cc = kb % p.conv_cchunks;
-                    const int kh = tap / 3, kw = tap % 3;
-                    const int par_f = (kw == 1) ? 0 : 1, f0 = (kw == 0) ? -1 : 0;
-                    const int par_t = (kh == 1) ? 1 : 0, dt = (kh == 2) ? 1 : 0;
-                    tma_load_5d(sa, &tmA, &full_bar[stage], cc * BK, par_f, f0, par_t, m_blk * p.conv_R + dt);
-                } else {
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                }
-                if (EPI == EPI_GLU) {
-                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN_OUT);
-                    tma_load_2d(sb + Cfg::B_BYTES / 2, &tmB, &full_bar[stage], kb * BK, p.N + n_blk * BN_OUT);
-                } else {
-                    tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (lane 0)
+        if (lane == 0) {
+            while (p_tile < num_tiles) {
+                mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
+                issue_load(p_tile, p_kb, p_stage);
+                if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
+                if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (lane 0)
         constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -164,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                if (it == 0 && kb == 0) DBG_STAMP(3);
                 const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -175,7 +212,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+            if (it == 0) DBG_STAMP(4);
         }
+        }
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (256 threads)
         const int et = threadIdx.x - 128;       // 0..255
@@ -187,10 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int pitch = BN_OUT * esize + 16;
         uint8_t* my_row = stg + row_in_tile * pitch;
 
-        if (EPI == EPI_RESID_LN) {
+        if (EPI == EPI_RESID_LN) {  // this CTA's 64-column slice of the LayerNorm affine parameters
             for (int i = et; i < BN; i += kEpiThreads) {
-                s_gamma[i] = p.gamma[i];
-                s_beta[i] = p.beta[i];
+                s_gamma[i] = p.gamma[cl_rank * BN + i];
+                s_beta[i] = p.beta[cl_rank * BN + i];
             }
         }
         int it = 0;
@@ -225,18 +265,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 s_rowmap[et] = ok ? out_row : -1;
             }
             if (EPI == EPI_RESID || EPI == EPI_RESID_LN) {
-                // residual rows are contiguous (no conv mode): warp copies one row segment per instruction
-                for (int r = ewarp; r < BM; r += 8) {
-                    const int grow = m_blk * BM + r;
-                    if (grow >= p.M) continue;
-                    const bf16* src = p.resid + (size_t)grow * p.ldr + col_base;
-                    uint8_t* dst = stg + r * pitch;
-                    for (int c = lane * 8; c < ncols; c += 256) {
-                        if (c + 8 <= ncols) {
-                            *reinterpret_cast<uint4*>(dst + c * 2) = *reinterpret_cast<const uint4*>(src + c);
-                        } else {
-                            for (int j = c; j < ncols; ++j) reinterpret_cast<bf16*>(dst)[j] = src[j];
+                // residual rows are contiguous (no conv mode); 16-byte chunks, 8 independent loads in flight per thread
+                if ((ncols & 7) == 0) {
+                    const int cpr = ncols >> 3;                        // 16-byte chunks per row
+                    const int rows_here = min(BM, p.M - m_blk * BM);
+                    const int total = rows_here * cpr;
+                    const bf16* rbase = p.resid + (size_t)(m_blk * BM) * p.ldr + col_base;
+                    for (int q0 = et; q0 < total; q0 += kEpiThreads * 8) {
+                        uint4 tmp[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int q = q0 + j * kEpiThreads;
+                            if (q < total) tmp[j] = *reinterpret_cast<const uint4*>(rbase + (size_t)(q / cpr) * p.ldr + (q % cpr) * 8);
                         }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int q = q0 + j * kEpiThreads;
+                            if (q < total) *reinterpret_cast<uint4*>(stg + (q / cpr) * pitch + (q % cpr) * 16) = tmp[j];
+                        }
+                    }
+                } else {
+                    for (int r = ewarp; r < BM; r += 8) {
+                        const int grow = m_blk * BM + r;
+                        if (grow >= p.M) continue;
+                        const bf16* src = p.resid + (size_t)grow * p.ldr + col_base;
+                        for (int c = lane; c < ncols; c += 32) reinterpret_cast<bf16*>(stg + r * pitch)[c] = src[c];
                     }
                 }
             }
@@ -252,55 +305,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
+            if (it == 0 && et == 0) DBG_STAMP(5);
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
             if (EPI == EPI_RESID_LN) {
-                // pass 1: v = resid + acc + bias parked back in TMEM; row statistics over both column halves
+                // One 32-column chunk per thread (BN = 64, two warpgroups): v = resid + acc + bias stays in
+                // registers; row statistics are summed over the 2 halves x cl_size CTAs through DSMEM.
+                const int c = half * 32;
+                uint32_t r[32];
+                tmem_ld32(t_row + c, r);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);  // accumulator consumed: the next tile's MMAs may start
+                float v[32];
                 float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c, r);
-                    tmem_ld_wait();
-                    const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
+                const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
+                const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint4 u = rs[i];
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 u = rs[i];
+                    const float4 b0 = bs[2 * i], b1 = bs[2 * i + 1];
+                    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                    const float rr[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = unpack_bf16(w[j]);
-                            const int e = 8 * i + 2 * j;
-                            float v0 = __uint_as_float(r[e]) + s_bias[c + e];
-                            float v1 = __uint_as_float(r[e + 1]) + s_bias[c + e + 1];
-                            v0 = (row_live ? v0 : 0.f) + f.x;
-                            v1 = (row_live ? v1 : 0.f) + f.y;
-                            s1 += v0 + v1;
-                            s2 += v0 * v0 + v1 * v1;
-                            r[e] = __float_as_uint(v0);
-                            r[e + 1] = __float_as_uint(v1);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        float x = __uint_as_float(r[8 * i + j]) + bb[j];
+                        x = (row_live ? x : 0.f) + rr[j];
+                        v[8 * i + j] = x;
+                        s1 += x;
+                        s2 += x * x;
                     }
-                    tmem_st32(t_row + c, r);
                 }
-                tmem_st_wait();
-                s_stats[half * BM + row_in_tile] = make_float2(s1, s2);
-                epi_bar();
-                const float2 o = s_stats[(half ^ 1) * BM + row_in_tile];
-                const float mean = (s1 + o.x) * (1.0f / BN);
-                const float var = fmaxf((s2 + o.y) * (1.0f / BN) - mean * mean, 0.f);
+                const int par = it & 1;
+                const uint32_t slot = smem_u32(&s_stats[(par * 8 + (int)cl_rank * 2 + half) * BM + row_in_tile]);
+                const uint32_t bar_local = smem_u32(ln_bar);
+                for (uint32_t dst = 0; dst < cl_size; ++dst) {
+                    st_cluster_f32x2(mapa_shared(slot, dst), s1, s2);
+                    mbar_arrive_cluster(mapa_shared(bar_local, dst));
+                }
+                mbar_wait_cluster(ln_bar, (uint32_t)par);
+                float t1 = 0.f, t2 = 0.f;
+                for (int j = 0; j < 2 * (int)cl_size; ++j) {
+                    const float2 o = s_stats[(par * 8 + j) * BM + row_in_tile];
+                    t1 += o.x;
+                    t2 += o.y;
+                }
+                const float inv_n = 1.0f / (float)(BN * cl_size);
+                const float mean = t1 * inv_n;
+                const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.eps);
-#pragma unroll 1
-                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c, r);
-                    tmem_ld_wait();
-                    float v[32];
+                const float4* gs = reinterpret_cast<const float4*>(s_gamma + c);
+                const float4* es = reinterpret_cast<const float4*>(s_beta + c);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
-                    stage32(my_row, c, p.out_f32, v);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 g = gs[i], e = es[i];
+                    v[4 * i] = (v[4 * i] - mean) * rstd * g.x + e.x;
+                    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + e.y;
+                    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + e.z;
+                    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + e.w;
                 }
+                stage32(my_row, c, 0, v);
             } else if (EPI == EPI_GLU) {
 #pragma unroll 1
                 for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
@@ -309,11 +374,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld32(t_row + BN_OUT + c, rg);
                     tmem_ld_wait();
                     float v[32];
+                    const float4* ba = reinterpret_cast<const float4*>(s_bias + c);
+                    const float4* bg = reinterpret_cast<const float4*>(s_bias + BN_OUT + c);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float a = __uint_as_float(ra[i]) + s_bias[c + i];
-                        const float g = __uint_as_float(rg[i]) + s_bias[BN_OUT + c + i];
-                        v[i] = row_live ? a * fast_sigmoid(g) : 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x = ba[i], y = bg[i];
+                        const float av[4] = {x.x, x.y, x.z, x.w}, gv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a = __uint_as_float(ra[4 * i + j]) + av[j];
+                            const float g = __uint_as_float(rg[4 * i + j]) + gv[j];
+                            v[4 * i + j] = row_live ? a * fast_sigmoid(g) : 0.f;
+                        }
                     }
                     stage32(my_row, c, p.out_f32, v);
                 }
@@ -340,9 +412,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float* trow = nullptr;
                     if (EPI == EPI_TABLE)
                         trow = p.table + (size_t)((out_row >= 0 ? out_row : 0) % p.period) * p.N + col_base + c;
+                    float bv[32];
+                    {
+                        const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b4 = bs[i];
+                            bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(r[i]) + s_bias[c + i];
+                        float x = __uint_as_float(r[i]) + bv[i];
                         if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
                         if (EPI == EPI_SWISH) x = x * fast_sigmoid(x);
                         if (EPI == EPI_GELU) x = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
@@ -355,32 +436,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     stage32(my_row, c, p.out_f32, v);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[as]);  // TMEM stage is free for the next tile's MMAs
+            if (EPI != EPI_RESID_LN) {
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[as]);  // TMEM stage is free for the next tile's MMAs
+            }
             epi_bar();
 
-            // ---- (e) coalesced copy-out: one output row segment per warp instruction
+            // ---- (e) coalesced copy-out: consecutive threads write consecutive 16-byte chunks of a row
             const int row_bytes = ncols * esize;
-            for (int r = ewarp; r < BM; r += 8) {
-                const int orow = s_rowmap[r];
-                if (orow < 0) continue;
-                const uint8_t* src = stg + r * pitch;
-                uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)orow * p.ldc + col_base) * esize;
-                for (int off = lane * 16; off < row_bytes; off += 512) {
-                    if (off + 16 <= row_bytes) {
-                        *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(src + off);
-                    } else {
-                        for (int j = off; j < row_bytes; j += 2)
-                            *reinterpret_cast<uint16_t*>(dst + j) = *reinterpret_cast<const uint16_t*>(src + j);
+            if ((row_bytes & 15) == 0) {
+                const int cpr = row_bytes >> 4;
+                const int total = BM * cpr;
+                uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (size_t)col_base * esize;
+                const size_t ld_bytes = (size_t)p.ldc * esize;
+                for (int q0 = et; q0 < total; q0 += kEpiThreads * 8) {
+                    uint4 tmp[8];
+                    int orow[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int q = q0 + j * kEpiThreads;
+                        orow[j] = -1;
+                        if (q < total) {
+                            const int r = q / cpr;
+                            orow[j] = s_rowmap[r];
+                            tmp[j] = *reinterpret_cast<const uint4*>(stg + r * pitch + (q % cpr) * 16);
+                        }
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int q = q0 + j * kEpiThreads;
+                        if (orow[j] >= 0) *reinterpret_cast<uint4*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16) = tmp[j];
+                    }
+                }
+            } else {
+                for (int r = ewarp; r < BM; r += 8) {
+                    const int orow = s_rowmap[r];
+                    if (orow < 0) continue;
+                    const uint8_t* src = stg + r * pitch;
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + ((size_t)orow * p.ldc + col_base) * esize;
+                    for (int off = lane * 2; off < row_bytes; off += 64)
+                        *reinterpret_cast<uint16_t*>(dst + off) = *reinterpret_cast<const uint16_t*>(src + off);
                 }
             }
             epi_bar();  // staging / bias smem may be rewritten for the next tile
+            if (it == 0 && et == 0) DBG_STAMP(6);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DBG_STAMP(7);
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -460,6 +565,37 @@ static const char* launch_inst(cudaStream_t st, const CUtensorMap& ta, const CUt
         attr_set = true;
     }
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    if (EPI == EPI_RESID_LN) {
+        const int cl = p.N / BN;              // CTAs per cluster == n-tiles per row block
+        grid = (grid / cl) * cl;              // whole clusters only (num_tiles is a multiple of cl)
+        if (grid < cl) return "gemm: grid smaller than one cluster";
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // co-resident clusters (GPC boundaries strand a few SMs): never launch more than fit in one wave
+        static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (cl <= 8 && max_clusters[cl] == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, EPI>, &cfg) != cudaSuccess || n < 1) n = num_sms() / cl / 2;
+            max_clusters[cl] = n;
+        }
+        if (cl <= 8 && grid > max_clusters[cl] * cl) {
+            grid = max_clusters[cl] * cl;
+            cfg.gridDim = dim3(grid);
+        }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, ta, tb, p);
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
     gemm_tc_kernel<BN, EPI><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
@@ -484,7 +620,7 @@ static const char* launch_bn(cudaStream_t st, const CUtensorMap& ta, const CUten
 
 // Pick the N tile that wastes the fewest MMA cycles across the persistent grid.
 static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
-    if (epi == EPI_RESID_LN) return n_cols;  // tile must span the row
+    if (epi == EPI_RESID_LN) return 64;  // row split over a cluster of n_cols/64 CTAs
     const int sms = num_sms();
     int best = 0;
     double best_cost = 1e30;
@@ -506,6 +642,7 @@ static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
 const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, int ldw, int w_rows, int epi,
                         GemmParams p, const CUtensorMap* conv_map) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
+    p.dbg = g_gemm_dbg;
     if (p.K % 8) return "gemm: K must be a multiple of 8";
     if (p.ldc % (p.out_f32 ? 4 : 8)) return "gemm: ldc must keep rows 16-byte aligned (ldc % 8 == 0 for bf16, % 4 for f32)";
     if (reinterpret_cast<uintptr_t>(p.out) & 15) return "gemm: out must be 16-byte aligned";

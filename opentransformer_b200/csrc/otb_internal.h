@@ -46,6 +46,7 @@ struct GemmParams {
     int conv_T2;       // valid output time rows per utterance
     int conv_B;        // batch
     int conv_cchunks;  // C_in / 64
+    unsigned long long* dbg;  // optional [grid][8] clock64 phase stamps (otb_debug_gemm_timing)
 };
 
 const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, int ldw, int w_rows, int epi,
@@ -107,6 +108,7 @@ const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalt
                                  long long* out_preds, float* out_scores);
 
 int num_sms();
+extern unsigned long long* g_gemm_dbg;
 void set_error(const char* msg);
 
 }  // namespace otb
