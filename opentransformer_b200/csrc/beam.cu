@@ -168,7 +168,19 @@ __global__ void __launch_bounds__(KMAX * 32) beam_step_kernel(const float* __res
     }
     if (threadIdx.x < 32) {
         ended = (int)warp_sum((float)ended);
-        if (threadIdx.x == 0 && ended) atomicAdd(&st.ctrl[2], ended);
+        if (threadIdx.x == 0) {
+            if (ended) atomicAdd(&st.ctrl[2], ended);
+            __threadfence();
+            // last CTA of this step advances {step, done}: replaces a separate 1-thread kernel per step
+            if (atomicAdd(&st.ctrl[3], 1) == (int)gridDim.x - 1) {
+                const int total = atomicAdd(&st.ctrl[2], 0);
+                st.ctrl[2] = 0;
+                st.ctrl[3] = 0;
+                __threadfence();
+                if (total == st.N) st.ctrl[1] = 1;      // every hypothesis ended (speech2text.py:66-67)
+                st.ctrl[0] = step + 1;
+            }
+        }
     }
 }
 
@@ -190,7 +202,6 @@ const char* beam_step_launch(cudaStream_t stream, const float* logp, int ldl, in
     if ((pre_val == nullptr) != (pre_idx == nullptr)) return "beam_step: pre_val / pre_idx must both be given";
     beam_step_kernel<<<st.N / st.beam, st.beam * 32, 0, stream>>>(logp, ldl, V, lm_logp, ld_lm, lm_weight, st,
                                                                   dbg_ktok, dbg_offs, pre_val, pre_idx);
-    beam_advance_kernel<<<1, 1, 0, stream>>>(st.ctrl, st.N, st.Lmax);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -346,25 +357,25 @@ __global__ void __launch_bounds__(TOPK_THREADS) logsoftmax_topk_kernel(const flo
         if (out_logp) out_logp[(size_t)row * ld_logp + i] = v;
     }
     __syncthreads();
-    // per-warp top-k over a contiguous slice
+    // per-warp top-k over a contiguous slice: k rounds of (lane-local scan of smem, warp arg-max, knock out)
     const int per = (V + 7) / 8;
     const int lo = warp * per, hi = min(V, lo + per);
-    {
-        TopList tl;
-        tl.init();
-        for (int idx = lo + lane; idx < hi; idx += 32) tl.push(srow[idx], idx);
-        for (int r = 0; r < k; ++r) {
-            float bv = tl.v[0];
-            int bi = tl.i[0];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-            }
-            if (tl.i[0] == bi && tl.v[0] == bv) tl.pop();
-            if (lane == 0) { cand_v[warp * KMAX + r] = bv; cand_i[warp * KMAX + r] = bi; }
+    for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int idx = lo + lane; idx < hi; idx += 32) {
+            const float v = srow[idx];
+            if (v > bv) { bv = v; bi = idx; }      // ascending scan + strict '>' keeps the lower index on ties
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (bi != 0x7fffffff && ((bi - lo) & 31) == lane) srow[bi] = -INFINITY;
+        if (lane == 0) { cand_v[warp * KMAX + r] = bv; cand_i[warp * KMAX + r] = bi; }
+        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {

@@ -301,15 +301,20 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
                                                                bf16* __restrict__ vc, const int* __restrict__ anc,
                                                                const int* __restrict__ step_ptr, bf16* __restrict__ out,
                                                                int N, int H, int Lmax, float scale) {
-    // Lanes run over KEYS for the scores (each lane owns up to KPL cached positions and reads whole 128-byte
-    // K rows with 16-byte loads: 8 independent loads in flight per key), then over the 64 head DIMS for P.V.
-    constexpr int KPL = 4;  // keys per lane -> up to 128 cached positions
+    // Lanes run over KEYS: each lane owns up to KPL cached positions, resolves their slots through the
+    // ancestry table and pulls the whole 128-byte K and V rows with 16-byte loads -- all loads of a lane are
+    // independent, so the kernel costs ~3 dependent memory round trips (anc -> K/V -> out) instead of a
+    // serial walk over the prefix.  V rows go through smem so that the P.V reduction is a column sum.
+    constexpr int KPL = 4;               // keys per lane -> up to 128 cached positions
+    extern __shared__ uint4 sv_raw[];    // [warps][128 keys][8 x 16 B]  V rows (bf16)
     const int n = blockIdx.x;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
     const int d = H * 64;
     const int step = *step_ptr;
+    const int nkeys = step + 1;
     const int* an = anc + ((size_t)(step & 1) * N + n) * Lmax;
+    uint4* sv = sv_raw + (size_t)wib * (32 * KPL) * 8;
     for (int h = wib; h < H; h += nw) {
         const bf16* base = qkv + (size_t)n * 3 * d + h * 64;
         // append the newest K/V to the cache (lane owns dims 2*lane, 2*lane+1)
@@ -327,56 +332,62 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
             q[8 * i] = a.x; q[8 * i + 1] = a.y; q[8 * i + 2] = b.x; q[8 * i + 3] = b.y;
             q[8 * i + 4] = c.x; q[8 * i + 5] = c.y; q[8 * i + 6] = e.x; q[8 * i + 7] = e.y;
         }
-        float sc[KPL];
         int slot[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int s = lane + 32 * j;
+            slot[j] = (s < step) ? an[s] : n;
+        }
+        float sc[KPL];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
             const int s = lane + 32 * j;
             sc[j] = -INFINITY;
-            slot[j] = n;
-            if (s <= step) {
-                const bf16* krow;
-                if (s == step) {
-                    krow = base + d;
-                } else {
-                    slot[j] = an[s];
-                    krow = kc + ((size_t)s * N + slot[j]) * d + h * 64;
-                }
+            if (s < nkeys) {   // warp-divergent only in the last group
+                const bf16* krow = (s == step) ? base + d : kc + ((size_t)s * N + slot[j]) * d + h * 64;
+                const bf16* vrow = (s == step) ? base + 2 * d : vc + ((size_t)s * N + slot[j]) * d + h * 64;
+                uint4 ku[8], vu[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ku[i] = *reinterpret_cast<const uint4*>(krow + 8 * i);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vu[i] = *reinterpret_cast<const uint4*>(vrow + 8 * i);
                 float dot = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(krow + 8 * i);
-                    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+                    const float2 a = unpack_bf16(ku[i].x), b = unpack_bf16(ku[i].y), c = unpack_bf16(ku[i].z),
+                                 e = unpack_bf16(ku[i].w);
                     dot += q[8 * i] * a.x + q[8 * i + 1] * a.y + q[8 * i + 2] * b.x + q[8 * i + 3] * b.y +
                            q[8 * i + 4] * c.x + q[8 * i + 5] * c.y + q[8 * i + 6] * e.x + q[8 * i + 7] * e.y;
                 }
                 sc[j] = dot * scale;
                 mx = fmaxf(mx, sc[j]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sv[s * 8 + ((i + s) & 7)] = vu[i];   // rotate chunks: conflict-free rows
             }
         }
         mx = warp_max(mx);
         float l = 0.f;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
-            sc[j] = (lane + 32 * j <= step) ? __expf(sc[j] - mx) : 0.f;
+            sc[j] = (lane + 32 * j < nkeys) ? __expf(sc[j] - mx) : 0.f;
             l += sc[j];
         }
         l = warp_sum(l);
-        // P.V : lane owns output dims 2*lane, 2*lane+1; probabilities / slots broadcast by shuffle
+        __syncwarp();
+        // P.V as a column sum over the staged V rows: lane owns output dims 2*lane, 2*lane+1
+        const uint32_t* svw = reinterpret_cast<const uint32_t*>(sv);
         float ax = 0.f, ay = 0.f;
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
-            const int s_hi = min(31, step - 32 * j);
-            if (s_hi < 0) break;   // warp-uniform
-#pragma unroll 8
-            for (int t = 0; t <= s_hi; ++t) {
+            const int cnt = min(32, nkeys - 32 * j);
+            if (cnt <= 0) break;   // warp-uniform
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
                 const int s = t + 32 * j;
                 const float pw = __shfl_sync(0xffffffffu, sc[j], t);
-                const int sl = __shfl_sync(0xffffffffu, slot[j], t);
-                uint32_t vv;
-                if (s == step) vv = vcur;
-                else vv = *reinterpret_cast<const uint32_t*>(vc + ((size_t)s * N + sl) * d + h * 64 + 2 * lane);
+                // dims 2*lane.. live in 16-byte chunk (lane >> 2), word (lane & 3); chunks were rotated by s
+                const uint32_t vv = svw[(s * 8 + (((lane >> 2) + s) & 7)) * 4 + (lane & 3)];
                 const float2 vf = unpack_bf16(vv);
                 ax = fmaf(pw, vf.x, ax);
                 ay = fmaf(pw, vf.y, ay);
@@ -384,6 +395,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
         }
         const float inv = 1.0f / l;
         *reinterpret_cast<uint32_t*>(out + (size_t)n * d + h * 64 + 2 * lane) = pack_bf16(ax * inv, ay * inv);
+        __syncwarp();
     }
 }
 
@@ -391,7 +403,14 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
                                     const int* step_ptr, bf16* out, int N, int H, int Lmax) {
     if (Lmax > 128) return "decode_self_attn: at most 128 cached positions (max_len <= 128)";
     const int warps = H < 4 ? H : 4;
-    decode_self_attn_kernel<<<N, warps * 32, 0, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
+    const size_t smem = (size_t)warps * 128 * 128;   // [warps][128 keys][128 B]
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(decode_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+            return "cudaFuncSetAttribute(decode_self_attn) failed";
+        attr_set = true;
+    }
+    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -253,12 +253,12 @@ class BeamState:
         check(_lib.lib().otb_beam_step(_p(logp), logp.stride(0), V, _p(lm_logp),
                                        lm_logp.stride(0) if lm_logp is not None else 0, lm_weight,
                                        ctypes.byref(self.c), _p(dbg_ktok), _p(dbg_offs), _stream()), 'otb_beam_step')
-        _count(2)   # beam_step_kernel + beam_advance_kernel
+        _count()
 
     def step_topk(self, topk_val, topk_idx, dbg_ktok=None, dbg_offs=None):
         check(_lib.lib().otb_beam_step_topk(_p(topk_val), _p(topk_idx), ctypes.byref(self.c), _p(dbg_ktok),
                                             _p(dbg_offs), _stream()), 'otb_beam_step_topk')
-        _count(2)
+        _count()
 
     def reconstruct(self, steps):
         preds = torch.empty(self.N, steps + 1, dtype=torch.int64, device=self.scores.device)
