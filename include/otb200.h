@@ -75,11 +75,19 @@ int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias
 /* Fused masked multi-head attention, d_k = 64 (attention.py:80,34-41): for batch b, head h
  *   out[b*Tq+i, h*64:(h+1)*64] = softmax_j((q_i . k_j + bd) / 8, j < kv_len[b], causal: j <= i) V
  * q/k/v are row-major bf16 matrices; batch b owns rows [b*Tq, (b+1)*Tq) of q and [b*Tk, (b+1)*Tk) of k,v;
- * head h starts at column q_col0/k_col0/v_col0 + 64*h.  bd (optional, f32 [B,H,Tq,ldbd]) holds
- * relative-position scores, bias(i,j) = bd[b,h,i, j-i+Tq-1] (attention.py:196-215). */
+ * head h starts at column q_col0/k_col0/v_col0 + 64*h.  bd (optional, f32 [H,B,Tq,ldbd]) holds
+ * relative-position scores, bias(i,j) = bd[h,b,i, j-i+Tq-1] (the gather of attention.py:196-215 done by
+ * indexing).  resid (optional, bf16 [B*Tq, ldr]) is added to the output (the rel-pos attention of the
+ * shipped Conformer has no output projection). */
 int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
                   void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
-                  int k_col0, int v_col0, const float* bd, int ldbd, void* stream);
+                  int k_col0, int v_col0, const float* bd, int ldbd, const void* resid, int ldr, void* stream);
+
+/* ConformerConvolutionModule middle (module/conformer.py:48-52): depthwise Conv1d(k, pad (k-1)/2) over time +
+ * eval-mode BatchNorm1d + swish.  x, out bf16 [B*T, d]; w f32 [k, d] and b f32 [d] carry the BatchNorm affine
+ * folded in by the caller (w' = w * gamma/sqrt(var+eps), b' = (b - mean) * gamma/sqrt(var+eps) + beta). */
+int otb_dwconv_swish(const void* x, const float* w, const float* b, void* out, int B, int T, int d, int k,
+                     void* stream);
 
 /* nn.LayerNorm (eps as given), optionally two in a row (encoder/conformer.py:87-89). g2/b2 may be NULL. */
 int otb_layernorm(const void* x, int ldx, void* out, int ldo, int out_f32, const float* g1, const float* b1,

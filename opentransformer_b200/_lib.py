@@ -31,7 +31,8 @@ _SIGS = {
     'otb_linear': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P,
                            c_float, c_float, _P, c_int, _P, c_int, _P]),
     'otb_attention': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int,
-                              _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+                              _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    'otb_dwconv_swish': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_layernorm': (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, _P, _P, c_float, c_int, c_int, _P]),
     'otb_scale_add_table': (c_int, [_P, c_int, c_int, _P, c_int, c_float, _P, c_int, c_int, c_int, _P]),
     'otb_sinusoid_table': (c_int, [_P, c_int, c_int, c_int, _P]),

@@ -109,7 +109,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float* bd_row = nullptr;
         if (HAS_BD) {
             const int qc = min(qi, p.Tq - 1);
-            bd_row = p.bd + (((size_t)b * p.H + h) * p.Tq + qc) * p.ldbd + (p.Tq - 1 - qc);
+            bd_row = p.bd + (((size_t)h * p.B + b) * p.Tq + qc) * p.ldbd + (p.Tq - 1 - qc);
         }
         float m_blk = -INFINITY;
 #pragma unroll 1
@@ -215,13 +215,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (qi < p.Tq) {
         const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
         bf16* o = p.out + (size_t)(b * p.Tq + qi) * p.ldo + h * 64;
+        if (p.resid) {
+            const bf16* rr = p.resid + (size_t)(b * p.Tq + qi) * p.ldr + h * 64;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rr + i);
+                const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+                acc[i] = acc[i] * inv + a.x; acc[i + 1] = acc[i + 1] * inv + a.y;
+                acc[i + 2] = acc[i + 2] * inv + bb.x; acc[i + 3] = acc[i + 3] * inv + bb.y;
+                acc[i + 4] = acc[i + 4] * inv + c.x; acc[i + 5] = acc[i + 5] * inv + c.y;
+                acc[i + 6] = acc[i + 6] * inv + e.x; acc[i + 7] = acc[i + 7] * inv + e.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] *= inv;
+        }
 #pragma unroll
         for (int i = 0; i < 64; i += 8) {
             uint4 u;
-            u.x = pack_bf16(acc[i] * inv, acc[i + 1] * inv);
-            u.y = pack_bf16(acc[i + 2] * inv, acc[i + 3] * inv);
-            u.z = pack_bf16(acc[i + 4] * inv, acc[i + 5] * inv);
-            u.w = pack_bf16(acc[i + 6] * inv, acc[i + 7] * inv);
+            u.x = pack_bf16(acc[i], acc[i + 1]);
+            u.y = pack_bf16(acc[i + 2], acc[i + 3]);
+            u.z = pack_bf16(acc[i + 4], acc[i + 5]);
+            u.w = pack_bf16(acc[i + 6], acc[i + 7]);
             *reinterpret_cast<uint4*>(o + i) = u;
         }
     }

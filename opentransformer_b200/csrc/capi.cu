@@ -131,7 +131,7 @@ int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias
 
 int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
                   void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
-                  int k_col0, int v_col0, const float* bd, int ldbd, void* stream) {
+                  int k_col0, int v_col0, const float* bd, int ldbd, const void* resid, int ldr, void* stream) {
     if (!q || !k || !v || !out) return fail("otb_attention", "null operand");
     if (q_col0 % 8 || k_col0 % 8 || v_col0 % 8 || ldo % 8) return fail("otb_attention", "column offsets / ldo must be multiples of 8");
     AttnParams p;
@@ -141,6 +141,8 @@ int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, in
     p.out = reinterpret_cast<bf16*>(out); p.ldo = ldo;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.bd = bd; p.ldbd = ldbd;
+    p.resid = reinterpret_cast<const bf16*>(resid); p.ldr = ldr;
+    if (resid && (ldr % 8)) return fail("otb_attention", "ldr must be a multiple of 8");
     RET("otb_attention", attn_launch(ST(stream), q, ldq, q_rows, k, ldk, k_rows, v, ldv, p));
 }
 
@@ -158,6 +160,13 @@ int otb_scale_add_table(const void* x, int ldx, int x_f32, void* out, int ldo, f
     if (table && period < 1) return fail("otb_scale_add_table", "table without period");
     RET("otb_scale_add_table", scale_add_table_launch(ST(stream), x, ldx, x_f32, reinterpret_cast<bf16*>(out), ldo, alpha,
                                                       table, period, M, N));
+}
+
+int otb_dwconv_swish(const void* x, const float* w, const float* b, void* out, int B, int T, int d, int k,
+                     void* stream) {
+    if (!x || !w || !b || !out || B < 1 || T < 1) return fail("otb_dwconv_swish", "bad arguments");
+    RET("otb_dwconv_swish", dwconv_swish_launch(ST(stream), reinterpret_cast<const bf16*>(x), w, b,
+                                                reinterpret_cast<bf16*>(out), B, T, d, k));
 }
 
 int otb_sinusoid_table(float* out, int n_pos, int d, int first_pos, void* stream) {

@@ -439,4 +439,54 @@ const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int 
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Conformer convolution-module middle: depthwise Conv1d over time (k taps, zero padding (k-1)/2) +
+// eval-mode BatchNorm (folded into w/b by the caller) + swish.   otrans/module/conformer.py:48-52
+// x, out bf16 [B*T, d].  HBM-bound: thread = (row, 8 channels), 16-byte loads of the k neighbour rows
+// (re-reads hit L1/L2), fp32 math.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, bf16* __restrict__ out, int B,
+                                                           int T, int d, int k) {
+    const int cg = d / 8;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * T * cg) return;
+    const int c0 = (int)(i % cg) * 8;
+    const int row = (int)(i / cg);
+    const int t = row % T;
+    const int pad = (k - 1) / 2;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b[c0 + j];
+    for (int tap = 0; tap < k; ++tap) {
+        const int tt = t + tap - pad;
+        if (tt < 0 || tt >= T) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)(row + tap - pad) * d + c0);
+        const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+        const float xv[8] = {a.x, a.y, bb.x, bb.y, c.x, c.y, e.x, e.y};
+        const float4 w0 = *reinterpret_cast<const float4*>(w + (size_t)tap * d + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + (size_t)tap * d + c0 + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wv[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] * __fdividef(1.0f, 1.0f + __expf(-acc[j]));
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]);
+    o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]);
+    o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)row * d + c0) = o;
+}
+
+const char* dwconv_swish_launch(cudaStream_t st, const bf16* x, const float* w, const float* b, bf16* out, int B, int T,
+                                int d, int k) {
+    if (d % 8 || !(k & 1)) return "dwconv: d must be a multiple of 8 and k odd";
+    const size_t n = (size_t)B * T * (d / 8);
+    dwconv_swish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, w, b, out, B, T, d, k);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 }  // namespace otb

@@ -66,8 +66,10 @@ struct AttnParams {
     bf16* out;
     int ldo;
     int q_col0, k_col0, v_col0;
-    const float* bd;    // optional relative-position scores, [B,H,Tq,ldbd]; bias(i,j) = bd[.., i, j - i + Tq - 1]
+    const float* bd;    // optional relative-position scores, [H,B,Tq,ldbd]; bias(i,j) = bd[h,b,i, j - i + Tq - 1]
     int ldbd;
+    const bf16* resid;  // optional: out = resid + softmax(..)V   (rel-pos attention has no output projection)
+    int ldr;
 };
 
 struct BeamState {
@@ -89,6 +91,8 @@ const char* layernorm_launch(cudaStream_t st, const bf16* x, int ldx, void* out,
                              const float* b1, const float* g2, const float* b2, float eps, int M, int N);
 const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int x_f32, bf16* out, int ldo, float alpha,
                                    const float* table, int period, int M, int N);
+const char* dwconv_swish_launch(cudaStream_t st, const bf16* x, const float* w, const float* b, bf16* out, int B, int T,
+                                int d, int k);
 const char* sinusoid_table_launch(cudaStream_t st, float* out, int n_pos, int d, int first_pos);
 const char* embed_posenc_launch(cudaStream_t st, const long long* tok, int tok_stride, const bf16* emb,
                                 const float* table, bf16* out, int N, int d, int period, const int* step_ptr,

@@ -9,10 +9,10 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import ConvFrontEnd, TransformerDecoder, TransformerEncoder, _lengths
+from .modules import ConformerEncoder, ConvFrontEnd, TransformerDecoder, TransformerEncoder, _lengths
 
 BuildFrontEnd = {'conv': ConvFrontEnd}
-BuildEncoder = {'transformer': TransformerEncoder}
+BuildEncoder = {'transformer': TransformerEncoder, 'conformer': ConformerEncoder}
 BuildDecoder = {'transformer': TransformerDecoder}
 
 

@@ -332,6 +332,198 @@ class TransformerEncoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+# Conformer encoder  (otrans/encoder/conformer.py, otrans/module/conformer.py, attention.py:176-257)
+# ------------------------------------------------------------------------------------------------
+class MultiHeadedSelfAttentionWithRelPos(nn.Module):
+    """Keys: qvk_proj.*, pos_proj.weight, posu, posv  (attention.py:176-194).  Quirk kept: the
+    reference passes dropout_rate into the enable_output_proj slot, so with the shipped slf_attn_dropout 0.0
+    there is NO output projection; a non-zero rate makes the reference itself crash."""
+
+    def __init__(self, n_heads, d_model, dropout_rate=0.0, skip_term_b=False, share_qvk_proj=False):
+        super().__init__()
+        if dropout_rate or skip_term_b or share_qvk_proj:
+            raise NotImplementedError('rel-pos attention: dropout / skip_term_b / share_qvk_proj')
+        if d_model != n_heads * 64:
+            raise NotImplementedError('the sm_100a attention kernel is specialised for d_k = 64')
+        self.nheads, self.d_model = n_heads, d_model
+        self.qvk_proj = nn.Linear(d_model, d_model * 3)
+        self.pos_proj = nn.Linear(d_model, d_model, bias=False)
+        self.posu = nn.Parameter(torch.Tensor(1, 1, n_heads, d_model // n_heads))
+        self.posv = nn.Parameter(torch.Tensor(1, 1, n_heads, d_model // n_heads))
+        torch.nn.init.xavier_normal_(self.posu)
+        torch.nn.init.xavier_normal_(self.posv)
+
+    def pack(self):
+        d = self.d_model
+        w, b = self.qvk_proj.weight.detach().float(), self.qvk_proj.bias.detach().float()
+        u, v = self.posu.detach().float().reshape(d), self.posv.detach().float().reshape(d)
+        # one projection producing [q+u | q+v | k | v]: (q+u) = x Wq^T + (bq + u)
+        w_ext = torch.cat([w[:d], w[:d], w[d:2 * d], w[2 * d:]], 0)
+        b_ext = torch.cat([b[:d] + u, b[:d] + v, b[d:2 * d], b[2 * d:]], 0)
+        return {'wext': w_ext.to(BF16).contiguous(), 'bext': b_ext.contiguous(), 'wpos': _w(self.pos_proj)}
+
+    def run(self, y, x_resid, pk, B, T, lengths, pos_bf16):
+        """y = LN(x) bf16 [B*T,d]; returns x_resid + attention (no output projection)."""
+        d, H = self.d_model, self.nheads
+        ext = ops.linear(y, pk['wext'], pk['bext'])                       # [M, 4d]
+        pproj = ops.linear(pos_bf16, pk['wpos'])                          # [2T-1, d]  pos_proj(PE[-(T-1)..T-1])
+        ld = (2 * T - 1 + 3) // 4 * 4
+        bd = torch.empty(H, B * T, ld, dtype=torch.float32, device=y.device)
+        for h in range(H):  # BD_full[h] = (q+v)_h P_h^T ; the attention kernel reads the j-i+T-1 diagonal band
+            ops.linear(ext[:, d + 64 * h: d + 64 * (h + 1)], pproj[:, 64 * h: 64 * (h + 1)], out=bd[h])
+        return ops.attention(ext, ext, ext, B, H, T, T, kv_len=lengths, q_col0=0, k_col0=2 * d, v_col0=3 * d,
+                             bd=bd, resid=x_resid)
+
+
+class ConformerConvolutionModule(nn.Module):
+    """Keys: pointwise_conv1.*, depthwise_conv.*, batch_norm.*, pointwise_conv2.*  (module/conformer.py:12-34)."""
+
+    def __init__(self, channels, kernel_size, bias=True, dropout=0.0):
+        super().__init__()
+        assert kernel_size % 2 == 1
+        self.pointwise_conv1 = nn.Linear(channels, 2 * channels, bias=bias)
+        self.depthwise_conv = nn.Conv1d(channels, channels, kernel_size, stride=1, padding=(kernel_size - 1) // 2,
+                                        groups=channels, bias=bias)
+        self.batch_norm = nn.BatchNorm1d(channels)
+        self.pointwise_conv2 = nn.Linear(channels, channels, bias=bias)
+
+    def pack(self):
+        bn, dw = self.batch_norm, self.depthwise_conv
+        s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = dw.weight.detach().float()[:, 0, :] * s[:, None]                       # [C,k] BN scale folded in
+        b0 = dw.bias.detach().float() if dw.bias is not None else torch.zeros_like(s)
+        b = (b0 - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+        return {'w1': _w(self.pointwise_conv1), 'b1': _b(self.pointwise_conv1),
+                'wd': w.t().contiguous(), 'bd': b.contiguous(),                     # tap-major [k,C]
+                'w2': _w(self.pointwise_conv2), 'b2': _b(self.pointwise_conv2)}
+
+    def run(self, y, x_resid, pk, B, T, lengths):
+        """x_resid + conv_module(y); padded frames are zeroed after the GLU and after the last Linear
+        (module/conformer.py:46,55) through the GEMM's row mask."""
+        g = ops.linear(y, pk['w1'], pk['b1'], EPI_GLU, row_len=lengths, row_period=T)
+        c = ops.dwconv_swish(g, pk['wd'], pk['bd'], B, T)
+        return ops.linear(c, pk['w2'], pk['b2'], EPI_RESID, resid=x_resid, row_len=lengths, row_period=T)
+
+
+class ConformerEncoderBlock(nn.Module):
+    def __init__(self, d_model, d_ff, cov_kernel_size, n_heads, slf_attn_dropout=0.0, ffn_dropout=0.0,
+                 residual_dropout=0.1, conv_dropout=0.0, macaron_style=True, conv_first=False, ffn_scale=0.5,
+                 conv_bias=True, relative_positional=True, activation='glu'):
+        super().__init__()
+        self.conv_first, self.macaron_style, self.ffn_scale = conv_first, macaron_style, ffn_scale
+        self.relative_positional, self.n_heads = relative_positional, n_heads
+        if macaron_style:
+            self.pre_ffn = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation=activation)
+            self.macaron_ffn_norm = nn.LayerNorm(d_model)
+        if relative_positional:
+            self.mha = MultiHeadedSelfAttentionWithRelPos(n_heads, d_model, slf_attn_dropout)
+        else:
+            self.mha = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
+        self.mha_norm = nn.LayerNorm(d_model)
+        self.conv = ConformerConvolutionModule(d_model, cov_kernel_size, conv_bias, conv_dropout)
+        self.conv_norm = nn.LayerNorm(d_model)
+        # kept for state_dict parity; the reference never applies post_ffn, only post_ffn_norm (conformer.py:87)
+        self.post_ffn = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation=activation)
+        self.post_ffn_norm = nn.LayerNorm(d_model)
+        self.final_norm = nn.LayerNorm(d_model)
+
+    def pack(self):
+        pk = {'mha_ln': _ln(self.mha_norm), 'conv_ln': _ln(self.conv_norm), 'post_ln': _ln(self.post_ffn_norm),
+              'final_ln': _ln(self.final_norm), 'conv': self.conv.pack()}
+        if self.macaron_style:
+            pk['pre_ffn'] = _ffn_pack(self.pre_ffn)
+            pk['mac_ln'] = _ln(self.macaron_ffn_norm)
+        if self.relative_positional:
+            pk['mha'] = self.mha.pack()
+        else:
+            a = self.mha
+            pk['mha'] = {'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj)}
+        return pk
+
+    def _attn(self, x, pk, B, T, lengths, pos_bf16):
+        y = ops.layernorm(x, *pk['mha_ln'])
+        if self.relative_positional:
+            return self.mha.run(y, x, pk['mha'], B, T, lengths, pos_bf16)
+        d, H, m = x.shape[1], self.n_heads, pk['mha']
+        qkv = ops.linear(y, m['wqkv'], m['bqkv'])
+        ctx = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
+        return ops.linear(ctx, m['wo'], m['bo'], EPI_RESID, resid=x)
+
+    def _conv(self, x, pk, B, T, lengths):
+        return self.conv.run(ops.layernorm(x, *pk['conv_ln']), x, pk['conv'], B, T, lengths)
+
+    def run(self, x, pk, B, T, lengths, pos_bf16):
+        """ConformerEncoderBlock.forward (encoder/conformer.py:75-89) with the residual dropout disabled."""
+        if self.macaron_style:
+            y = ops.layernorm(x, *pk['mac_ln'])
+            f = pk['pre_ffn']
+            h = ops.linear(y, f['w1'], f['b1'], f['act'])
+            x = ops.linear(h, f['w2'], f['b2'], EPI_RESID, resid=x, alpha=self.ffn_scale)
+        if self.conv_first:
+            x = self._attn(self._conv(x, pk, B, T, lengths), pk, B, T, lengths, pos_bf16)
+        else:
+            x = self._conv(self._attn(x, pk, B, T, lengths, pos_bf16), pk, B, T, lengths)
+        return ops.layernorm(x, *pk['post_ln'], *pk['final_ln'])   # post_ffn_norm then final_norm, one kernel
+
+
+class ConformerEncoder(nn.Module):
+    """forward(inputs f32 [B,T,D], mask bool [B,T]) -> (f32 [B,T,D], mask, attn_weights)   (encoder/conformer.py:117-164)
+
+    The reference applies F.dropout(p=residual_dropout) with training=True even in eval() (conformer.py:53,58,63,72),
+    i.e. its inference is stochastic for residual_dropout > 0.  This implementation is the
+    deterministic network (no dropout at inference); parity is defined against residual_dropout = 0.0."""
+
+    def __init__(self, d_model, d_ff, cov_kernel_size, n_heads, nblocks=12, pos_dropout=0.0, slf_attn_dropout=0.0,
+                 ffn_dropout=0.0, residual_dropout=0.1, conv_dropout=0.0, macaron_style=True, ffn_scale=0.5,
+                 conv_bias=True, positional_encoding=True, relative_positional=True, conv_first=False,
+                 activation='glu'):
+        super().__init__()
+        self.positional_encoding = positional_encoding
+        self.relative_positional = relative_positional
+        self.output_size = self.d_model = d_model
+        if positional_encoding:
+            self.pos_emb = PositionalEncoding(d_model, pos_dropout)
+        self.blocks = nn.ModuleList([
+            ConformerEncoderBlock(d_model, d_ff, cov_kernel_size, n_heads, slf_attn_dropout, ffn_dropout,
+                                  residual_dropout, conv_dropout, macaron_style, conv_first, ffn_scale, conv_bias,
+                                  relative_positional, activation) for _ in range(nblocks)])
+        self._pack = _Packed(self, lambda: [b.pack() for b in self.blocks])
+        self._pos_cache = {}
+
+    def fuse_abs_posenc(self):
+        return self.positional_encoding and not self.relative_positional
+
+    def apply_posenc_bf16(self, x, B, T):
+        if self.positional_encoding and not self.relative_positional:
+            scale, table = self.pos_emb.scale_and_table(T, x.device)
+            return ops.scale_add_table(x, scale, table, T)
+        return x if x.dtype == BF16 else ops.scale_add_table(x)
+
+    def _rel_pos(self, T, device):
+        key = (T, device.index)
+        p = self._pos_cache.get(key)
+        if p is None:   # PE[-(T-1) .. T-1] (encoder/conformer.py:140-143), bf16 GEMM operand
+            p = ops.scale_add_table(ops.sinusoid_table(2 * T - 1, self.d_model, -(T - 1), device))
+            self._pos_cache[key] = p
+        return p
+
+    def forward_bf16(self, x, B, T, lengths):
+        _no_train(self)
+        pks = self._pack.get()
+        pos = self._rel_pos(T, x.device) if (self.positional_encoding and self.relative_positional) else None
+        for blk, pk in zip(self.blocks, pks):
+            x = blk.run(x, pk, B, T, lengths, pos)
+        return x
+
+    def forward(self, inputs, mask):
+        B, T, D = inputs.shape
+        x = self.apply_posenc_bf16(inputs.contiguous().view(B * T, D), B, T)
+        y = self.forward_bf16(x, B, T, _lengths(mask))
+        attn = {'enc_block_%d' % i: {'slf_attn_weights': None} for i in range(len(self.blocks))}
+        return y.float().view(B, T, D), mask, attn
+
+
+# ------------------------------------------------------------------------------------------------
 # decoder
 # ------------------------------------------------------------------------------------------------
 class TransformerDecoderLayer(nn.Module):

@@ -100,8 +100,13 @@ def conv2_relu(h1, w, bias, B, T, F, out=None):
 
 def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=None, gamma=None, beta=None,
            eps=1e-5, alpha=1.0, table=None, period=0, row_len=None, row_period=0, n_out=None):
-    """out[M,N] = epi(a[M,K] @ w[N(,2N),K]^T + bias).  a, w bf16 2-D (row stride = shape[1])."""
-    _need(a, BF16, 'a'); _need(w, BF16, 'w')
+    """out[M,N] = epi(a[M,K] @ w[N(,2N),K]^T + bias).  a, w bf16 2-D, unit column stride (row-strided views
+    such as one head's 64 columns of a wider matrix are fine: the TMA map takes the row pitch)."""
+    for t, n in ((a, 'a'), (w, 'w')):
+        if not t.is_cuda:
+            raise RuntimeError(f'{n} must be a CUDA tensor: the B200 hot path has no CPU fallback')
+        if t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError(f'{n} must be a 2-D bf16 tensor with unit column stride')
     M, K = a.shape
     N = w.shape[0] // 2 if epilogue == EPI_GLU else w.shape[0]
     if w.shape[1] != K:
@@ -119,7 +124,8 @@ def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=No
     return out
 
 
-def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0=0, v_col0=0, out=None, bd=None):
+def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0=0, v_col0=0, out=None, bd=None,
+              resid=None):
     """q/k/v: bf16 2-D matrices (may be the same [M,3d] buffer with different column offsets)."""
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _need(t, BF16, n)
@@ -130,8 +136,21 @@ def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0
         _need(kv_len, torch.int32, 'kv_len')
     check(_lib.lib().otb_attention(_p(q), q.stride(0), q.shape[0], _p(k), k.stride(0), k.shape[0], _p(v), v.stride(0),
                                    _p(out), out.stride(0), B, H, Tq, Tk, _p(kv_len), 1 if causal else 0, q_col0,
-                                   k_col0, v_col0, _p(bd), bd.shape[-1] if bd is not None else 0, _stream()),
+                                   k_col0, v_col0, _p(bd), bd.shape[-1] if bd is not None else 0, _p(resid),
+                                   resid.stride(0) if resid is not None else 0, _stream()),
           'otb_attention')
+    _count()
+    return out
+
+
+def dwconv_swish(x, w, b, B, T, out=None):
+    """depthwise conv over time + folded BatchNorm + swish; x bf16 [B*T, d], w f32 [k, d], b f32 [d]."""
+    _need(x, BF16, 'x'); _need(w, torch.float32, 'w'); _need(b, torch.float32, 'b')
+    d = x.shape[1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().otb_dwconv_swish(_p(x), _p(w), _p(b), _p(out), B, T, d, w.shape[0], _stream()),
+          'otb_dwconv_swish')
     _count()
     return out
 

@@ -95,6 +95,44 @@ def test_frontend_encoder_states_match_oracle(pre_norm, act):
     assert set(attn) == {f'enc_block_{i}' for i in range(3)}
 
 
+def _conformer_params(n_enc=2, relpos=True):
+    p = _params(n_enc=1, n_dec=1)
+    p['encoder_type'] = 'conformer'
+    p['frontend'].update(mid_channel=64, out_channel=128)
+    p['encoder'] = dict(d_model=256, d_ff=768, cov_kernel_size=5, n_heads=4, nblocks=n_enc, pos_dropout=0.0,
+                        slf_attn_dropout=0.0, ffn_dropout=0.0, residual_dropout=0.0, conv_dropout=0.0,
+                        macaron_style=True, ffn_scale=0.5, conv_bias=True, activation='glu',
+                        positional_encoding=True, relative_positional=relpos)
+    return p
+
+
+@pytest.mark.parametrize('relpos', [True, False])
+def test_conformer_encoder_states_match_oracle(relpos):
+    params = _conformer_params(relpos=relpos)
+    model, sd = _build(params)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():                      # non-trivial BatchNorm running statistics
+        for n, b in model.named_buffers():
+            if n.endswith('running_mean'):
+                b.copy_(0.3 * torch.randn(b.shape, generator=g))
+            if n.endswith('running_var'):
+                b.copy_(1.0 + 0.5 * torch.rand(b.shape, generator=g))
+    sd = {}
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k, v in getattr(model, part).state_dict().items():
+            sd[f'{part}.{k}'] = v.detach().clone().float().cpu() if v.dtype.is_floating_point else v.cpu()
+    x, mask = _batch(3, 400, 80, [400, 300, 255])
+    mem_ref, mmask, fe_ref, layers = om.encode(x, mask, sd, params, return_layers=True)
+    with torch.no_grad():
+        fe, fmask = model.frontend(x.to(DEV), mask.to(DEV))
+        mem, _, _ = model.encoder(fe, fmask)
+        fused, lens, B, T2 = model.encode_bf16(x.to(DEV), mask.to(DEV))
+    r1 = _rel(_valid(mem.cpu(), mmask), _valid(mem_ref, mmask))
+    r2 = _rel(_valid(fused.float().view(B, T2, -1).cpu(), mmask), _valid(mem_ref, mmask))
+    print(f'conformer(relpos={relpos}) encoder rel_l2 module-API={r1:.3e} fused={r2:.3e}')
+    assert r1 < REL_L2_STATES and r2 < REL_L2_STATES
+
+
 def test_decoder_logits_match_oracle_teacher_forced():
     params = _params(n_enc=1, n_dec=3)
     model, sd = _build(params)

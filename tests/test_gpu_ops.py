@@ -205,6 +205,56 @@ def test_cross_attention(B, H, Tq, Tk):
     print(_report(f'cross-attn[{B},{H},{Tq},{Tk}]', out, ref, 6e-3))
 
 
+def test_relpos_bias_and_residual_attention():
+    """scores = (q k^T + BD[i, j-i+T-1]) / 8, output added to a residual (attention.py:196-253 without out-proj)."""
+    B, H, T = 3, 4, 150
+    d = H * 64
+    qkv = _rnd(B * T, 3 * d, seed=1).to(BF)
+    ld = (2 * T - 1 + 3) // 4 * 4
+    bd = _rnd(H, B * T, ld, scale=2.0, seed=2)
+    res = _rnd(B * T, d, seed=3).to(BF)
+    lens = torch.tensor([150, 90, 129], dtype=torch.int32, device=DEV)
+    out = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lens, q_col0=0, k_col0=d, v_col0=2 * d, bd=bd, resid=res)
+    qh = qkv[:, :d].float().view(B, T, H, 64).transpose(1, 2)
+    kh = qkv[:, d:2 * d].float().view(B, T, H, 64).transpose(1, 2)
+    vh = qkv[:, 2 * d:].float().view(B, T, H, 64).transpose(1, 2)
+    idx = (torch.arange(T, device=DEV)[None, :] - torch.arange(T, device=DEV)[:, None]) + (T - 1)
+    full = bd.view(H, B, T, ld).permute(1, 0, 2, 3)[..., :2 * T - 1]
+    band = torch.gather(full, 3, idx.view(1, 1, T, T).expand(B, H, T, T))
+    s = (qh @ kh.transpose(2, 3) + band) / 8.0
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None].long())[:, None, None, :]
+    p = torch.softmax(s.masked_fill(~mask, float('-inf')), -1)
+    ref = (p @ vh).transpose(1, 2).reshape(B * T, d) + res.float()
+    print(_report('relpos-attn+resid', out, ref, 6e-3))
+
+
+@pytest.mark.parametrize('B,T,d,k', [(3, 249, 256, 5), (2, 17, 384, 15), (1, 3, 64, 7)])
+def test_depthwise_conv_bn_swish(B, T, d, k):
+    x = _rnd(B * T, d, seed=1).to(BF)
+    w = _rnd(d, 1, k, scale=0.5, seed=2)
+    b = _rnd(d, scale=0.2, seed=3)
+    mean, var = _rnd(d, scale=0.3, seed=4), 1 + 0.5 * torch.rand(d, device=DEV)
+    gam, bet = 1 + 0.2 * _rnd(d, seed=5), 0.2 * _rnd(d, seed=6)
+    s = gam / torch.sqrt(var + 1e-5)
+    out = ops.dwconv_swish(x, (w[:, 0, :] * s[:, None]).t().contiguous(), ((b - mean) * s + bet).contiguous(), B, T)
+    y = F.conv1d(x.float().view(B, T, d).transpose(1, 2), w, b, padding=(k - 1) // 2, groups=d)
+    y = F.batch_norm(y, mean, var, gam, bet, False, 0.0, 1e-5)
+    ref = (y * torch.sigmoid(y)).transpose(1, 2).reshape(B * T, d)
+    print(_report(f'dwconv+bn+swish[{B},{T},{d},{k}]', out, ref, 4e-3))
+
+
+def test_linear_on_strided_head_views():
+    """BD_full[h] = (q+v)_h P_h^T: A and W are 64-column views of wider matrices (row-strided TMA maps)."""
+    M, d, R = 500, 256, 497
+    ext = _rnd(M, 4 * d, seed=1).to(BF)
+    pp = _rnd(R, d, seed=2).to(BF)
+    out = torch.empty(M, 500, device=DEV)
+    for h in range(4):
+        ops.linear(ext[:, d + 64 * h: d + 64 * (h + 1)], pp[:, 64 * h: 64 * (h + 1)], out=out)
+        ref = ext[:, d + 64 * h: d + 64 * (h + 1)].float() @ pp[:, 64 * h: 64 * (h + 1)].float().t()
+        print(_report(f'head-view gemm h={h}', out[:, :R], ref, 2e-5, 1e-4))
+
+
 # ------------------------------------------------------------------------------------------------ small SIMT ops
 @pytest.mark.parametrize('M,N', [(1000, 256), (33, 384), (7, 1024), (5, 64)])
 def test_layernorm_single_and_double(M, N):
