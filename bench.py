@@ -321,16 +321,16 @@ def run_b200(args):
         with torch.no_grad():
             return rec._encode_bf16(*ring_dev[i % RING])
     ms_enc = timed(enc_only, 8, 1) / 8
+    ops.PROFILE = []            # per-launch CUDA events on the GEMMs of the single-lane (uncontended) timed passes
     ms_lat = timed(step_resident, 4, 1) / 4
+    prof, ops.PROFILE = ops.PROFILE, None
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ops.PROFILE = []
     n0 = ops.COUNTERS['launches']
     ms_total = timed(step_resident, args.steps, L)
     launches = ops.COUNTERS['launches'] - n0
-    prof, ops.PROFILE = ops.PROFILE, None
     ms_e2e = timed(step_e2e, args.steps, L)
     clocks = sampler.stop() if sampler else None
 
@@ -365,7 +365,8 @@ def run_b200(args):
                           'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3)},
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': ach / peak if peak else None, 'traffic': None,
-                         'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all eager launches in the timed region: '
+                         'kernel': 'gemm_tc_kernel (tcgen05 GEMM; every eager launch of 4 single-lane timed passes, i.e. '
+                                   'without other streams contending for SMs: '
                                    f'{len(gemm)} launches, {flops / 1e9:.1f} GFLOP algorithmic, {gms:.3f} ms by CUDA events)',
                          'peak_source': f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'},
             'clocks': clocks,

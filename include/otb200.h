@@ -116,6 +116,12 @@ int otb_log_softmax(const float* x, int ldx, float* out, int ldo, int rows, int 
 int otb_decode_self_attn(const void* qkv, void* kc, void* vc, const int* anc, const int* step_ptr, void* out, int N,
                          int H, int Lmax, void* stream);
 
+/* LabelSmoothingLoss.forward (module/loss.py:21-48) fused: per-token KL(smoothed one-hot || softmax), PAD rows 0,
+ * mean over non-PAD tokens.  logits f32 [rows, ldl]; targets i64 [rows]; tok_loss f32 [rows]; loss f32 [1];
+ * n_valid i32 [1]; dlogits (optional, f32 [rows, ldd]) receives d loss / d logits. */
+int otb_ls_ce(const float* logits, int ldl, const int64_t* targets, int rows, int V, float smoothing, int pad_id,
+              float* tok_loss, float* loss, int32_t* n_valid, float* dlogits, int ldd, void* stream);
+
 /* Device-resident beam-search state, N = B*beam hypotheses (all device pointers). */
 typedef struct {
     int32_t* tok_hist;  /* [Lmax, N] */

@@ -197,6 +197,13 @@ int otb_decode_self_attn(const void* qkv, void* kc, void* vc, const int* anc, co
                                 reinterpret_cast<bf16*>(vc), anc, step_ptr, reinterpret_cast<bf16*>(out), N, H, Lmax));
 }
 
+int otb_ls_ce(const float* logits, int ldl, const int64_t* targets, int rows, int V, float smoothing, int pad_id,
+              float* tok_loss, float* loss, int32_t* n_valid, float* dlogits, int ldd, void* stream) {
+    if (!logits || !targets || !tok_loss || !loss || !n_valid) return fail("otb_ls_ce", "null operand");
+    RET("otb_ls_ce", ls_ce_launch(ST(stream), logits, ldl, reinterpret_cast<const long long*>(targets), rows, V, smoothing,
+                                  pad_id, tok_loss, loss, n_valid, dlogits, ldd));
+}
+
 int otb_beam_init(const otb_beam_state* st, void* stream) {
     if (!st) return fail("otb_beam_init", "null state");
     RET("otb_beam_init", beam_init_launch(ST(stream), to_state(st)));

@@ -7,12 +7,12 @@
 //   otrans/module/attention.py:68,128-129,44   otrans/module/ffn.py:39-41
 //   otrans/frontend/conv.py:63-64,146          otrans/decoder/transformer.py:181
 //
-// Structure (persistent, one CTA per SM, 384 threads):
+// Structure (persistent, one CTA per SM, 640 threads):
 //   warp 0 lane 0 : TMA producer   (A tile 128x64, B tile BNx64 per k-block, SWIZZLE_128B)
 //   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, 4 per k-block), tcgen05.commit -> mbarriers
 //   warp 2        : TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4..11   : epilogue, two warpgroups: warp w reads TMEM lanes 32*(w%4).., warpgroup (w-4)/4 takes
-//                   one half of the tile's columns.  tcgen05.ld -> registers -> fused math (bias / LN
+//   warps 4..19   : epilogue, four warpgroups: warp w reads TMEM lanes 32*(w%4).., warpgroup (w-4)/4 takes
+//                   one quarter of the tile's columns.  tcgen05.ld -> registers -> fused math (bias / LN
 //                   parameters broadcast from smem) -> staged in smem -> coalesced 16-byte global stores
 //                   (one full output row segment per warp instruction; the residual tile is fetched the
 //                   same way).  Round-1 profile: per-thread row stores were 32 sectors/request and the
@@ -35,8 +35,8 @@ unsigned long long* g_gemm_dbg = nullptr;
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kThreads = 384;
-static constexpr int kEpiThreads = 256;
+static constexpr int kThreads = 640;
+static constexpr int kEpiThreads = 512;
 static constexpr int STG_PITCH_MAX = 512 + 16;          // bytes per staged row (+16 B pad: conflict-free 16 B accesses)
 static constexpr int STG_BYTES = BM * STG_PITCH_MAX;    // 67,584
 static constexpr int AUX_BYTES = 6144;                  // barriers, TMEM slot, bias / gamma / beta, row map, LN stats
@@ -53,18 +53,18 @@ struct GemmCfg {
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// 32 fp32 values -> staged row (bf16 or f32), 16-byte shared stores
-__device__ __forceinline__ void stage32(uint8_t* row_ptr, int col, int out_f32, const float (&v)[32]) {
+// 16 fp32 values -> staged row (bf16 or f32), 16-byte shared stores
+__device__ __forceinline__ void stage16(uint8_t* row_ptr, int col, int out_f32, const float (&v)[16]) {
     if (out_f32) {
         float4* d = reinterpret_cast<float4*>(row_ptr + col * 4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
         uint4* d = reinterpret_cast<uint4*>(row_ptr + col * 2);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             uint4 u;
             u.x = pack_bf16(v[8 * i], v[8 * i + 1]);
             u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
@@ -81,7 +81,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int BN_OUT = (EPI == EPI_GLU) ? BN / 2 : BN;  // output columns per tile
-    constexpr int HALF = BN_OUT / 2;                        // output columns per epilogue warpgroup
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_gamma = s_bias + 256;                          // [256]
     float* s_beta = s_gamma + 256;                          // [256]
     int* s_rowmap = reinterpret_cast<int*>(s_beta + 256);   // [128] output row of each tile row, -1 = skip
-    // LN partial statistics [2 tile parities][cluster ranks * 2 halves <= 8][128 rows] live in the upper part of
+    // LN partial statistics [2 tile parities][cluster ranks * 4 quarters <= 16][128 rows] live in the upper part of
     // the staging buffer (the LN kernels stage only 128 x 144 B there)
     float2* s_stats = reinterpret_cast<float2*>(stg + 32768);
     const uint32_t cl_rank = (EPI == EPI_RESID_LN) ? cluster_ctarank() : 0;
@@ -217,15 +216,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (256 threads)
-        const int et = threadIdx.x - 128;       // 0..255
-        const int ewarp = warp - 4;             // 0..7
+        // ------------------------------------------------------------------ epilogue (512 threads, 16 warps)
+        // warp w reads TMEM lanes 32*(w%4)..; the four warpgroups split the tile's columns into quarters and
+        // walk them in 16-column chunks (4 warps per SM sub-partition hide the TMEM / MUFU / LDS latencies
+        // that bounded the 8-warp version, profiles/r1_gemm_phases_v2.txt).
+        const int et = threadIdx.x - 128;       // 0..511
+        const int ewarp = warp - 4;             // 0..15
         const int quad = ewarp & 3;             // TMEM lane quadrant == warp % 4
-        const int half = ewarp >> 2;            // column half handled by this warpgroup
+        const int part = ewarp >> 2;            // column quarter handled by this warpgroup
         const int row_in_tile = quad * 32 + lane;
         const int esize = p.out_f32 ? 4 : 2;
         const int pitch = BN_OUT * esize + 16;
         uint8_t* my_row = stg + row_in_tile * pitch;
+        constexpr int PART = BN_OUT / 4;        // output columns per warpgroup (16, 32 or 64)
 
         if (EPI == EPI_RESID_LN) {  // this CTA's 64-column slice of the LayerNorm affine parameters
             for (int i = et; i < BN; i += kEpiThreads) {
@@ -241,31 +244,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col_base = n_blk * BN_OUT;             // first output column of the tile
             const int ncols = min(BN_OUT, p.N - col_base);   // valid output columns
 
-            // ---- (a) per-tile smem setup: bias slice, row map, residual tile (all coalesced)
-            for (int i = et; i < BN; i += kEpiThreads) {
+            // ---- (a) per-tile smem setup: bias slice, row map, residual tile (all coalesced, loads batched)
+            if (et < BN) {
+                const int i = et;
                 int c;
                 if (EPI == EPI_GLU) c = (i < BN_OUT) ? col_base + i : p.N + col_base + (i - BN_OUT);
                 else c = col_base + i;
                 const bool ok = (EPI == EPI_GLU) ? ((i % BN_OUT) < ncols) : (i < ncols);
                 s_bias[i] = (p.bias != nullptr && ok) ? p.bias[c] : 0.f;
-            }
-            if (et < BM) {
+            } else if (et >= 256 && et < 256 + BM) {
+                const int rr = et - 256;
                 int out_row;
                 bool ok;
                 if (p.conv) {
-                    const int r = et / p.conv_F2, f = et % p.conv_F2;
+                    const int r = rr / p.conv_F2, f = rr % p.conv_F2;
                     const int bt = m_blk * p.conv_R + r;
                     const int b = bt / p.conv_T1h, t = bt % p.conv_T1h;
                     ok = (r < p.conv_R) && (b < p.conv_B) && (t < p.conv_T2);
                     out_row = (b * p.conv_T2 + t) * p.conv_F2 + f;
                 } else {
-                    out_row = m_blk * BM + et;
+                    out_row = m_blk * BM + rr;
                     ok = out_row < p.M;
                 }
-                s_rowmap[et] = ok ? out_row : -1;
+                s_rowmap[rr] = ok ? out_row : -1;
             }
             if (EPI == EPI_RESID || EPI == EPI_RESID_LN) {
-                // residual rows are contiguous (no conv mode); 16-byte chunks, 8 independent loads in flight per thread
+                // residual rows are contiguous (no conv mode); 16-byte chunks, up to 8 independent loads per thread
                 if ((ncols & 7) == 0) {
                     const int cpr = ncols >> 3;                        // 16-byte chunks per row
                     const int rows_here = min(BM, p.M - m_blk * BM);
@@ -285,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 } else {
-                    for (int r = ewarp; r < BM; r += 8) {
+                    for (int r = ewarp; r < BM; r += 16) {
                         const int grow = m_blk * BM + r;
                         if (grow >= p.M) continue;
                         const bf16* src = p.resid + (size_t)grow * p.ldr + col_base;
@@ -309,20 +313,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
             if (EPI == EPI_RESID_LN) {
-                // One 32-column chunk per thread (BN = 64, two warpgroups): v = resid + acc + bias stays in
-                // registers; row statistics are summed over the 2 halves x cl_size CTAs through DSMEM.
-                const int c = half * 32;
-                uint32_t r[32];
-                tmem_ld32(t_row + c, r);
+                // One 16-column chunk per thread (BN = 64): v = resid + acc + bias stays in registers; row statistics
+                // are summed over the 4 column quarters x cl_size CTAs through distributed shared memory.
+                const int c = part * 16;
+                uint32_t r[16];
+                tmem_ld16(t_row + c, r);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);  // accumulator consumed: the next tile's MMAs may start
-                float v[32];
+                float v[16];
                 float s1 = 0.f, s2 = 0.f;
                 const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
                 const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     const uint4 u = rs[i];
                     const float4 b0 = bs[2 * i], b1 = bs[2 * i + 1];
                     const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
@@ -338,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 const int par = it & 1;
-                const uint32_t slot = smem_u32(&s_stats[(par * 8 + (int)cl_rank * 2 + half) * BM + row_in_tile]);
+                const uint32_t slot = smem_u32(&s_stats[(par * 16 + (int)cl_rank * 4 + part) * BM + row_in_tile]);
                 const uint32_t bar_local = smem_u32(ln_bar);
                 for (uint32_t dst = 0; dst < cl_size; ++dst) {
                     st_cluster_f32x2(mapa_shared(slot, dst), s1, s2);
@@ -346,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 mbar_wait_cluster(ln_bar, (uint32_t)par);
                 float t1 = 0.f, t2 = 0.f;
-                for (int j = 0; j < 2 * (int)cl_size; ++j) {
-                    const float2 o = s_stats[(par * 8 + j) * BM + row_in_tile];
+                for (int j = 0; j < 4 * (int)cl_size; ++j) {
+                    const float2 o = s_stats[(par * 16 + j) * BM + row_in_tile];
                     t1 += o.x;
                     t2 += o.y;
                 }
@@ -358,26 +362,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4* gs = reinterpret_cast<const float4*>(s_gamma + c);
                 const float4* es = reinterpret_cast<const float4*>(s_beta + c);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const float4 g = gs[i], e = es[i];
                     v[4 * i] = (v[4 * i] - mean) * rstd * g.x + e.x;
                     v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + e.y;
                     v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + e.z;
                     v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + e.w;
                 }
-                stage32(my_row, c, 0, v);
+                stage16(my_row, c, 0, v);
             } else if (EPI == EPI_GLU) {
 #pragma unroll 1
-                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
-                    uint32_t ra[32], rg[32];
-                    tmem_ld32(t_row + c, ra);
-                    tmem_ld32(t_row + BN_OUT + c, rg);
+                for (int c = part * PART; c < (part + 1) * PART; c += 16) {
+                    uint32_t ra[16], rg[16];
+                    tmem_ld16(t_row + c, ra);
+                    tmem_ld16(t_row + BN_OUT + c, rg);
                     tmem_ld_wait();
-                    float v[32];
+                    float v[16];
                     const float4* ba = reinterpret_cast<const float4*>(s_bias + c);
                     const float4* bg = reinterpret_cast<const float4*>(s_bias + BN_OUT + c);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         const float4 x = ba[i], y = bg[i];
                         const float av[4] = {x.x, x.y, x.z, x.w}, gv[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -387,21 +391,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[4 * i + j] = row_live ? a * fast_sigmoid(g) : 0.f;
                         }
                     }
-                    stage32(my_row, c, p.out_f32, v);
+                    stage16(my_row, c, p.out_f32, v);
                 }
             } else {
 #pragma unroll 1
-                for (int c = half * HALF; c < (half + 1) * HALF; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c, r);
+                for (int c = part * PART; c < (part + 1) * PART; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + c, r);
                     tmem_ld_wait();
                     if (c >= ncols) continue;  // warp-uniform
-                    float v[32];
-                    float res[32];
+                    float v[16];
+                    float res[16];
                     if (EPI == EPI_RESID) {
                         const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             const uint4 u = rs[i];
                             const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z),
                                          f3 = unpack_bf16(u.w);
@@ -412,17 +416,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float* trow = nullptr;
                     if (EPI == EPI_TABLE)
                         trow = p.table + (size_t)((out_row >= 0 ? out_row : 0) % p.period) * p.N + col_base + c;
-                    float bv[32];
+                    float bv[16];
                     {
                         const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < 4; ++i) {
                             const float4 b4 = bs[i];
                             bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < 16; ++i) {
                         float x = __uint_as_float(r[i]) + bv[i];
                         if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
                         if (EPI == EPI_SWISH) x = x * fast_sigmoid(x);
@@ -433,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (EPI == EPI_RESID) x = res[i] + p.alpha * x;
                         v[i] = x;
                     }
-                    stage32(my_row, c, p.out_f32, v);
+                    stage16(my_row, c, p.out_f32, v);
                 }
             }
             if (EPI != EPI_RESID_LN) {
@@ -449,11 +453,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int total = BM * cpr;
                 uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (size_t)col_base * esize;
                 const size_t ld_bytes = (size_t)p.ldc * esize;
-                for (int q0 = et; q0 < total; q0 += kEpiThreads * 8) {
-                    uint4 tmp[8];
-                    int orow[8];
+                for (int q0 = et; q0 < total; q0 += kEpiThreads * 4) {
+                    uint4 tmp[4];
+                    int orow[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const int q = q0 + j * kEpiThreads;
                         orow[j] = -1;
                         if (q < total) {
@@ -463,13 +467,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const int q = q0 + j * kEpiThreads;
                         if (orow[j] >= 0) *reinterpret_cast<uint4*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16) = tmp[j];
                     }
                 }
             } else {
-                for (int r = ewarp; r < BM; r += 8) {
+                for (int r = ewarp; r < BM; r += 16) {
                     const int orow = s_rowmap[r];
                     if (orow < 0) continue;
                     const uint8_t* src = stg + r * pitch;
@@ -629,7 +633,7 @@ static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
         const int bn = cands[i];
         const int bn_out = (epi == EPI_GLU) ? bn / 2 : bn;
         if (bn_out * (out_f32 ? 4 : 2) > 512) continue;  // staged row must fit the staging pitch
-        if (bn_out < 64) continue;                       // each epilogue warpgroup needs >= 32 columns
+        if (bn_out < 64) continue;                       // each epilogue warpgroup needs >= 16 columns
         const int n_tiles = (n_cols + bn_out - 1) / bn_out;
         const long tiles = (long)m_tiles * n_tiles;
         const long waves = (tiles + sms - 1) / sms;

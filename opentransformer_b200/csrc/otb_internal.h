@@ -111,6 +111,9 @@ const char* beam_reconstruct_launch(cudaStream_t stream, BeamState st, long long
 const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalty, float lamda, int nbest,
                                  long long* out_preds, float* out_scores);
 
+const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const long long* tgt, int rows, int V, float eps,
+                         int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd);
+
 int num_sms();
 extern unsigned long long* g_gemm_dbg;
 void set_error(const char* msg);

@@ -50,8 +50,16 @@ class SpeechToText(nn.Module):
         return logits.view(B, L, -1)[:, :, :self.decoder.vocab_size]
 
     def forward(self, inputs, targets):
-        raise NotImplementedError('training step (loss + backward kernels) is scheduled for round 2; '
-                                  'use forward_logits / the Recognizer for inference')
+        """SpeechToText.forward (model/speech2text.py:39-58), forward only: (loss, None).  The backward kernels
+        (dgrad/wgrad GEMMs, attention and LayerNorm backward) are the next scope row; call under eval()/no_grad()."""
+        truth = targets['targets']
+        logits_pad = self._logits_padded(inputs['inputs'], inputs['mask'], truth[:, :-1].contiguous())
+        loss, _ = ops.ls_cross_entropy(logits_pad, truth[:, 1:].contiguous(), self.decoder.vocab_size, self.smoothing)
+        return loss, None
+
+    def _logits_padded(self, inputs, mask, targets_in):
+        mem, lengths, B, T2 = self.encode_bf16(inputs, mask)
+        return self.decoder.forward_bf16(targets_in, mem, lengths, B, targets_in.shape[1], T2)
 
     def save_checkpoint(self, params, name):
         torch.save({'params': params, 'frontend': self.frontend.state_dict(),

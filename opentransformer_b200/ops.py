@@ -232,6 +232,23 @@ def logsoftmax_topk(logits, V, k, lm_logp=None, lm_weight=0.0, out_val=None, out
     return out_val, out_idx
 
 
+def ls_cross_entropy(logits, targets, V, smoothing=0.1, pad_id=0, want_grad=False):
+    """Label-smoothed CE (module/loss.py:21-48).  logits f32 [rows, ld]; targets i64 [rows].
+    Returns (loss f32 scalar tensor, dlogits f32 [rows, V] or None)."""
+    _need(logits, torch.float32, 'logits')
+    rows = logits.shape[0]
+    targets = targets.contiguous().view(-1)
+    dev = logits.device
+    tok = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nv = torch.empty(1, dtype=torch.int32, device=dev)
+    dl = torch.empty(rows, V, dtype=torch.float32, device=dev) if want_grad else None
+    check(_lib.lib().otb_ls_ce(_p(logits), logits.stride(0), _p(targets), rows, V, smoothing, pad_id, _p(tok), _p(loss),
+                               _p(nv), _p(dl), V if want_grad else 0, _stream()), 'otb_ls_ce')
+    _count(3)
+    return loss[0], dl
+
+
 def decode_self_attn(qkv, kc, vc, anc, step_ptr, N, H, Lmax, out=None):
     if out is None:
         out = torch.empty(N, H * 64, dtype=BF16, device=qkv.device)

@@ -1,0 +1,59 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: utterance sharding covers every item exactly
+once with no overlap, per-rank results gather back in order, timings reduce with MAX."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from opentransformer_b200 import dp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = dp.shard_range(n_items, rank, world)
+    ids = torch.arange(lo, hi, dtype=torch.int64).view(-1, 1).repeat(1, 3)     # stand-in for n-best ids
+    allids = dp.gather_variable(ids)
+    tmax = dp.max_over_ranks([float(rank + 1), 10.0 - rank], torch.device('cpu'))
+    q.put((rank, lo, hi, allids[:, 0].tolist(), tmax))
+    dist.destroy_process_group()
+
+
+def test_shard_gather_and_max_over_two_ranks():
+    world, n_items = 2, 7
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, all0, t0), (r1, lo1, hi1, all1, t1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 4, 4, 7)
+    assert all0 == all1 == list(range(n_items))
+    assert t0 == t1 == [2.0, 10.0]
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 5, 32, 257):
+        for w in (1, 2, 3, 8):
+            cover = []
+            for r in range(w):
+                lo, hi = dp.shard_range(n, r, w)
+                assert 0 <= hi - lo <= n // w + 1
+                cover += list(range(lo, hi))
+            assert cover == list(range(n))

@@ -159,6 +159,23 @@ def test_decoder_logits_match_oracle_teacher_forced():
     assert r < REL_L2_LOGITS and r_full < REL_L2_LOGITS and r_lp < REL_L2_LOGITS and d_lp < lim
 
 
+def test_model_forward_loss_matches_oracle():
+    params = _params(n_enc=1, n_dec=2)
+    model, sd = _build(params)
+    x, mask = _batch(3, 200, 80, [200, 160, 181])
+    g = torch.Generator().manual_seed(9)
+    tgt = torch.randint(3, 4234, (3, 12), generator=g)
+    tgt[:, 0] = 1
+    tgt[0, 9:] = torch.tensor([1, 0, 0])
+    tgt[1, 11] = 1
+    tgt[2, 6:] = torch.tensor([1, 0, 0, 0, 0, 0])
+    loss_ref, _ = om.model_forward_loss(x, mask, tgt, sd, params)
+    with torch.no_grad():
+        loss, aux = model({'inputs': x.to(DEV), 'mask': mask.to(DEV)}, {'targets': tgt.to(DEV), 'targets_length': None})
+    print(f'label-smoothed CE: gpu {float(loss):.5f} oracle {float(loss_ref):.5f}')
+    assert aux is None and abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+
+
 def test_beam_search_lockstep_with_oracle():
     """Drive the oracle's beam_step with the CUDA decoder's log-probs: every integer decision of every
     step must be bit-exact, and the KV-cached log-probs must equal the oracle's full-prefix recompute."""

@@ -311,6 +311,21 @@ def test_logsoftmax_topk_fused(rows, V, k, lm):
     assert torch.equal(idx2, idx) and torch.equal(val2, val)
 
 
+def test_label_smoothing_cross_entropy_forward_and_grad():
+    from oracle import speech_model as om
+    rows, V = 93, 4234
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(rows, 4240, generator=g) * 3).to(DEV)
+    tgt = torch.randint(1, V, (rows,), generator=g)
+    tgt[::7] = 0                                                   # PAD rows
+    loss, dl = ops.ls_cross_entropy(logits, tgt.to(DEV), V, 0.1, want_grad=True)
+    x = logits[:, :V].detach().cpu().double().requires_grad_(True)
+    ref = om.label_smoothing_loss(x.unsqueeze(0), tgt.unsqueeze(0), 0.1)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+    print(_report('ls-ce dlogits', dl.cpu(), x.grad.float(), 1e-5, 1e-7))
+
+
 def test_decode_self_attention_with_ancestry_cache():
     N, H, Lmax, step = 12, 4, 60, 45
     d = H * 64
