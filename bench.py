@@ -325,6 +325,8 @@ def run_b200(args):
     ms_lat = timed(step_resident, 4, 1) / 4
     prof, ops.PROFILE = ops.PROFILE, None
 
+    if L > 1:
+        timed(step_resident, 2 * L, L)      # untimed multi-lane pass: thread start-up, allocator growth per stream
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -388,13 +390,84 @@ def run_b200(args):
     return 0
 
 
+def conformer_params():
+    """egs/aishell/conf/conformer_baseline.yaml with the SURVEY.md 8(d) config-4 overrides (d_model 256,
+    residual_dropout 0.0 because the reference applies dropout in eval mode otherwise)."""
+    p = model_params()
+    p['encoder_type'] = 'conformer'
+    p['frontend'].update(mid_channel=256, out_channel=256)
+    p['encoder'] = dict(d_model=256, d_ff=768, cov_kernel_size=5, n_heads=4, nblocks=12, pos_dropout=0.0,
+                        slf_attn_dropout=0.0, ffn_dropout=0.0, residual_dropout=0.0, conv_dropout=0.0,
+                        macaron_style=True, ffn_scale=0.5, conv_bias=True, activation='glu',
+                        positional_encoding=True, relative_positional=True)
+    p['decoder'].update(d_ff=768)
+    return p
+
+
+def run_conformer(args):
+    """BASELINE config 4: Conformer encoder forward, 64 x 1000 frames per GPU, utterance-sharded over ranks."""
+    import torch.distributed as dist
+    from opentransformer_b200.model import SpeechToText
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(1234)
+    model = SpeechToText(conformer_params()).eval().to(dev)
+    B = 64
+    ring = [tuple(t.to(dev) for t in synthetic_batch(B, 1000 * rank + i)) for i in range(8)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            model.encode_bf16(*ring[i % 8])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            model.encode_bf16(*ring[i % 8])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    ms = float(t[0])
+    if rank == 0:
+        peaks, src = measured_peaks()
+        flop = 898.0e9      # SURVEY.md 8(d): ~898 GFLOP per 64-utterance batch
+        ach = flop * args.steps / (ms * 1e-3) / 1e12
+        print(json.dumps({'metric': 'utterances/sec (Conformer encoder forward)', 'value': B * world * args.steps / (ms * 1e-3),
+                          'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                          'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                          'config': {'workload': 'Conformer encoder 12L d_model=256 d_ff=768 k=5 rel-pos, frontend 1->256->256, '
+                                                 f'{B} utt x {T_FRAMES} frames per GPU (BASELINE config 4)',
+                                     'parallelism': f'dp{world}'},
+                          'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks.get('bf16_tflops_sustained'),
+                                       'unit': 'TFLOP/s', 'frac': ach / peaks.get('bf16_tflops_sustained', 1400.0),
+                                       'traffic': None, 'kernel': 'whole encoder pass (898 GFLOP algorithmic per batch)',
+                                       'peak_source': src}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=32)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--ref-sample', type=int, default=2, help='utterances per CPU reference pass')
+    ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer'],
+                    help="'conformer' = BASELINE config 4 (encoder forward only); default is the headline workload")
     ap.add_argument('--lanes', type=int, default=4, help='utterance batches kept in flight per GPU (streams)')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     args = ap.parse_args()
@@ -402,6 +475,8 @@ def main():
         return run_reference(args)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)')
+    if args.workload == 'conformer':
+        return run_conformer(args)
     return run_b200(args)
 
 

@@ -44,6 +44,8 @@ int otb_version(void);
 int otb_num_sms(void);
 /* Profiling aid: buf (device, u64 [grid*8]) receives per-CTA clock64 phase stamps of the next GEMMs; NULL disables. */
 int otb_debug_gemm_timing(unsigned long long* buf);
+/* Profiling aid: 0 = normal, 1 = GEMM mainloop without TMA traffic, 2 = without MMAs (results are garbage). */
+int otb_debug_gemm_mode(int mode);
 
 /* Conv2dLayer output geometry, kernel 3, stride 2, padding (0,1)  (frontend/conv.py:10-11,27):
  * T1 = (T-3)/2+1, F1 = (F-1)/2+1, T2 = (T1-3)/2+1, F2 = (F1-1)/2+1.  The conv1 activation buffer is

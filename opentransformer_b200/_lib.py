@@ -25,6 +25,7 @@ _SIGS = {
     'otb_version': (c_int, []),
     'otb_num_sms': (c_int, []),
     'otb_debug_gemm_timing': (c_int, [_P]),
+    'otb_debug_gemm_mode': (c_int, [c_int]),
     'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_conv2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

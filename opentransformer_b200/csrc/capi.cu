@@ -50,6 +50,10 @@ int otb_debug_gemm_timing(unsigned long long* buf) {
     g_gemm_dbg = buf;
     return 0;
 }
+int otb_debug_gemm_mode(int mode) {
+    g_gemm_dbg_mode = mode;
+    return 0;
+}
 
 int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2) {
     if (T < 7 || F < 1) return fail("otb_conv_geometry", "need T >= 7 and F >= 1");

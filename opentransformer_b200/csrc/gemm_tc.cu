@@ -31,7 +31,10 @@
 namespace otb {
 
 unsigned long long* g_gemm_dbg = nullptr;
+int g_gemm_dbg_mode = 0;
 #define DBG_STAMP(i) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (i)] = clock64(); } while (0)
+// per-k-block traces of the first tile: kind 0 = TMA issue, 1 = full barrier observed by the MMA thread
+#define DBG_KB(kind, kb) do { if (p.dbg && (kb) < 64) p.dbg[148 * 8 + (blockIdx.x * 2 + (kind)) * 64 + (kb)] = clock64(); } while (0)
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
@@ -117,6 +120,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
+        if (p.dbg_mode == 1) {  // profiling aid: signal "full" without moving any data
+            mbar_arrive(&full_bar[stage]);
+            return;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], a_tx + (uint32_t)Cfg::B_BYTES);
         if (p.conv) {
             // k-block -> (tap, channel chunk); tap (kh,kw): input row 2t'+kh, col 2f'+kw-1
@@ -158,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < STAGES && p_tile < num_tiles; ++i) {
                 issue_load(p_tile, p_kb, p_stage);
                 if (i == 0) DBG_STAMP(2);
+                if (p_tile == (int)blockIdx.x) DBG_KB(0, p_kb);
                 if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
                 if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
             }
@@ -178,6 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (p_tile < num_tiles) {
                 mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
                 issue_load(p_tile, p_kb, p_stage);
+                if (p_tile == (int)blockIdx.x) DBG_KB(0, p_kb);
                 if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
                 if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
             }
@@ -200,12 +209,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (it == 0 && kb == 0) DBG_STAMP(3);
+                if (it == 0) DBG_KB(1, kb);
                 const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                if (p.dbg_mode != 2) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                              (uint32_t)((kb | k) != 0));
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -647,6 +659,7 @@ const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, 
                         GemmParams p, const CUtensorMap* conv_map) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
     p.dbg = g_gemm_dbg;
+    p.dbg_mode = g_gemm_dbg_mode;
     if (p.K % 8) return "gemm: K must be a multiple of 8";
     if (p.ldc % (p.out_f32 ? 4 : 8)) return "gemm: ldc must keep rows 16-byte aligned (ldc % 8 == 0 for bf16, % 4 for f32)";
     if (reinterpret_cast<uintptr_t>(p.out) & 15) return "gemm: out must be 16-byte aligned";

@@ -47,6 +47,7 @@ struct GemmParams {
     int conv_B;        // batch
     int conv_cchunks;  // C_in / 64
     unsigned long long* dbg;  // optional [grid][8] clock64 phase stamps (otb_debug_gemm_timing)
+    int dbg_mode;             // 0 normal; 1 = no TMA traffic (MMA-only cadence); 2 = no MMA (TMA-only cadence)
 };
 
 const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, int ldw, int w_rows, int epi,
@@ -116,6 +117,7 @@ const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const lo
 
 int num_sms();
 extern unsigned long long* g_gemm_dbg;
+extern int g_gemm_dbg_mode;
 void set_error(const char* msg);
 
 }  // namespace otb

@@ -5,7 +5,7 @@ import torch
 from opentransformer_b200 import ops, _lib
 dev = torch.device('cuda:0')
 L = _lib.lib()
-buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(148 * 8 + 148 * 2 * 64, dtype=torch.int64, device=dev)
 names = ['entry', 'setup_done', 'first_tma_issued', 'first_full', 'mma_committed', 'tfull_seen', 'epi_done', 'exit']
 
 
@@ -19,13 +19,19 @@ def run(tag, fn):
     e0.record(); fn(); e1.record()
     torch.cuda.synchronize()
     L.otb_debug_gemm_timing(None)
-    b = buf.view(148, 8).cpu()
+    kbt = buf[148 * 8:].view(148, 2, 64).cpu()
+    b = buf[:148 * 8].view(148, 8).cpu()
     live = b[:, 0] > 0
     b = b[live]
     d = (b - b[:, :1]).float()
     print(f'{tag}: {e0.elapsed_time(e1)*1e3:.1f} us by events, {int(live.sum())} CTAs; cycles since entry (mean over CTAs / max):')
     for i, n in enumerate(names):
         print(f'    {n:18s} {d[:, i].mean():9.0f} {d[:, i].max():9.0f}')
+    t0 = int(buf[0])
+    iss = [int(v) - t0 for v in kbt[0, 0] if int(v) > 0][:20]
+    ful = [int(v) - t0 for v in kbt[0, 1] if int(v) > 0][:20]
+    print('    CTA0 TMA issue  times:', iss)
+    print('    CTA0 full seen  times:', ful)
 
 
 def mk(M, N, K, epi, **kw):
@@ -41,6 +47,8 @@ def mk(M, N, K, epi, **kw):
     return lambda: ops.linear(a, w, b, epi, out=out, **extra)
 
 
+for (M, N, K) in [(7968, 256, 2048), (7968, 2048, 2048), (7968, 768, 1024), (128, 64, 2048), (128, 256, 2048)]:
+    run(f'BIAS M={M} N={N} K={K} (per-k-block cycles = (mma_committed - first_full) / {K // 64})', mk(M, N, K, ops.EPI_BIAS))
 run('decode out-proj  M=320 N=256 K=256  RESID_LN', mk(320, 256, 256, ops.EPI_RESID_LN))
 run('decode w2        M=320 N=256 K=2048 RESID_LN', mk(320, 256, 2048, ops.EPI_RESID_LN))
 run('decode qkv       M=320 N=768 K=256  BIAS    ', mk(320, 768, 256, ops.EPI_BIAS))
