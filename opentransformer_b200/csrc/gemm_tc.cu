@@ -93,8 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* ln_bar = tempty_bar + 2;                     // cluster LayerNorm statistics exchange
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 1);
+    uint64_t* ln_bar = tempty_bar + 2;                     // [2] cluster LayerNorm statistics exchange (alternate per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 2);
     float* s_bias = reinterpret_cast<float*>(aux + 256);   // [256]  (GLU: value half | gate half)
     float* s_gamma = s_bias + 256;                          // [256]
     float* s_beta = s_gamma + 256;                          // [256]
@@ -158,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_init(&tfull_bar[i], 1);
                 mbar_init(&tempty_bar[i], kEpiThreads);
             }
-            mbar_init(ln_bar, kEpiThreads * cl_size);
+            mbar_init(&ln_bar[0], 1);
+            mbar_init(&ln_bar[1], 1);
             fence_barrier_init();
             // the first STAGES slots are free by construction: start the loads before the CTA-wide sync so
             // their latency overlaps the TMEM allocation
@@ -353,14 +354,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         s2 += x * x;
                     }
                 }
+                // Tiles alternate between two (stats buffer, mbarrier) pairs: a peer that runs ahead signals the
+                // OTHER barrier, so statistics of consecutive tiles can never be mixed.  Each remote store carries
+                // its own byte count (st.async ... complete_tx), the owner expects 8 B x 512 threads x cl_size.
                 const int par = it & 1;
+                if (et == 0) mbar_arrive_expect_tx(&ln_bar[par], (uint32_t)(8 * kEpiThreads) * cl_size);
                 const uint32_t slot = smem_u32(&s_stats[(par * 16 + (int)cl_rank * 4 + part) * BM + row_in_tile]);
-                const uint32_t bar_local = smem_u32(ln_bar);
-                for (uint32_t dst = 0; dst < cl_size; ++dst) {
-                    st_cluster_f32x2(mapa_shared(slot, dst), s1, s2);
-                    mbar_arrive_cluster(mapa_shared(bar_local, dst));
-                }
-                mbar_wait_cluster(ln_bar, (uint32_t)par);
+                const uint32_t bar_local = smem_u32(&ln_bar[par]);
+                for (uint32_t dst = 0; dst < cl_size; ++dst)
+                    st_async_f32x2(mapa_shared(slot, dst), s1, s2, mapa_shared(bar_local, dst));
+                mbar_wait_cluster(&ln_bar[par], (uint32_t)((it >> 1) & 1));
                 float t1 = 0.f, t2 = 0.f;
                 for (int j = 0; j < 4 * (int)cl_size; ++j) {
                     const float2 o = s_stats[(par * 16 + j) * BM + row_in_tile];

@@ -166,10 +166,95 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
     }
 }
 
+// N <= 256 fast path: one warp normalises 4 rows at a time so that 4 independent 16-byte loads (and 4
+// independent reduction chains) are in flight per lane -- the one-row-per-warp version was latency-bound
+// (14.8 us for 16 MB at Conformer cfg 4, profiles/r1_launches_conformer_v0.csv).
+__global__ void __launch_bounds__(256) layernorm256_kernel(const bf16* __restrict__ x, int ldx, void* __restrict__ out,
+                                                           int ldo, int out_f32, const float* __restrict__ g1,
+                                                           const float* __restrict__ b1, const float* __restrict__ g2,
+                                                           const float* __restrict__ b2, float eps, int M, int N) {
+    constexpr int R = 4;
+    const int lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= M) return;
+    const int col = lane * 8;
+    const bool live = col < N;
+    float v[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (live && row0 + r < M) u = *reinterpret_cast<const uint4*>(x + (size_t)(row0 + r) * ldx + col);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        v[r][0] = a.x; v[r][1] = a.y; v[r][2] = b.x; v[r][3] = b.y; v[r][4] = c.x; v[r][5] = c.y; v[r][6] = d.x; v[r][7] = d.y;
+    }
+    float gg[8], bb[8];
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* g = pass ? g2 : g1;
+        const float* be = pass ? b2 : b1;
+        if (g == nullptr) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gg[j] = live ? g[col + j] : 0.f; bb[j] = live ? be[col + j] : 0.f; }
+        float s[R], q[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s[r] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[r] += v[r][j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            s[r] /= N;
+            q[r] = 0.f;
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float d = v[r][j] - s[r]; q[r] += d * d; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float rstd = rsqrtf(q[r] / N + eps);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[r][j] = live ? (v[r][j] - s[r]) * rstd * gg[j] + bb[j] : 0.f;
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (row0 + r >= M) break;
+        if (out_f32) {
+            float* o = reinterpret_cast<float*>(out) + (size_t)(row0 + r) * ldo + col;
+            *reinterpret_cast<float4*>(o) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+        } else {
+            uint4 u;
+            u.x = pack_bf16(v[r][0], v[r][1]);
+            u.y = pack_bf16(v[r][2], v[r][3]);
+            u.z = pack_bf16(v[r][4], v[r][5]);
+            u.w = pack_bf16(v[r][6], v[r][7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + (size_t)(row0 + r) * ldo + col) = u;
+        }
+    }
+}
+
 const char* layernorm_launch(cudaStream_t st, const bf16* x, int ldx, void* out, int ldo, int out_f32, const float* g1,
                              const float* b1, const float* g2, const float* b2, float eps, int M, int N) {
     if (N % 8 || ldx % 8 || N > 1024) return "layernorm: N must be a multiple of 8 and <= 1024";
     if ((out_f32 && ldo % 4) || (!out_f32 && ldo % 8)) return "layernorm: bad output stride";
+    if (N <= 256) {
+        const int rows_per_block = 8 * 4;
+        layernorm256_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2,
+                                                                                       b2, eps, M, N);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+    }
     const int rows_per_block = 8;
     dim3 grid((M + rows_per_block - 1) / rows_per_block);
     const int ch = (N + 255) / 256;

@@ -268,13 +268,15 @@ class TransformerEncoderLayer(nn.Module):
         return {'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj),
                 'ffn': _ffn_pack(self.feed_forward), 'ln1': _ln(self.norm1), 'ln2': _ln(self.norm2)}
 
-    def run(self, x, pk, B, T, lengths):
-        """x bf16 [B*T, d] -> bf16 [B*T, d]   (encoder/transformer.py:41-65)"""
+    def run(self, x, pk, B, T, lengths, causal=False):
+        """x bf16 [B*T, d] -> bf16 [B*T, d]   (encoder/transformer.py:41-65); causal=True is the tril mask the
+        Transformer LM feeds to the same layer (model/lm.py:14-18,148-151)."""
         d, H = x.shape[1], self.n_heads
         if self.normalize_before:
             x = ops.layernorm(x, *pk['ln1'])          # residual is taken AFTER the norm (transformer.py:42-44)
         qkv = ops.linear(x, pk['wqkv'], pk['bqkv'])
-        ctx = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
+        ctx = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lengths, causal=causal, q_col0=0, k_col0=d,
+                            v_col0=2 * d)
         x = _proj_resid_ln(ctx, pk['wo'], pk['bo'], x, None if self.normalize_before else pk['ln1'])
         if self.normalize_before:
             x = ops.layernorm(x, *pk['ln2'])

@@ -33,8 +33,14 @@ class Recognizer:
         self.lm = lm
         if self.lm is not None:
             self.lm.eval()
+            if self.ngpu > 0:
+                self.lm.cuda()
         self.idx2unit = idx2unit
         self.lm_weight = lm_weight
+
+    def lm_decode(self, preds, hidden=None):
+        """recognize/base.py:26-37 (Transformer LM branch)."""
+        return self.lm.predict(preds, last_frame=True), hidden
 
     def translate(self, seqs):
         results = []
@@ -164,6 +170,21 @@ class BeamDecoder:
         self.graph.replay()
         ops.COUNTERS['launches'] += self.launches_per_step
 
+    def run_with_lm(self, max_steps, lm, lm_weight):
+        """Shallow fusion (speech2text.py:102-105, base.py:26-37): every step the LM re-scores the full prefixes
+        (as the reference's TransformerLanguageModel.predict does) and lm_weight * log-probs are added inside the
+        fused log-softmax/top-k kernel.  Eager mode: the prefix length is host-side state."""
+        assert not self.use_graph, 'LM fusion runs the decode loop eagerly'
+        self.lm_weight = float(lm_weight)
+        for i in range(max_steps):
+            preds = self.state.reconstruct(i)                       # [N, i+1], column 0 = BOS
+            self.lm_logp = lm.predict(preds, last_frame=True).squeeze(1).contiguous()
+            self._step_kernels()
+            if int(self.state.ctrl[1].item()):
+                break
+        self.lm_logp = None
+        return int(self.state.ctrl[0].item())
+
     def run(self, max_steps, poll_every=8):
         """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
         (speech2text.py:66-67).  Steps launched after the end are no-ops on the search state."""
@@ -181,9 +202,9 @@ class SpeechToTextRecognizer(Recognizer):
     def __init__(self, model, lm=None, lm_weight=0.1, ctc_weight=0.0, beam_width=5, nbest=1, max_len=50,
                  idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True):
         super().__init__(model, idx2unit, lm, lm_weight, ngpu)
-        if lm is not None:
-            raise NotImplementedError('LM shallow fusion: the beam kernel takes lm_log_probs, but no B200 LM '
-                                      'is wired in yet (SURVEY.md 8f "next" row 2)')
+        if lm is not None and getattr(lm, 'model_type', None) != 'transformer_lm':
+            raise NotImplementedError('shallow fusion is implemented for the Transformer LM (opentransformer_b200.lm); '
+                                      'the RNN LM is out of scope')
         self.beam_width, self.max_len, self.nbest = beam_width, max_len, nbest
         self.penalty, self.lamda = penalty, lamda
         self.ctc_weight, self.lm_weight = ctc_weight, lm_weight
@@ -237,7 +258,8 @@ class SpeechToTextRecognizer(Recognizer):
         key = (B, self.beam_width, T2, self.max_len, device.index)
         bd = self._decoders.get(key)
         if bd is None:
-            bd = BeamDecoder(self.model.decoder, B, self.beam_width, T2, self.max_len, device, self.use_graph)
+            bd = BeamDecoder(self.model.decoder, B, self.beam_width, T2, self.max_len, device,
+                             self.use_graph and self.lm is None)
             self._decoders[key] = bd
         return bd
 
@@ -247,7 +269,10 @@ class SpeechToTextRecognizer(Recognizer):
             mem, mem_len, B, T2 = self._encode_bf16(inputs, inputs_mask)
             bd = self._decoder_for(B, T2, inputs.device)
             bd.setup(mem, mem_len)
-            steps = bd.run(self.max_len)
+            if self.lm is not None:
+                steps = bd.run_with_lm(self.max_len, self.lm, self.lm_weight)
+            else:
+                steps = bd.run(self.max_len)
             preds, scores = bd.state.finalize(self.penalty, self.lamda, self.nbest)
         return preds[:, :, :steps], scores, steps
 

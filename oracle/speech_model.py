@@ -381,6 +381,22 @@ def decoder_inference(preds, memory, memory_mask, sd, prefix, **kw):
     return F.log_softmax(logits[:, -1, :], dim=-1)
 
 
+def transformer_lm_log_probs(targets, sd, prefix, n_blocks, n_heads, last_frame=True, policy=None):
+    """TransformerLanguageModel.predict (model/lm.py:143-163): embedding -> x*sqrt(d)+PE -> post-norm encoder
+    layers (GLU) under the causal tril mask (lm.py:14-18) -> output_project -> log_softmax."""
+    x = _r(sd[prefix + 'embedding.weight'], policy)[targets]
+    x, _ = abs_posenc(x)
+    x = _r(x, policy)
+    L = targets.shape[1]
+    causal = torch.tril(torch.ones(L, L)).bool().unsqueeze(0).expand(targets.shape[0], L, L)
+    for i in range(n_blocks):
+        x = transformer_encoder_layer(x, causal, None, sd, f'{prefix}blocks.{i}', n_heads, 'glu', False, False, policy)
+    logits = linear(x, sd, prefix + 'output_project', policy)
+    if last_frame:
+        return F.log_softmax(logits[:, -1, :].unsqueeze(1), dim=-1)
+    return F.log_softmax(logits, dim=-1)
+
+
 # ----------------------------------------------------------------------------------------------
 # loss: otrans/module/loss.py:21-48
 # ----------------------------------------------------------------------------------------------

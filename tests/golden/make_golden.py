@@ -158,7 +158,27 @@ def beam_step_cases():
     print('beam_step_cases', len(cases))
 
 
+def lm_case():
+    """TransformerLanguageModel.predict of the real reference on a tiny config (model/lm.py:93-163)."""
+    from otrans.model import LanguageModel
+    params = dict(vocab_size=40, num_blocks=2, d_model=32, n_heads=4, d_ff=48, residual_dropout=0.0, smoothing=0.1,
+                  share_embedding=True)
+    torch.manual_seed(4321)
+    lm = LanguageModel['transformer_lm'](params).eval()
+    with torch.no_grad():
+        lm.embedding.weight.mul_(0.3)
+    g = torch.Generator().manual_seed(5)
+    toks = torch.randint(2, 40, (4, 7), generator=g)
+    toks[:, 0] = 1
+    with torch.no_grad():
+        out = {'params': params, 'state_dict': {'lm.' + k: v.clone() for k, v in lm.state_dict().items()},
+               'tokens': toks, 'last': lm.predict(toks, last_frame=True), 'all': lm.predict(toks, last_frame=False)}
+    torch.save(out, os.path.join(HERE, 'small_transformer_lm.pt'))
+    print('small_transformer_lm', tuple(out['last'].shape), tuple(out['all'].shape))
+
+
 if __name__ == '__main__':
+    lm_case()
     run_case('small_transformer_postnorm_glu', small_params('transformer'))
     run_case('small_transformer_prenorm_relu',
              small_params('transformer', normalize_before=True, activation='relu'),

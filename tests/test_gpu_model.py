@@ -216,6 +216,52 @@ def test_beam_search_lockstep_with_oracle():
         torch.testing.assert_close(gs.cpu(), ns, rtol=1e-5, atol=1e-5)
 
 
+def test_transformer_lm_and_shallow_fusion_lockstep():
+    """LM log-probs vs the oracle; beam search with lm_weight: every integer decision bit-exact when the oracle's
+    beam_step is fed the CUDA decoder AND CUDA LM log-probs (speech2text.py:102-105)."""
+    from opentransformer_b200.lm import TransformerLanguageModel
+    lm_params = dict(vocab_size=4234, num_blocks=2, d_model=256, n_heads=4, d_ff=1024, residual_dropout=0.0,
+                     smoothing=0.1, share_embedding=True)
+    torch.manual_seed(77)
+    lm = TransformerLanguageModel(lm_params).eval()
+    lm_sd = {'lm.' + k: v.detach().clone().float() for k, v in lm.state_dict().items()}
+    lm = lm.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    toks = torch.randint(2, 4234, (5, 9), generator=g)
+    toks[:, 0] = 1
+    ref = om.transformer_lm_log_probs(toks, lm_sd, 'lm.', 2, 4, last_frame=False)
+    got = lm.predict(toks.to(DEV), last_frame=False).cpu()
+    r = _rel(got, ref)
+    print(f'transformer LM log-probs rel_l2={r:.3e}')
+    assert r < REL_L2_LOGITS
+    assert lm.predict(toks.to(DEV), last_frame=True).shape == (5, 1, 4234)
+
+    params = _params(n_enc=1, n_dec=2)
+    model, sd = _build(params)
+    B, beam, max_len, lmw = 2, 3, 6, 0.3
+    x, mask = _batch(B, 160, 80, [160, 131])
+    with torch.no_grad():
+        mem, lens, _, T2 = model.encode_bf16(x.to(DEV), mask.to(DEV))
+        bd = BeamDecoder(model.decoder, B, beam, T2, max_len, DEV, use_graph=False)
+        bd.setup(mem, lens)
+        bd.lm_weight = lmw
+        preds = torch.full((B * beam, 1), 1, dtype=torch.long)
+        scores = torch.tensor([0.0] + [float('-inf')] * (beam - 1)).repeat(B).unsqueeze(1)
+        flag = torch.zeros_like(scores, dtype=torch.bool)
+        for s in range(max_len):
+            bd.lm_logp = lm.predict(bd.state.reconstruct(s), last_frame=True).squeeze(1).contiguous()
+            lm_cpu = bd.lm_logp.cpu()
+            bd._step_kernels()
+            # bd.logp holds log_softmax(logits) + lmw * lm (the fused kernel materialises it in eager mode)
+            dec_lp = bd.logp.cpu() - lmw * lm_cpu
+            preds, scores, flag = obs.beam_step(dec_lp, preds, scores, flag, beam, lm_log_probs=lm_cpu, lm_weight=lmw)
+            assert torch.equal(bd.state.reconstruct(s + 1).cpu(), preds), f'fusion: ids differ at step {s}'
+    rec = SpeechToTextRecognizer(model, lm=lm, lm_weight=lmw, beam_width=beam, nbest=1, max_len=max_len, penalty=0.6,
+                                 lamda=5, ngpu=1)
+    ids, sc, n = rec.recognize_ids(x.to(DEV), mask.to(DEV))
+    assert ids.shape == (B, 1, n)
+
+
 def test_recognizer_graph_replay_equals_eager_and_decode_step_seam():
     params = _params(n_enc=1, n_dec=2)
     model, sd = _build(params)
