@@ -343,11 +343,26 @@ def run_b200(args):
 
     if rank == 0:
         peaks, src = measured_peaks()
-        gemm = [(k, f, a.elapsed_time(b)) for k, f, a, b in prof if k == 'gemm']
-        flops = sum(f for _, f, _ in gemm)
-        gms = sum(m for _, _, m in gemm)
+        # dominant kernel = the GEMM launch shape with the largest summed device time in the (single-lane) timed passes
+        groups = {}
+        for k, f, a, b, tag in prof:
+            if k == 'gemm':
+                g = groups.setdefault(tag, [0, 0.0, 0.0])
+                g[0] += 1
+                g[1] += f
+                g[2] += a.elapsed_time(b)
+        tag, (cnt, flops, gms) = max(groups.items(), key=lambda kv: kv[1][2])
+        all_ms = sum(v[2] for v in groups.values())
+        all_fl = sum(v[1] for v in groups.values())
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        epi_names = ['bias', 'relu', 'glu', 'posenc-table', 'residual', 'residual+layernorm', 'swish', 'gelu', 'tanh']
+        traffic = None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+                traffic = json.load(f).get('%s_M%d_N%d_K%d' % (epi_names[tag[0]], tag[1], tag[2], tag[3]))
+        except Exception:
+            pass
         utt = B_PER_GPU * world * args.steps
         value = utt / (ms_total * 1e-3)
         e2e = utt / (ms_e2e * 1e-3)
@@ -366,10 +381,12 @@ def run_b200(args):
                           'beam_decode_ms': ms_lat - ms_enc,
                           'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3)},
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': ach / peak if peak else None, 'traffic': None,
-                         'kernel': 'gemm_tc_kernel (tcgen05 GEMM; every eager launch of 4 single-lane timed passes, i.e. '
-                                   'without other streams contending for SMs: '
-                                   f'{len(gemm)} launches, {flops / 1e9:.1f} GFLOP algorithmic, {gms:.3f} ms by CUDA events)',
+                         'frac': ach / peak if peak else None, 'traffic': traffic,
+                         'kernel': f'gemm_tc_kernel, epilogue {epi_names[tag[0]]}, M={tag[1]} N={tag[2]} K={tag[3]} '
+                                   f'(dominant GEMM shape: {cnt} launches, {flops / cnt / 1e9:.2f} GFLOP algorithmic each = 2MNK, '
+                                   f'avg {gms / cnt * 1e3:.1f} us by CUDA events in 4 single-lane timed passes)',
+                         'all_gemms': {'launches': sum(v[0] for v in groups.values()), 'gflop': all_fl / 1e9, 'ms': all_ms,
+                                       'tflops': all_fl / (all_ms * 1e-3) / 1e12 if all_ms > 0 else None},
                          'peak_source': f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'},
             'clocks': clocks,
         }
@@ -468,7 +485,7 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=2, help='utterances per CPU reference pass')
     ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer'],
                     help="'conformer' = BASELINE config 4 (encoder forward only); default is the headline workload")
-    ap.add_argument('--lanes', type=int, default=4, help='utterance batches kept in flight per GPU (streams)')
+    ap.add_argument('--lanes', type=int, default=6, help='utterance batches kept in flight per GPU (streams)')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     args = ap.parse_args()
     if args.impl == 'reference':

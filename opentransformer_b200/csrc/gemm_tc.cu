@@ -42,7 +42,7 @@ static constexpr int kThreads = 640;
 static constexpr int kEpiThreads = 512;
 static constexpr int STG_PITCH_MAX = 512 + 16;          // bytes per staged row (+16 B pad: conflict-free 16 B accesses)
 static constexpr int STG_BYTES = BM * STG_PITCH_MAX;    // 67,584
-static constexpr int AUX_BYTES = 6144;                  // barriers, TMEM slot, bias / gamma / beta, row map, LN stats
+static constexpr int AUX_BYTES = 6144 + 8192;           // barriers, TMEM slot, bias / gamma / beta, row map | LN stats (wide tiles)
 
 template <int BN>
 struct GemmCfg {
@@ -99,9 +99,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_gamma = s_bias + 256;                          // [256]
     float* s_beta = s_gamma + 256;                          // [256]
     int* s_rowmap = reinterpret_cast<int*>(s_beta + 256);   // [128] output row of each tile row, -1 = skip
-    // LN partial statistics [2 tile parities][cluster ranks * 4 quarters <= 16][128 rows] live in the upper part of
-    // the staging buffer (the LN kernels stage only 128 x 144 B there)
-    float2* s_stats = reinterpret_cast<float2*>(stg + 32768);
+    // LN partial statistics [2 tile parities][cluster ranks * 4 quarters <= 16][128 rows]: in the upper part of the
+    // staging buffer when the LN tile is 64 wide (staging needs 128 x 144 B), else (one CTA per row block, at most
+    // 4 partials per parity) in the pipeline-stage area's tail
+    float2* s_stats = (BN == 64) ? reinterpret_cast<float2*>(stg + 32768) : reinterpret_cast<float2*>(aux + 6144);
     const uint32_t cl_rank = (EPI == EPI_RESID_LN) ? cluster_ctarank() : 0;
     const uint32_t cl_size = (EPI == EPI_RESID_LN) ? cluster_nctarank() : 1;
 
@@ -326,47 +327,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
             if (EPI == EPI_RESID_LN) {
-                // One 16-column chunk per thread (BN = 64): v = resid + acc + bias stays in registers; row statistics
-                // are summed over the 4 column quarters x cl_size CTAs through distributed shared memory.
-                const int c = part * 16;
-                uint32_t r[16];
-                tmem_ld16(t_row + c, r);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&tempty_bar[as]);  // accumulator consumed: the next tile's MMAs may start
+                // Each thread owns PART = BN/4 columns of its row (16-column chunks).  Pass 1: v = resid + acc + bias,
+                // (sum, sum of squares); v is parked back in TMEM when it does not fit one chunk.  The partials of
+                // the 4 column quarters x cl_size CTAs meet through (distributed) shared memory.  Pass 2 normalises.
                 float v[16];
                 float s1 = 0.f, s2 = 0.f;
-                const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
-                const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll 1
+                for (int c = part * PART; c < (part + 1) * PART; c += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_row + c, r);
+                    tmem_ld_wait();
+                    const uint4* rs = reinterpret_cast<const uint4*>(my_row + c * 2);
+                    const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint4 u = rs[i];
-                    const float4 b0 = bs[2 * i], b1 = bs[2 * i + 1];
-                    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-                    const float rr[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 u = rs[i];
+                        const float4 b0 = bs[2 * i], b1 = bs[2 * i + 1];
+                        const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                        const float rr[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float x = __uint_as_float(r[8 * i + j]) + bb[j];
-                        x = (row_live ? x : 0.f) + rr[j];
-                        v[8 * i + j] = x;
-                        s1 += x;
-                        s2 += x * x;
+                        for (int j = 0; j < 8; ++j) {
+                            float x = __uint_as_float(r[8 * i + j]) + bb[j];
+                            x = (row_live ? x : 0.f) + rr[j];
+                            v[8 * i + j] = x;
+                            s1 += x;
+                            s2 += x * x;
+                            r[8 * i + j] = __float_as_uint(x);
+                        }
                     }
+                    if (PART > 16) tmem_st16(t_row + c, r);
+                }
+                if (PART > 16) tmem_st_wait();
+                if (PART == 16) {
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);  // accumulator consumed: the next tile's MMAs may start
                 }
                 // Tiles alternate between two (stats buffer, mbarrier) pairs: a peer that runs ahead signals the
                 // OTHER barrier, so statistics of consecutive tiles can never be mixed.  Each remote store carries
                 // its own byte count (st.async ... complete_tx), the owner expects 8 B x 512 threads x cl_size.
                 const int par = it & 1;
-                if (et == 0) mbar_arrive_expect_tx(&ln_bar[par], (uint32_t)(8 * kEpiThreads) * cl_size);
-                const uint32_t slot = smem_u32(&s_stats[(par * 16 + (int)cl_rank * 4 + part) * BM + row_in_tile]);
-                const uint32_t bar_local = smem_u32(&ln_bar[par]);
-                for (uint32_t dst = 0; dst < cl_size; ++dst)
-                    st_async_f32x2(mapa_shared(slot, dst), s1, s2, mapa_shared(bar_local, dst));
-                mbar_wait_cluster(&ln_bar[par], (uint32_t)((it >> 1) & 1));
+                const int nslot = 4 * (int)cl_size;
+                float2* my_slot = &s_stats[(par * nslot + (int)cl_rank * 4 + part) * BM + row_in_tile];
+                if (cl_size == 1) {
+                    *my_slot = make_float2(s1, s2);     // whole row in this CTA: plain shared memory + named barrier
+                    epi_bar();
+                } else {
+                    if (et == 0) mbar_arrive_expect_tx(&ln_bar[par], (uint32_t)(8 * kEpiThreads) * cl_size);
+                    const uint32_t slot = smem_u32(my_slot);
+                    const uint32_t bar_local = smem_u32(&ln_bar[par]);
+                    for (uint32_t dst = 0; dst < cl_size; ++dst)
+                        st_async_f32x2(mapa_shared(slot, dst), s1, s2, mapa_shared(bar_local, dst));
+                    mbar_wait_cluster(&ln_bar[par], (uint32_t)((it >> 1) & 1));
+                }
                 float t1 = 0.f, t2 = 0.f;
                 for (int j = 0; j < 4 * (int)cl_size; ++j) {
-                    const float2 o = s_stats[(par * 16 + j) * BM + row_in_tile];
+                    const float2 o = s_stats[(par * nslot + j) * BM + row_in_tile];
                     t1 += o.x;
                     t2 += o.y;
                 }
@@ -374,17 +390,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float mean = t1 * inv_n;
                 const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.eps);
-                const float4* gs = reinterpret_cast<const float4*>(s_gamma + c);
-                const float4* es = reinterpret_cast<const float4*>(s_beta + c);
+#pragma unroll 1
+                for (int c = part * PART; c < (part + 1) * PART; c += 16) {
+                    if (PART > 16) {
+                        uint32_t r[16];
+                        tmem_ld16(t_row + c, r);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 g = gs[i], e = es[i];
-                    v[4 * i] = (v[4 * i] - mean) * rstd * g.x + e.x;
-                    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + e.y;
-                    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + e.z;
-                    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + e.w;
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    }
+                    const float4* gs = reinterpret_cast<const float4*>(s_gamma + c);
+                    const float4* es = reinterpret_cast<const float4*>(s_beta + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 g = gs[i], e = es[i];
+                        v[4 * i] = (v[4 * i] - mean) * rstd * g.x + e.x;
+                        v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + e.y;
+                        v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + e.z;
+                        v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + e.w;
+                    }
+                    stage16(my_row, c, 0, v);
                 }
-                stage16(my_row, c, 0, v);
+                if (PART > 16) {
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                }
             } else if (EPI == EPI_GLU) {
 #pragma unroll 1
                 for (int c = part * PART; c < (part + 1) * PART; c += 16) {
@@ -584,7 +614,7 @@ static const char* launch_inst(cudaStream_t st, const CUtensorMap& ta, const CUt
         attr_set = true;
     }
     int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (EPI == EPI_RESID_LN) {
+    if (EPI == EPI_RESID_LN && p.N / BN > 1) {
         const int cl = p.N / BN;              // CTAs per cluster == n-tiles per row block
         grid = (grid / cl) * cl;              // whole clusters only (num_tiles is a multiple of cl)
         if (grid < cl) return "gemm: grid smaller than one cluster";
@@ -639,7 +669,12 @@ static const char* launch_bn(cudaStream_t st, const CUtensorMap& ta, const CUten
 
 // Pick the N tile that wastes the fewest MMA cycles across the persistent grid.
 static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
-    if (epi == EPI_RESID_LN) return 64;  // row split over a cluster of n_cols/64 CTAs
+    if (epi == EPI_RESID_LN) {
+        // A tcgen05.mma from shared memory costs ~160 cycles for any N <= 256 (profiles/r1_bench_history.md), so a
+        // 256-wide tile does the same main loop as four 64-wide ones: with enough row blocks to occupy the SMs keep
+        // the whole row in one CTA; with few row blocks (decode, M = 320) split it over a cluster of N/64 CTAs.
+        return (m_tiles >= 32) ? n_cols : 64;
+    }
     const int sms = num_sms();
     int best = 0;
     double best_cost = 1e30;

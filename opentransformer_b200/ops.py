@@ -29,8 +29,8 @@ def _count(n=1):
 class _Timed:
     """Record CUDA events around one launch on the current stream when PROFILE is enabled."""
 
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, tag=None):
+        self.kind, self.flops, self.tag = kind, flops, tag
 
     def __enter__(self):
         if PROFILE is not None and not torch.cuda.is_current_stream_capturing():
@@ -43,7 +43,7 @@ class _Timed:
     def __exit__(self, *exc):
         if self.e0 is not None:
             self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.tag))
 
 
 def _stream():
@@ -115,7 +115,7 @@ def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=No
         ldc = n_out if n_out is not None else N
         out = torch.empty(M, ldc, dtype=torch.float32 if out_f32 else BF16, device=a.device)
     ldc = out.stride(0)
-    with _Timed('gemm', 2.0 * M * w.shape[0] * K):
+    with _Timed('gemm', 2.0 * M * w.shape[0] * K, (epilogue, M, w.shape[0], K)):
         check(_lib.lib().otb_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), ldc, M, N, K, epilogue,
                                     1 if out.dtype == torch.float32 else 0, _p(resid),
                                     resid.stride(0) if resid is not None else 0, _p(gamma), _p(beta), eps, alpha,

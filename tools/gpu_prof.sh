@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-# decode: skip encoder (9 kernels) + setup (6 gemm + init) + 2 full steps (53 each), capture 1 step
-timeout 1200 ncu --set full --clock-control none --import-source on -s 122 -c 53 \
-   -o gpurun_out/prof_decode -f python tools/prof_decode.py 4 > gpurun_out/prof_decode.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/prof_decode.log; ls -la gpurun_out/*.ncu-rep
+# full capture of the dominant GEMM shapes of one encoder layer (second pass = warm code paths)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel|attn_tc_kernel" -s 9 -c 5 \
+   -o gpurun_out/prof_layer_v4 -f python tools/prof_layer.py 3 > gpurun_out/prof_layer.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/prof_layer.log
+for L in 6 8 12; do
+timeout 900 python bench.py --steps 48 --warmup 3 --lanes $L --no-cpu-baseline > gpurun_out/bench_l$L.json 2> gpurun_out/bench_l$L.err; echo "bench lanes=$L rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/bench_l$L.json'));print({k:d[k] for k in ['value','ms_per_step']}, d['e2e']['value'], d['roofline'])"; tail -3 gpurun_out/bench_l$L.err
+done
