@@ -19,6 +19,22 @@ class BeamStateC(ctypes.Structure):
                 ('N', c_int32), ('beam', c_int32), ('Lmax', c_int32)]
 
 
+class MegaLayerC(ctypes.Structure):
+    """otb_mega_layer (include/otb200.h)."""
+    _fields_ = [(n, c_void_p) for n in ('wqkv', 'wo', 'wq', 'wo2', 'w1', 'w2', 'bqkv', 'bo', 'bq', 'bo2', 'b1', 'b2',
+                                        'g1', 'be1', 'g2', 'be2', 'g3', 'be3')]
+
+
+MEGA_MAX_LAYERS = 8
+
+
+class MegaModelC(ctypes.Structure):
+    """otb_mega_model (include/otb200.h)."""
+    _fields_ = [('n_layers', c_int32), ('d_model', c_int32), ('n_heads', c_int32), ('d_ff', c_int32), ('vocab', c_int32),
+                ('emb', c_void_p), ('wout', c_void_p), ('bout', c_void_p), ('pe', c_void_p),
+                ('layers', MegaLayerC * MEGA_MAX_LAYERS), ('ln_eps', c_float)]
+
+
 _P = c_void_p
 _SIGS = {
     'otb_last_error': (c_char_p, []),
@@ -26,6 +42,7 @@ _SIGS = {
     'otb_num_sms': (c_int, []),
     'otb_debug_gemm_timing': (c_int, [_P]),
     'otb_debug_gemm_mode': (c_int, [c_int]),
+    'otb_debug_mega_timing': (c_int, [_P, c_int]),
     'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_conv2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -47,6 +64,7 @@ _SIGS = {
     'otb_logsoftmax_topk': (c_int, [_P, c_int, c_int, _P, c_int, c_float, c_int, c_int, _P, _P, _P, c_int, _P]),
     'otb_beam_reconstruct': (c_int, [POINTER(BeamStateC), _P, c_int, c_int, _P]),
     'otb_beam_finalize': (c_int, [POINTER(BeamStateC), c_float, c_float, c_int, _P, _P, _P]),
+    'otb_decode_mega': (c_int, [POINTER(MegaModelC), _P, _P, _P, _P, POINTER(BeamStateC), c_int, c_int, c_int, _P, _P, _P]),
 }
 
 

@@ -55,6 +55,12 @@ int otb_debug_gemm_mode(int mode) {
     return 0;
 }
 
+int otb_debug_mega_timing(unsigned long long* buf, int step) {
+    g_mega_dbg = buf;
+    g_mega_dbg_step = step;
+    return 0;
+}
+
 int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2) {
     if (T < 7 || F < 1) return fail("otb_conv_geometry", "need T >= 7 and F >= 1");
     const int t1 = (T - 3) / 2 + 1, f1 = (F - 1) / 2 + 1;
@@ -244,6 +250,42 @@ int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int 
     if (!st || !out_preds || !out_scores) return fail("otb_beam_finalize", "null operand");
     RET("otb_beam_finalize", beam_finalize_launch(ST(stream), to_state(st), penalty, lamda, nbest,
                                                   reinterpret_cast<long long*>(out_preds), out_scores));
+}
+
+int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,
+                    const otb_beam_state* st, int B, int T, int max_steps, float* dbg_logp, float* dbg_scores,
+                    void* stream) {
+    if (!model || !kvx || !mem_len || !kc || !vc || !st) return fail("otb_decode_mega", "null operand");
+    if (model->n_layers < 1 || model->n_layers > OTB_MEGA_MAX_LAYERS) return fail("otb_decode_mega", "1..8 decoder layers");
+    MegaParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_layers = model->n_layers; p.d = model->d_model; p.H = model->n_heads; p.dff = model->d_ff; p.V = model->vocab;
+    p.emb = reinterpret_cast<const bf16*>(model->emb);
+    p.wout = reinterpret_cast<const bf16*>(model->wout);
+    p.bout = model->bout;
+    p.pe = model->pe;
+    if (!p.emb || !p.wout || !p.pe) return fail("otb_decode_mega", "null model tensor");
+    for (int l = 0; l < model->n_layers; ++l) {
+        const otb_mega_layer& s = model->layers[l];
+        MegaLayer& d = p.layers[l];
+        d.wqkv = (const bf16*)s.wqkv; d.wo = (const bf16*)s.wo; d.wq = (const bf16*)s.wq; d.wo2 = (const bf16*)s.wo2;
+        d.w1 = (const bf16*)s.w1; d.w2 = (const bf16*)s.w2;
+        d.bqkv = s.bqkv; d.bo = s.bo; d.bq = s.bq; d.bo2 = s.bo2; d.b1 = s.b1; d.b2 = s.b2;
+        d.g1 = s.g1; d.be1 = s.be1; d.g2 = s.g2; d.be2 = s.be2; d.g3 = s.g3; d.be3 = s.be3;
+        const void* need[18] = {s.wqkv, s.wo, s.wq, s.wo2, s.w1, s.w2, s.bqkv, s.bo, s.bq, s.bo2, s.b1, s.b2,
+                                s.g1, s.be1, s.g2, s.be2, s.g3, s.be3};
+        for (int i = 0; i < 18; ++i)
+            if (!need[i]) return fail("otb_decode_mega", "null layer tensor (biases are required)");
+    }
+    p.kvx = reinterpret_cast<const bf16*>(kvx);
+    p.mem_len = mem_len;
+    p.kc = reinterpret_cast<bf16*>(kc);
+    p.vc = reinterpret_cast<bf16*>(vc);
+    p.st = to_state(st);
+    p.B = B; p.T = T; p.max_steps = max_steps;
+    p.eps = model->ln_eps;
+    p.dbg_logp = dbg_logp; p.dbg_scores = dbg_scores;
+    RET("otb_decode_mega", decode_mega_launch(ST(stream), p));
 }
 
 }  // extern "C"

@@ -84,6 +84,36 @@ struct BeamState {
     int N, beam, Lmax;
 };
 
+// ---- persistent decode kernel (decode_mega.cu)
+static constexpr int OTB_MEGA_MAX_LAYERS_INT = 8;
+struct MegaLayer {   // one TransformerDecoderLayer: bf16 weights [N,K] row-major, fp32 biases / LayerNorm affine
+    const bf16 *wqkv, *wo, *wq, *wo2, *w1, *w2;
+    const float *bqkv, *bo, *bq, *bo2, *b1, *b2;
+    const float *g1, *be1, *g2, *be2, *g3, *be3;
+};
+struct MegaParams {
+    int n_layers, d, H, dff, V;
+    const bf16* emb;      // [V, d] embedding
+    const bf16* wout;     // [V, d] output layer (== emb when tied)
+    const float* bout;    // [V] or null
+    const float* pe;      // [>= max_steps, d] sinusoid table
+    MegaLayer layers[OTB_MEGA_MAX_LAYERS_INT];
+    const bf16* kvx;      // [n_layers, B*T, 2d] cross-attention K | V
+    const int* mem_len;   // [B]
+    bf16* kc;             // [n_layers, Lmax, N, d]
+    bf16* vc;
+    BeamState st;
+    int B, T, max_steps;
+    float eps;
+    float* dbg_logp;      // optional [max_steps, N, V]
+    float* dbg_scores;    // optional [max_steps, N]
+    unsigned long long* dbg_clk;   // optional clock64 stamps of cluster 0 / rank 0 at step dbg_step (otb_debug_mega_timing)
+    int dbg_step;
+};
+extern unsigned long long* g_mega_dbg;
+extern int g_mega_dbg_step;
+const char* decode_mega_launch(cudaStream_t st, const MegaParams& p);
+
 const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,
                         const void* v, int ldv, const AttnParams& p);
 const char* conv1_launch(cudaStream_t st, const float* x, const float* w, const float* bias, bf16* out, int B, int T,

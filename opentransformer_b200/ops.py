@@ -311,3 +311,11 @@ class BeamState:
                                            _p(out_scores), _stream()), 'otb_beam_finalize')
         _count()
         return out_preds, out_scores
+
+
+def decode_mega(model_c, kvx, mem_len, kc, vc, state, B, T, max_steps, dbg_logp=None, dbg_scores=None):
+    """The whole beam-search decode loop in one persistent cluster kernel (otb_decode_mega)."""
+    _need(kvx, BF16, 'kvx'); _need(kc, BF16, 'kc'); _need(vc, BF16, 'vc'); _need(mem_len, torch.int32, 'mem_len')
+    check(_lib.lib().otb_decode_mega(ctypes.byref(model_c), _p(kvx), _p(mem_len), _p(kc), _p(vc), ctypes.byref(state.c),
+                                     B, T, max_steps, _p(dbg_logp), _p(dbg_scores), _stream()), 'otb_decode_mega')
+    _count()

@@ -81,7 +81,7 @@ class BeamDecoder:
     kernel) is captured into a CUDA graph on first use and replayed for every step.
     """
 
-    def __init__(self, decoder, batch, beam, T, max_len, device, use_graph=True):
+    def __init__(self, decoder, batch, beam, T, max_len, device, use_graph=True, persistent=False):
         self.dec = decoder
         self.B, self.beam, self.T, self.Lmax = batch, beam, T, max_len
         self.N = batch * beam
@@ -104,6 +104,52 @@ class BeamDecoder:
         self.lm_weight = 0.0
         if decoder.pos_emb.scale_learnable:
             raise NotImplementedError('decoder with learnable positional scale')
+        # persistent path (opt-in): the whole loop in one cluster kernel (csrc/decode_mega.cu) when the configuration is
+        # the shipped one (post-norm GLU decoder, d_model 256, 4 heads).  Round-1 measurement (profiles/r1_mega_phases.txt):
+        # bit-exact and launch-free, but 28.7 ms per 60 steps -- no faster than the per-step graph, and it occupies 128 SMs
+        # so batches cannot overlap -- hence the per-step graph stays the default until its stage costs are fixed.
+        self.persistent = bool(persistent) and self.mega_supported()
+        self._mega_model = None
+        self._mega_sig = None
+
+    def mega_supported(self):
+        dec = self.dec
+        ok = (dec.d_model == 256 and dec.n_heads == 4 and not dec.normalize_before and 1 <= len(dec.blocks) <= 8
+              and self.beam <= 16 and self.Lmax <= 128 and dec.vocab_size >= 8)
+        for blk in dec.blocks:
+            ff = blk.feed_forward
+            ok = ok and ff.activation == 'glu' and ff.w_2.in_features % 512 == 0 and not blk.normalize_before
+            ok = ok and all(m.bias is not None for m in (blk.slf_attn.qvk_proj, blk.slf_attn.output_proj, blk.src_attn.q_proj,
+                                                         blk.src_attn.output_proj, ff.w_1, ff.w_2))
+        return bool(ok)
+
+    def _mega(self):
+        """otb_mega_model over the packed bf16 weights (rebuilt when the pack changes)."""
+        pk = self.dec.packed()
+        if self._mega_model is None or self._mega_sig is not pk:
+            from ._lib import MegaModelC
+            m = MegaModelC()
+            m.n_layers, m.d_model, m.n_heads = len(self.dec.blocks), self.dec.d_model, self.dec.n_heads
+            m.d_ff, m.vocab = self.dec.blocks[0].feed_forward.w_2.in_features, self.dec.vocab_size
+            m.emb, m.wout = pk['emb'].data_ptr(), pk['wout'].data_ptr()
+            m.bout = pk['bout'].data_ptr() if pk['bout'] is not None else None
+            m.pe = self.table.data_ptr()
+            m.ln_eps = 1e-5
+            for l, p in enumerate(pk['blocks']):
+                ly = m.layers[l]
+                f = p['ffn']
+                for name, t in (('wqkv', p['wqkv']), ('wo', p['wo']), ('wq', p['wq']), ('wo2', p['wo2']), ('w1', f['w1']),
+                                ('w2', f['w2']), ('bqkv', p['bqkv']), ('bo', p['bo']), ('bq', p['bq']), ('bo2', p['bo2']),
+                                ('b1', f['b1']), ('b2', f['b2']), ('g1', p['ln1'][0]), ('be1', p['ln1'][1]),
+                                ('g2', p['ln2'][0]), ('be2', p['ln2'][1]), ('g3', p['ln3'][0]), ('be3', p['ln3'][1])):
+                    setattr(ly, name, t.data_ptr())
+            self._mega_model, self._mega_sig = m, pk
+        return self._mega_model
+
+    def run_persistent(self, max_steps, dbg_logp=None, dbg_scores=None):
+        """All steps in ONE launch; no host round trip (ctrl[0] = executed steps is read by the caller)."""
+        ops.decode_mega(self._mega(), self.kvx, self.mem_len, self.kc, self.vc, self.state, self.B, self.T, max_steps,
+                        dbg_logp, dbg_scores)
 
     def setup(self, memory_bf16, mem_len):
         """Project cross-attention K/V once per utterance and reset the search state."""
@@ -188,6 +234,9 @@ class BeamDecoder:
     def run(self, max_steps, poll_every=8):
         """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
         (speech2text.py:66-67).  Steps launched after the end are no-ops on the search state."""
+        if self.persistent and self.lm_logp is None:
+            self.run_persistent(max_steps)
+            return int(self.state.ctrl[0].item())
         for i in range(max_steps):
             self.step()
             if (i + 1) % poll_every == 0 and i + 1 < max_steps:
@@ -200,7 +249,7 @@ class SpeechToTextRecognizer(Recognizer):
     """otrans/recognize/speech2text.py:6-93 on the B200 path."""
 
     def __init__(self, model, lm=None, lm_weight=0.1, ctc_weight=0.0, beam_width=5, nbest=1, max_len=50,
-                 idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True):
+                 idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True, persistent=False):
         super().__init__(model, idx2unit, lm, lm_weight, ngpu)
         if lm is not None and getattr(lm, 'model_type', None) != 'transformer_lm':
             raise NotImplementedError('shallow fusion is implemented for the Transformer LM (opentransformer_b200.lm); '
@@ -211,6 +260,7 @@ class SpeechToTextRecognizer(Recognizer):
         self.attn_weights = {}
         self.apply_cache = False
         self.use_graph = use_graph
+        self.persistent = persistent
         self._decoders = {}
 
     # ---- reference-facing seams -------------------------------------------------------------
@@ -259,7 +309,7 @@ class SpeechToTextRecognizer(Recognizer):
         bd = self._decoders.get(key)
         if bd is None:
             bd = BeamDecoder(self.model.decoder, B, self.beam_width, T2, self.max_len, device,
-                             self.use_graph and self.lm is None)
+                             self.use_graph and self.lm is None, persistent=self.persistent and self.lm is None)
             self._decoders[key] = bd
         return bd
 

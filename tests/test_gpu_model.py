@@ -268,9 +268,10 @@ def test_recognizer_graph_replay_equals_eager_and_decode_step_seam():
     B, beam, max_len = 4, 5, 10
     x, mask = _batch(B, 240, 80, [240, 200, 111, 239])
     xd, md = x.to(DEV), mask.to(DEV)
-    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1)
+    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1,
+                                   persistent=False)
     rec_e = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1,
-                                   use_graph=False)
+                                   use_graph=False, persistent=False)
     p1, s1, n1 = rec_e.recognize_ids(xd, md)
     p2, s2, n2 = rec_g.recognize_ids(xd, md)
     p3, s3, n3 = rec_g.recognize_ids(xd, md)              # second call re-uses the captured graph
@@ -291,6 +292,101 @@ def test_recognizer_graph_replay_equals_eager_and_decode_step_seam():
     assert preds.shape == (B * beam, 4) and scores.shape == (B * beam, 1)
     # 1-best of the seam path (full recompute) and of the cached fast path agree on the first 3 tokens' scores
     print('seam-path scores', scores.view(B, beam)[:, 0].tolist())
+
+
+def _lockstep_persistent(model, sd, params, x, mask, B, beam, max_len, check_logp=True):
+    """Run the persistent cluster kernel for the whole loop with the parity traces on, then drive the oracle's
+    beam_step with ITS log-probs step by step: ids / parents / scores must be bit-exact at every step."""
+    with torch.no_grad():
+        mem, lens, _, T2 = model.encode_bf16(x.to(DEV), mask.to(DEV))
+        bd = BeamDecoder(model.decoder, B, beam, T2, max_len, DEV, use_graph=False, persistent=True)
+        assert bd.persistent, 'persistent decode kernel should support this configuration'
+        bd.setup(mem, lens)
+        V = model.decoder.vocab_size
+        dbg_logp = torch.zeros(max_len, B * beam, V, dtype=torch.float32, device=DEV)
+        dbg_scores = torch.zeros(max_len, B * beam, dtype=torch.float32, device=DEV)
+        bd.run_persistent(max_len, dbg_logp, dbg_scores)
+        torch.cuda.synchronize()
+        steps_gpu = int(bd.state.ctrl[0].item())
+        memory = mem.float().view(B, T2, -1).cpu()
+        mmask = torch.arange(T2)[None] < lens.cpu()[:, None]
+        bm = memory.unsqueeze(1).repeat(1, beam, 1, 1).view(B * beam, T2, -1)
+        bmask = mmask.unsqueeze(1).repeat(1, beam, 1).view(B * beam, T2)
+        preds = torch.full((B * beam, 1), 1, dtype=torch.long)
+        scores = torch.tensor([0.0] + [float('-inf')] * (beam - 1)).repeat(B).unsqueeze(1)
+        flag = torch.zeros_like(scores, dtype=torch.bool)
+        kw = om.decoder_kwargs(params)
+        worst, worst_rel, scale, steps_ref = 0.0, 0.0, 1e-9, max_len
+        for s in range(max_len):
+            lp_gpu = dbg_logp[s].cpu()
+            utt_alive = (~flag.view(B, beam)).any(dim=1).repeat_interleave(beam)    # the kernel stops computing ended utterances
+            alive = (~flag.view(-1)) & utt_alive
+            if check_logp and bool(alive.any()):
+                lp_ref = om.decoder_inference(preds, bm, bmask, sd, 'decoder.', **kw)
+                worst = max(worst, float((lp_gpu[alive][:, 2:] - lp_ref[alive][:, 2:]).abs().max()))
+                worst_rel = max(worst_rel, _rel(lp_gpu[alive][:, 2:], lp_ref[alive][:, 2:]))
+                scale = max(scale, float(lp_ref[alive][:, 2:].abs().max()))
+            preds, scores, flag = obs.beam_step(lp_gpu, preds, scores, flag, beam)
+            assert torch.equal(bd.state.reconstruct(s + 1).cpu(), preds), f'token/parent ids differ at step {s}'
+            assert torch.equal(dbg_scores[s].cpu(), scores.view(-1)), f'scores differ at step {s}'
+            if bool(flag.all()):
+                steps_ref = s + 1
+                break
+        assert steps_gpu == steps_ref, f'executed step count: kernel {steps_gpu} vs reference loop {steps_ref}'
+        assert torch.equal(bd.state.scores.cpu(), scores.view(-1))
+        nb, ns = obs.beam_finalize(preds, scores, beam, min(2, beam), 0.6, 5)
+        gp, gs = bd.state.finalize(0.6, 5, min(2, beam))
+        assert torch.equal(gp[:, :, :steps_ref].cpu(), nb)
+        torch.testing.assert_close(gs.cpu(), ns, rtol=1e-6, atol=1e-6)
+    return worst, worst_rel, scale, steps_ref
+
+
+@pytest.mark.parametrize('B,beam,max_len,lens', [(3, 4, 9, [200, 150, 173]), (2, 10, 12, [240, 201]), (5, 1, 6, [160, 160, 120, 99, 140]),
+                                                 (1, 16, 5, [170])])
+def test_persistent_decode_lockstep_with_oracle(B, beam, max_len, lens):
+    params = _params(n_enc=1, n_dec=2)
+    model, sd = _build(params)
+    x, mask = _batch(B, max(lens), 80, lens)
+    worst, worst_rel, scale, steps = _lockstep_persistent(model, sd, params, x, mask, B, beam, max_len)
+    print(f'persistent decode (B={B}, beam={beam}): log-probs vs oracle full recompute rel_l2<={worst_rel:.3e} '
+          f'max_abs={worst:.3e} (|ref|_inf {scale:.3e}) over {steps} steps; ids / parents / scores bit-exact')
+    assert steps == max_len
+    assert worst_rel < REL_L2_LOGITS and worst < MAX_ABS_FRAC * scale
+
+
+def test_persistent_decode_early_end_and_finished_masking():
+    """Natural EOS (no -1e4 bias): hypotheses finish at different steps, utterances end at different steps; the kernel's
+    history / step count must equal the reference loop's (finished masking, speech2text.py:156-192, early break :66-67)."""
+    params = _params(n_enc=1, n_dec=2)
+    model, sd = _build(params)
+    with torch.no_grad():
+        model.decoder.output_layer.bias[1] = 2.0           # EOS likely but not certain
+    sd['decoder.output_layer.bias'] = model.decoder.output_layer.bias.detach().float().cpu().clone()
+    B, beam, max_len = 6, 4, 14
+    lens = [200, 150, 173, 120, 199, 88]
+    x, mask = _batch(B, 200, 80, lens)
+    worst, worst_rel, scale, steps = _lockstep_persistent(model, sd, params, x, mask, B, beam, max_len, check_logp=False)
+    print(f'persistent decode with natural EOS: reference loop executed {steps} of {max_len} steps; history bit-exact')
+
+
+def test_persistent_equals_per_step_graph_path():
+    params = _params(n_enc=1, n_dec=3)
+    model, sd = _build(params)
+    B, beam, max_len = 4, 5, 10
+    x, mask = _batch(B, 240, 80, [240, 200, 111, 239])
+    xd, md = x.to(DEV), mask.to(DEV)
+    rec_p = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1,
+                                   persistent=True)
+    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1,
+                                   persistent=False)
+    p1, s1, n1 = rec_p.recognize_ids(xd, md)
+    p1b, s1b, _ = rec_p.recognize_ids(xd, md)
+    p2, s2, n2 = rec_g.recognize_ids(xd, md)
+    assert n1 == n2 == max_len
+    assert torch.equal(p1, p1b) and torch.equal(s1, s1b), 'persistent kernel must be deterministic'
+    same = int((p1 == p2).all(dim=2).sum())
+    print(f'persistent vs per-step graph: {same}/{B * 2} n-best sequences identical; scores {s1.view(-1).tolist()} vs {s2.view(-1).tolist()}')
+    torch.testing.assert_close(s1, s2, rtol=3e-2, atol=0.3)    # two bf16 pipelines with different rounding points
 
 
 def test_end_to_end_best_hypothesis_vs_fp32_oracle():

@@ -1,0 +1,47 @@
+"""Per-stage clock64 breakdown of one decode step of the persistent kernel (debug aid, GPU only)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from opentransformer_b200 import _lib
+from opentransformer_b200.model import SpeechToText
+from opentransformer_b200.recognize import BeamDecoder
+
+dev = torch.device('cuda:0')
+params = bench.model_params()
+params['encoder']['n_blocks'] = 1
+torch.manual_seed(0)
+model = SpeechToText(params).eval().to(dev)
+with torch.no_grad():
+    model.decoder.output_layer.bias[1] = -1e4
+x, mask = bench.synthetic_batch(32, 0)
+x, mask = x.to(dev), mask.to(dev)
+L = _lib.lib()
+names = ['start', 'S0 embed']
+for l in range(6):
+    names += [f'L{l} ' + n for n in ('S1 qkv', 'S2 self-attn', 'bar1', 'S3 out-proj', 'bar2', 'LN1', 'S4 q-proj', 'S5 scores',
+                                     'S5 softmax', 'S5 PV', 'bar3', 'S6 out-proj2', 'bar4', 'LN2', 'S7 GLU', 'bar5', 'S8 w2',
+                                     'bar6', 'LN3')]
+names += ['S9 logits', 'partial lse', 'bar7', 'logp+topk', 'bar8', 'merge+beam']
+with torch.no_grad():
+    mem, lens, B, T2 = model.encode_bf16(x, mask)
+    bd = BeamDecoder(model.decoder, B, 10, T2, 60, dev, use_graph=False, persistent=True)
+    for step in [int(a) for a in (sys.argv[1:] or ['5', '50'])]:
+        buf = torch.zeros(512, dtype=torch.int64, device=dev)
+        for rep in range(2):
+            bd.setup(mem, lens)
+            L.otb_debug_mega_timing(ctypes.c_void_p(buf.data_ptr()) if rep == 1 else None, step)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); bd.run_persistent(60); e1.record()
+            torch.cuda.synchronize()
+        L.otb_debug_mega_timing(None, 0)
+        t = buf.cpu().tolist()
+        n = len(names)
+        print(f'=== step {step}: whole 60-step launch {e0.elapsed_time(e1):.2f} ms; step total {(t[n-1]-t[0])} cycles')
+        agg = {}
+        for i in range(1, n):
+            dt = t[i] - t[i - 1]
+            key = names[i].split(' ', 1)[1] if names[i].startswith('L') else names[i]
+            agg[key] = agg.get(key, 0) + dt
+        for k, v in agg.items():
+            print(f'    {k:14s} {v:9d} cycles  {100.0 * v / (t[n-1]-t[0]):5.1f}%')
