@@ -194,6 +194,46 @@ int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t*
                     const otb_beam_state* st, int B, int T, int max_steps, float* dbg_logp, float* dbg_scores,
                     void* stream);
 
+/* ---- Training step (SpeechToText.forward + loss.backward() + clip + Adam, model/speech2text.py:39-64,
+ * train/trainer.py:206-234).  The reference differentiates through torch autograd; the entry points below are the
+ * hand-written backward of each forward op above.  bf16 activations / gradients, fp32 parameter gradients. */
+
+/* otb_attention that also stores the per-row log-sum-exp (log2 units) [B,H,Tq] the backward needs. */
+int otb_attention_lse(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                      void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
+                      int k_col0, int v_col0, const float* bd, int ldbd, const void* resid, int ldr, float* lse,
+                      void* stream);
+/* Backward of otb_attention (no bd / resid): dq, dk, dv written at column offsets d*_col0 + 64*h of their matrices
+ * (e.g. the three thirds of one [M,3d] dqkv buffer).  dsum f32 [B,H,Tq] is scratch.  tcgen05, scores recomputed. */
+int otb_attention_bwd(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                      const void* out, int ldo, const void* dout, int lddo, const float* lse, float* dsum, void* dq,
+                      int lddq, int dq_col0, void* dk, int lddk, int dk_col0, void* dv, int lddv, int dv_col0, int B, int H,
+                      int Tq, int Tk, const int* kv_len, int causal, int q_col0, int k_col0, int v_col0, void* stream);
+/* nn.Linear weight gradient dW[N,K] (fp32) = dy[M,N]^T x[M,K] (bf16), tcgen05 with MN-major operands + split-K.
+ * (The input gradient dx = dy W is otb_linear with the transposed weight.) */
+int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, void* stream);
+/* nn.Linear bias gradient: out[n] = sum_m x[m,n]. */
+int otb_colsum(const void* x, int ldx, float* out, int M, int N, void* stream);
+/* nn.LayerNorm backward (N <= 256): dz, dgamma, dbeta from dy and the pre-norm input z. */
+int otb_layernorm_bwd(const void* dy, int lddy, const void* z, int ldz, const float* gamma, void* dz, int lddz,
+                      float* dgamma, float* dbeta, float eps, int M, int N, void* stream);
+/* F.glu (ffn.py:18) un-fused for training: u = [a | g] bf16 [M,2F] -> h [M,F]; and its backward. */
+int otb_glu_fwd(const void* u, void* h, int M, int F, void* stream);
+int otb_glu_bwd(const void* dh, const void* u, void* du, int M, int F, void* stream);
+/* ReLU backward through the output (frontend/conv.py:64). */
+int otb_relu_bwd(const void* dy, const void* y, void* dx, long long n, void* stream);
+/* nn.Embedding backward: dE[tok[n]] += scale * dx[n]  (fp32 atomics). */
+int otb_embed_bwd(const int64_t* tok, const void* dx, float* dE, int N, int d, int vocab, float scale, void* stream);
+/* otb_ls_ce that also writes d(mean loss)/dlogits as bf16 [rows, ldd] (zero-padded columns) for the backward GEMMs. */
+int otb_ls_ce_train(const float* logits, int ldl, const int64_t* targets, int rows, int V, float smoothing, int pad_id,
+                    float* tok_loss, float* loss, int32_t* n_valid, void* dlogits_bf16, int ldd, void* stream);
+/* out (+)= sum g^2 over a flat fp32 buffer (global gradient norm, trainer.py:221). */
+int otb_sumsq(const float* g, long long n, float* out, int zero_first, void* stream);
+/* clip_grad_norm_(max_norm) + torch.optim.Adam step on flat fp32 buffers; a non-finite norm skips the update
+ * (trainer.py:229-230).  `sumsq` is the device scalar written by otb_sumsq; `step` is the 1-based update count. */
+int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

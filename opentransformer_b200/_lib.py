@@ -64,6 +64,20 @@ _SIGS = {
     'otb_logsoftmax_topk': (c_int, [_P, c_int, c_int, _P, c_int, c_float, c_int, c_int, _P, _P, _P, c_int, _P]),
     'otb_beam_reconstruct': (c_int, [POINTER(BeamStateC), _P, c_int, c_int, _P]),
     'otb_beam_finalize': (c_int, [POINTER(BeamStateC), c_float, c_float, c_int, _P, _P, _P]),
+    'otb_attention_lse': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int,
+                                  _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P]),
+    'otb_attention_bwd': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
+                                  _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    'otb_linear_wgrad': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    'otb_colsum': (c_int, [_P, c_int, _P, c_int, c_int, _P]),
+    'otb_layernorm_bwd': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, _P, c_float, c_int, c_int, _P]),
+    'otb_glu_fwd': (c_int, [_P, _P, c_int, c_int, _P]),
+    'otb_glu_bwd': (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    'otb_relu_bwd': (c_int, [_P, _P, _P, c_int64, _P]),
+    'otb_embed_bwd': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    'otb_ls_ce_train': (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_int, _P]),
+    'otb_sumsq': (c_int, [_P, c_int64, _P, c_int, _P]),
+    'otb_adam_step': (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, _P]),
     'otb_decode_mega': (c_int, [POINTER(MegaModelC), _P, _P, _P, _P, POINTER(BeamStateC), c_int, c_int, c_int, _P, _P, _P]),
 }
 

@@ -213,6 +213,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 
     if (qi < p.Tq) {
+        if (p.lse) p.lse[((size_t)b * p.H + h) * p.Tq + qi] = (l_run > 0.f) ? m_run + log2f(l_run) : INFINITY;
         const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
         bf16* o = p.out + (size_t)(b * p.Tq + qi) * p.ldo + h * 64;
         if (p.resid) {

@@ -142,6 +142,14 @@ int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias
 int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
                   void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
                   int k_col0, int v_col0, const float* bd, int ldbd, const void* resid, int ldr, void* stream) {
+    return otb_attention_lse(q, ldq, q_rows, k, ldk, k_rows, v, ldv, out, ldo, B, H, Tq, Tk, kv_len, causal, q_col0, k_col0,
+                             v_col0, bd, ldbd, resid, ldr, nullptr, stream);
+}
+
+int otb_attention_lse(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                      void* out, int ldo, int B, int H, int Tq, int Tk, const int* kv_len, int causal, int q_col0,
+                      int k_col0, int v_col0, const float* bd, int ldbd, const void* resid, int ldr, float* lse,
+                      void* stream) {
     if (!q || !k || !v || !out) return fail("otb_attention", "null operand");
     if (q_col0 % 8 || k_col0 % 8 || v_col0 % 8 || ldo % 8) return fail("otb_attention", "column offsets / ldo must be multiples of 8");
     AttnParams p;
@@ -152,6 +160,7 @@ int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, in
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.bd = bd; p.ldbd = ldbd;
     p.resid = reinterpret_cast<const bf16*>(resid); p.ldr = ldr;
+    p.lse = lse;
     if (resid && (ldr % 8)) return fail("otb_attention", "ldr must be a multiple of 8");
     RET("otb_attention", attn_launch(ST(stream), q, ldq, q_rows, k, ldk, k_rows, v, ldv, p));
 }
@@ -286,6 +295,87 @@ int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t*
     p.eps = model->ln_eps;
     p.dbg_logp = dbg_logp; p.dbg_scores = dbg_scores;
     RET("otb_decode_mega", decode_mega_launch(ST(stream), p));
+}
+
+int otb_attention_bwd(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
+                      const void* out, int ldo, const void* dout, int lddo, const float* lse, float* dsum, void* dq,
+                      int lddq, int dq_col0, void* dk, int lddk, int dk_col0, void* dv, int lddv, int dv_col0, int B, int H,
+                      int Tq, int Tk, const int* kv_len, int causal, int q_col0, int k_col0, int v_col0, void* stream) {
+    if (!q || !k || !v || !out || !dout || !lse || !dsum || !dq || !dk || !dv) return fail("otb_attention_bwd", "null operand");
+    if ((q_col0 | k_col0 | v_col0 | dq_col0 | dk_col0 | dv_col0 | ldo | lddo | lddq | lddk | lddv) % 8)
+        return fail("otb_attention_bwd", "column offsets / leading dimensions must be multiples of 8");
+    AttnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.kv_len = kv_len; p.causal = causal;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.o = reinterpret_cast<const bf16*>(out); p.ldo = ldo;
+    p.dout = reinterpret_cast<const bf16*>(dout); p.lddo = lddo;
+    p.lse = lse; p.dsum = dsum;
+    p.dq = reinterpret_cast<bf16*>(dq); p.lddq = lddq; p.dq_col0 = dq_col0;
+    p.dk = reinterpret_cast<bf16*>(dk); p.lddk = lddk; p.dk_col0 = dk_col0;
+    p.dv = reinterpret_cast<bf16*>(dv); p.lddv = lddv; p.dv_col0 = dv_col0;
+    RET("otb_attention_bwd", attn_bwd_launch(ST(stream), q, ldq, q_rows, k, ldk, k_rows, v, ldv, p));
+}
+
+int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, void* stream) {
+    if (!dy || !x || !dw) return fail("otb_linear_wgrad", "null operand");
+    RET("otb_linear_wgrad", gemm_wgrad_launch(ST(stream), dy, lddy, x, ldx, dw, lddw, M, N, K));
+}
+
+int otb_colsum(const void* x, int ldx, float* out, int M, int N, void* stream) {
+    if (!x || !out || M < 1 || N < 1) return fail("otb_colsum", "bad arguments");
+    RET("otb_colsum", colsum_launch(ST(stream), reinterpret_cast<const bf16*>(x), ldx, out, M, N));
+}
+
+int otb_layernorm_bwd(const void* dy, int lddy, const void* z, int ldz, const float* gamma, void* dz, int lddz,
+                      float* dgamma, float* dbeta, float eps, int M, int N, void* stream) {
+    if (!dy || !z || !gamma || !dz || !dgamma || !dbeta) return fail("otb_layernorm_bwd", "null operand");
+    RET("otb_layernorm_bwd", layernorm_bwd_launch(ST(stream), reinterpret_cast<const bf16*>(dy), lddy,
+                                                  reinterpret_cast<const bf16*>(z), ldz, gamma, reinterpret_cast<bf16*>(dz),
+                                                  lddz, dgamma, dbeta, eps, M, N));
+}
+
+int otb_glu_fwd(const void* u, void* h, int M, int F, void* stream) {
+    if (!u || !h || M < 1 || F < 8) return fail("otb_glu_fwd", "bad arguments");
+    RET("otb_glu_fwd", glu_launch(ST(stream), reinterpret_cast<const bf16*>(u), nullptr, reinterpret_cast<bf16*>(h), M, F));
+}
+
+int otb_glu_bwd(const void* dh, const void* u, void* du, int M, int F, void* stream) {
+    if (!dh || !u || !du || M < 1 || F < 8) return fail("otb_glu_bwd", "bad arguments");
+    RET("otb_glu_bwd", glu_launch(ST(stream), reinterpret_cast<const bf16*>(u), reinterpret_cast<const bf16*>(dh),
+                                  reinterpret_cast<bf16*>(du), M, F));
+}
+
+int otb_relu_bwd(const void* dy, const void* y, void* dx, long long n, void* stream) {
+    if (!dy || !y || !dx || n < 8) return fail("otb_relu_bwd", "bad arguments");
+    RET("otb_relu_bwd", relu_bwd_launch(ST(stream), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(y),
+                                        reinterpret_cast<bf16*>(dx), (size_t)n));
+}
+
+int otb_embed_bwd(const int64_t* tok, const void* dx, float* dE, int N, int d, int vocab, float scale, void* stream) {
+    if (!tok || !dx || !dE || N < 1) return fail("otb_embed_bwd", "bad arguments");
+    RET("otb_embed_bwd", embed_bwd_launch(ST(stream), reinterpret_cast<const long long*>(tok), reinterpret_cast<const bf16*>(dx),
+                                          dE, N, d, vocab, scale));
+}
+
+int otb_ls_ce_train(const float* logits, int ldl, const int64_t* targets, int rows, int V, float smoothing, int pad_id,
+                    float* tok_loss, float* loss, int32_t* n_valid, void* dlogits_bf16, int ldd, void* stream) {
+    if (!logits || !targets || !tok_loss || !loss || !n_valid || !dlogits_bf16) return fail("otb_ls_ce_train", "null operand");
+    if (ldd < V || ldd % 8) return fail("otb_ls_ce_train", "ldd must be >= V and a multiple of 8");
+    RET("otb_ls_ce_train", ls_ce_launch(ST(stream), logits, ldl, reinterpret_cast<const long long*>(targets), rows, V, smoothing,
+                                        pad_id, tok_loss, loss, n_valid, nullptr, ldd, reinterpret_cast<bf16*>(dlogits_bf16)));
+}
+
+int otb_sumsq(const float* g, long long n, float* out, int zero_first, void* stream) {
+    if (!g || !out || n < 1) return fail("otb_sumsq", "bad arguments");
+    RET("otb_sumsq", sumsq_launch(ST(stream), g, (size_t)n, out, zero_first));
+}
+
+int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+    if (!p || !g || !m || !v || !sumsq || n < 1) return fail("otb_adam_step", "bad arguments");
+    RET("otb_adam_step", adam_launch(ST(stream), p, g, m, v, (size_t)n, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step));
 }
 
 }  // extern "C"

@@ -78,7 +78,10 @@ __device__ __forceinline__ void stage16(uint8_t* row_ptr, int col, int out_f32, 
     }
 }
 
-template <int BN, int EPI>
+// TN = true: weight-gradient mode, C[M,N] = A^T B with A = dY [K rows, M cols] and B = X [K rows, N cols], both row-major,
+// i.e. both operands are MN-major in shared memory (64x64 TMA boxes, LBO = 8 KB between 64-wide MN groups, SBO = 1 KB
+// between 8-row K groups).  p.splitk > 1 splits the contraction over `splitk` tiles that accumulate with fp32 atomics.
+template <int BN, int EPI, bool TN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -112,15 +115,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int m_tiles = p.conv ? (p.conv_B * p.conv_T1h + p.conv_R - 1) / p.conv_R : (p.M + BM - 1) / BM;
     const int n_tiles = (p.N + BN_OUT - 1) / BN_OUT;
-    const int num_tiles = m_tiles * n_tiles;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int splitk = TN ? max(p.splitk, 1) : 1;
+    const int num_tiles = m_tiles * n_tiles * splitk;
+    const int num_kb_all = (p.K + BK - 1) / BK;
+    // k-blocks of split ks: [ks*num_kb_all/splitk, (ks+1)*num_kb_all/splitk); without split-K: all of them
+    auto kb_begin = [&](int tile) { return TN ? (int)(((long long)(tile % splitk) * num_kb_all) / splitk) : 0; };
+    auto kb_end = [&](int tile) { return TN ? (int)(((long long)(tile % splitk + 1) * num_kb_all) / splitk) : num_kb_all; };
     const uint32_t a_tx = p.conv ? (uint32_t)(p.conv_R * p.conv_F2 * BK * 2) : (uint32_t)Cfg::A_BYTES;
 
     // One k-block load of the flat (tile, kb) sequence this CTA walks through.
     auto issue_load = [&](int tile, int kb, int stage) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int mn = TN ? tile / splitk : tile;
+        const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
+        if (TN) {
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES));
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+            return;
+        }
         if (p.dbg_mode == 1) {  // profiling aid: signal "full" without moving any data
             mbar_arrive(&full_bar[stage]);
             return;
@@ -145,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
 
     // Producer state (meaningful in warp 0 lane 0 only): next load = (p_tile, p_kb) into p_stage.
-    int p_tile = blockIdx.x, p_kb = 0, p_stage = 0;
+    int p_tile = blockIdx.x, p_kb = kb_begin(blockIdx.x), p_stage = 0;
     uint32_t p_phase = 0;
     if (warp == 0) {
         if (lane == 0) {
@@ -168,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 issue_load(p_tile, p_kb, p_stage);
                 if (i == 0) DBG_STAMP(2);
                 if (p_tile == (int)blockIdx.x) DBG_KB(0, p_kb);
-                if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
+                if (++p_kb >= kb_end(p_tile)) { p_tile += gridDim.x; p_kb = kb_begin(p_tile); }
                 if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
             }
         }
@@ -189,14 +205,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
                 issue_load(p_tile, p_kb, p_stage);
                 if (p_tile == (int)blockIdx.x) DBG_KB(0, p_kb);
-                if (++p_kb == num_kb) { p_kb = 0; p_tile += gridDim.x; }
+                if (++p_kb >= kb_end(p_tile)) { p_tile += gridDim.x; p_kb = kb_begin(p_tile); }
                 if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (lane 0)
-        constexpr uint32_t idesc = umma_idesc_bf16(BN);
+        constexpr uint32_t idesc = umma_idesc_bf16(BN, TN, 128, TN);
         if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
@@ -207,18 +223,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tempty_bar[as], aph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int kb0 = kb_begin(tile), kb1 = kb_end(tile);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (it == 0 && kb == 0) DBG_STAMP(3);
+                if (it == 0 && kb == kb0) DBG_STAMP(3);
                 if (it == 0) DBG_KB(1, kb);
                 const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
                 if (p.dbg_mode != 2) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                  (uint32_t)((kb | k) != 0));
+                        if (TN)   // MN-major operands: one k16 step = 16 rows of 128 B
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 2048, 1024, 8192),
+                                      umma_desc_sw128(b_addr + k * 2048, 1024, 8192), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+                        else
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (uint32_t)((kb | k) != 0));
                     }
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -252,7 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int mn_ = TN ? tile / splitk : tile;
+            const int m_blk = mn_ / n_tiles, n_blk = mn_ % n_tiles;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int col_base = n_blk * BN_OUT;             // first output column of the tile
@@ -514,7 +536,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int q = q0 + j * kEpiThreads;
-                        if (orow[j] >= 0) *reinterpret_cast<uint4*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16) = tmp[j];
+                        if (orow[j] < 0) continue;
+                        if (TN && splitk > 1) {   // partial sums of the split contraction meet in the (pre-zeroed) fp32 output
+                            float* dst = reinterpret_cast<float*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16);
+                            atomicAdd(dst, __uint_as_float(tmp[j].x));
+                            atomicAdd(dst + 1, __uint_as_float(tmp[j].y));
+                            atomicAdd(dst + 2, __uint_as_float(tmp[j].z));
+                            atomicAdd(dst + 3, __uint_as_float(tmp[j].w));
+                        } else {
+                            *reinterpret_cast<uint4*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16) = tmp[j];
+                        }
                     }
                 }
             } else {
@@ -730,6 +761,59 @@ const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, 
         case 64: return launch_bn<64>(st, ta, tb, p, epi, num_tiles);
     }
     return "gemm: bad tile";
+}
+
+// Weight gradient dW[Nw, Kw] (fp32) = dY[Mact, Nw]^T X[Mact, Kw]  (both bf16 row-major): TN mode of the kernel above.
+// The contraction (Mact rows, thousands) is split over enough tiles to fill the SMs; splits meet through fp32 atomics,
+// so `out` must be zero on entry when the returned split count is > 1 (the launcher zeroes it with a memset node).
+const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const void* X, int ldx, float* out, int ldc,
+                              int Mact, int Nw, int Kw) {
+    if (Mact <= 0 || Nw <= 0 || Kw <= 0) return "wgrad: empty problem";
+    if ((lddy % 8) || (ldx % 8) || (ldc % 4) || (reinterpret_cast<uintptr_t>(out) & 15)) return "wgrad: operands must be 16-byte aligned (ld % 8 bf16, ldc % 4 f32)";
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = Nw; p.N = Kw; p.K = Mact;
+    p.out = out; p.ldc = ldc; p.out_f32 = 1; p.alpha = 1.f;
+    p.dbg = nullptr; p.dbg_mode = 0;
+    const int bn = (Kw > 64) ? 128 : 64;
+    const int m_tiles = (Nw + BM - 1) / BM, n_tiles = (Kw + bn - 1) / bn;
+    const int num_kb = (Mact + BK - 1) / BK;
+    int splitk = num_sms() / (m_tiles * n_tiles);
+    if (splitk > num_kb / 4) splitk = num_kb / 4;      // at least 4 k-blocks per split
+    if (splitk < 1) splitk = 1;
+    p.splitk = splitk;
+    if (splitk > 1) {
+        cudaError_t e = cudaMemset2DAsync(out, (size_t)ldc * 4, 0, (size_t)Kw * 4, (size_t)Nw, st);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+    }
+    CUtensorMap ta, tb;
+    const char* err;
+    if ((err = encode_tmap_2d(&ta, dY, (uint64_t)Nw, (uint64_t)Mact, (uint64_t)lddy, 64, 64))) return err;
+    if ((err = encode_tmap_2d(&tb, X, (uint64_t)Kw, (uint64_t)Mact, (uint64_t)ldx, 64, 64))) return err;
+    const int num_tiles = m_tiles * n_tiles * splitk;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    cudaError_t e;
+    if (bn == 128) {
+        using Cfg = GemmCfg<128>;
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(gemm_tc_kernel<128, EPI_BIAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+                return "cudaFuncSetAttribute(wgrad) failed";
+            attr = true;
+        }
+        gemm_tc_kernel<128, EPI_BIAS, true><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    } else {
+        using Cfg = GemmCfg<64>;
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(gemm_tc_kernel<64, EPI_BIAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+                return "cudaFuncSetAttribute(wgrad) failed";
+            attr = true;
+        }
+        gemm_tc_kernel<64, EPI_BIAS, true><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 }  // namespace otb

@@ -25,7 +25,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 
 __global__ void __launch_bounds__(256) ls_ce_kernel(const float* __restrict__ logits, int ldl, const long long* __restrict__ tgt,
                                                     int V, float eps, int pad_id, float* __restrict__ tok_loss,
-                                                    float* __restrict__ dlogits, int ldd, const int* __restrict__ n_valid_ptr) {
+                                                    float* __restrict__ dlogits, int ldd, const int* __restrict__ n_valid_ptr,
+                                                    bf16* __restrict__ dlogits_bf16) {
     __shared__ float red[8];
     const int row = blockIdx.x;
     const float* x = logits + (size_t)row * ldl;
@@ -60,6 +61,15 @@ __global__ void __launch_bounds__(256) ls_ce_kernel(const float* __restrict__ lo
             d[i] = (p - ((i == t) ? hi : lo)) * inv;
         }
     }
+    if (dlogits_bf16 != nullptr) {   // bf16 copy for the backward GEMMs (columns [V, ldd) are zero padding)
+        const float inv = is_pad ? 0.f : 1.0f / (float)max(*n_valid_ptr, 1);
+        bf16* d = dlogits_bf16 + (size_t)row * ldd;
+        for (int i = threadIdx.x; i < ldd; i += blockDim.x) {
+            float gv = 0.f;
+            if (i < V) gv = (expf(x[i] - lse) - ((i == t) ? hi : lo)) * inv;
+            d[i] = __float2bfloat16(gv);
+        }
+    }
 }
 
 // n_valid = #(target != PAD); loss = sum(tok_loss) / n_valid   (single CTA, deterministic order)
@@ -80,10 +90,10 @@ __global__ void __launch_bounds__(256) ls_mean_kernel(const float* __restrict__ 
 }
 
 const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const long long* tgt, int rows, int V, float eps,
-                         int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd) {
+                         int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd, bf16* dlogits_bf16) {
     if (rows < 1 || V < 2) return "ls_ce: empty problem";
     ls_count_kernel<<<1, 256, 0, st>>>(tgt, rows, pad_id, n_valid);
-    ls_ce_kernel<<<rows, 256, 0, st>>>(logits, ldl, tgt, V, eps, pad_id, tok_loss, dlogits, ldd, n_valid);
+    ls_ce_kernel<<<rows, 256, 0, st>>>(logits, ldl, tgt, V, eps, pad_id, tok_loss, dlogits_bf16 ? nullptr : dlogits, ldd, n_valid, dlogits_bf16);
     ls_mean_kernel<<<1, 256, 0, st>>>(tok_loss, rows, n_valid, loss);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -46,12 +46,16 @@ struct GemmParams {
     int conv_T2;       // valid output time rows per utterance
     int conv_B;        // batch
     int conv_cchunks;  // C_in / 64
+    int splitk;        // TN (weight-gradient) mode: number of contraction splits (fp32 atomics when > 1)
     unsigned long long* dbg;  // optional [grid][8] clock64 phase stamps (otb_debug_gemm_timing)
     int dbg_mode;             // 0 normal; 1 = no TMA traffic (MMA-only cadence); 2 = no MMA (TMA-only cadence)
 };
 
 const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, int ldw, int w_rows, int epi,
                         GemmParams p, const CUtensorMap* conv_map);
+
+const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const void* X, int ldx, float* out, int ldc,
+                              int Mact, int Nw, int Kw);
 
 // encode helpers (driver entry point fetched at runtime; libcuda is not a link-time dependency)
 const char* encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
@@ -71,7 +75,36 @@ struct AttnParams {
     int ldbd;
     const bf16* resid;  // optional: out = resid + softmax(..)V   (rel-pos attention has no output projection)
     int ldr;
+    float* lse;         // optional [B,H,Tq]: row log-sum-exp of the scaled scores in log2 units (saved for the backward)
 };
+
+struct AttnBwdParams {
+    int B, H, Tq, Tk;
+    const int* kv_len;
+    int causal;
+    float scale_log2;
+    int q_col0, k_col0, v_col0;
+    const bf16* o;      // forward output [B*Tq, ldo]
+    int ldo;
+    const bf16* dout;   // gradient of the forward output [B*Tq, lddo]
+    int lddo;
+    const float* lse;   // [B,H,Tq] from the forward
+    float* dsum;        // [B,H,Tq] scratch: D_i = dO_i . O_i (written by the dQ kernel, read by the dK/dV kernel)
+    bf16* dq; int lddq, dq_col0;
+    bf16* dk; int lddk, dk_col0;
+    bf16* dv; int lddv, dv_col0;
+};
+const char* attn_bwd_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,
+                            const void* v, int ldv, const AttnBwdParams& p);
+const char* colsum_launch(cudaStream_t st, const bf16* x, int ldx, float* out, int M, int N);
+const char* layernorm_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, const bf16* z, int ldz, const float* gamma,
+                                 bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N);
+const char* glu_launch(cudaStream_t st, const bf16* u, const bf16* dh, bf16* out, int M, int F);
+const char* relu_bwd_launch(cudaStream_t st, const bf16* dy, const bf16* y, bf16* dx, size_t n);
+const char* embed_bwd_launch(cudaStream_t st, const long long* tok, const bf16* dx, float* dE, int N, int d, int vocab, float scale);
+const char* sumsq_launch(cudaStream_t st, const float* g, size_t n, float* out, int zero_first);
+const char* adam_launch(cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
+                        float max_norm, float lr, float b1, float b2, float eps, float wd, int step);
 
 struct BeamState {
     int* tok_hist;
@@ -143,7 +176,8 @@ const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalt
                                  long long* out_preds, float* out_scores);
 
 const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const long long* tgt, int rows, int V, float eps,
-                         int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd);
+                         int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd,
+                         bf16* dlogits_bf16 = nullptr);
 
 int num_sms();
 extern unsigned long long* g_gemm_dbg;

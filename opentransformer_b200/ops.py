@@ -319,3 +319,138 @@ def decode_mega(model_c, kvx, mem_len, kc, vc, state, B, T, max_steps, dbg_logp=
     check(_lib.lib().otb_decode_mega(ctypes.byref(model_c), _p(kvx), _p(mem_len), _p(kc), _p(vc), ctypes.byref(state.c),
                                      B, T, max_steps, _p(dbg_logp), _p(dbg_scores), _stream()), 'otb_decode_mega')
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: backward kernels (include/otb200.h "Training step")
+# ------------------------------------------------------------------------------------------------
+def attention_train(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0=0, v_col0=0):
+    """otb_attention + the per-row log-sum-exp the backward needs -> (out bf16 [B*Tq, H*64], lse f32 [B,H,Tq])."""
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _need(t, BF16, n)
+    out = torch.empty(B * Tq, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, Tq, dtype=torch.float32, device=q.device)
+    check(_lib.lib().otb_attention_lse(_p(q), q.stride(0), q.shape[0], _p(k), k.stride(0), k.shape[0], _p(v), v.stride(0),
+                                       _p(out), out.stride(0), B, H, Tq, Tk, _p(kv_len), 1 if causal else 0, q_col0, k_col0,
+                                       v_col0, None, 0, None, 0, _p(lse), _stream()), 'otb_attention_lse')
+    _count()
+    return out, lse
+
+
+def attention_bwd(q, k, v, out, dout, lse, B, H, Tq, Tk, dq, dk, dv, kv_len=None, causal=False, q_col0=0, k_col0=0,
+                  v_col0=0, dq_col0=0, dk_col0=0, dv_col0=0):
+    """Gradients of otb_attention written into dq/dk/dv (bf16 matrices, column offsets d*_col0)."""
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v'), (out, 'out'), (dout, 'dout'), (dq, 'dq'), (dk, 'dk'), (dv, 'dv')):
+        _need(t, BF16, n) if t.is_contiguous() else None
+    dsum = torch.empty(B, H, Tq, dtype=torch.float32, device=q.device)
+    check(_lib.lib().otb_attention_bwd(_p(q), q.stride(0), q.shape[0], _p(k), k.stride(0), k.shape[0], _p(v), v.stride(0),
+                                       _p(out), out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum),
+                                       _p(dq), dq.stride(0), dq_col0, _p(dk), dk.stride(0), dk_col0, _p(dv), dv.stride(0),
+                                       dv_col0, B, H, Tq, Tk, _p(kv_len), 1 if causal else 0, q_col0, k_col0, v_col0,
+                                       _stream()), 'otb_attention_bwd')
+    _count(2)
+
+
+def linear_wgrad(dy, x, out=None):
+    """dW f32 [N,K] = dy[M,N]^T x[M,K]  (bf16 2-D, unit column stride)."""
+    for t, n in ((dy, 'dy'), (x, 'x')):
+        if not t.is_cuda or t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError(f'{n} must be a 2-D bf16 CUDA tensor with unit column stride')
+    M, N = dy.shape
+    K = x.shape[1]
+    if x.shape[0] != M:
+        raise ValueError('linear_wgrad: row mismatch')
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+    with _Timed('wgrad', 2.0 * M * N * K, (M, N, K)):
+        check(_lib.lib().otb_linear_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(out), out.stride(0), M, N, K,
+                                          _stream()), 'otb_linear_wgrad')
+    _count(2)
+    return out
+
+
+def colsum(x, out=None):
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(_lib.lib().otb_colsum(_p(x), x.stride(0), _p(out), M, N, _stream()), 'otb_colsum')
+    _count()
+    return out
+
+
+def layernorm_bwd(dy, z, gamma, eps=1e-5):
+    """-> (dz bf16 [M,N], dgamma f32 [N], dbeta f32 [N])."""
+    _need(dy, BF16, 'dy'); _need(z, BF16, 'z')
+    M, N = z.shape
+    dz = torch.empty(M, N, dtype=BF16, device=z.device)
+    dg = torch.empty(N, dtype=torch.float32, device=z.device)
+    db = torch.empty(N, dtype=torch.float32, device=z.device)
+    check(_lib.lib().otb_layernorm_bwd(_p(dy), dy.stride(0), _p(z), z.stride(0), _p(gamma), _p(dz), dz.stride(0), _p(dg),
+                                       _p(db), eps, M, N, _stream()), 'otb_layernorm_bwd')
+    _count()
+    return dz, dg, db
+
+
+def glu_fwd(u):
+    _need(u, BF16, 'u')
+    M, F2 = u.shape
+    h = torch.empty(M, F2 // 2, dtype=BF16, device=u.device)
+    check(_lib.lib().otb_glu_fwd(_p(u), _p(h), M, F2 // 2, _stream()), 'otb_glu_fwd')
+    _count()
+    return h
+
+
+def glu_bwd(dh, u):
+    _need(u, BF16, 'u'); _need(dh, BF16, 'dh')
+    M, F2 = u.shape
+    du = torch.empty(M, F2, dtype=BF16, device=u.device)
+    check(_lib.lib().otb_glu_bwd(_p(dh), _p(u), _p(du), M, F2 // 2, _stream()), 'otb_glu_bwd')
+    _count()
+    return du
+
+
+def relu_bwd(dy, y, out=None):
+    _need(dy, BF16, 'dy'); _need(y, BF16, 'y')
+    if out is None:
+        out = torch.empty_like(dy)
+    check(_lib.lib().otb_relu_bwd(_p(dy), _p(y), _p(out), dy.numel(), _stream()), 'otb_relu_bwd')
+    _count()
+    return out
+
+
+def embed_bwd(tok, dx, dE, scale):
+    """dE[tok[n]] += scale * dx[n]   (dE f32 [V,d], accumulated in place)."""
+    _need(dx, BF16, 'dx'); _need(dE, torch.float32, 'dE')
+    tok = tok.contiguous().view(-1)
+    check(_lib.lib().otb_embed_bwd(_p(tok), _p(dx), _p(dE), tok.numel(), dx.shape[1], dE.shape[0], scale, _stream()),
+          'otb_embed_bwd')
+    _count()
+
+
+def ls_cross_entropy_train(logits, targets, V, smoothing=0.1, pad_id=0):
+    """-> (loss f32 scalar tensor, dlogits bf16 [rows, ld] with ld = logits.stride(0); pad columns zero)."""
+    _need(logits, torch.float32, 'logits')
+    rows, ld = logits.shape[0], logits.stride(0)
+    targets = targets.contiguous().view(-1)
+    dev = logits.device
+    tok = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    nv = torch.empty(1, dtype=torch.int32, device=dev)
+    dl = torch.empty(rows, ld, dtype=BF16, device=dev)
+    check(_lib.lib().otb_ls_ce_train(_p(logits), ld, _p(targets), rows, V, smoothing, pad_id, _p(tok), _p(loss), _p(nv),
+                                     _p(dl), ld, _stream()), 'otb_ls_ce_train')
+    _count(3)
+    return loss[0], dl
+
+
+def sumsq(g, out, zero_first=True):
+    check(_lib.lib().otb_sumsq(_p(g), g.numel(), _p(out), 1 if zero_first else 0, _stream()), 'otb_sumsq')
+    _count()
+
+
+def adam_step(p, g, m, v, sumsq_buf, max_norm, lr, betas, eps, weight_decay, step):
+    for t, n in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v')):
+        _need(t, torch.float32, n)
+    check(_lib.lib().otb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq_buf), max_norm, lr, betas[0], betas[1],
+                                   eps, weight_decay, step, _stream()), 'otb_adam_step')
+    _count()
