@@ -234,6 +234,15 @@ int otb_sumsq(const float* g, long long n, float* out, int zero_first, void* str
 int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* Conv2d front end backward (frontend/conv.py:50-76 under autograd).  h1 = conv1 activation buffer (layout of
+ * otb_conv1_relu).  col bf16 [B*T2*F2, 9*C1] = im2col of h1 for conv2 (k = (kh*3+kw)*C1 + c): conv2's weight gradient is
+ * otb_linear_wgrad(dpre2, col) and its input gradient dcol = otb_linear(dpre2, W2^T).  otb_conv_col2im_relu folds dcol
+ * back onto the conv1 grid and applies ReLU' -> dpre1 (h1 layout).  otb_conv1_wgrad: out f32 [C1, 10] = 9 tap
+ * gradients + the bias gradient of conv1 (C_in = 1). */
+int otb_conv_im2col(const void* h1, void* col, int B, int T, int F, int C1, void* stream);
+int otb_conv_col2im_relu(const void* dcol, const void* h1, void* dpre1, int B, int T, int F, int C1, void* stream);
+int otb_conv1_wgrad(const void* dpre1, const float* x, float* out, int B, int T, int F, int C1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -296,3 +296,147 @@ const char* adam_launch(cudaStream_t st, float* p, const float* g, float* m, flo
 }
 
 }  // namespace otb
+
+namespace otb {
+
+// ------------------------------------------------------------------------------------------------
+// Conv2d subsampling front end, backward (frontend/conv.py:50-76 under autograd).
+// Layouts as in the forward: conv1 activation h1 = NHWC bf16 [B, T1p = 2*(T2+1), F1p = 2*F2, C]; conv2 output rows are
+// (b, t2, f2) with C2 channels.  conv2's weight / input gradients are GEMMs over the explicit im2col matrix
+//   col[(b,t2,f2), (kh*3+kw)*C + c] = h1[b, 2*t2+kh, 2*f2+kw-1, c]      (f = -1 is the left zero padding)
+// (wgrad: dW2 = dpre2^T col on the TN tcgen05 kernel; dgrad: dcol = dpre2 W2, then the gather below).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__ h1, bf16* __restrict__ col, int B, int T2,
+                                                        int F2, int C, int T1p, int F1p) {
+    const int cg = C / 8;
+    const size_t total = (size_t)B * T2 * F2 * 9 * cg;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int f2 = (int)(r % F2);
+    r /= F2;
+    const int t2 = (int)(r % T2), b = (int)(r / T2);
+    const int kh = tap / 3, kw = tap % 3;
+    const int t = 2 * t2 + kh, f = 2 * f2 + kw - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (f >= 0) v = *reinterpret_cast<const uint4*>(h1 + (((size_t)b * T1p + t) * F1p + f) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(col + (((size_t)(b * T2 + t2) * F2 + f2) * 9 + tap) * C + c8 * 8) = v;
+}
+
+// dpre1[b,t1,f1,c] = relu'(h1) * sum over the (kh,kw) taps that read this input position of dcol[(b,t2,f2),(kh,kw,c)],
+// t2 = (t1-kh)/2, f2 = (f1+1-kw)/2 (both must be integral and in range).  Output in the h1 layout (positions outside
+// [0,T1) x [0,F1) are written as zero so that the buffer is fully defined).
+__global__ void __launch_bounds__(256) col2im_s2_relu_kernel(const bf16* __restrict__ dcol, const bf16* __restrict__ h1,
+                                                             bf16* __restrict__ dpre1, int B, int T1, int F1, int T2, int F2,
+                                                             int C, int T1p, int F1p) {
+    const int cg = C / 8;
+    const size_t total = (size_t)B * T1p * F1p * cg;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c8 = (int)(i % cg);
+    size_t r = i / cg;
+    const int f1 = (int)(r % F1p);
+    r /= F1p;
+    const int t1 = (int)(r % T1p), b = (int)(r / T1p);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (t1 < T1 && f1 < F1) {
+        for (int kh = 0; kh < 3; ++kh) {
+            const int tt = t1 - kh;
+            if (tt < 0 || (tt & 1)) continue;
+            const int t2 = tt >> 1;
+            if (t2 >= T2) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ff = f1 + 1 - kw;
+                if (ff < 0 || (ff & 1)) continue;
+                const int f2 = ff >> 1;
+                if (f2 >= F2) continue;
+                float v[8];
+                unpack8(*reinterpret_cast<const uint4*>(dcol + (((size_t)(b * T2 + t2) * F2 + f2) * 9 + kh * 3 + kw) * C + c8 * 8), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+        }
+        float hv[8];
+        unpack8(*reinterpret_cast<const uint4*>(h1 + i * 8), hv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = hv[j] > 0.f ? acc[j] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(dpre1 + i * 8) = pack8(acc);
+}
+
+// conv1 (C_in = 1) weight / bias gradient: dW1[c, kh*3+kw] = sum dpre1[b,t1,f1,c] * x[b, 2*t1+kh, 2*f1+kw-1], db1[c] = sum dpre1
+// out f32 [C, 10] (9 taps + bias), zeroed by the launcher.  CTA = (b, 8 rows of t1); thread = (channel, position lane).
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const bf16* __restrict__ dpre1, const float* __restrict__ x,
+                                                          float* __restrict__ out, int B, int T, int F, int T1, int F1,
+                                                          int T1p, int F1p, int C) {
+    extern __shared__ float sx[];   // [17][F + 2]
+    __shared__ float red[256 * 10];
+    constexpr int ROWS = 8;
+    const int chunks = (T1 + ROWS - 1) / ROWS;
+    const int b = blockIdx.x / chunks, t1_0 = (blockIdx.x % chunks) * ROWS;
+    const int nrows = min(ROWS, T1 - t1_0);
+    const int W2 = F + 2;
+    for (int i = threadIdx.x; i < (2 * nrows + 1) * W2; i += blockDim.x) {
+        const int r = i / W2, f = i % W2 - 1;
+        sx[i] = (f >= 0 && f < F) ? x[((size_t)b * T + 2 * t1_0 + r) * F + f] : 0.f;
+    }
+    __syncthreads();
+    const int lanes = blockDim.x / C;
+    const int c = threadIdx.x % C, pl = threadIdx.x / C;
+    float acc[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+    if (pl < lanes) {
+        for (int pos = pl; pos < nrows * F1; pos += lanes) {
+            const int r = pos / F1, f1 = pos % F1;
+            const float g = __bfloat162float(dpre1[(((size_t)b * T1p + t1_0 + r) * F1p + f1) * C + c]);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf(g, sx[(2 * r + kh) * W2 + 2 * f1 + kw], acc[kh * 3 + kw]);
+            acc[9] += g;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) red[threadIdx.x * 10 + j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 10; i += blockDim.x) {
+        const int cc = i / 10, j = i % 10;
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(l * C + cc) * 10 + j];
+        atomicAdd(out + cc * 10 + j, s);
+    }
+}
+
+const char* im2col_s2_launch(cudaStream_t st, const bf16* h1, bf16* col, int B, int T2, int F2, int C) {
+    if (C % 8) return "im2col: C must be a multiple of 8";
+    const size_t total = (size_t)B * T2 * F2 * 9 * (C / 8);
+    im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h1, col, B, T2, F2, C, 2 * (T2 + 1), 2 * F2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+const char* col2im_s2_relu_launch(cudaStream_t st, const bf16* dcol, const bf16* h1, bf16* dpre1, int B, int T1, int F1, int T2,
+                                  int F2, int C) {
+    if (C % 8) return "col2im: C must be a multiple of 8";
+    const size_t total = (size_t)B * 2 * (T2 + 1) * 2 * F2 * (C / 8);
+    col2im_s2_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dcol, h1, dpre1, B, T1, F1, T2, F2, C, 2 * (T2 + 1), 2 * F2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+const char* conv1_wgrad_launch(cudaStream_t st, const bf16* dpre1, const float* x, float* out, int B, int T, int F, int T1,
+                               int F1, int T2, int F2, int C) {
+    if (C < 1 || C > 256 || 256 % C) return "conv1_wgrad: C must divide 256";
+    const size_t smem = (size_t)17 * (F + 2) * sizeof(float);
+    if (smem > 40 * 1024) return "conv1_wgrad: F too large";
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)C * 10 * 4, st);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    const int chunks = (T1 + 7) / 8;
+    conv1_wgrad_kernel<<<B * chunks, 256, smem, st>>>(dpre1, x, out, B, T, F, T1, F1, 2 * (T2 + 1), 2 * F2, C);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace otb

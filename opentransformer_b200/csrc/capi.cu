@@ -378,4 +378,26 @@ int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, con
     RET("otb_adam_step", adam_launch(ST(stream), p, g, m, v, (size_t)n, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step));
 }
 
+int otb_conv_im2col(const void* h1, void* col, int B, int T, int F, int C1, void* stream) {
+    int T1, F1, T2, F2;
+    if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;
+    if (!h1 || !col) return fail("otb_conv_im2col", "null operand");
+    RET("otb_conv_im2col", im2col_s2_launch(ST(stream), reinterpret_cast<const bf16*>(h1), reinterpret_cast<bf16*>(col), B, T2, F2, C1));
+}
+
+int otb_conv_col2im_relu(const void* dcol, const void* h1, void* dpre1, int B, int T, int F, int C1, void* stream) {
+    int T1, F1, T2, F2;
+    if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;
+    if (!dcol || !h1 || !dpre1) return fail("otb_conv_col2im_relu", "null operand");
+    RET("otb_conv_col2im_relu", col2im_s2_relu_launch(ST(stream), reinterpret_cast<const bf16*>(dcol), reinterpret_cast<const bf16*>(h1),
+                                                      reinterpret_cast<bf16*>(dpre1), B, T1, F1, T2, F2, C1));
+}
+
+int otb_conv1_wgrad(const void* dpre1, const float* x, float* out, int B, int T, int F, int C1, void* stream) {
+    int T1, F1, T2, F2;
+    if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;
+    if (!dpre1 || !x || !out) return fail("otb_conv1_wgrad", "null operand");
+    RET("otb_conv1_wgrad", conv1_wgrad_launch(ST(stream), reinterpret_cast<const bf16*>(dpre1), x, out, B, T, F, T1, F1, T2, F2, C1));
+}
+
 }  // extern "C"

@@ -102,6 +102,11 @@ const char* layernorm_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, cons
 const char* glu_launch(cudaStream_t st, const bf16* u, const bf16* dh, bf16* out, int M, int F);
 const char* relu_bwd_launch(cudaStream_t st, const bf16* dy, const bf16* y, bf16* dx, size_t n);
 const char* embed_bwd_launch(cudaStream_t st, const long long* tok, const bf16* dx, float* dE, int N, int d, int vocab, float scale);
+const char* im2col_s2_launch(cudaStream_t st, const bf16* h1, bf16* col, int B, int T2, int F2, int C);
+const char* col2im_s2_relu_launch(cudaStream_t st, const bf16* dcol, const bf16* h1, bf16* dpre1, int B, int T1, int F1, int T2,
+                                  int F2, int C);
+const char* conv1_wgrad_launch(cudaStream_t st, const bf16* dpre1, const float* x, float* out, int B, int T, int F, int T1,
+                               int F1, int T2, int F2, int C);
 const char* sumsq_launch(cudaStream_t st, const float* g, size_t n, float* out, int zero_first);
 const char* adam_launch(cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
                         float max_norm, float lr, float b1, float b2, float eps, float wd, int step);

@@ -34,3 +34,15 @@ def max_over_ranks(values, device, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t.tolist()
+
+
+def allreduce_mean_(flat, group=None):
+    """In-place mean over ranks of a flat gradient buffer: the single exchange step of synchronous data-parallel
+    training (the reference's DistributedDataParallel, train/trainer.py:59-61).  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+    return flat

@@ -50,9 +50,12 @@ class SpeechToText(nn.Module):
         return logits.view(B, L, -1)[:, :, :self.decoder.vocab_size]
 
     def forward(self, inputs, targets):
-        """SpeechToText.forward (model/speech2text.py:39-58), forward only: (loss, None).  The backward kernels
-        (dgrad/wgrad GEMMs, attention and LayerNorm backward) are the next scope row; call under eval()/no_grad()."""
+        """SpeechToText.forward (model/speech2text.py:39-58) -> (loss, None).  In train mode with grad enabled the loss
+        carries the hand-written backward (train.py): loss.backward() fills .grad of the fp32 parameters."""
         truth = targets['targets']
+        if self.training and torch.is_grad_enabled():
+            from . import train
+            return train.loss_with_grad(self, inputs['inputs'], inputs['mask'], truth), None
         logits_pad = self._logits_padded(inputs['inputs'], inputs['mask'], truth[:, :-1].contiguous())
         loss, _ = ops.ls_cross_entropy(logits_pad, truth[:, 1:].contiguous(), self.decoder.vocab_size, self.smoothing)
         return loss, None

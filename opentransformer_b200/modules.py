@@ -13,7 +13,8 @@ compute goes through ``ops`` -> libotb200.so (hand-written sm_100a kernels).  Th
 calling a module with CPU tensors raises.
 
 Numerics: GEMM operands / activations are bf16, accumulation fp32, LayerNorm / softmax statistics
-fp32 (DESIGN.md "rounding points").  Inference only in round 1 (no backward kernels yet).
+fp32 (DESIGN.md "rounding points").  The module-level forward is the inference path; training goes through
+``SpeechToText.forward`` in train mode -> train.py (hand-written backward).
 """
 import math
 
@@ -29,6 +30,15 @@ def _lengths(mask):
     return mask.sum(dim=1).to(torch.int32).contiguous()
 
 
+_PARAM_GENERATION = [0]
+
+
+def bump_param_generation():
+    """Invalidate every bf16 shadow copy: called after parameters were updated outside torch's version tracking
+    (the fused Adam kernel of train.FusedTrainer writes the flat fp32 buffer directly)."""
+    _PARAM_GENERATION[0] += 1
+
+
 class _Packed:
     """bf16 shadow copies of fp32 master parameters, refreshed when any parameter changes
     (load_state_dict / optimizer steps bump ``Tensor._version``)."""
@@ -37,7 +47,7 @@ class _Packed:
         self._module, self._builder, self._sig, self._val = module, builder, None, None
 
     def get(self):
-        sig = tuple((p.data_ptr(), p._version) for p in self._module.parameters())
+        sig = (_PARAM_GENERATION[0],) + tuple((p.data_ptr(), p._version) for p in self._module.parameters())
         if self._val is None or sig != self._sig:
             with torch.no_grad():
                 self._val = self._builder()
@@ -59,8 +69,8 @@ def _ln(norm):
 
 def _no_train(module):
     if module.training and torch.is_grad_enabled():
-        raise NotImplementedError('opentransformer_b200 round 1 implements the forward hot path only; '
-                                  'call under model.eval() / torch.no_grad()')
+        raise NotImplementedError('module-level forward is the inference path: call under model.eval() / torch.no_grad(); '
+                                  'training runs through SpeechToText.forward (opentransformer_b200.train)')
 
 
 # ------------------------------------------------------------------------------------------------

@@ -454,3 +454,25 @@ def adam_step(p, g, m, v, sumsq_buf, max_norm, lr, betas, eps, weight_decay, ste
     check(_lib.lib().otb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq_buf), max_norm, lr, betas[0], betas[1],
                                    eps, weight_decay, step, _stream()), 'otb_adam_step')
     _count()
+
+
+def conv_im2col(h1, B, T, F, C1):
+    _, _, T2, F2 = conv_geometry(T, F)
+    col = torch.empty(B * T2 * F2, 9 * C1, dtype=BF16, device=h1.device)
+    check(_lib.lib().otb_conv_im2col(_p(h1), _p(col), B, T, F, C1, _stream()), 'otb_conv_im2col')
+    _count()
+    return col
+
+
+def conv_col2im_relu(dcol, h1, B, T, F, C1):
+    dpre1 = torch.empty_like(h1)
+    check(_lib.lib().otb_conv_col2im_relu(_p(dcol), _p(h1), _p(dpre1), B, T, F, C1, _stream()), 'otb_conv_col2im_relu')
+    _count()
+    return dpre1
+
+
+def conv1_wgrad(dpre1, x, B, T, F, C1):
+    out = torch.empty(C1, 10, dtype=torch.float32, device=x.device)
+    check(_lib.lib().otb_conv1_wgrad(_p(dpre1), _p(x), _p(out), B, T, F, C1, _stream()), 'otb_conv1_wgrad')
+    _count()
+    return out

@@ -1,0 +1,339 @@
+"""Training step of the speech transformer on the B200 path.
+
+Mirror of the inner step of otrans/train/trainer.py:206-234 for `SpeechToText` (model/speech2text.py:39-64):
+
+    loss, _ = model(inputs, targets); loss.backward(); clip_grad_norm_(params, 5); scheduler.step(); optimizer.step()
+
+The reference differentiates its forward through torch autograd.  Here the backward is written by hand as a reverse
+walk over a tape of saved bf16 activations, so that every contraction runs on the tcgen05 kernels (dgrad = otb_linear
+with the transposed weight, residual gradients fused into its epilogue; wgrad = otb_linear_wgrad; attention backward =
+otb_attention_bwd) and everything else on the HBM-bound backward kernels (csrc/backward.cu).  The only torch autograd
+node is `_SpeechToTextLoss`, which makes `model(inputs, targets)[0].backward()` populate `.grad` of the fp32 master
+parameters exactly like the reference module.
+
+Scope (round 1): the shipped Speech-Transformer configuration -- conv front end, post-norm Transformer encoder /
+decoder with GLU feed-forward, tied or untied output layer, all dropout rates 0 (the reference's residual_dropout is
+stochastic; gradient parity is defined without it).  Conformer / pre-norm training is not
+built yet and raises.
+"""
+import math
+
+import torch
+
+from . import ops
+from . import modules
+from .dp import allreduce_mean_
+from .modules import TransformerDecoder, TransformerEncoder, ConvFrontEnd, _lengths
+from .ops import BF16, EPI_BIAS, EPI_RESID, EPI_TABLE
+
+
+def _bf(t):
+    return t.detach().to(BF16).contiguous()
+
+
+def _bft(t):
+    return t.detach().to(BF16).t().contiguous()
+
+
+def _f(t):
+    return t.detach().float().contiguous()
+
+
+class TrainPack:
+    """bf16 operands of one training step: W [N,K] for the forward / wgrad, W^T [K,N] for the dgrad GEMMs."""
+
+    def __init__(self, model):
+        fe, enc, dec = model.frontend, model.encoder, model.decoder
+        if not isinstance(fe, ConvFrontEnd) or not isinstance(enc, TransformerEncoder) or not isinstance(dec, TransformerDecoder):
+            raise NotImplementedError('training path: conv front end + Transformer encoder / decoder only (round 1)')
+        if enc.normalize_before or dec.normalize_before or enc.relative_positional:
+            raise NotImplementedError('training path: post-norm, absolute positions only (round 1)')
+        if fe.front_end_layer_norm or enc.pos_emb.scale_learnable or dec.pos_emb.scale_learnable:
+            raise NotImplementedError('training path: front_end_layer_norm / learnable positional scale')
+        for blk in list(enc.blocks) + list(dec.blocks):
+            if blk.feed_forward.activation != 'glu':
+                raise NotImplementedError('training path: GLU feed-forward only (round 1)')
+        self.fe = self._frontend(fe)
+        self.enc = [self._enc_layer(b) for b in enc.blocks]
+        self.dec = [self._dec_layer(b) for b in dec.blocks]
+        V, d = dec.vocab_size, dec.d_model
+        self.ld_logits = dec.ld_logits
+        emb = _bf(dec.embedding.weight)
+        self.tied = dec.output_layer.weight is dec.embedding.weight
+        wout = emb if self.tied else _bf(dec.output_layer.weight)
+        wout_t = torch.zeros(d, self.ld_logits, dtype=BF16, device=emb.device)      # [d, V padded]: dgrad of the logits GEMM
+        wout_t[:, :V] = wout.t()
+        self.out = {'emb': emb, 'wout': wout, 'wout_t': wout_t, 'bout': _f(dec.output_layer.bias)}
+
+    @staticmethod
+    def _lin(lin):
+        return _bf(lin.weight), _bft(lin.weight), _f(lin.bias)
+
+    @staticmethod
+    def _ln(norm):
+        return _f(norm.weight), _f(norm.bias)
+
+    def _frontend(self, fe):
+        pk = dict(fe._build_pack())
+        pk['w2_t'] = pk['w2'].t().contiguous()           # [9*C1p, C2]
+        pk['wo_t'] = pk['wo'].t().contiguous()           # [F2*C2, D]
+        return pk
+
+    def _enc_layer(self, b):
+        a, f = b.slf_attn, b.feed_forward
+        return {'qkv': self._lin(a.qvk_proj), 'o': self._lin(a.output_proj), 'w1': self._lin(f.w_1), 'w2': self._lin(f.w_2),
+                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2)}
+
+    def _dec_layer(self, b):
+        a, c, f = b.slf_attn, b.src_attn, b.feed_forward
+        return {'qkv': self._lin(a.qvk_proj), 'o': self._lin(a.output_proj), 'q': self._lin(c.q_proj),
+                'kv': self._lin(c.vk_proj), 'o2': self._lin(c.output_proj), 'w1': self._lin(f.w_1), 'w2': self._lin(f.w_2),
+                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2), 'ln3': self._ln(b.norm3)}
+
+
+def _linear_bwd(dy, x, wt, grads, wname, bname, resid=None):
+    """Gradients of y = x W^T + b: parameter grads into `grads`, returns dx (+ resid) as bf16."""
+    grads[wname] = ops.linear_wgrad(dy, x)
+    grads[bname] = ops.colsum(dy)
+    if wt is None:
+        return None
+    if resid is not None:
+        return ops.linear(dy, wt, None, EPI_RESID, resid=resid)
+    return ops.linear(dy, wt)
+
+
+def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True):
+    """One forward (+ backward) pass.  inputs f32 [B,T,F], mask bool [B,T], truth i64 [B,L+1] (BOS ... EOS PAD*).
+    Returns (loss 0-d f32 tensor, {parameter name -> fp32 gradient}) with names as in model.named_parameters()."""
+    fe, enc, dec = model.frontend, model.encoder, model.decoder
+    pk = TrainPack(model)
+    dev = inputs.device
+    B, T, F = inputs.shape
+    H, d = enc.blocks[0].n_heads, enc.d_model
+    x_in = inputs.contiguous().float()
+    _, _, T2, F2 = ops.conv_geometry(T, F)
+    T1, F1 = (T - 3) // 2 + 1, (F - 1) // 2 + 1
+    lengths = _lengths(fe.output_mask(mask))
+    fpk = pk.fe
+    C1p, C2 = fpk['C1p'], fpk['w2'].shape[0]
+
+    # ------------------------------------------------------------------ forward
+    h1 = ops.conv1_relu(x_in, fpk['w1'], fpk['b1'])
+    h2 = ops.conv2_relu(h1, fpk['w2'], fpk['b2'], B, T, F)                       # [B*T2, F2*C2]
+    scale, table = enc.pos_emb.scale_and_table(T2, dev)
+    x = ops.linear(h2, fpk['wo'], fpk['bo'], EPI_TABLE, alpha=scale, table=table, period=T2)
+    enc_tape = []
+    for p in pk.enc:
+        qkv = ops.linear(x, p['qkv'][0], p['qkv'][2])
+        ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
+        z1 = ops.linear(ctx, p['o'][0], p['o'][2], EPI_RESID, resid=x)
+        x1 = ops.layernorm(z1, *p['ln1'])
+        u = ops.linear(x1, p['w1'][0], p['w1'][2])
+        h = ops.glu_fwd(u)
+        z2 = ops.linear(h, p['w2'][0], p['w2'][2], EPI_RESID, resid=x1)
+        enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, z2))
+        x = ops.layernorm(z2, *p['ln2'])
+    mem = x
+
+    tgt_in = truth[:, :-1].contiguous()
+    tgt_out = truth[:, 1:].contiguous()
+    L = tgt_in.shape[1]
+    Hd = dec.n_heads
+    _, dtable = dec.pos_emb.scale_and_table(L, dev)
+    y = ops.embed_posenc(tgt_in, pk.out['emb'], dtable, B * L, d, period=L)
+    dec_tape = []
+    for p in pk.dec:
+        qkv = ops.linear(y, p['qkv'][0], p['qkv'][2])
+        ctx, lse = ops.attention_train(qkv, qkv, qkv, B, Hd, L, L, causal=True, q_col0=0, k_col0=d, v_col0=2 * d)
+        z1 = ops.linear(ctx, p['o'][0], p['o'][2], EPI_RESID, resid=y)
+        y1 = ops.layernorm(z1, *p['ln1'])
+        q = ops.linear(y1, p['q'][0], p['q'][2])
+        kv = ops.linear(mem, p['kv'][0], p['kv'][2])
+        ctx2, lse2 = ops.attention_train(q, kv, kv, B, Hd, L, T2, kv_len=lengths, k_col0=0, v_col0=d)
+        z2 = ops.linear(ctx2, p['o2'][0], p['o2'][2], EPI_RESID, resid=y1)
+        y2 = ops.layernorm(z2, *p['ln2'])
+        u = ops.linear(y2, p['w1'][0], p['w1'][2])
+        h = ops.glu_fwd(u)
+        z3 = ops.linear(h, p['w2'][0], p['w2'][2], EPI_RESID, resid=y2)
+        dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3))
+        y = ops.layernorm(z3, *p['ln3'])
+    V = dec.vocab_size
+    logits = ops.linear(y, pk.out['wout'], pk.out['bout'], EPI_BIAS, out_f32=True, n_out=pk.ld_logits)
+    sm = model.smoothing if smoothing is None else smoothing
+    if not want_grads:
+        loss, _ = ops.ls_cross_entropy(logits, tgt_out, V, sm)
+        return loss, None
+    loss, dlogits = ops.ls_cross_entropy_train(logits, tgt_out, V, sm)
+
+    # ------------------------------------------------------------------ backward
+    g = {}
+    dwout = ops.linear_wgrad(dlogits, y)[:V]                                     # [V, d]
+    g['decoder.output_layer.bias'] = ops.colsum(dlogits)[:V].contiguous()
+    dy = ops.linear(dlogits, pk.out['wout_t'])                                   # [B*L, d]
+    dmem = None
+    for i in reversed(range(len(pk.dec))):
+        p, pre = pk.dec[i], f'decoder.blocks.{i}.'
+        (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3) = dec_tape[i]
+        dz3, g[pre + 'norm3.weight'], g[pre + 'norm3.bias'] = ops.layernorm_bwd(dy, z3, p['ln3'][0])
+        dh = _linear_bwd(dz3, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+        du = ops.glu_bwd(dh, u)
+        dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz3)
+        dz2, g[pre + 'norm2.weight'], g[pre + 'norm2.bias'] = ops.layernorm_bwd(dy2, z2, p['ln2'][0])
+        dctx2 = _linear_bwd(dz2, ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        ops.attention_bwd(q, kv, kv, ctx2, dctx2, lse2, B, Hd, L, T2, dq, dkv, dkv, kv_len=lengths, k_col0=0, v_col0=d,
+                          dq_col0=0, dk_col0=0, dv_col0=d)
+        dmem = _linear_bwd(dkv, mem, p['kv'][1], g, pre + 'src_attn.vk_proj.weight', pre + 'src_attn.vk_proj.bias', resid=dmem)
+        dy1 = _linear_bwd(dq, y1, p['q'][1], g, pre + 'src_attn.q_proj.weight', pre + 'src_attn.q_proj.bias', resid=dz2)
+        dz1, g[pre + 'norm1.weight'], g[pre + 'norm1.bias'] = ops.layernorm_bwd(dy1, z1, p['ln1'][0])
+        dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, Hd, L, L, dqkv, dqkv, dqkv, causal=True, q_col0=0, k_col0=d,
+                          v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
+        dy = _linear_bwd(dqkv, y0, p['qkv'][1], g, pre + 'slf_attn.qvk_proj.weight', pre + 'slf_attn.qvk_proj.bias', resid=dz1)
+    # embedding (decoder/transformer.py:163,169); with tied weights the output-layer gradient lands in the same tensor
+    if pk.tied:
+        demb = dwout.contiguous()
+        ops.embed_bwd(tgt_in, dy, demb, math.sqrt(d))
+        g['decoder.embedding.weight'] = demb
+    else:
+        g['decoder.output_layer.weight'] = dwout.contiguous()
+        demb = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        ops.embed_bwd(tgt_in, dy, demb, math.sqrt(d))
+        g['decoder.embedding.weight'] = demb
+
+    dx = dmem
+    for i in reversed(range(len(pk.enc))):
+        p, pre = pk.enc[i], f'encoder.blocks.{i}.'
+        (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
+        dz2, g[pre + 'norm2.weight'], g[pre + 'norm2.bias'] = ops.layernorm_bwd(dx, z2, p['ln2'][0])
+        dh = _linear_bwd(dz2, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+        du = ops.glu_bwd(dh, u)
+        dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz2)
+        dz1, g[pre + 'norm1.weight'], g[pre + 'norm1.bias'] = ops.layernorm_bwd(dx1, z1, p['ln1'][0])
+        dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, H, T2, T2, dqkv, dqkv, dqkv, kv_len=lengths, q_col0=0, k_col0=d,
+                          v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
+        dx = _linear_bwd(dqkv, x0, p['qkv'][1], g, pre + 'slf_attn.qvk_proj.weight', pre + 'slf_attn.qvk_proj.bias', resid=dz1)
+
+    # front end: x = (h2 Wo^T + bo) * sqrt(d) + PE  ->  conv2 (implicit-GEMM forward, im2col GEMMs backward) -> conv1
+    dyl = ops.scale_add_table(dx, scale)                                          # d(h2 Wo^T + bo) = sqrt(d) * dx
+    D_out = fe.output_size
+    dwo = ops.linear_wgrad(dyl, h2)                                               # [D, F2*C2], feature index f*C2 + c
+    g['frontend.output_layer.weight'] = dwo.view(D_out, F2, C2).permute(0, 2, 1).reshape(D_out, C2 * F2).contiguous()
+    g['frontend.output_layer.bias'] = ops.colsum(dyl)
+    dh2 = ops.linear(dyl, fpk['wo_t'])                                            # [B*T2, F2*C2]
+    dpre2 = ops.relu_bwd(dh2, h2).view(B * T2 * F2, C2)
+    col = ops.conv_im2col(h1, B, T, F, C1p)
+    C1 = fe.conv1.conv_layer.out_channels
+    dw2 = ops.linear_wgrad(dpre2, col)                                            # [C2, 9*C1p], k = (kh*3+kw)*C1p + c
+    g['frontend.conv2.conv_layer.weight'] = dw2.view(C2, 3, 3, C1p)[..., :C1].permute(0, 3, 1, 2).contiguous()
+    g['frontend.conv2.conv_layer.bias'] = ops.colsum(dpre2)
+    dcol = ops.linear(dpre2, fpk['w2_t'])                                         # [B*T2*F2, 9*C1p]
+    del col
+    dpre1 = ops.conv_col2im_relu(dcol, h1, B, T, F, C1p)
+    g1 = ops.conv1_wgrad(dpre1, x_in, B, T, F, C1p)                               # [C1p, 9 taps + bias]
+    g['frontend.conv1.conv_layer.weight'] = g1[:C1, :9].reshape(C1, 1, 3, 3).contiguous()
+    g['frontend.conv1.conv_layer.bias'] = g1[:C1, 9].contiguous()
+    return loss, g
+
+
+class _SpeechToTextLoss(torch.autograd.Function):
+    """loss = SpeechToText.forward(...) as ONE autograd node over the fp32 master parameters."""
+
+    @staticmethod
+    def forward(ctx, model, inputs, mask, truth, names, *params):
+        with torch.no_grad():
+            loss, grads = forward_backward(model, inputs, mask, truth)
+        ctx.grads = [grads.get(n) for n in names]
+        ctx.shapes = [p.shape for p in params]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        out = []
+        for gr, shp in zip(ctx.grads, ctx.shapes):
+            out.append(None if gr is None else (gr.view(shp) * gloss))
+        return (None, None, None, None, None) + tuple(out)
+
+
+def loss_with_grad(model, inputs, mask, truth):
+    """Training-mode SpeechToText.forward: a loss tensor whose .backward() fills `.grad` of every parameter."""
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    names = [n for n, _ in named]
+    return _SpeechToTextLoss.apply(model, inputs, mask, truth, names, *[p for _, p in named])
+
+
+def transformer_lr(step, model_size, warmup_steps, factor=1.0):
+    """TransformerScheduler.get_step_lr (otrans/train/scheduler.py:137-138)."""
+    return factor * model_size ** (-0.5) * min(step ** (-0.5), step * warmup_steps ** (-1.5))
+
+
+class FusedTrainer:
+    """The inner step of Trainer.train_one_epoch (trainer.py:206-234) on flat fp32 buffers:
+    forward + hand-written backward -> (data-parallel) gradient all-reduce over NCCL -> global-norm clip + Adam in two
+    kernels, no host synchronisation.  Parameters become views into one flat buffer (state_dict keys / shapes unchanged)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, clip_grad=5.0, model_size=256,
+                 warmup_steps=12000, factor=1.0, accum_steps=1, process_group=None):
+        self.model = model
+        self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        dev = self.params[0][1].device
+        total = sum(p.numel() for _, p in self.params)
+        self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.offsets = {}
+        o = 0
+        with torch.no_grad():
+            for n, p in self.params:
+                k = p.numel()
+                self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[o:o + k].view_as(p)            # parameters now alias the flat buffer
+                self.offsets[n] = (o, k)
+                o += k
+        self.betas, self.eps, self.wd, self.clip = betas, eps, weight_decay, clip_grad
+        self.base_lr, self.model_size, self.warmup, self.factor = lr, model_size, warmup_steps, factor
+        self.accum_steps = accum_steps
+        self.group = process_group
+        # BaseScheduler starts at global_step 1 and its constructor already calls step() once (scheduler.py:22,42-46);
+        # the trainer steps it again before every optimizer.step() (trainer.py:232): the first update uses lr(3)
+        self.global_step = 2
+        self.opt_steps = 0
+        self.micro = 0
+
+    def lr(self):
+        if self.warmup:
+            return transformer_lr(self.global_step, self.model_size, self.warmup, self.factor)
+        return self.base_lr
+
+    def step(self, inputs, mask, truth):
+        """One micro-batch; every `accum_steps` calls an optimizer step.  Returns the (un-scaled) loss tensor."""
+        with torch.no_grad():
+            loss, grads = forward_backward(self.model, inputs, mask, truth)
+            first = self.micro % self.accum_steps == 0
+            inv = 1.0 / self.accum_steps
+            for n, _ in self.params:
+                o, k = self.offsets[n]
+                gsl = self.flat_g[o:o + k]
+                gr = grads[n].reshape(-1)
+                if first:
+                    gsl.copy_(gr) if inv == 1.0 else torch.mul(gr, inv, out=gsl)
+                else:
+                    gsl.add_(gr, alpha=inv)
+            self.micro += 1
+            if self.micro % self.accum_steps == 0:
+                # the one exchange step of data-parallel training: mean of the flat gradient over ranks,
+                # ONE NCCL all-reduce per optimizer step (the reference's DDP reduces on every micro-batch)
+                allreduce_mean_(self.flat_g, self.group)
+                ops.sumsq(self.flat_g, self.sumsq)
+                self.global_step += 1
+                self.opt_steps += 1
+                ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.sumsq, self.clip, self.lr(), self.betas, self.eps,
+                              self.wd, self.opt_steps)
+                modules.bump_param_generation()     # bf16 shadow copies (modules._Packed) must be rebuilt
+        return loss

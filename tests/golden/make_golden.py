@@ -177,7 +177,59 @@ def lm_case():
     print('small_transformer_lm', tuple(out['last'].shape), tuple(out['all'].shape))
 
 
+def train_case():
+    """One inner step of Trainer.train_one_epoch (train/trainer.py:206-234) through the REAL reference:
+    model.train() forward -> loss.backward() -> clip_grad_norm_(5) -> TransformerScheduler.step -> Adam.step.
+    Dropout rates are 0 (gradient parity is defined without the stochastic residual dropout)."""
+    from otrans.train.scheduler import TransformerScheduler
+    params = small_params('transformer')
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k in list(params[part]):
+            if 'dropout' in k:
+                params[part][k] = 0.0
+    torch.manual_seed(1234)
+    model = End2EndModel['speech2text'](params)
+    model.train()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'norm' in n:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith('.bias'):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        model.decoder.embedding.weight.mul_(0.12)
+    x, mask = make_batch(0, 3, 90, params['frontend']['input_size'], [90, 61, 74])
+    gt = torch.Generator().manual_seed(3)
+    tgt = torch.randint(3, params['decoder']['vocab_size'], (3, 9), generator=gt)
+    tgt[:, 0] = 1
+    tgt[0, 7:] = torch.tensor([1, 0])
+    tgt[1, 5:] = torch.tensor([1, 0, 0, 0])
+    tgt[2, 8] = 1
+    sd = {}
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k, v in getattr(model, part).state_dict().items():
+            sd[f'{part}.{k}'] = v.clone()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, amsgrad=False)
+    sched = TransformerScheduler(opt, model_size=32, warmup_steps=100, factor=1.0)
+    loss, _ = model({'inputs': x, 'mask': mask}, {'targets': tgt, 'targets_length': None})
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)      # small max_norm so that clipping is active
+    sched.step()
+    opt.step()
+    after = {n: p.detach().clone() for n, p in model.named_parameters()}
+    out = {'params': params, 'state_dict': sd, 'x': x, 'mask': mask, 'targets': tgt, 'loss': loss.detach(), 'grads': grads,
+           'grad_norm': torch.as_tensor(float(grad_norm)), 'clip': 0.5, 'lr': sched.lr, 'after': after,
+           'adam': dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6), 'sched': dict(model_size=32, warmup_steps=100)}
+    path = os.path.join(HERE, 'train_step_postnorm_glu.pt')
+    torch.save(out, path)
+    print('train_step', os.path.getsize(path) // 1024, 'KiB loss', float(loss), 'grad_norm', float(grad_norm), 'lr', sched.lr)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':
+        train_case()
+        sys.exit(0)
     lm_case()
     run_case('small_transformer_postnorm_glu', small_params('transformer'))
     run_case('small_transformer_prenorm_relu',

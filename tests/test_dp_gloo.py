@@ -26,6 +26,10 @@ def _worker(rank, world, port, n_items, q):
     ids = torch.arange(lo, hi, dtype=torch.int64).view(-1, 1).repeat(1, 3)     # stand-in for n-best ids
     allids = dp.gather_variable(ids)
     tmax = dp.max_over_ranks([float(rank + 1), 10.0 - rank], torch.device('cpu'))
+    # the one exchange step of data-parallel training: mean of the flat gradient buffer over ranks
+    flat = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    dp.allreduce_mean_(flat)
+    assert torch.equal(flat, torch.arange(6, dtype=torch.float32) * 1.5)
     q.put((rank, lo, hi, allids[:, 0].tolist(), tmax))
     dist.destroy_process_group()
 
