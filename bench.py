@@ -217,6 +217,38 @@ def run_reference(args):
     return 0
 
 
+def time_gemm_shape(tag, dev, reps=50):
+    """Average duration (ms) of one otb_linear launch of shape `tag` = (epilogue, M, weight rows, K, out_f32): `reps`
+    back-to-back launches on synthetic operands between two CUDA events (per-launch events around 8 us kernels mostly
+    measure the gap between launches)."""
+    from opentransformer_b200 import ops
+    epi, M, Nw, K, of32 = tag
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(Nw, K, generator=g) * 0.05).to(torch.bfloat16).to(dev)
+    bias = torch.zeros(Nw, device=dev)
+    n_out = Nw // 2 if epi == ops.EPI_GLU else Nw
+    kw = {}
+    if epi in (ops.EPI_RESID, ops.EPI_RESID_LN):
+        kw['resid'] = torch.randn(M, n_out, generator=g).to(torch.bfloat16).to(dev)
+    if epi == ops.EPI_RESID_LN:
+        kw['gamma'], kw['beta'] = torch.ones(n_out, device=dev), torch.zeros(n_out, device=dev)
+    if epi == ops.EPI_TABLE:
+        kw['table'], kw['period'] = torch.zeros(M, n_out, device=dev), M
+    ld = (n_out + 7) // 8 * 8
+    out = torch.empty(M, ld, dtype=torch.float32 if of32 else torch.bfloat16, device=dev)
+    for _ in range(5):
+        ops.linear(a, w, bias, epi, out=out, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.linear(a, w, bias, epi, out=out, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def workload_config(args, batch):
     return {'workload': 'Speech-Transformer 12-enc/6-dec d_model=256 h=4 d_ff=2048(GLU) V=4234; '
                         f'{batch} utt x {T_FRAMES} frames x {F_BINS}-dim fbank per GPU; frontend+encoder forward + '
@@ -324,6 +356,22 @@ def run_b200(args):
     ops.PROFILE = []            # per-launch CUDA events on the GEMMs of the single-lane (uncontended) timed passes
     ms_lat = timed(step_resident, 4, 1) / 4
     prof, ops.PROFILE = ops.PROFILE, None
+    # the same decode-step kernels, eager (outside the CUDA graph) so that each GEMM launch can be bracketed by events
+    from opentransformer_b200.recognize import BeamDecoder
+    with torch.no_grad():
+        mem0, len0, B0, T20 = lanes[0][1]._encode_bf16(*ring_dev[0])
+        bd0 = BeamDecoder(model.decoder, B0, BEAM, T20, MAX_LEN, dev, use_graph=False)
+        bd0.keep_logp = False
+        bd0.setup(mem0, len0)
+        for _ in range(4):
+            bd0.step()
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        for _ in range(8):
+            bd0.step()
+        torch.cuda.synchronize()
+    prof_dec, ops.PROFILE = ops.PROFILE, None
+    del bd0
 
     if L > 1:
         timed(step_resident, 2 * L, L)      # untimed multi-lane pass: thread start-up, allocator growth per stream
@@ -343,26 +391,48 @@ def run_b200(args):
 
     if rank == 0:
         peaks, src = measured_peaks()
-        # dominant kernel = the GEMM launch shape with the largest summed device time in the (single-lane) timed passes
-        groups = {}
-        for k, f, a, b, tag in prof:
-            if k == 'gemm':
-                g = groups.setdefault(tag, [0, 0.0, 0.0])
-                g[0] += 1
-                g[1] += f
-                g[2] += a.elapsed_time(b)
-        tag, (cnt, flops, gms) = max(groups.items(), key=lambda kv: kv[1][2])
-        all_ms = sum(v[2] for v in groups.values())
-        all_fl = sum(v[1] for v in groups.values())
-        ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
+        # Dominant kernel = the GEMM launch shape with the largest device time per recognize pass.  The decode loop runs
+        # inside a CUDA graph (no per-launch events), so its GEMM shapes are timed in `prof_dec`: 8 eager decode steps of
+        # the same kernels on the same shapes, x MAX_LEN steps per pass.  Encoder / setup shapes come from the 4 eager
+        # single-lane passes in `prof`.
         epi_names = ['bias', 'relu', 'glu', 'posenc-table', 'residual', 'residual+layernorm', 'swish', 'gelu', 'tanh']
+        shapes = {}
+        for records, per_pass in ((prof, 1.0 / 4), (prof_dec, MAX_LEN / 8.0)):
+            for k, f, a, b, tag in records:
+                if k == 'gemm':
+                    e = shapes.setdefault(tag, {'launches_per_pass': 0.0})
+                    e['launches_per_pass'] += per_pass
+        for tag, e in shapes.items():       # launch counts from the recorded passes, durations from back-to-back launches
+            e['avg_ms'] = time_gemm_shape(tag, dev)
+            e['ms_per_pass'] = e['avg_ms'] * e['launches_per_pass']
+        tag, e = max(shapes.items(), key=lambda kv: kv[1]['ms_per_pass'])
+        epi, M_, Nw_, K_, _of32 = tag
+        avg_ms = e['avg_ms']
+        flops = 2.0 * M_ * Nw_ * K_
+        n_out = Nw_ // 2 if epi == 2 else Nw_
+        nbytes = 2.0 * (M_ * K_ + Nw_ * K_ + M_ * n_out) + (2.0 * M_ * n_out if epi in (4, 5) else 0.0)
+        tf, gbs = flops / (avg_ms * 1e-3) / 1e12, nbytes / (avg_ms * 1e-3) / 1e9
+        peak_tf, peak_bw = peaks.get('bf16_tflops_sustained', 1400.0), peaks.get('hbm_gbs', 6650.0)
+        use_hbm = gbs / peak_bw > tf / peak_tf
+        ach, peak = (gbs, peak_bw) if use_hbm else (tf, peak_tf)
+        all_ms = sum(v['ms_per_pass'] for v in shapes.values())
         traffic = None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-                traffic = json.load(f).get('%s_M%d_N%d_K%d' % (epi_names[tag[0]], tag[1], tag[2], tag[3]))
+                traffic = json.load(f).get('%s_M%d_N%d_K%d' % (epi_names[epi], M_, Nw_, K_))
         except Exception:
             pass
+        roofline = {'bound': 'hbm' if use_hbm else 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'GB/s' if use_hbm else 'TFLOP/s',
+                    'frac': ach / peak if peak else None, 'traffic': traffic,
+                    'kernel': f'gemm_tc_kernel, epilogue {epi_names[epi]}, M={M_} N={Nw_} K={K_}: {e["launches_per_pass"]:.0f} launches and '
+                              f'{e["ms_per_pass"]:.2f} ms per recognize pass (largest share of {all_ms:.2f} ms of GEMM time per pass), '
+                              f'avg {avg_ms * 1e3:.1f} us per launch (50 back-to-back launches between CUDA events); algorithmic {flops / 1e9:.3f} GFLOP (2MNK) and '
+                              f'{nbytes / 1e6:.2f} MB (A + W + out [+ resid]) per launch = {tf:.1f} TFLOP/s, {gbs:.0f} GB/s: a '
+                              f'latency-bound launch (few CTAs, {K_ // 64} dependent k-blocks), far from either roof',
+                    'alt': {'tflops': tf, 'frac_tensor': tf / peak_tf, 'gbs': gbs, 'frac_hbm': gbs / peak_bw},
+                    'all_gemm_shapes_ms_per_pass': {('%s_M%d_N%d_K%d' % (epi_names[t[0]], t[1], t[2], t[3])): round(v['ms_per_pass'], 3)
+                                                    for t, v in sorted(shapes.items(), key=lambda kv: -kv[1]['ms_per_pass'])[:8]},
+                    'peak_source': f'MEASURED_PEAKS.json ({src})'}
         utt = B_PER_GPU * world * args.steps
         value = utt / (ms_total * 1e-3)
         e2e = utt / (ms_e2e * 1e-3)
@@ -380,14 +450,7 @@ def run_b200(args):
                           'encoder_fwd_ms': ms_enc, 'encoder_fwd_utt_per_s': B_PER_GPU * world / (ms_enc * 1e-3),
                           'beam_decode_ms': ms_lat - ms_enc,
                           'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3)},
-            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': ach / peak if peak else None, 'traffic': traffic,
-                         'kernel': f'gemm_tc_kernel, epilogue {epi_names[tag[0]]}, M={tag[1]} N={tag[2]} K={tag[3]} '
-                                   f'(dominant GEMM shape: {cnt} launches, {flops / cnt / 1e9:.2f} GFLOP algorithmic each = 2MNK, '
-                                   f'avg {gms / cnt * 1e3:.1f} us by CUDA events in 4 single-lane timed passes)',
-                         'all_gemms': {'launches': sum(v[0] for v in groups.values()), 'gflop': all_fl / 1e9, 'ms': all_ms,
-                                       'tflops': all_fl / (all_ms * 1e-3) / 1e12 if all_ms > 0 else None},
-                         'peak_source': f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'},
+            'roofline': roofline,
             'clocks': clocks,
         }
         if args.cpu_baseline and world == 1:
@@ -476,6 +539,137 @@ def run_conformer(args):
     return 0
 
 
+def train_params():
+    """BASELINE config 5: the config-2 model with every dropout rate 0 (the reference's residual_dropout 0.1 is stochastic;
+    the B200 training path implements the deterministic network)."""
+    p = model_params()
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k in list(p[part]):
+            if 'dropout' in k:
+                p[part][k] = 0.0
+    return p
+
+
+def synthetic_targets(batch, seed):
+    """collate_fn_with_eos_bos (data/loader.py:85-86): <S/E> ids <S/E> then PAD(0); 20-30 ids in [3, V)."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(20, 31, (batch,), generator=g)
+    L = 32                                   # 30 ids + <S/E> on both sides: one step geometry for every batch
+    t = torch.zeros(batch, L, dtype=torch.long)
+    for b in range(batch):
+        n = int(lens[b])
+        t[b, 0] = 1
+        t[b, 1:n + 1] = torch.randint(3, 4234, (n,), generator=g)
+        t[b, n + 1] = 1
+    return t
+
+
+def run_train(args):
+    """BASELINE config 5: one optimizer step per `step` -- SpecAugment (device) -> forward -> hand-written backward ->
+    gradient all-reduce over NCCL (N > 1) -> global-norm clip + Adam.  32 utterances x 1000 frames per GPU (weak scaling:
+    global batch 32 N; N = 8 is the reference's 256)."""
+    import random
+    import numpy as np
+    import torch.distributed as dist
+    from opentransformer_b200 import ops
+    from opentransformer_b200.augment import spec_augment_
+    from opentransformer_b200.model import SpeechToText
+    from opentransformer_b200.train import FusedTrainer
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(1234)                       # identical initial weights on every rank (run.py:23-33)
+    model = SpeechToText(train_params()).to(dev).train()
+    trainer = FusedTrainer(model, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, clip_grad=5.0, model_size=256,
+                           warmup_steps=12000, accum_steps=1)
+    random.seed(100 + rank)
+    np.random.seed(100 + rank)
+    RING = 8
+    ring = []
+    for i in range(RING):
+        x, m = synthetic_batch(B_PER_GPU, 5000 * rank + i)
+        ring.append((x.pin_memory(), m.pin_memory(), synthetic_targets(B_PER_GPU, 7000 * rank + i).pin_memory()))
+    ring_dev = [tuple(t.to(dev) for t in item) for item in ring]
+    lens = [T_FRAMES] * B_PER_GPU
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        x, m, t = ring_dev[i % RING]
+        xa = spec_augment_(x.clone(), lens)
+        return trainer.step(xa, m, t)
+
+    def step_e2e(i):
+        xp, mp, tp = ring[i % RING]
+        x = xp.to(dev, non_blocking=True)
+        m = mp.to(dev, non_blocking=True)
+        t = tp.to(dev, non_blocking=True)
+        spec_augment_(x, lens)
+        return float(trainer.step(x, m, t))        # the loss is read back every step (trainer.py:216)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    step_e2e(0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = ops.COUNTERS['launches']
+    ms = timed(step_resident, args.steps)
+    launches = ops.COUNTERS['launches'] - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(step_resident(0))
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        peaks, src = measured_peaks()
+        # SURVEY.md 8(d): encoder-fwd 410.0 + teacher-forced decoder ~38.9 GFLOP per 32-utt batch; backward = 2x forward
+        flop = 3.0 * (410.0e9 + 38.9e9)
+        ach = flop * args.steps / (ms * 1e-3) / 1e12
+        utt = B_PER_GPU * world * args.steps
+        item = ring[0]
+        print(json.dumps({
+            'metric': 'utterances/sec (training step: SpecAugment + fwd + bwd + grad all-reduce + clip + Adam)',
+            'value': utt / (ms * 1e-3), 'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': 'BASELINE config 5: training step, Speech-Transformer 12-enc/6-dec d_model=256, '
+                                   f'{B_PER_GPU} utt x {T_FRAMES} frames per GPU, targets 20-30 tokens, label smoothing 0.1, '
+                                   'SpecAugment on (2 freq + 2 time masks), Adam + Noam(256, 12000), clip 5, bf16 compute / fp32 '
+                                   'master weights, all dropout rates 0',
+                       'global_batch': B_PER_GPU * world, 'parallelism': f'dp{world} (one NCCL all-reduce of the flat fp32 gradient per step)',
+                       'l2_policy': '8 distinct batches rotate; every step streams > 2 GB of activations / gradients'},
+            'e2e': {'value': utt / (ms_e2e * 1e-3), 'unit': 'utt/s',
+                    'h2d_bytes_per_step': item[0].numel() * 4 + item[1].numel() + item[2].numel() * 8, 'd2h_bytes_per_step': 4},
+            'gpu_launches': launches, 'final_loss': final_loss,
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks.get('bf16_tflops_sustained'), 'unit': 'TFLOP/s',
+                         'frac': ach / peaks.get('bf16_tflops_sustained', 1400.0), 'traffic': None,
+                         'kernel': 'whole training step (3 x 448.9 GFLOP algorithmic per 32-utterance batch)',
+                         'peak_source': src},
+            'clocks': clocks}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -483,9 +677,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--ref-sample', type=int, default=2, help='utterances per CPU reference pass')
-    ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer'],
-                    help="'conformer' = BASELINE config 4 (encoder forward only); default is the headline workload")
-    ap.add_argument('--lanes', type=int, default=6, help='utterance batches kept in flight per GPU (streams)')
+    ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer', 'train'],
+                    help="'conformer' = BASELINE config 4 (encoder forward only), 'train' = config 5 (training step); "
+                         "default is the headline workload")
+    ap.add_argument('--lanes', type=int, default=8, help='utterance batches kept in flight per GPU (streams)')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -494,6 +689,8 @@ def main():
         raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)')
     if args.workload == 'conformer':
         return run_conformer(args)
+    if args.workload == 'train':
+        return run_train(args)
     return run_b200(args)
 
 

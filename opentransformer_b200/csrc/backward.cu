@@ -440,3 +440,32 @@ const char* conv1_wgrad_launch(cudaStream_t st, const bf16* dpre1, const float* 
 }
 
 }  // namespace otb
+
+namespace otb {
+
+// ------------------------------------------------------------------------------------------------
+// SpecAugment application (otrans/data/augment.py:9-41): zero `nf` frequency bands and `nt` time bands per utterance.
+// The band positions are drawn on the host with the reference's RNG call order (opentransformer_b200/augment.py) and
+// replayed here on the device-resident batch: x f32 [B, T, F] in place; bands i32 [B, 2*(nf+nt)] = (f0, f)*nf, (t0, t)*nt.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spec_augment_kernel(float* __restrict__ x, const int* __restrict__ bands, int B, int T,
+                                                           int F, int nf, int nt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * T * F) return;
+    const int f = (int)(i % F);
+    const int t = (int)((i / F) % T);
+    const int b = (int)(i / ((size_t)F * T));
+    const int* bd = bands + (size_t)b * 2 * (nf + nt);
+    bool kill = false;
+    for (int j = 0; j < nf; ++j) kill |= (f >= bd[2 * j] && f < bd[2 * j] + bd[2 * j + 1]);
+    for (int j = 0; j < nt; ++j) kill |= (t >= bd[2 * (nf + j)] && t < bd[2 * (nf + j)] + bd[2 * (nf + j) + 1]);
+    if (kill) x[i] = 0.f;
+}
+const char* spec_augment_launch(cudaStream_t st, float* x, const int* bands, int B, int T, int F, int nf, int nt) {
+    const size_t n = (size_t)B * T * F;
+    spec_augment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, bands, B, T, F, nf, nt);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace otb

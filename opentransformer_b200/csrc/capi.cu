@@ -400,4 +400,9 @@ int otb_conv1_wgrad(const void* dpre1, const float* x, float* out, int B, int T,
     RET("otb_conv1_wgrad", conv1_wgrad_launch(ST(stream), reinterpret_cast<const bf16*>(dpre1), x, out, B, T, F, T1, F1, T2, F2, C1));
 }
 
+int otb_spec_augment(float* x, const int32_t* bands, int B, int T, int F, int n_freq, int n_time, void* stream) {
+    if (!x || !bands || B < 1 || T < 1 || F < 1 || n_freq < 0 || n_time < 0) return fail("otb_spec_augment", "bad arguments");
+    RET("otb_spec_augment", spec_augment_launch(ST(stream), x, bands, B, T, F, n_freq, n_time));
+}
+
 }  // extern "C"

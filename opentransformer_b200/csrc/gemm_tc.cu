@@ -718,6 +718,9 @@ static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
         const int n_tiles = (n_cols + bn_out - 1) / bn_out;
         const long tiles = (long)m_tiles * n_tiles;
         const long waves = (tiles + sms - 1) / sms;
+        // Measured alternative (round 1): preferring the widest tile in the decode regime (fewer, fatter CTAs) cut the
+        // SM-time of a decode step by ~15 % but added ~1.5 us to every launch (35.0 vs 31.5 ms per 60-step decode) and did
+        // not raise the throughput of concurrent batches -- profiles/r1_bench_history.md -- so latency decides.
         const double cost = (double)waves * (bn + 48);  // +48: per-tile fixed overhead in "column" units
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }

@@ -385,7 +385,7 @@ const char* log_softmax_launch(cudaStream_t st, const float* x, int ldx, float* 
 __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
                                                                bf16* __restrict__ vc, const int* __restrict__ anc,
                                                                const int* __restrict__ step_ptr, bf16* __restrict__ out,
-                                                               int N, int H, int Lmax, float scale) {
+                                                               int N, int H, int Lmax, float scale, int keys_pad) {
     // Lanes run over KEYS: each lane owns up to KPL cached positions, resolves their slots through the
     // ancestry table and pulls the whole 128-byte K and V rows with 16-byte loads -- all loads of a lane are
     // independent, so the kernel costs ~3 dependent memory round trips (anc -> K/V -> out) instead of a
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
     const int step = *step_ptr;
     const int nkeys = step + 1;
     const int* an = anc + ((size_t)(step & 1) * N + n) * Lmax;
-    uint4* sv = sv_raw + (size_t)wib * (32 * KPL) * 8;
+    uint4* sv = sv_raw + (size_t)wib * keys_pad * 8;    // [keys_pad][8 x 16 B] per warp
     for (int h = wib; h < H; h += nw) {
         const bf16* base = qkv + (size_t)n * 3 * d + h * 64;
         // append the newest K/V to the cache (lane owns dims 2*lane, 2*lane+1)
@@ -488,14 +488,17 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
                                     const int* step_ptr, bf16* out, int N, int H, int Lmax) {
     if (Lmax > 128) return "decode_self_attn: at most 128 cached positions (max_len <= 128)";
     const int warps = H < 4 ? H : 4;
-    const size_t smem = (size_t)warps * 128 * 128;   // [warps][128 keys][128 B]
+    // V staging sized by the longest prefix this search can reach (not the 128-key maximum): at max_len 60 this halves the
+    // shared memory per CTA and doubles the resident CTAs of this latency-bound kernel (less SM-time per decode step)
+    const int keys_pad = (Lmax + 31) / 32 * 32;
+    const size_t smem = (size_t)warps * keys_pad * 128;   // [warps][keys_pad][128 B]
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(decode_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
             return "cudaFuncSetAttribute(decode_self_attn) failed";
         attr_set = true;
     }
-    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f);
+    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f, keys_pad);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -115,7 +115,7 @@ def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=No
         ldc = n_out if n_out is not None else N
         out = torch.empty(M, ldc, dtype=torch.float32 if out_f32 else BF16, device=a.device)
     ldc = out.stride(0)
-    with _Timed('gemm', 2.0 * M * w.shape[0] * K, (epilogue, M, w.shape[0], K)):
+    with _Timed('gemm', 2.0 * M * w.shape[0] * K, (epilogue, M, w.shape[0], K, out.dtype == torch.float32)):
         check(_lib.lib().otb_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), ldc, M, N, K, epilogue,
                                     1 if out.dtype == torch.float32 else 0, _p(resid),
                                     resid.stride(0) if resid is not None else 0, _p(gamma), _p(beta), eps, alpha,
@@ -476,3 +476,4 @@ def conv1_wgrad(dpre1, x, B, T, F, C1):
     check(_lib.lib().otb_conv1_wgrad(_p(dpre1), _p(x), _p(out), B, T, F, C1, _stream()), 'otb_conv1_wgrad')
     _count()
     return out
+

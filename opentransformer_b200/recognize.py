@@ -175,6 +175,8 @@ class BeamDecoder:
                 x = ops.layernorm(x, *p['ln2'])
             q = ops.linear(x, p['wq'], p['bq'])
             # the `beam` hypotheses of utterance b are the query rows [b*beam, (b+1)*beam) of one attention problem
+            # (a SIMT kernel specialised for <= 16 query rows was measured at 14.9 us against 10.0 us for this tcgen05 kernel
+            # padded to 128 rows and was dropped: profiles/r1_bench_history.md)
             ctx = ops.attention(q, self.kvx[l], self.kvx[l], self.B, H, self.beam, self.T, kv_len=self.mem_len,
                                 k_col0=0, v_col0=d)
             x = _proj_resid_ln(ctx, p['wo2'], p['bo2'], x, None if nb else p['ln2'])

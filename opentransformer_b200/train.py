@@ -277,7 +277,7 @@ class FusedTrainer:
     kernels, no host synchronisation.  Parameters become views into one flat buffer (state_dict keys / shapes unchanged)."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, clip_grad=5.0, model_size=256,
-                 warmup_steps=12000, factor=1.0, accum_steps=1, process_group=None):
+                 warmup_steps=12000, factor=1.0, accum_steps=1, process_group=None, use_graph=True):
         self.model = model
         self.params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         dev = self.params[0][1].device
@@ -305,26 +305,60 @@ class FusedTrainer:
         self.global_step = 2
         self.opt_steps = 0
         self.micro = 0
+        self.use_graph = use_graph
+        self._graphs = {}
 
     def lr(self):
         if self.warmup:
             return transformer_lr(self.global_step, self.model_size, self.warmup, self.factor)
         return self.base_lr
 
+    def _micro(self, inputs, mask, truth):
+        """forward + backward of one micro-batch; gradients / accum_steps are ADDED into the flat buffer."""
+        loss, grads = forward_backward(self.model, inputs, mask, truth)
+        inv = 1.0 / self.accum_steps
+        for n, _ in self.params:
+            o, k = self.offsets[n]
+            self.flat_g[o:o + k].add_(grads[n].reshape(-1), alpha=inv)
+        return loss
+
+    def _graph_for(self, inputs, mask, truth):
+        """The ~870 launches of one micro-batch captured once per input geometry and replayed: launched one by one from
+        Python the step is host-bound (14.6 ms against 10.2 ms of kernel time, profiles/r1_launches_train_v0.csv)."""
+        key = (tuple(inputs.shape), tuple(truth.shape), inputs.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx, sm, st = inputs.clone(), mask.clone(), truth.clone()
+            snap = self.flat_g.clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # warm-up outside capture: lazy kernel attributes, cached tables
+                self._micro(sx, sm, st)
+            cur.wait_stream(side)
+            self.flat_g.copy_(snap)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.COUNTERS['launches']
+            with torch.cuda.graph(graph):
+                loss = self._micro(sx, sm, st)
+            launches = ops.COUNTERS['launches'] - n0
+            ops.COUNTERS['launches'] = n0           # capture records, it does not launch
+            ent = (graph, sx, sm, st, loss, launches)
+            self._graphs[key] = ent
+        return ent
+
     def step(self, inputs, mask, truth):
         """One micro-batch; every `accum_steps` calls an optimizer step.  Returns the (un-scaled) loss tensor."""
         with torch.no_grad():
-            loss, grads = forward_backward(self.model, inputs, mask, truth)
-            first = self.micro % self.accum_steps == 0
-            inv = 1.0 / self.accum_steps
-            for n, _ in self.params:
-                o, k = self.offsets[n]
-                gsl = self.flat_g[o:o + k]
-                gr = grads[n].reshape(-1)
-                if first:
-                    gsl.copy_(gr) if inv == 1.0 else torch.mul(gr, inv, out=gsl)
-                else:
-                    gsl.add_(gr, alpha=inv)
+            if self.use_graph:
+                graph, sx, sm, st, loss, launches = self._graph_for(inputs, mask, truth)
+                sx.copy_(inputs)
+                sm.copy_(mask)
+                st.copy_(truth)
+                graph.replay()
+                ops.COUNTERS['launches'] += launches
+            else:
+                loss = self._micro(inputs, mask, truth)
             self.micro += 1
             if self.micro % self.accum_steps == 0:
                 # the one exchange step of data-parallel training (SURVEY.md 8e): mean of the flat gradient over ranks,
@@ -335,5 +369,6 @@ class FusedTrainer:
                 self.opt_steps += 1
                 ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.sumsq, self.clip, self.lr(), self.betas, self.eps,
                               self.wd, self.opt_steps)
+                self.flat_g.zero_()
                 modules.bump_param_generation()     # bf16 shadow copies (modules._Packed) must be rebuilt
         return loss

@@ -435,3 +435,4 @@ def test_beam_multi_step_reconstruct_and_finalize():
     got_p, got_s = st.finalize(0.6, 5, 2)
     assert torch.equal(got_p[:, :, :steps].cpu(), nb)
     torch.testing.assert_close(got_s.cpu(), ns, rtol=1e-6, atol=1e-6)
+

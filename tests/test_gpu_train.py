@@ -116,14 +116,15 @@ def test_autograd_seam_fills_param_grads():
     assert abs(float(l2) - float(loss)) < 2e-2 * abs(float(loss))
 
 
-def test_fused_trainer_step_matches_oracle_step():
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_fused_trainer_step_matches_oracle_step(use_graph):
     """Two optimizer steps with gradient accumulation over 2 micro-batches each: weights after clip + lr(3), lr(4) +
     Adam must follow the oracle's (= the reference trainer's) update."""
     params = _params(n_enc=1, n_dec=1)
     model, sd = _build(params)
     model.train()
     tr = train.FusedTrainer(model, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, clip_grad=0.05, model_size=256,
-                            warmup_steps=12000, accum_steps=2)
+                            warmup_steps=12000, accum_steps=2, use_graph=use_graph)
     names = [n for n, _ in model.named_parameters()]
     w = {n: sd[n].clone() for n in names}
     m = {n: torch.zeros_like(w[n]) for n in names}

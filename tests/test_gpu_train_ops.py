@@ -186,3 +186,23 @@ def test_ls_ce_train_grad_and_adam():
     ops.sumsq(bad, ss)
     ops.adam_step(p, bad, m, v, ss, 5.0, 1e-3, (0.9, 0.98), 1e-9, 1e-6, 4)
     assert torch.equal(p, before), 'non-finite gradient norm must skip the update (trainer.py:229-230)'
+
+
+def test_spec_augment_kernel_matches_numpy_slicing():
+    import random
+    import numpy as np
+    from opentransformer_b200.augment import draw_bands, spec_augment_
+    B, T, F = 3, 300, 80
+    lens = [300, 211, 257]
+    x = torch.randn(B, T, F, generator=torch.Generator().manual_seed(1)) + 3.0
+    random.seed(5); np.random.seed(6)
+    ref = x.clone()
+    for b, n in enumerate(lens):           # data/augment.py:28-39 on the un-padded utterance
+        bd = draw_bands(n, F)
+        for j in range(2):
+            ref[b, :, bd[2 * j]:bd[2 * j] + bd[2 * j + 1]] = 0
+        for j in range(2, 4):
+            ref[b, bd[2 * j]:bd[2 * j] + bd[2 * j + 1], :] = 0
+    random.seed(5); np.random.seed(6)
+    got = spec_augment_(x.to(DEV).clone(), lens)
+    assert torch.equal(got.cpu(), ref)
