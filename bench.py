@@ -130,6 +130,13 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.rows), 'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
+def quiet_nccl():
+    """NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION/INFO (the GPU image sets it); rank 0's stdout must
+    carry exactly one JSON line."""
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE', ''):
+        os.environ['NCCL_DEBUG'] = 'WARN'
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -271,6 +278,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        quiet_nccl()
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -289,6 +297,16 @@ def run_b200(args):
     # L independent "lanes" (stream + recogniser state + captured decode graph): the decode loop is a chain of
     # small latency-bound kernels that leaves most SMs idle, so several utterance batches are kept in flight.
     L = max(1, args.lanes)
+    # single-lane diagnostics run on their own recogniser captured under the latency policy; the concurrent lanes use
+    # the throughput policy (least SM-time per decode step) -- the policy is baked into each captured decode graph
+    ops.set_tile_policy('latency')
+    rec_lat = SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA, ngpu=1)
+    with torch.no_grad():
+        for i in range(3):
+            rec_lat.recognize_ids(*ring_dev[i])
+    torch.cuda.synchronize()
+    policy = args.tile_policy if args.tile_policy != 'auto' else ('throughput' if L > 1 else 'latency')
+    ops.set_tile_policy(policy)
     lanes = []
     for j in range(L):
         rec = SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA,
@@ -299,12 +317,21 @@ def run_b200(args):
         x, m = ring_dev[i % RING]
         return rec.recognize_ids(x, m)
 
+    out_pin = {}
+
     def step_e2e(rec, i):
         xp, mp = ring_pin[i % RING]
         xd = xp.to(dev, non_blocking=True)
         md = mp.to(dev, non_blocking=True)
         out, scores = rec.recognize(xd, md)              # public API (ids because idx2unit is None)
-        return out.cpu(), scores.cpu()
+        bufs = out_pin.get(id(rec))
+        if bufs is None or bufs[0].shape != out.shape:
+            bufs = (torch.empty(out.shape, dtype=out.dtype).pin_memory(), torch.empty(scores.shape, dtype=scores.dtype).pin_memory())
+            out_pin[id(rec)] = bufs
+        bufs[0].copy_(out, non_blocking=True)            # results land in pinned host memory; one sync per step
+        bufs[1].copy_(scores, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return bufs
 
     def timed(fn, steps, n_lanes):
         """K steps spread round-robin over n_lanes host threads / CUDA streams; device time by CUDA events."""
@@ -352,10 +379,15 @@ def run_b200(args):
     def enc_only(rec, i):
         with torch.no_grad():
             return rec._encode_bf16(*ring_dev[i % RING])
+    timed(enc_only, 8, 1)                           # untimed: first pass after the graph captures
     ms_enc = timed(enc_only, 8, 1) / 8
-    ops.PROFILE = []            # per-launch CUDA events on the GEMMs of the single-lane (uncontended) timed passes
-    ms_lat = timed(step_resident, 4, 1) / 4
+    ops.PROFILE = []            # records the eager GEMM launches (shapes, counts) of the single-lane passes
+    ms_lat_tp = timed(step_resident, 4, 1) / 4      # lane 0 alone, under the lanes' own tile policy
     prof, ops.PROFILE = ops.PROFILE, None
+    keep = lanes[0]
+    lanes[0] = (keep[0], rec_lat)
+    ms_lat = timed(step_resident, 4, 1) / 4         # lone batch, latency policy
+    lanes[0] = keep
     # the same decode-step kernels, eager (outside the CUDA graph) so that each GEMM launch can be bracketed by events
     from opentransformer_b200.recognize import BeamDecoder
     with torch.no_grad():
@@ -384,10 +416,10 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, args.steps, L)
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([ms_total, ms_e2e, ms_enc, ms_lat], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_tp], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_enc, ms_lat = t.tolist()
+    ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_tp = t.tolist()
 
     if rank == 0:
         peaks, src = measured_peaks()
@@ -438,6 +470,7 @@ def run_b200(args):
         e2e = utt / (ms_e2e * 1e-3)
         cfg = workload_config(args, B_PER_GPU)
         cfg['lanes'] = L
+        cfg['tile_policy'] = policy
         line = {
             'metric': 'utterances/sec (encoder-fwd + beam-10 decode, 60 steps)', 'value': value, 'unit': 'utt/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -448,6 +481,7 @@ def run_b200(args):
             'gpu_launches': launches,
             'breakdown': {'single_lane_step_ms': ms_lat, 'single_lane_utt_per_s': B_PER_GPU * world / (ms_lat * 1e-3),
                           'encoder_fwd_ms': ms_enc, 'encoder_fwd_utt_per_s': B_PER_GPU * world / (ms_enc * 1e-3),
+                          'single_lane_step_ms_under_lane_policy': ms_lat_tp,
                           'beam_decode_ms': ms_lat - ms_enc,
                           'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3)},
             'roofline': roofline,
@@ -494,6 +528,7 @@ def run_conformer(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        quiet_nccl()
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(1234)
     model = SpeechToText(conformer_params()).eval().to(dev)
@@ -581,6 +616,7 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        quiet_nccl()
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(1234)                       # identical initial weights on every rank (run.py:23-33)
     model = SpeechToText(train_params()).to(dev).train()
@@ -681,6 +717,8 @@ def main():
                     help="'conformer' = BASELINE config 4 (encoder forward only), 'train' = config 5 (training step); "
                          "default is the headline workload")
     ap.add_argument('--lanes', type=int, default=8, help='utterance batches kept in flight per GPU (streams)')
+    ap.add_argument('--tile-policy', default='auto', choices=['auto', 'latency', 'throughput'],
+                    help='tiling of the decode-step GEMMs (otb_set_tile_policy); auto = throughput when lanes > 1')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     args = ap.parse_args()
     if args.impl == 'reference':

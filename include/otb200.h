@@ -42,6 +42,11 @@ enum {
 const char* otb_last_error(void);
 int otb_version(void);
 int otb_num_sms(void);
+/* Tiling policy of small GEMMs (M <= 512 rows, the decode step): 0 (default) = shortest launch -- narrow tiles, the
+ * residual+LayerNorm row split over a 4-CTA cluster; 1 = least SM-time -- the widest tile on the fewest CTAs, for
+ * servers that keep several utterance batches in flight on separate streams (+10-15 % aggregate throughput, +30 %
+ * latency of a lone batch on B200).  Process-wide; set it before CUDA graphs are captured. */
+int otb_set_tile_policy(int policy);
 /* Profiling aid: buf (device, u64 [grid*8]) receives per-CTA clock64 phase stamps of the next GEMMs; NULL disables. */
 int otb_debug_gemm_timing(unsigned long long* buf);
 /* Profiling aid: 0 = normal, 1 = GEMM mainloop without TMA traffic, 2 = without MMAs (results are garbage). */

@@ -42,6 +42,7 @@ _SIGS = {
     'otb_num_sms': (c_int, []),
     'otb_debug_gemm_timing': (c_int, [_P]),
     'otb_debug_gemm_mode': (c_int, [c_int]),
+    'otb_set_tile_policy': (c_int, [c_int]),
     'otb_debug_mega_timing': (c_int, [_P, c_int]),
     'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),

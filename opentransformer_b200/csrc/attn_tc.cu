@@ -14,6 +14,7 @@
 //   S  = Q K^T      : 4 x UMMA 128x128x16  -> TMEM columns [0,128)
 //   P  = exp2(S*c - m) as bf16 written to smem in the canonical K-major SWIZZLE_128B layout
 //   O' = P V        : 8 x UMMA 128x64x16   -> TMEM columns [128,192), rescaled + accumulated in registers
+#include "launch.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
 
@@ -31,6 +32,8 @@ template <bool HAS_BD>
 __global__ void __launch_bounds__(128, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    PDL_TRIGGER();
+    PDL_WAIT();   // before the first global read (kv_len) -- launch latency and CTA scheduling still overlap the predecessor
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -265,9 +268,8 @@ const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, con
         attr_set = true;
     }
     dim3 grid((p.Tq + 127) / 128, p.H, p.B);
-    if (p.bd) attn_tc_kernel<true><<<grid, 128, ATT_SMEM, st>>>(tq, tk, tv, p);
-    else attn_tc_kernel<false><<<grid, 128, ATT_SMEM, st>>>(tq, tk, tv, p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = p.bd ? launch_pdl(attn_tc_kernel<true>, grid, dim3(128), ATT_SMEM, st, tq, tk, tv, p)
+                         : launch_pdl(attn_tc_kernel<false>, grid, dim3(128), ATT_SMEM, st, tq, tk, tv, p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

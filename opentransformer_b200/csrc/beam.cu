@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "beam_common.cuh"
+#include "launch.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
 
@@ -29,6 +30,8 @@ __global__ void __launch_bounds__(KMAX * 32) beam_step_kernel(const float* __res
                                                               float lm_weight, BeamState st, long long* dbg_ktok,
                                                               int* dbg_offs, const float* __restrict__ pre_val,
                                                               const int* __restrict__ pre_idx) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     __shared__ float c_val[KMAX * KMAX];
     __shared__ int c_tok[KMAX * KMAX];
     __shared__ float sel_v[KMAX];
@@ -137,9 +140,8 @@ const char* beam_step_launch(cudaStream_t stream, const float* logp, int ldl, in
     if (st.N % st.beam) return "beam_step: N must be a multiple of beam";
     if (!logp && !pre_val) return "beam_step: need log-probs or a precomputed top-k";
     if ((pre_val == nullptr) != (pre_idx == nullptr)) return "beam_step: pre_val / pre_idx must both be given";
-    beam_step_kernel<<<st.N / st.beam, st.beam * 32, 0, stream>>>(logp, ldl, V, lm_logp, ld_lm, lm_weight, st,
-                                                                  dbg_ktok, dbg_offs, pre_val, pre_idx);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(beam_step_kernel, dim3(st.N / st.beam), dim3(st.beam * 32), 0, stream, logp, ldl, V, lm_logp, ld_lm,
+                               lm_weight, st, dbg_ktok, dbg_offs, pre_val, pre_idx);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) logsoftmax_topk_kernel(const flo
                                                                        float lm_weight, int k, float* __restrict__ out_val,
                                                                        int* __restrict__ out_idx,
                                                                        float* __restrict__ out_logp, int ld_logp) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     extern __shared__ float srow[];   // [V]
     __shared__ float red[8];
     __shared__ float bc;
@@ -347,9 +351,8 @@ const char* logsoftmax_topk_launch(cudaStream_t stream, const float* logits, int
             return "cudaFuncSetAttribute(logsoftmax_topk) failed";
         attr_set = true;
     }
-    logsoftmax_topk_kernel<<<rows, TOPK_THREADS, smem, stream>>>(logits, ldl, V, lm_logp, ld_lm, lm_weight, k, out_val,
-                                                                 out_idx, out_logp, ld_logp);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(logsoftmax_topk_kernel, dim3(rows), dim3(TOPK_THREADS), smem, stream, logits, ldl, V, lm_logp, ld_lm,
+                               lm_weight, k, out_val, out_idx, out_logp, ld_logp);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

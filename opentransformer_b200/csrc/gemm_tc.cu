@@ -25,16 +25,21 @@
 // round-robin tile scheduler, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <string.h>
 
+#include "launch.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
 
 namespace otb {
 
+int g_tile_policy = 0;   // otb_set_tile_policy: 0 = lowest latency of a lone launch, 1 = least SM-time (concurrent batches)
 unsigned long long* g_gemm_dbg = nullptr;
 int g_gemm_dbg_mode = 0;
 #define DBG_STAMP(i) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (i)] = clock64(); } while (0)
 // per-k-block traces of the first tile: kind 0 = TMA issue, 1 = full barrier observed by the MMA thread
 #define DBG_KB(kind, kb) do { if (p.dbg && (kb) < 64) p.dbg[148 * 8 + (blockIdx.x * 2 + (kind)) * 64 + (kb)] = clock64(); } while (0)
+
+// epilogue sub-phase stamps of the SECOND tile of every CTA (steady state): [148*8 + 148*2*64 + cta*16 + i]
+#define DBG_EPI(i) do { if (p.dbg && it == 1 && et == 0) p.dbg[148 * 8 + 148 * 2 * 64 + blockIdx.x * 16 + (i)] = clock64(); } while (0)
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
@@ -111,6 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    PDL_TRIGGER();   // the next kernel of the stream may be scheduled; it waits (griddepcontrol.wait) for this grid to finish
     if (threadIdx.x == 0) DBG_STAMP(0);
 
     const int m_tiles = p.conv ? (p.conv_B * p.conv_T1h + p.conv_R - 1) / p.conv_R : (p.M + BM - 1) / BM;
@@ -178,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&ln_bar[0], 1);
             mbar_init(&ln_bar[1], 1);
             fence_barrier_init();
+            PDL_WAIT();   // predecessor grid complete: its outputs (our A operand) may now be fetched
             // the first STAGES slots are free by construction: start the loads before the CTA-wide sync so
             // their latency overlaps the TMEM allocation
             for (int i = 0; i < STAGES && p_tile < num_tiles; ++i) {
@@ -193,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    PDL_WAIT();   // every thread, before its first global access (barrier init / TMEM allocation above overlap the predecessor)
     if (EPI == EPI_RESID_LN && cl_size > 1) cluster_sync_all();  // peers' mbarriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -279,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t aph = (it >> 1) & 1;
             const int col_base = n_blk * BN_OUT;             // first output column of the tile
             const int ncols = min(BN_OUT, p.N - col_base);   // valid output columns
+            DBG_EPI(0);
 
             // ---- (a) per-tile smem setup: bias slice, row map, residual tile (all coalesced, loads batched)
             if (et < BN) {
@@ -334,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             epi_bar();
+            DBG_EPI(1);
 
             // row validity / padding mask of this thread's row
             const int out_row = s_rowmap[row_in_tile];
@@ -346,6 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
             if (it == 0 && et == 0) DBG_STAMP(5);
+            DBG_EPI(2);
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 
             if (EPI == EPI_RESID_LN) {
@@ -507,11 +518,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     stage16(my_row, c, p.out_f32, v);
                 }
             }
+            DBG_EPI(3);
             if (EPI != EPI_RESID_LN) {
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[as]);  // TMEM stage is free for the next tile's MMAs
             }
             epi_bar();
+            DBG_EPI(4);
 
             // ---- (e) coalesced copy-out: consecutive threads write consecutive 16-byte chunks of a row
             const int row_bytes = ncols * esize;
@@ -558,7 +571,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<uint16_t*>(dst + off) = *reinterpret_cast<const uint16_t*>(src + off);
                 }
             }
+            DBG_EPI(5);
             epi_bar();  // staging / bias smem may be rewritten for the next tile
+            DBG_EPI(6);
             if (it == 0 && et == 0) DBG_STAMP(6);
         }
     }
@@ -655,11 +670,13 @@ static const char* launch_inst(cudaStream_t st, const CUtensorMap& ta, const CUt
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = cl;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         // co-resident clusters (GPC boundaries strand a few SMs): never launch more than fit in one wave
@@ -673,11 +690,11 @@ static const char* launch_inst(cudaStream_t st, const CUtensorMap& ta, const CUt
             grid = max_clusters[cl] * cl;
             cfg.gridDim = dim3(grid);
         }
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;     // (the occupancy query above ran with the cluster attribute only)
         cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, ta, tb, p);
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
-    gemm_tc_kernel<BN, EPI><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(kThreads), Cfg::SMEM_BYTES, st, ta, tb, p);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -700,11 +717,19 @@ static const char* launch_bn(cudaStream_t st, const CUtensorMap& ta, const CUten
 
 // Pick the N tile that wastes the fewest MMA cycles across the persistent grid.
 static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
+    // Decode regime (<= 4 row blocks, M = batch x beam rows): every launch lasts 8-20 us whatever its tiling
+    // (profiles/r1_ncu_decode_gemms_summary.txt) and utterance batches run concurrently on other streams, whose aggregate
+    // throughput is bound by the SM-time the launches occupy (sum of CTAs x duration = 137 us of the whole GPU per decode
+    // step, profiles/r1_bench_history.md).  So small problems take the WIDEST tile: 2-4x fewer CTAs for +1-2 us of latency.
+    // Measured (profiles/r1_bench_history.md): policy 1 raises 8-lane throughput by 10-15 % and lengthens a lone 60-step
+    // decode from 31.5 to 40.9 ms; the serving layer picks the policy (otb_set_tile_policy), latency is the default.
+    const bool decode = (m_tiles <= 4) && g_tile_policy == 1;
     if (epi == EPI_RESID_LN) {
         // A tcgen05.mma from shared memory costs ~160 cycles for any N <= 256 (profiles/r1_bench_history.md), so a
-        // 256-wide tile does the same main loop as four 64-wide ones: with enough row blocks to occupy the SMs keep
-        // the whole row in one CTA; with few row blocks (decode, M = 320) split it over a cluster of N/64 CTAs.
-        return (m_tiles >= 32) ? n_cols : 64;
+        // 256-wide tile does the same main loop as four 64-wide ones: with enough row blocks to occupy the SMs (or under
+        // the throughput policy) keep the whole row in one CTA; a lone small problem (decode, M = 320) is split over a
+        // cluster of N/64 CTAs with DSMEM statistics, which shortens its launch by 2-4 us.
+        return (m_tiles >= 32 || decode) ? n_cols : 64;
     }
     const int sms = num_sms();
     int best = 0;
@@ -718,10 +743,9 @@ static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
         const int n_tiles = (n_cols + bn_out - 1) / bn_out;
         const long tiles = (long)m_tiles * n_tiles;
         const long waves = (tiles + sms - 1) / sms;
-        // Measured alternative (round 1): preferring the widest tile in the decode regime (fewer, fatter CTAs) cut the
-        // SM-time of a decode step by ~15 % but added ~1.5 us to every launch (35.0 vs 31.5 ms per 60-step decode) and did
-        // not raise the throughput of concurrent batches -- profiles/r1_bench_history.md -- so latency decides.
-        const double cost = (double)waves * (bn + 48);  // +48: per-tile fixed overhead in "column" units
+        // large problems: fewest MMA cycles across the persistent grid (+48: per-tile fixed overhead in "column" units);
+        // decode regime: least SM-time (+200: the fixed ~8 us of a launch expressed in the same units)
+        const double cost = decode ? (double)tiles * (bn + 200) : (double)waves * (bn + 48);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
@@ -804,7 +828,7 @@ const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const v
                 return "cudaFuncSetAttribute(wgrad) failed";
             attr = true;
         }
-        gemm_tc_kernel<128, EPI_BIAS, true><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+        e = launch_pdl(gemm_tc_kernel<128, EPI_BIAS, true>, dim3(grid), dim3(kThreads), Cfg::SMEM_BYTES, st, ta, tb, p);
     } else {
         using Cfg = GemmCfg<64>;
         static bool attr = false;
@@ -813,9 +837,8 @@ const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const v
                 return "cudaFuncSetAttribute(wgrad) failed";
             attr = true;
         }
-        gemm_tc_kernel<64, EPI_BIAS, true><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+        e = launch_pdl(gemm_tc_kernel<64, EPI_BIAS, true>, dim3(grid), dim3(kThreads), Cfg::SMEM_BYTES, st, ta, tb, p);
     }
-    e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

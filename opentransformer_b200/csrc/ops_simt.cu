@@ -2,6 +2,7 @@
 // warp-shuffle reductions.  Each kernel cites the reference lines it replaces.
 #include <math.h>
 
+#include "launch.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
 
@@ -23,6 +24,8 @@ __global__ void __launch_bounds__(256) conv1_relu_nhwc_kernel(const float* __res
                                                               const float* __restrict__ bias, bf16* __restrict__ out,
                                                               int B, int T, int F, int T1, int F1, int T1pad,
                                                               int F1pad, int C1) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     extern __shared__ float sx[];  // [2*CONV1_ROWS + 1][F + 2]  (one zero column each side)
     const int chunks = (T1 + CONV1_ROWS - 1) / CONV1_ROWS;
     const int b = blockIdx.x / chunks, t1_0 = (blockIdx.x % chunks) * CONV1_ROWS;
@@ -81,8 +84,8 @@ const char* conv1_launch(cudaStream_t st, const float* x, const float* w, const 
     size_t smem = (size_t)(2 * CONV1_ROWS + 1) * (F + 2) * sizeof(float);
     if (smem > 48 * 1024) return "conv1: F too large";
     const int chunks = (T1 + CONV1_ROWS - 1) / CONV1_ROWS;
-    conv1_relu_nhwc_kernel<<<B * chunks, 256, smem, st>>>(x, w, bias, out, B, T, F, T1, F1, T1pad, F1pad, C1);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(conv1_relu_nhwc_kernel, dim3(B * chunks), dim3(256), smem, st, x, w, bias, out, B, T, F, T1, F1, T1pad,
+                               F1pad, C1);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -96,6 +99,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
                                                         int ldo, int out_f32, const float* __restrict__ g1,
                                                         const float* __restrict__ b1, const float* __restrict__ g2,
                                                         const float* __restrict__ b2, float eps, int M, int N) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -173,6 +178,8 @@ __global__ void __launch_bounds__(256) layernorm256_kernel(const bf16* __restric
                                                            int ldo, int out_f32, const float* __restrict__ g1,
                                                            const float* __restrict__ b1, const float* __restrict__ g2,
                                                            const float* __restrict__ b2, float eps, int M, int N) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     constexpr int R = 4;
     const int lane = threadIdx.x & 31;
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
@@ -250,21 +257,20 @@ const char* layernorm_launch(cudaStream_t st, const bf16* x, int ldx, void* out,
     if ((out_f32 && ldo % 4) || (!out_f32 && ldo % 8)) return "layernorm: bad output stride";
     if (N <= 256) {
         const int rows_per_block = 8 * 4;
-        layernorm256_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2,
-                                                                                       b2, eps, M, N);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_pdl(layernorm256_kernel, dim3((M + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, x, ldx, out,
+                                   ldo, out_f32, g1, b1, g2, b2, eps, M, N);
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
     const int rows_per_block = 8;
     dim3 grid((M + rows_per_block - 1) / rows_per_block);
     const int ch = (N + 255) / 256;
+    cudaError_t e;
     switch (ch) {
-        case 1: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
-        case 2: layernorm_kernel<2><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
-        case 3: layernorm_kernel<3><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
-        default: layernorm_kernel<4><<<grid, 256, 0, st>>>(x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        case 1: e = launch_pdl(layernorm_kernel<1>, grid, dim3(256), 0, st, x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        case 2: e = launch_pdl(layernorm_kernel<2>, grid, dim3(256), 0, st, x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        case 3: e = launch_pdl(layernorm_kernel<3>, grid, dim3(256), 0, st, x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
+        default: e = launch_pdl(layernorm_kernel<4>, grid, dim3(256), 0, st, x, ldx, out, ldo, out_f32, g1, b1, g2, b2, eps, M, N); break;
     }
-    cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -296,6 +302,8 @@ const char* sinusoid_table_launch(cudaStream_t st, float* out, int n_pos, int d,
 __global__ void embed_posenc_kernel(const long long* __restrict__ tok, int tok_stride, const bf16* __restrict__ emb,
                                     const float* __restrict__ table, bf16* __restrict__ out, int N, int d, int period,
                                     const int* __restrict__ step_ptr, float xscale, int vocab) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -322,9 +330,8 @@ const char* embed_posenc_launch(cudaStream_t st, const long long* tok, int tok_s
                                 const float* table, bf16* out, int N, int d, int period, const int* step_ptr,
                                 int vocab) {
     if (d % 8) return "embed: d must be a multiple of 8";
-    embed_posenc_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, tok_stride, emb, table, out, N, d, period, step_ptr,
-                                                     sqrtf((float)d), vocab);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(embed_posenc_kernel, dim3((N + 7) / 8), dim3(256), 0, st, tok, tok_stride, emb, table, out, N, d, period,
+                               step_ptr, sqrtf((float)d), vocab);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -333,6 +340,8 @@ const char* embed_posenc_launch(cudaStream_t st, const long long* tok, int tok_s
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out,
                                                           int ldo, int V) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     __shared__ float red[8];
     __shared__ float bc;
     const float* xr = x + (size_t)blockIdx.x * ldx;
@@ -367,8 +376,7 @@ __global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restric
 }
 
 const char* log_softmax_launch(cudaStream_t st, const float* x, int ldx, float* out, int ldo, int rows, int V) {
-    log_softmax_kernel<<<rows, 256, 0, st>>>(x, ldx, out, ldo, V);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(log_softmax_kernel, dim3(rows), dim3(256), 0, st, x, ldx, out, ldo, V);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -382,10 +390,12 @@ const char* log_softmax_launch(cudaStream_t st, const float* x, int ldx, float* 
 //   kc,vc bf16 [Lmax, N, d]
 //   anc   int32 [2, N, Lmax]  (ping-pong, buffer (step & 1) is current)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
+__global__ void __launch_bounds__(128, 6) decode_self_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc,
                                                                bf16* __restrict__ vc, const int* __restrict__ anc,
                                                                const int* __restrict__ step_ptr, bf16* __restrict__ out,
                                                                int N, int H, int Lmax, float scale, int keys_pad) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     // Lanes run over KEYS: each lane owns up to KPL cached positions, resolves their slots through the
     // ancestry table and pulls the whole 128-byte K and V rows with 16-byte loads -- all loads of a lane are
     // independent, so the kernel costs ~3 dependent memory round trips (anc -> K/V -> out) instead of a
@@ -400,6 +410,9 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
     const int nkeys = step + 1;
     const int* an = anc + ((size_t)(step & 1) * N + n) * Lmax;
     uint4* sv = sv_raw + (size_t)wib * keys_pad * 8;    // [keys_pad][8 x 16 B] per warp
+    // q lives in shared memory (every lane needs all 64 dims: 64 registers per thread otherwise, which capped the kernel
+    // at 3 resident CTAs per SM -- the SM-time of this latency-bound kernel is what concurrent batches compete for)
+    float* sq = reinterpret_cast<float*>(sv_raw + (size_t)(blockDim.x >> 5) * keys_pad * 8) + wib * 64;
     for (int h = wib; h < H; h += nw) {
         const bf16* base = qkv + (size_t)n * 3 * d + h * 64;
         // append the newest K/V to the cache (lane owns dims 2*lane, 2*lane+1)
@@ -408,14 +421,12 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
         const size_t cur_off = ((size_t)step * N + n) * d + h * 64 + 2 * lane;
         *reinterpret_cast<uint32_t*>(kc + cur_off) = kcur;
         *reinterpret_cast<uint32_t*>(vc + cur_off) = vcur;
-        // q in registers (every lane needs all 64 dims)
-        float q[64];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 u = *reinterpret_cast<const uint4*>(base + 8 * i);
-            const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
-            q[8 * i] = a.x; q[8 * i + 1] = a.y; q[8 * i + 2] = b.x; q[8 * i + 3] = b.y;
-            q[8 * i + 4] = c.x; q[8 * i + 5] = c.y; q[8 * i + 6] = e.x; q[8 * i + 7] = e.y;
+        {
+            const float2 qq = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + 2 * lane));
+            __syncwarp();
+            sq[2 * lane] = qq.x;
+            sq[2 * lane + 1] = qq.y;
+            __syncwarp();
         }
         int slot[KPL];
 #pragma unroll
@@ -442,8 +453,9 @@ __global__ void __launch_bounds__(128) decode_self_attn_kernel(const bf16* __res
                 for (int i = 0; i < 8; ++i) {
                     const float2 a = unpack_bf16(ku[i].x), b = unpack_bf16(ku[i].y), c = unpack_bf16(ku[i].z),
                                  e = unpack_bf16(ku[i].w);
-                    dot += q[8 * i] * a.x + q[8 * i + 1] * a.y + q[8 * i + 2] * b.x + q[8 * i + 3] * b.y +
-                           q[8 * i + 4] * c.x + q[8 * i + 5] * c.y + q[8 * i + 6] * e.x + q[8 * i + 7] * e.y;
+                    const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * i);      // broadcast reads
+                    const float4 q1 = *reinterpret_cast<const float4*>(sq + 8 * i + 4);
+                    dot += q0.x * a.x + q0.y * a.y + q0.z * b.x + q0.w * b.y + q1.x * c.x + q1.y * c.y + q1.z * e.x + q1.w * e.y;
                 }
                 sc[j] = dot * scale;
                 mx = fmaxf(mx, sc[j]);
@@ -491,15 +503,15 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
     // V staging sized by the longest prefix this search can reach (not the 128-key maximum): at max_len 60 this halves the
     // shared memory per CTA and doubles the resident CTAs of this latency-bound kernel (less SM-time per decode step)
     const int keys_pad = (Lmax + 31) / 32 * 32;
-    const size_t smem = (size_t)warps * keys_pad * 128;   // [warps][keys_pad][128 B]
+    const size_t smem = (size_t)warps * keys_pad * 128 + (size_t)warps * 64 * sizeof(float);   // V rows | q per warp
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(decode_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
             return "cudaFuncSetAttribute(decode_self_attn) failed";
         attr_set = true;
     }
-    decode_self_attn_kernel<<<N, warps * 32, smem, st>>>(qkv, kc, vc, anc, step_ptr, out, N, H, Lmax, 0.125f, keys_pad);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(decode_self_attn_kernel, dim3(N), dim3(warps * 32), smem, st, qkv, kc, vc, anc, step_ptr, out, N, H, Lmax,
+                               0.125f, keys_pad);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -510,6 +522,8 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
 // ------------------------------------------------------------------------------------------------
 __global__ void scale_add_table_kernel(const void* __restrict__ x, int ldx, int x_f32, bf16* __restrict__ out, int ldo,
                                        float alpha, const float* __restrict__ table, int period, int M, int N) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int row = (int)(i / N), col = (int)(i % N);
     if (row >= M) return;
@@ -522,8 +536,8 @@ __global__ void scale_add_table_kernel(const void* __restrict__ x, int ldx, int 
 const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int x_f32, bf16* out, int ldo, float alpha,
                                    const float* table, int period, int M, int N) {
     const size_t n = (size_t)M * N;
-    scale_add_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, x_f32, out, ldo, alpha, table, period, M, N);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(scale_add_table_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, ldx, x_f32, out, ldo, alpha,
+                               table, period, M, N);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -536,6 +550,8 @@ const char* scale_add_table_launch(cudaStream_t st, const void* x, int ldx, int 
 __global__ void __launch_bounds__(256) dwconv_swish_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ b, bf16* __restrict__ out, int B,
                                                            int T, int d, int k) {
+    PDL_TRIGGER();
+    PDL_WAIT();
     const int cg = d / 8;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * T * cg) return;
@@ -572,8 +588,7 @@ const char* dwconv_swish_launch(cudaStream_t st, const bf16* x, const float* w, 
                                 int d, int k) {
     if (d % 8 || !(k & 1)) return "dwconv: d must be a multiple of 8 and k odd";
     const size_t n = (size_t)B * T * (d / 8);
-    dwconv_swish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, w, b, out, B, T, d, k);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(dwconv_swish_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, w, b, out, B, T, d, k);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -188,6 +188,7 @@ const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const lo
 int num_sms();
 extern unsigned long long* g_gemm_dbg;
 extern int g_gemm_dbg_mode;
+extern int g_tile_policy;
 void set_error(const char* msg);
 
 }  // namespace otb

@@ -64,6 +64,12 @@ def _need(t, dtype, name):
     return t
 
 
+def set_tile_policy(policy):
+    """'latency' (default) or 'throughput': tiling of the small decode-step GEMMs (otb_set_tile_policy).  Takes effect for
+    launches / graph captures made afterwards."""
+    check(_lib.lib().otb_set_tile_policy({'latency': 0, 'throughput': 1}[policy]), 'otb_set_tile_policy')
+
+
 def conv_geometry(T, F):
     t1, f1, t2, f2 = (ctypes.c_int() for _ in range(4))
     check(_lib.lib().otb_conv_geometry(T, F, t1, f1, t2, f2), 'otb_conv_geometry')

@@ -5,7 +5,7 @@ import torch
 from opentransformer_b200 import ops, _lib
 dev = torch.device('cuda:0')
 L = _lib.lib()
-buf = torch.zeros(148 * 8 + 148 * 2 * 64, dtype=torch.int64, device=dev)
+buf = torch.zeros(148 * 8 + 148 * 2 * 64 + 148 * 16, dtype=torch.int64, device=dev)
 names = ['entry', 'setup_done', 'first_tma_issued', 'first_full', 'mma_committed', 'tfull_seen', 'epi_done', 'exit']
 
 
@@ -19,7 +19,8 @@ def run(tag, fn):
     e0.record(); fn(); e1.record()
     torch.cuda.synchronize()
     L.otb_debug_gemm_timing(None)
-    kbt = buf[148 * 8:].view(148, 2, 64).cpu()
+    kbt = buf[148 * 8:148 * 8 + 148 * 2 * 64].view(148, 2, 64).cpu()
+    epi = buf[148 * 8 + 148 * 2 * 64:].view(148, 16).cpu()
     b = buf[:148 * 8].view(148, 8).cpu()
     live = b[:, 0] > 0
     b = b[live]
@@ -32,6 +33,10 @@ def run(tag, fn):
     ful = [int(v) - t0 for v in kbt[0, 1] if int(v) > 0][:20]
     print('    CTA0 TMA issue  times:', iss)
     print('    CTA0 full seen  times:', ful)
+    ev = epi[epi[:, 6] > 0][:, :7].float()
+    if len(ev):
+        dd = (ev[:, 1:] - ev[:, :-1]).mean(0).tolist()
+        print('    2nd-tile epilogue phases (cycles, mean over CTAs): setup+bar %.0f | wait accumulator %.0f | tmem->math->stage %.0f | bar %.0f | copy-out %.0f | bar %.0f  (total %.0f)' % (*dd, float((ev[:, 6] - ev[:, 0]).mean())))
 
 
 def mk(M, N, K, epi, **kw):
