@@ -215,13 +215,15 @@ int otb_attention_bwd(const void* q, int ldq, int q_rows, const void* k, int ldk
                       int lddq, int dq_col0, void* dk, int lddk, int dk_col0, void* dv, int lddv, int dv_col0, int B, int H,
                       int Tq, int Tk, const int* kv_len, int causal, int q_col0, int k_col0, int v_col0, void* stream);
 /* nn.Linear weight gradient dW[N,K] (fp32) = dy[M,N]^T x[M,K] (bf16), tcgen05 with MN-major operands + split-K.
- * (The input gradient dx = dy W is otb_linear with the transposed weight.) */
-int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, void* stream);
-/* nn.Linear bias gradient: out[n] = sum_m x[m,n]. */
-int otb_colsum(const void* x, int ldx, float* out, int M, int N, void* stream);
-/* nn.LayerNorm backward (N <= 256): dz, dgamma, dbeta from dy and the pre-norm input z. */
+ * (The input gradient dx = dy W is otb_linear with the transposed weight.)  accumulate != 0: dW += ... (gradient
+ * accumulation straight into the optimizer's flat gradient buffer, the way autograd accumulates into .grad). */
+int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, int accumulate,
+                     void* stream);
+/* nn.Linear bias gradient: out[n] (+)= sum_m x[m,n]. */
+int otb_colsum(const void* x, int ldx, float* out, int M, int N, int accumulate, void* stream);
+/* nn.LayerNorm backward (N <= 256): dz, dgamma (+)=, dbeta (+)= from dy and the pre-norm input z. */
 int otb_layernorm_bwd(const void* dy, int lddy, const void* z, int ldz, const float* gamma, void* dz, int lddz,
-                      float* dgamma, float* dbeta, float eps, int M, int N, void* stream);
+                      float* dgamma, float* dbeta, float eps, int M, int N, int accumulate, void* stream);
 /* F.glu (ffn.py:18) un-fused for training: u = [a | g] bf16 [M,2F] -> h [M,F]; and its backward. */
 int otb_glu_fwd(const void* u, void* h, int M, int F, void* stream);
 int otb_glu_bwd(const void* dh, const void* u, void* du, int M, int F, void* stream);

@@ -69,9 +69,9 @@ _SIGS = {
                                   _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P, _P]),
     'otb_attention_bwd': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
                                   _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P]),
-    'otb_linear_wgrad': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
-    'otb_colsum': (c_int, [_P, c_int, _P, c_int, c_int, _P]),
-    'otb_layernorm_bwd': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, _P, c_float, c_int, c_int, _P]),
+    'otb_linear_wgrad': (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'otb_colsum': (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
+    'otb_layernorm_bwd': (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, _P, c_float, c_int, c_int, c_int, _P]),
     'otb_glu_fwd': (c_int, [_P, _P, c_int, c_int, _P]),
     'otb_glu_bwd': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'otb_relu_bwd': (c_int, [_P, _P, _P, c_int64, _P]),

@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     }
 }
 
-const char* colsum_launch(cudaStream_t st, const bf16* x, int ldx, float* out, int M, int N) {
+const char* colsum_launch(cudaStream_t st, const bf16* x, int ldx, float* out, int M, int N, int accumulate) {
     if (N % 8 || ldx % 8) return "colsum: N and ldx must be multiples of 8";
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * 4, st);
+    cudaError_t e = accumulate ? cudaSuccess : cudaMemsetAsync(out, 0, (size_t)N * 4, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     int gy = (M + 255) / 256;
     if (gy > 64) gy = 64;
@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 }
 
 const char* layernorm_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, const bf16* z, int ldz, const float* gamma,
-                                 bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N) {
+                                 bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N, int accumulate) {
     if (N % 8 || N > 256 || lddy % 8 || ldz % 8 || lddz % 8) return "layernorm_bwd: N must be a multiple of 8, <= 256";
-    cudaError_t e = cudaMemsetAsync(dgamma, 0, (size_t)N * 4, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, (size_t)N * 4, st);
+    cudaError_t e = accumulate ? cudaSuccess : cudaMemsetAsync(dgamma, 0, (size_t)N * 4, st);
+    if (e == cudaSuccess && !accumulate) e = cudaMemsetAsync(dbeta, 0, (size_t)N * 4, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     int grid = (M + 7) / 8;
     if (grid > 4 * num_sms()) grid = 4 * num_sms();

@@ -323,22 +323,23 @@ int otb_attention_bwd(const void* q, int ldq, int q_rows, const void* k, int ldk
     RET("otb_attention_bwd", attn_bwd_launch(ST(stream), q, ldq, q_rows, k, ldk, k_rows, v, ldv, p));
 }
 
-int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, void* stream) {
+int otb_linear_wgrad(const void* dy, int lddy, const void* x, int ldx, float* dw, int lddw, int M, int N, int K, int accumulate,
+                     void* stream) {
     if (!dy || !x || !dw) return fail("otb_linear_wgrad", "null operand");
-    RET("otb_linear_wgrad", gemm_wgrad_launch(ST(stream), dy, lddy, x, ldx, dw, lddw, M, N, K));
+    RET("otb_linear_wgrad", gemm_wgrad_launch(ST(stream), dy, lddy, x, ldx, dw, lddw, M, N, K, accumulate));
 }
 
-int otb_colsum(const void* x, int ldx, float* out, int M, int N, void* stream) {
+int otb_colsum(const void* x, int ldx, float* out, int M, int N, int accumulate, void* stream) {
     if (!x || !out || M < 1 || N < 1) return fail("otb_colsum", "bad arguments");
-    RET("otb_colsum", colsum_launch(ST(stream), reinterpret_cast<const bf16*>(x), ldx, out, M, N));
+    RET("otb_colsum", colsum_launch(ST(stream), reinterpret_cast<const bf16*>(x), ldx, out, M, N, accumulate));
 }
 
 int otb_layernorm_bwd(const void* dy, int lddy, const void* z, int ldz, const float* gamma, void* dz, int lddz,
-                      float* dgamma, float* dbeta, float eps, int M, int N, void* stream) {
+                      float* dgamma, float* dbeta, float eps, int M, int N, int accumulate, void* stream) {
     if (!dy || !z || !gamma || !dz || !dgamma || !dbeta) return fail("otb_layernorm_bwd", "null operand");
     RET("otb_layernorm_bwd", layernorm_bwd_launch(ST(stream), reinterpret_cast<const bf16*>(dy), lddy,
                                                   reinterpret_cast<const bf16*>(z), ldz, gamma, reinterpret_cast<bf16*>(dz),
-                                                  lddz, dgamma, dbeta, eps, M, N));
+                                                  lddz, dgamma, dbeta, eps, M, N, accumulate));
 }
 
 int otb_glu_fwd(const void* u, void* h, int M, int F, void* stream) {

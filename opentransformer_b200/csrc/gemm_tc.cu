@@ -59,7 +59,13 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 * tanh(x / 2) + 0.5 with ONE MUFU op (tanh.approx, |rel err| ~ 2^-11, far below the bf16 output
+// rounding) instead of ex2 + rcp: the GLU epilogue of the K = 256 GEMMs is MUFU-bound (32 K sigmoids per 128x128 tile).
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -550,7 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 4; ++j) {
                         const int q = q0 + j * kEpiThreads;
                         if (orow[j] < 0) continue;
-                        if (TN && splitk > 1) {   // partial sums of the split contraction meet in the (pre-zeroed) fp32 output
+                        if (TN && (splitk > 1 || p.accum)) {   // partial sums meet in the fp32 output (pre-zeroed, or a running gradient)
                             float* dst = reinterpret_cast<float*>(obase + (size_t)orow[j] * ld_bytes + (q % cpr) * 16);
                             atomicAdd(dst, __uint_as_float(tmp[j].x));
                             atomicAdd(dst + 1, __uint_as_float(tmp[j].y));
@@ -794,7 +800,7 @@ const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, 
 // The contraction (Mact rows, thousands) is split over enough tiles to fill the SMs; splits meet through fp32 atomics,
 // so `out` must be zero on entry when the returned split count is > 1 (the launcher zeroes it with a memset node).
 const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const void* X, int ldx, float* out, int ldc,
-                              int Mact, int Nw, int Kw) {
+                              int Mact, int Nw, int Kw, int accumulate) {
     if (Mact <= 0 || Nw <= 0 || Kw <= 0) return "wgrad: empty problem";
     if ((lddy % 8) || (ldx % 8) || (ldc % 4) || (reinterpret_cast<uintptr_t>(out) & 15)) return "wgrad: operands must be 16-byte aligned (ld % 8 bf16, ldc % 4 f32)";
     GemmParams p;
@@ -809,7 +815,8 @@ const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const v
     if (splitk > num_kb / 4) splitk = num_kb / 4;      // at least 4 k-blocks per split
     if (splitk < 1) splitk = 1;
     p.splitk = splitk;
-    if (splitk > 1) {
+    p.accum = accumulate ? 1 : 0;      // out += dY^T X (gradient accumulation): no memset, every tile adds atomically
+    if (splitk > 1 && !accumulate) {
         cudaError_t e = cudaMemset2DAsync(out, (size_t)ldc * 4, 0, (size_t)Kw * 4, (size_t)Nw, st);
         if (e != cudaSuccess) return cudaGetErrorString(e);
     }

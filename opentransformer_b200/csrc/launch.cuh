@@ -44,7 +44,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    if (e != cudaSuccess) (void)cudaGetLastError();   // reported through the return value: do not leave it pending for a later launch
+    return e;
 }
 
 }  // namespace otb

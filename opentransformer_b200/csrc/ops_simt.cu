@@ -506,7 +506,7 @@ const char* decode_self_attn_launch(cudaStream_t st, const bf16* qkv, bf16* kc, 
     const size_t smem = (size_t)warps * keys_pad * 128 + (size_t)warps * 64 * sizeof(float);   // V rows | q per warp
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(decode_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(decode_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess)
             return "cudaFuncSetAttribute(decode_self_attn) failed";
         attr_set = true;
     }

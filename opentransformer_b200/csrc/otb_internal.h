@@ -47,6 +47,7 @@ struct GemmParams {
     int conv_B;        // batch
     int conv_cchunks;  // C_in / 64
     int splitk;        // TN (weight-gradient) mode: number of contraction splits (fp32 atomics when > 1)
+    int accum;         // TN mode: add into `out` instead of overwriting it
     unsigned long long* dbg;  // optional [grid][8] clock64 phase stamps (otb_debug_gemm_timing)
     int dbg_mode;             // 0 normal; 1 = no TMA traffic (MMA-only cadence); 2 = no MMA (TMA-only cadence)
 };
@@ -55,7 +56,7 @@ const char* gemm_launch(cudaStream_t st, const void* A, int lda, const void* W, 
                         GemmParams p, const CUtensorMap* conv_map);
 
 const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const void* X, int ldx, float* out, int ldc,
-                              int Mact, int Nw, int Kw);
+                              int Mact, int Nw, int Kw, int accumulate);
 
 // encode helpers (driver entry point fetched at runtime; libcuda is not a link-time dependency)
 const char* encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
@@ -96,9 +97,9 @@ struct AttnBwdParams {
 };
 const char* attn_bwd_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,
                             const void* v, int ldv, const AttnBwdParams& p);
-const char* colsum_launch(cudaStream_t st, const bf16* x, int ldx, float* out, int M, int N);
+const char* colsum_launch(cudaStream_t st, const bf16* x, int ldx, float* out, int M, int N, int accumulate);
 const char* layernorm_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, const bf16* z, int ldz, const float* gamma,
-                                 bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N);
+                                 bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N, int accumulate);
 const char* glu_launch(cudaStream_t st, const bf16* u, const bf16* dh, bf16* out, int M, int F);
 const char* relu_bwd_launch(cudaStream_t st, const bf16* dy, const bf16* y, bf16* dx, size_t n);
 const char* embed_bwd_launch(cudaStream_t st, const long long* tok, const bf16* dx, float* dE, int N, int d, int vocab, float scale);

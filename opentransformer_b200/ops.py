@@ -357,8 +357,8 @@ def attention_bwd(q, k, v, out, dout, lse, B, H, Tq, Tk, dq, dk, dv, kv_len=None
     _count(2)
 
 
-def linear_wgrad(dy, x, out=None):
-    """dW f32 [N,K] = dy[M,N]^T x[M,K]  (bf16 2-D, unit column stride)."""
+def linear_wgrad(dy, x, out=None, accumulate=False):
+    """dW f32 [N,K] (+)= dy[M,N]^T x[M,K]  (bf16 2-D, unit column stride)."""
     for t, n in ((dy, 'dy'), (x, 'x')):
         if not t.is_cuda or t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
             raise TypeError(f'{n} must be a 2-D bf16 CUDA tensor with unit column stride')
@@ -370,29 +370,29 @@ def linear_wgrad(dy, x, out=None):
         out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
     with _Timed('wgrad', 2.0 * M * N * K, (M, N, K)):
         check(_lib.lib().otb_linear_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(out), out.stride(0), M, N, K,
-                                          _stream()), 'otb_linear_wgrad')
+                                          1 if accumulate else 0, _stream()), 'otb_linear_wgrad')
     _count(2)
     return out
 
 
-def colsum(x, out=None):
+def colsum(x, out=None, accumulate=False):
     M, N = x.shape
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=x.device)
-    check(_lib.lib().otb_colsum(_p(x), x.stride(0), _p(out), M, N, _stream()), 'otb_colsum')
+    check(_lib.lib().otb_colsum(_p(x), x.stride(0), _p(out), M, N, 1 if accumulate else 0, _stream()), 'otb_colsum')
     _count()
     return out
 
 
-def layernorm_bwd(dy, z, gamma, eps=1e-5):
-    """-> (dz bf16 [M,N], dgamma f32 [N], dbeta f32 [N])."""
+def layernorm_bwd(dy, z, gamma, eps=1e-5, dgamma=None, dbeta=None, accumulate=False):
+    """-> (dz bf16 [M,N], dgamma f32 [N], dbeta f32 [N]); with accumulate the given dgamma / dbeta are added to."""
     _need(dy, BF16, 'dy'); _need(z, BF16, 'z')
     M, N = z.shape
     dz = torch.empty(M, N, dtype=BF16, device=z.device)
-    dg = torch.empty(N, dtype=torch.float32, device=z.device)
-    db = torch.empty(N, dtype=torch.float32, device=z.device)
+    dg = dgamma if dgamma is not None else torch.empty(N, dtype=torch.float32, device=z.device)
+    db = dbeta if dbeta is not None else torch.empty(N, dtype=torch.float32, device=z.device)
     check(_lib.lib().otb_layernorm_bwd(_p(dy), dy.stride(0), _p(z), z.stride(0), _p(gamma), _p(dz), dz.stride(0), _p(dg),
-                                       _p(db), eps, M, N, _stream()), 'otb_layernorm_bwd')
+                                       _p(db), eps, M, N, 1 if accumulate else 0, _stream()), 'otb_layernorm_bwd')
     _count()
     return dz, dg, db
 

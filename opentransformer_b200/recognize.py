@@ -235,26 +235,18 @@ class BeamDecoder:
 
     def run(self, max_steps, poll_every=8):
         """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
-        (speech2text.py:66-67).  Steps launched after the end are no-ops on the search state, so the "all ended" flag is
-        polled WITHOUT draining the stream: every `poll_every` steps it is copied to pinned memory asynchronously and
-        the copy issued one poll earlier is inspected -- the loop overruns the end by at most 2 * poll_every frozen steps
-        and the stream never idles waiting for the host."""
+        (speech2text.py:66-67).  Steps launched after the end are no-ops on the search state.
+        (A sync-free variant -- the flag copied asynchronously to pinned memory and inspected one poll later -- shortened a
+        lone decode by 0.5 ms but cost 8 concurrent lanes 18 % of their throughput: free-running lanes fall into lockstep
+        and queue for the same SMs, whereas this 4-byte poll staggers them.  profiles/r1_bench_history.md)"""
         if self.persistent and self.lm_logp is None:
             self.run_persistent(max_steps)
             return int(self.state.ctrl[0].item())
-        if getattr(self, '_done_pin', None) is None:
-            self._done_pin = torch.zeros(2, dtype=torch.int32).pin_memory()
-            self._done_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        pending = None
         for i in range(max_steps):
             self.step()
             if (i + 1) % poll_every == 0 and i + 1 < max_steps:
-                if pending is not None and self._done_ev[pending].query() and int(self._done_pin[pending]):
+                if int(self.state.ctrl[1].item()):
                     break
-                slot = ((i + 1) // poll_every) & 1
-                self._done_pin[slot:slot + 1].copy_(self.state.ctrl[1:2], non_blocking=True)
-                self._done_ev[slot].record()
-                pending = slot
         return int(self.state.ctrl[0].item())
 
 

@@ -40,9 +40,12 @@ def _f(t):
 
 
 class TrainPack:
-    """bf16 operands of one training step: W [N,K] for the forward / wgrad, W^T [K,N] for the dgrad GEMMs."""
+    """bf16 operands of one training step: W [N,K] for the forward / wgrad, W^T [K,N] for the dgrad GEMMs.
+    `bf16_of(param)` (optional) returns a bf16 copy of a parameter without a per-tensor cast kernel (FusedTrainer casts
+    its flat fp32 master buffer once per step and hands out views)."""
 
-    def __init__(self, model):
+    def __init__(self, model, bf16_of=None):
+        self._bf16_of = bf16_of
         fe, enc, dec = model.frontend, model.encoder, model.decoder
         if not isinstance(fe, ConvFrontEnd) or not isinstance(enc, TransformerEncoder) or not isinstance(dec, TransformerDecoder):
             raise NotImplementedError('training path: conv front end + Transformer encoder / decoder only (round 1)')
@@ -58,16 +61,19 @@ class TrainPack:
         self.dec = [self._dec_layer(b) for b in dec.blocks]
         V, d = dec.vocab_size, dec.d_model
         self.ld_logits = dec.ld_logits
-        emb = _bf(dec.embedding.weight)
+        emb = self._w(dec.embedding.weight)
         self.tied = dec.output_layer.weight is dec.embedding.weight
-        wout = emb if self.tied else _bf(dec.output_layer.weight)
+        wout = emb if self.tied else self._w(dec.output_layer.weight)
         wout_t = torch.zeros(d, self.ld_logits, dtype=BF16, device=emb.device)      # [d, V padded]: dgrad of the logits GEMM
         wout_t[:, :V] = wout.t()
         self.out = {'emb': emb, 'wout': wout, 'wout_t': wout_t, 'bout': _f(dec.output_layer.bias)}
 
-    @staticmethod
-    def _lin(lin):
-        return _bf(lin.weight), _bft(lin.weight), _f(lin.bias)
+    def _w(self, param):
+        return self._bf16_of(param) if self._bf16_of is not None else _bf(param)
+
+    def _lin(self, lin):
+        w = self._w(lin.weight)
+        return w, w.t().contiguous(), _f(lin.bias)
 
     @staticmethod
     def _ln(norm):
@@ -91,10 +97,39 @@ class TrainPack:
                 'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2), 'ln3': self._ln(b.norm3)}
 
 
+class _Grads(dict):
+    """name -> fp32 gradient.  With `sink` (name -> fp32 view of the optimizer's flat gradient buffer) the kernels ADD
+    their result straight into the sink (otb_linear_wgrad / otb_colsum / otb_layernorm_bwd accumulate flags) -- what
+    autograd's AccumulateGrad does, without one torch add per parameter."""
+
+    def __init__(self, sink=None):
+        super().__init__()
+        self.sink = sink
+
+    def out(self, name):
+        return self.sink[name] if self.sink is not None else None
+
+    def put(self, name, value):
+        """For gradients produced by code that cannot accumulate in place."""
+        if self.sink is not None:
+            self.sink[name].add_(value.reshape(self.sink[name].shape))
+            self[name] = self.sink[name]
+        else:
+            self[name] = value.contiguous()
+
+
+def _ln_bwd(dy, z, gamma, grads, wname, bname):
+    acc = grads.sink is not None
+    dz, dg, db = ops.layernorm_bwd(dy, z, gamma, dgamma=grads.out(wname), dbeta=grads.out(bname), accumulate=acc)
+    grads[wname], grads[bname] = dg, db
+    return dz
+
+
 def _linear_bwd(dy, x, wt, grads, wname, bname, resid=None):
     """Gradients of y = x W^T + b: parameter grads into `grads`, returns dx (+ resid) as bf16."""
-    grads[wname] = ops.linear_wgrad(dy, x)
-    grads[bname] = ops.colsum(dy)
+    acc = grads.sink is not None
+    grads[wname] = ops.linear_wgrad(dy, x, out=grads.out(wname), accumulate=acc)
+    grads[bname] = ops.colsum(dy, out=grads.out(bname), accumulate=acc)
     if wt is None:
         return None
     if resid is not None:
@@ -102,11 +137,13 @@ def _linear_bwd(dy, x, wt, grads, wname, bname, resid=None):
     return ops.linear(dy, wt)
 
 
-def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True):
+def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True, grad_sink=None, grad_scale=1.0,
+                     bf16_of=None):
     """One forward (+ backward) pass.  inputs f32 [B,T,F], mask bool [B,T], truth i64 [B,L+1] (BOS ... EOS PAD*).
-    Returns (loss 0-d f32 tensor, {parameter name -> fp32 gradient}) with names as in model.named_parameters()."""
+    Returns (loss 0-d f32 tensor, {parameter name -> fp32 gradient}) with names as in model.named_parameters().
+    grad_sink: name -> fp32 tensor the gradients (x grad_scale) are ADDED into (gradient accumulation buffer)."""
     fe, enc, dec = model.frontend, model.encoder, model.decoder
-    pk = TrainPack(model)
+    pk = TrainPack(model, bf16_of)
     dev = inputs.device
     B, T, F = inputs.shape
     H, d = enc.blocks[0].n_heads, enc.d_model
@@ -164,21 +201,26 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         loss, _ = ops.ls_cross_entropy(logits, tgt_out, V, sm)
         return loss, None
     loss, dlogits = ops.ls_cross_entropy_train(logits, tgt_out, V, sm)
+    if grad_scale != 1.0:
+        dlogits = ops.scale_add_table(dlogits, grad_scale)                       # loss / accum_steps (trainer.py:216)
 
     # ------------------------------------------------------------------ backward
-    g = {}
-    dwout = ops.linear_wgrad(dlogits, y)[:V]                                     # [V, d]
-    g['decoder.output_layer.bias'] = ops.colsum(dlogits)[:V].contiguous()
+    g = _Grads(grad_sink)
+    acc = grad_sink is not None
+    wname = 'decoder.embedding.weight' if pk.tied else 'decoder.output_layer.weight'
+    # dlogits[:, :V] as a strided view: the TMA map stops at column V, so the result has exactly V rows
+    dwout = ops.linear_wgrad(dlogits[:, :V], y, out=g.out(wname), accumulate=acc)          # [V, d]
+    g.put('decoder.output_layer.bias', ops.colsum(dlogits)[:V])
     dy = ops.linear(dlogits, pk.out['wout_t'])                                   # [B*L, d]
     dmem = None
     for i in reversed(range(len(pk.dec))):
         p, pre = pk.dec[i], f'decoder.blocks.{i}.'
         (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3) = dec_tape[i]
-        dz3, g[pre + 'norm3.weight'], g[pre + 'norm3.bias'] = ops.layernorm_bwd(dy, z3, p['ln3'][0])
+        dz3 = _ln_bwd(dy, z3, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
         dh = _linear_bwd(dz3, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
         du = ops.glu_bwd(dh, u)
         dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz3)
-        dz2, g[pre + 'norm2.weight'], g[pre + 'norm2.bias'] = ops.layernorm_bwd(dy2, z2, p['ln2'][0])
+        dz2 = _ln_bwd(dy2, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
         dctx2 = _linear_bwd(dz2, ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
@@ -186,7 +228,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
                           dq_col0=0, dk_col0=0, dv_col0=d)
         dmem = _linear_bwd(dkv, mem, p['kv'][1], g, pre + 'src_attn.vk_proj.weight', pre + 'src_attn.vk_proj.bias', resid=dmem)
         dy1 = _linear_bwd(dq, y1, p['q'][1], g, pre + 'src_attn.q_proj.weight', pre + 'src_attn.q_proj.bias', resid=dz2)
-        dz1, g[pre + 'norm1.weight'], g[pre + 'norm1.bias'] = ops.layernorm_bwd(dy1, z1, p['ln1'][0])
+        dz1 = _ln_bwd(dy1, z1, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
         dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, Hd, L, L, dqkv, dqkv, dqkv, causal=True, q_col0=0, k_col0=d,
@@ -194,12 +236,13 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         dy = _linear_bwd(dqkv, y0, p['qkv'][1], g, pre + 'slf_attn.qvk_proj.weight', pre + 'slf_attn.qvk_proj.bias', resid=dz1)
     # embedding (decoder/transformer.py:163,169); with tied weights the output-layer gradient lands in the same tensor
     if pk.tied:
-        demb = dwout.contiguous()
-        ops.embed_bwd(tgt_in, dy, demb, math.sqrt(d))
-        g['decoder.embedding.weight'] = demb
+        ops.embed_bwd(tgt_in, dy, dwout, math.sqrt(d))          # atomics on top of the output-layer gradient
+        g['decoder.embedding.weight'] = dwout
     else:
-        g['decoder.output_layer.weight'] = dwout.contiguous()
-        demb = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        g['decoder.output_layer.weight'] = dwout
+        demb = g.out('decoder.embedding.weight')
+        if demb is None:
+            demb = torch.zeros(V, d, dtype=torch.float32, device=dev)
         ops.embed_bwd(tgt_in, dy, demb, math.sqrt(d))
         g['decoder.embedding.weight'] = demb
 
@@ -207,11 +250,11 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     for i in reversed(range(len(pk.enc))):
         p, pre = pk.enc[i], f'encoder.blocks.{i}.'
         (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
-        dz2, g[pre + 'norm2.weight'], g[pre + 'norm2.bias'] = ops.layernorm_bwd(dx, z2, p['ln2'][0])
+        dz2 = _ln_bwd(dx, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
         dh = _linear_bwd(dz2, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
         du = ops.glu_bwd(dh, u)
         dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz2)
-        dz1, g[pre + 'norm1.weight'], g[pre + 'norm1.bias'] = ops.layernorm_bwd(dx1, z1, p['ln1'][0])
+        dz1 = _ln_bwd(dx1, z1, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
         dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, H, T2, T2, dqkv, dqkv, dqkv, kv_len=lengths, q_col0=0, k_col0=d,
@@ -222,21 +265,21 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     dyl = ops.scale_add_table(dx, scale)                                          # d(h2 Wo^T + bo) = sqrt(d) * dx
     D_out = fe.output_size
     dwo = ops.linear_wgrad(dyl, h2)                                               # [D, F2*C2], feature index f*C2 + c
-    g['frontend.output_layer.weight'] = dwo.view(D_out, F2, C2).permute(0, 2, 1).reshape(D_out, C2 * F2).contiguous()
-    g['frontend.output_layer.bias'] = ops.colsum(dyl)
+    g.put('frontend.output_layer.weight', dwo.view(D_out, F2, C2).permute(0, 2, 1).reshape(D_out, C2 * F2))
+    g['frontend.output_layer.bias'] = ops.colsum(dyl, out=g.out('frontend.output_layer.bias'), accumulate=acc)
     dh2 = ops.linear(dyl, fpk['wo_t'])                                            # [B*T2, F2*C2]
     dpre2 = ops.relu_bwd(dh2, h2).view(B * T2 * F2, C2)
     col = ops.conv_im2col(h1, B, T, F, C1p)
     C1 = fe.conv1.conv_layer.out_channels
     dw2 = ops.linear_wgrad(dpre2, col)                                            # [C2, 9*C1p], k = (kh*3+kw)*C1p + c
-    g['frontend.conv2.conv_layer.weight'] = dw2.view(C2, 3, 3, C1p)[..., :C1].permute(0, 3, 1, 2).contiguous()
-    g['frontend.conv2.conv_layer.bias'] = ops.colsum(dpre2)
+    g.put('frontend.conv2.conv_layer.weight', dw2.view(C2, 3, 3, C1p)[..., :C1].permute(0, 3, 1, 2))
+    g['frontend.conv2.conv_layer.bias'] = ops.colsum(dpre2, out=g.out('frontend.conv2.conv_layer.bias'), accumulate=acc)
     dcol = ops.linear(dpre2, fpk['w2_t'])                                         # [B*T2*F2, 9*C1p]
     del col
     dpre1 = ops.conv_col2im_relu(dcol, h1, B, T, F, C1p)
     g1 = ops.conv1_wgrad(dpre1, x_in, B, T, F, C1p)                               # [C1p, 9 taps + bias]
-    g['frontend.conv1.conv_layer.weight'] = g1[:C1, :9].reshape(C1, 1, 3, 3).contiguous()
-    g['frontend.conv1.conv_layer.bias'] = g1[:C1, 9].contiguous()
+    g.put('frontend.conv1.conv_layer.weight', g1[:C1, :9].reshape(C1, 1, 3, 3))
+    g.put('frontend.conv1.conv_layer.bias', g1[:C1, 9])
     return loss, g
 
 
@@ -287,6 +330,7 @@ class FusedTrainer:
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.flat_bf16 = torch.empty(total, dtype=BF16, device=dev)      # ONE cast of the master weights per micro-step
         self.offsets = {}
         o = 0
         with torch.no_grad():
@@ -296,6 +340,8 @@ class FusedTrainer:
                 p.data = self.flat_p[o:o + k].view_as(p)            # parameters now alias the flat buffer
                 self.offsets[n] = (o, k)
                 o += k
+        self.sink = {n: self.flat_g[o:o + k].view_as(p) for (n, p), (o, k) in zip(self.params, [self.offsets[n] for n, _ in self.params])}
+        self._by_ptr = {p.data_ptr(): (self.offsets[n], p.shape) for n, p in self.params}
         self.betas, self.eps, self.wd, self.clip = betas, eps, weight_decay, clip_grad
         self.base_lr, self.model_size, self.warmup, self.factor = lr, model_size, warmup_steps, factor
         self.accum_steps = accum_steps
@@ -313,13 +359,16 @@ class FusedTrainer:
             return transformer_lr(self.global_step, self.model_size, self.warmup, self.factor)
         return self.base_lr
 
+    def _bf16_of(self, param):
+        (o, k), shape = self._by_ptr[param.data_ptr()]
+        return self.flat_bf16[o:o + k].view(shape)
+
     def _micro(self, inputs, mask, truth):
-        """forward + backward of one micro-batch; gradients / accum_steps are ADDED into the flat buffer."""
-        loss, grads = forward_backward(self.model, inputs, mask, truth)
-        inv = 1.0 / self.accum_steps
-        for n, _ in self.params:
-            o, k = self.offsets[n]
-            self.flat_g[o:o + k].add_(grads[n].reshape(-1), alpha=inv)
+        """forward + backward of one micro-batch; gradients / accum_steps are ADDED into the flat buffer by the backward
+        kernels themselves (no per-parameter add)."""
+        self.flat_bf16.copy_(self.flat_p)
+        loss, _ = forward_backward(self.model, inputs, mask, truth, grad_sink=self.sink, grad_scale=1.0 / self.accum_steps,
+                                   bf16_of=self._bf16_of)
         return loss
 
     def _graph_for(self, inputs, mask, truth):
