@@ -13,12 +13,13 @@ namespace otb {
 // in : x f32 [B, T, F]
 // out: bf16 NHWC [B, 2*T1h, 2*F1h, C1]; columns f >= F1 are written as zero (they are the right
 //      frequency padding of conv2); rows t >= T1 are never read for valid outputs and left untouched.
-// HBM-bound on the output write (82 MB at cfg 2).  One CTA = 8 consecutive output rows of one
-// utterance: the 17 input rows are staged in smem once, each thread keeps the 3x3 filters + bias of
+// HBM-bound on the output write (82 MB at cfg 2).  One CTA = 24 consecutive output rows of one
+// utterance: the 49 input rows are staged in smem once, each thread keeps the 3x3 filters + bias of
 // its 8 channels in registers and walks over (row, f1) positions, one 16-byte store per position,
-// fully coalesced along (f1, c).
+// fully coalesced along (f1, c).  (With 8 rows per CTA the 80 weight loads per thread outnumbered the
+// stores 8:1 -- 65 us for 22 MB, profiles/r1_ncu_layer_v5_summary.txt.)
 // ------------------------------------------------------------------------------------------------
-static constexpr int CONV1_ROWS = 8;
+static constexpr int CONV1_ROWS = 24;
 
 __global__ void __launch_bounds__(256) conv1_relu_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, bf16* __restrict__ out,
