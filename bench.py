@@ -711,14 +711,14 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--steps', type=int, default=96)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--ref-sample', type=int, default=2, help='utterances per CPU reference pass')
     ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer', 'train'],
                     help="'conformer' = BASELINE config 4 (encoder forward only), 'train' = config 5 (training step); "
                          "default is the headline workload")
-    ap.add_argument('--lanes', type=int, default=8, help='utterance batches kept in flight per GPU (streams)')
+    ap.add_argument('--lanes', type=int, default=16, help='utterance batches kept in flight per GPU (streams)')
     ap.add_argument('--tile-policy', default='auto', choices=['auto', 'latency', 'throughput'],
                     help='tiling of the decode-step GEMMs (otb_set_tile_policy); auto = throughput when lanes > 1')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')

@@ -696,6 +696,7 @@ static const char* launch_inst(cudaStream_t st, const CUtensorMap& ta, const CUt
             grid = max_clusters[cl] * cl;
             cfg.gridDim = dim3(grid);
         }
+        prefer_max_smem_carveout(gemm_tc_kernel<BN, EPI>);
         cfg.numAttrs = pdl_enabled() ? 2 : 1;     // (the occupancy query above ran with the cluster attribute only)
         cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, ta, tb, p);
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

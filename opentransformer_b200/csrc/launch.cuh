@@ -32,8 +32,35 @@ inline bool pdl_enabled() {
     return on;
 }
 
+// One shared-memory carve-out for every hot-path kernel.  The L1 / shared-memory split of an SM is a per-kernel
+// preference; kernels that prefer different splits cannot share an SM and switching the split needs the SM idle.  A decode
+// step alternates 230 KB GEMMs, an 82 KB attention kernel, 34 KB / 17 KB / 0 KB SIMT kernels, and several utterance
+// batches run such chains concurrently on separate streams -- so all of them ask for the maximum shared-memory carve-out
+// (OTB_CARVEOUT=0 restores the driver default).
+inline bool carveout_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("OTB_CARVEOUT");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KArgs>
+inline void prefer_max_smem_carveout(void (*kern)(KArgs...)) {
+    static thread_local const void* seen[64];
+    static thread_local int nseen = 0;
+    const void* key = reinterpret_cast<const void*>(kern);
+    for (int i = 0; i < nseen; ++i)
+        if (seen[i] == key) return;
+    if (carveout_enabled() &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        (void)cudaGetLastError();
+    if (nseen < 64) seen[nseen++] = key;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    prefer_max_smem_carveout(kern);
     cudaLaunchConfig_t cfg;
     cfg.gridDim = grid;
     cfg.blockDim = block;
