@@ -228,10 +228,22 @@ class BeamDecoder:
             preds = self.state.reconstruct(i)                       # [N, i+1], column 0 = BOS
             self.lm_logp = lm.predict(preds, last_frame=True).squeeze(1).contiguous()
             self._step_kernels()
-            if int(self.state.ctrl[1].item()):
+            if int(self._read_ctrl()[1]):
                 break
         self.lm_logp = None
-        return int(self.state.ctrl[0].item())
+        return int(self._read_ctrl()[0])
+
+    def _read_ctrl(self):
+        """{step, done, ...} of the search state on the host.  The copy lands in pinned memory and the thread SLEEPS on a
+        blocking-sync event instead of spinning in cudaStreamSynchronize (`.item()`): a server keeps many of these loops
+        alive on few cores (16 lanes x 8 ranks on one host in bench.py)."""
+        if getattr(self, '_ctrl_pin', None) is None:
+            self._ctrl_pin = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self._ctrl_ev = torch.cuda.Event(blocking=True)
+        self._ctrl_pin.copy_(self.state.ctrl, non_blocking=True)
+        self._ctrl_ev.record()
+        self._ctrl_ev.synchronize()
+        return self._ctrl_pin
 
     def run(self, max_steps, poll_every=8):
         """Run up to max_steps decode steps; stops early once the device reports every hypothesis ended
@@ -241,13 +253,13 @@ class BeamDecoder:
         and queue for the same SMs, whereas this 4-byte poll staggers them.  profiles/r1_bench_history.md)"""
         if self.persistent and self.lm_logp is None:
             self.run_persistent(max_steps)
-            return int(self.state.ctrl[0].item())
+            return int(self._read_ctrl()[0])
         for i in range(max_steps):
             self.step()
             if (i + 1) % poll_every == 0 and i + 1 < max_steps:
-                if int(self.state.ctrl[1].item()):
+                if int(self._read_ctrl()[1]):
                     break
-        return int(self.state.ctrl[0].item())
+        return int(self._read_ctrl()[0])
 
 
 class SpeechToTextRecognizer(Recognizer):
