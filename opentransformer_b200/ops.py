@@ -2,7 +2,7 @@
 
 PyTorch is plumbing here: it owns device memory and the current CUDA stream; all compute is in
 libotb200.so.  Every wrapper launches on ``torch.cuda.current_stream()`` so the calls can be
-captured into a CUDA graph (see graphs.py).
+captured into a CUDA graph (recognize.BeamDecoder captures a decode step, train.FusedTrainer a training micro-step).
 """
 import ctypes
 import math
