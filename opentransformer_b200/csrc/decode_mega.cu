@@ -67,28 +67,37 @@ __device__ __forceinline__ float mg_sigmoid(float x) { return __fdividef(1.0f, 1
 //   epi(i, acc): acc[0..1] = (row g, cols 2t, 2t+1), acc[2..3] = (row g+8, same cols) of tile i, g = lane/4, t = lane%4
 // A 16-byte weight load per lane feeds two MMAs: within a 32-wide k slice, lane t's chunk k = 8t..8t+7 is used as
 // logical k pairs (2t, 2t+8) of the first MMA and of the second -- the same permutation is applied to the A fragment, so
-// the contraction is unchanged.  Work unit = (tile, 256-wide k chunk) = 8 loads per lane, double buffered in registers.
+// the contraction is unchanged.  Work unit = (tile, 256-wide k chunk) = 8 loads per lane, three units buffered in registers.
+// `rot` rotates the order in which the warp walks its tiles (tile (i + rot) % ntile first): the 32 clusters of a launch
+// stream the SAME weights in the same order at the same time, i.e. they all hit the same few L2 slices at any moment;
+// starting each cluster at a different tile spreads the requests over the slices.
 template <class RowFn, class EpiFn>
 __device__ __forceinline__ void stream_tiles(const uint8_t* xs, int xpitch, int K, const bf16* __restrict__ W, int ldw,
-                                             int row_lim, int ntile, RowFn row_of, EpiFn epi) {
+                                             int row_lim, int ntile, int rot, RowFn row_of_, EpiFn epi_) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int kch = K >> 8;
     const int nunit = ntile * kch;
     if (nunit <= 0) return;
-    uint4 wa[8], wb[8];
+    // a single tile (the K = 2048 projection: 8 chunks): rotate the order of its k chunks instead (fp32 sum order only)
+    const int krot = (ntile == 1) ? rot % kch : 0;
+    rot = rot % ntile;
+    auto kc_of = [&](int kc) { int k2 = kc + krot; return k2 >= kch ? k2 - kch : k2; };
+    auto row_of = [&](int i) { int j = i + rot; if (j >= ntile) j -= ntile; return row_of_(j); };
+    auto epi = [&](int i, const float(&a)[4]) { int j = i + rot; if (j >= ntile) j -= ntile; epi_(j, a); };
+    uint4 w0[8], w1[8], w2[8];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     auto issue = [&](uint4(&w)[8], int u) {
         const int tile = u / kch, kc = u - tile * kch;
         int row = row_of(tile) + g;
         row = row < row_lim ? row : row_lim - 1;
-        const uint4* src = reinterpret_cast<const uint4*>(W + (size_t)row * ldw + kc * 256 + t * 8);
+        const uint4* src = reinterpret_cast<const uint4*>(W + (size_t)row * ldw + kc_of(kc) * 256 + t * 8);
 #pragma unroll
         for (int s = 0; s < 8; ++s) w[s] = ldg_stream(src + s * 4);
     };
     auto compute = [&](const uint4(&w)[8], int u) {
         const int tile = u / kch, kc = u - tile * kch;
         if (kc == 0) { acc[0] = 0.f; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f; }
-        const uint8_t* xa = xs + g * xpitch + kc * 512 + t * 16;
+        const uint8_t* xa = xs + g * xpitch + kc_of(kc) * 512 + t * 16;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const uint4 lo = *reinterpret_cast<const uint4*>(xa + s * 64);
@@ -98,23 +107,37 @@ __device__ __forceinline__ void stream_tiles(const uint8_t* xs, int xpitch, int 
         }
         if (kc == kch - 1) epi(tile, acc);
     };
-    issue(wa, 0);
-    for (int u = 0; u < nunit; u += 2) {
-        if (u + 1 < nunit) issue(wb, u + 1);
-        compute(wa, u);
+    // Three units (= 24 sixteen-byte loads per lane, 96 KB per SM) in flight: with two, every unit waited ~500 cycles for
+    // its weights and the stream reached ~20 B/clk/SM (profiles/r1_mega_phases.txt); four spill (255 registers).
+    issue(w0, 0);
+    if (nunit > 1) issue(w1, 1);
+    for (int u = 0; u < nunit; u += 3) {
+        if (u + 2 < nunit) issue(w2, u + 2);
+        compute(w0, u);
         if (u + 1 < nunit) {
-            if (u + 2 < nunit) issue(wa, u + 2);
-            compute(wb, u + 1);
+            if (u + 3 < nunit) issue(w0, u + 3);
+            compute(w1, u + 1);
+        }
+        if (u + 2 < nunit) {
+            if (u + 4 < nunit) issue(w1, u + 4);
+            compute(w2, u + 2);
         }
     }
 }
 
+__device__ __forceinline__ void mg_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mg_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct MegaSmem {   // byte offsets into dynamic shared memory (identical in every CTA of the cluster)
     int xs, ctxf, yf, big, qs, kcur, vcur, sc, stats, cand_v, cand_i, misc, total;
     int sc_pitch, hf_pitch, lg_pitch;
+    int keys_pad;   // cached positions per warp of the self-attention V staging (multiple of 32)
+    int kv_tile;    // bytes of one cross-attention K (or V) tile inside `big`: K at +0 (later the P.V partials), V at +kv_tile
 };
 
-__host__ __device__ inline MegaSmem mega_layout(int dff, int V, int T) {
+__host__ __device__ inline MegaSmem mega_layout(int dff, int V, int T, int Lmax) {
     MegaSmem L;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
@@ -123,7 +146,10 @@ __host__ __device__ inline MegaSmem mega_layout(int dff, int V, int T) {
     L.lg_pitch = tpc * 8;
     int big = 16 * L.hf_pitch;                                         // GLU activations [16][dff] bf16 (peer-written)
     if (16 * L.lg_pitch * 4 > big) big = 16 * L.lg_pitch * 4;          // | local logits slice [16][lg_pitch] f32
-    if (8 * 16 * 64 * 4 > big) big = 8 * 16 * 64 * 4;                  // | P.V partials [8 key groups][16][64] f32
+    L.keys_pad = (Lmax + 31) / 32 * 32;
+    if (8 * L.keys_pad * 128 > big) big = 8 * L.keys_pad * 128;        // | self-attention V rows staged per warp [8][keys_pad][128 B]
+    L.kv_tile = T * 128 > 8 * 16 * 64 * 4 ? T * 128 : 8 * 16 * 64 * 4; // | cross-attention K tile (then P.V partials [8][16][64] f32) + V tile
+    if (2 * L.kv_tile > big) big = 2 * L.kv_tile;
     const int sc_cols = ((T > MG_LMAX ? T : MG_LMAX) + 31) / 32 * 32 + 1;
     L.sc_pitch = sc_cols;
     L.xs = take(16 * MG_XP);
@@ -162,13 +188,15 @@ __global__ void __cluster_dims__(MG_C, 1, 1) __launch_bounds__(MG_THREADS, 1)
 decode_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const MegaSmem L = mega_layout(p.dff, p.V, p.T);
+    const MegaSmem L = mega_layout(p.dff, p.V, p.T, p.st.Lmax);
     uint8_t* xs = smem + L.xs;
     uint8_t* ctxf = smem + L.ctxf;
     float* yf = reinterpret_cast<float*>(smem + L.yf);
     uint8_t* hf = smem + L.big;
     float* lg = reinterpret_cast<float*>(smem + L.big);
-    float* red = reinterpret_cast<float*>(smem + L.big);
+    float* red = reinterpret_cast<float*>(smem + L.big);          // aliases the cross-attention K tile once the scores are done
+    uint8_t* sKx = smem + L.big;                                  // cross-attention K tile [T][128 B], 16-byte chunks XOR-swizzled by row
+    uint8_t* sVx = smem + L.big + L.kv_tile;                      // cross-attention V tile, same layout
     float* qs = reinterpret_cast<float*>(smem + L.qs);
     bf16* kcur = reinterpret_cast<bf16*>(smem + L.kcur);
     bf16* vcur = reinterpret_cast<bf16*>(smem + L.vcur);
@@ -261,7 +289,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
         };
         // Y[:, c*64 + warp*8 ..] = X W^T + bias -> fp32 into every CTA's yf (each warp owns one n8 tile of the CTA's 64 columns)
         auto proj_to_yf = [&](const uint8_t* X, int xpitch, int K, const bf16* W, const float* bias) {
-            stream_tiles(X, xpitch, K, W, K, d, 1, [&](int) { return c * 64 + warp * 8; },
+            stream_tiles(X, xpitch, K, W, K, d, 1, b, [&](int) { return c * 64 + warp * 8; },
                          [&](int, const float(&acc)[4]) {
                              const int col = c * 64 + warp * 8 + 2 * t;
                              const float b0 = bias[col], b1 = bias[col + 1];
@@ -284,7 +312,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
         for (int l = 0; l < p.n_layers; ++l) {
             const MegaLayer& ly = p.layers[l];
             // ---- S1: Q,K,V of head c (attention.py:68-73): warp w -> tile w of Q, of K and of V
-            stream_tiles(xs, MG_XP, d, ly.wqkv, d, 3 * d, 3, [&](int i) { return i * d + c * 64 + warp * 8; },
+            stream_tiles(xs, MG_XP, d, ly.wqkv, d, 3 * d, 3, b, [&](int i) { return i * d + c * 64 + warp * 8; },
                          [&](int i, const float(&acc)[4]) {
                              const int col = warp * 8 + 2 * t;                 // column inside the head
                              const float b0 = ly.bqkv[i * d + c * 64 + col], b1 = ly.bqkv[i * d + c * 64 + col + 1];
@@ -304,36 +332,38 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
             __syncthreads();
             MG_STAMP();   // S1 qkv
             // ---- S2: self-attention of head c over the cached prefix (the cache the reference stubbed out,
-            //      decoder/transformer.py:92-126); warp = hypothesis row, lanes over keys, then over dims
+            //      decoder/transformer.py:92-126); warp = hypothesis row.  Lanes run over KEYS: a lane resolves its cached
+            //      positions through the ancestry table and pulls the whole 128-byte K and V rows with sixteen independent
+            //      16-byte loads, V rows are staged in the warp's slice of `big` so that P.V is a column sum over shared
+            //      memory -- one or two L2 round trips per row instead of one per key.
             {
                 const int nkeys = step + 1;
+                uint8_t* stage = hf + (size_t)warp * L.keys_pad * 128;
                 for (int r = warp; r < beam; r += 8) {
                     const unsigned char* an = ms.anc[cur][r];
                     float mx = -INFINITY;
                     for (int s = lane; s < nkeys; s += 32) {
+                        const bf16* krow = (s == step) ? (kcur + r * 64) : (p.kc + (((size_t)l * Lmax + s) * N + n0 + an[s]) * d + c * 64);
+                        const bf16* vrow = (s == step) ? (vcur + r * 64) : (p.vc + (((size_t)l * Lmax + s) * N + n0 + an[s]) * d + c * 64);
+                        uint4 ku[8], vu[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ku[i] = *reinterpret_cast<const uint4*>(krow + 8 * i);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) vu[i] = *reinterpret_cast<const uint4*>(vrow + 8 * i);
                         float dot = 0.f;
-                        if (s == step) {
 #pragma unroll
-                            for (int i = 0; i < 64; i += 2) {
-                                const float2 kk = unpack_bf16(*reinterpret_cast<const uint32_t*>(kcur + r * 64 + i));
-                                dot += qs[r * 64 + i] * kk.x + qs[r * 64 + i + 1] * kk.y;
-                            }
-                        } else {
-                            const bf16* krow = p.kc + (((size_t)l * Lmax + s) * N + n0 + an[s]) * d + c * 64;
-                            uint4 ku[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) ku[i] = *reinterpret_cast<const uint4*>(krow + 8 * i);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 k0 = unpack_bf16(ku[i].x), k1 = unpack_bf16(ku[i].y), k2 = unpack_bf16(ku[i].z), k3 = unpack_bf16(ku[i].w);
-                                const float4 q0 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i);
-                                const float4 q1 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i + 4);
-                                dot += q0.x * k0.x + q0.y * k0.y + q0.z * k1.x + q0.w * k1.y + q1.x * k2.x + q1.y * k2.y + q1.z * k3.x + q1.w * k3.y;
-                            }
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 k0 = unpack_bf16(ku[i].x), k1 = unpack_bf16(ku[i].y), k2 = unpack_bf16(ku[i].z), k3 = unpack_bf16(ku[i].w);
+                            const float4 q0 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i);
+                            const float4 q1 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i + 4);
+                            dot += q0.x * k0.x + q0.y * k0.y + q0.z * k1.x + q0.w * k1.y + q1.x * k2.x + q1.y * k2.y + q1.z * k3.x + q1.w * k3.y;
                         }
                         dot *= 0.125f;
                         sc[r * scp + s] = dot;
                         mx = fmaxf(mx, dot);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)      // chunks rotated by the row index: conflict-free 16-byte stores
+                            *reinterpret_cast<uint4*>(stage + (size_t)s * 128 + (((i + s) & 7) << 4)) = vu[i];
                     }
                     mx = warp_max(mx);
                     float lsum = 0.f;
@@ -347,14 +377,26 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
                     float ax = 0.f, ay = 0.f;
 #pragma unroll 4
                     for (int s = 0; s < nkeys; ++s) {
-                        const bf16* vrow = (s == step) ? (vcur + r * 64) : (p.vc + (((size_t)l * Lmax + s) * N + n0 + an[s]) * d + c * 64);
-                        const float2 vv = unpack_bf16(*reinterpret_cast<const uint32_t*>(vrow + 2 * lane));
+                        // dims 2*lane.. live in chunk lane/4 (rotated by s), word lane%4
+                        const float2 vv = unpack_bf16(*reinterpret_cast<const uint32_t*>(stage + (size_t)s * 128 + ((((lane >> 2) + s) & 7) << 4) + (lane & 3) * 4));
                         const float pw = sc[r * scp + s];
                         ax = fmaf(pw, vv.x, ax);
                         ay = fmaf(pw, vv.y, ay);
                     }
                     const float inv = 1.0f / lsum;
                     put_ctx(r, lane, ax * inv, ay * inv);
+                    __syncwarp();      // the next row of this warp re-uses the staging slice
+                }
+            }
+            __syncthreads();           // every warp is done with its staging slice: `big` may receive the cross-attention tiles
+            {   // cross-attention K / V tiles of (layer l, utterance b, head c) -> shared memory, asynchronously: they arrive
+                // while the out-projection, LayerNorm and the query projection run (S3, LN1, S4)
+                const bf16* kb = p.kvx + ((size_t)l * p.B * p.T + (size_t)b * p.T) * (2 * d) + c * 64;
+                for (int i = tid; i < kv_len * 8; i += MG_THREADS) {
+                    const int j = i >> 3, ch = i & 7;
+                    const int dst = j * 128 + ((ch ^ (j & 7)) << 4);
+                    mg_cp_async16(sKx + dst, kb + (size_t)j * (2 * d) + ch * 8);
+                    mg_cp_async16(sVx + dst, kb + (size_t)j * (2 * d) + d + ch * 8);
                 }
             }
             MG_STAMP();   // S2 self-attention
@@ -368,7 +410,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
             __syncthreads();
             MG_STAMP();   // LN1
             // ---- S4: cross-attention query of head c (attention.py:128)
-            stream_tiles(xs, MG_XP, d, ly.wq, d, d, 1, [&](int) { return c * 64 + warp * 8; },
+            stream_tiles(xs, MG_XP, d, ly.wq, d, d, 1, 0, [&](int) { return c * 64 + warp * 8; },
                          [&](int, const float(&acc)[4]) {
                              const int col = warp * 8 + 2 * t;
                              const float b0 = ly.bq[c * 64 + col], b1 = ly.bq[c * 64 + col + 1];
@@ -377,26 +419,24 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
                          });
             __syncthreads();
             MG_STAMP();   // S4 q-proj
-            // ---- S5: cross-attention of head c over the utterance's memory (attention.py:129-141,34-41)
+            // ---- S5: cross-attention of head c over the utterance's memory (attention.py:129-141,34-41), K / V tiles in
+            //      shared memory (staged above): thread per key for the scores, warp per row for the soft-max, warps over
+            //      key groups for P.V
             {
-                const bf16* kbase = p.kvx + ((size_t)l * p.B * p.T + (size_t)b * p.T) * (2 * d) + c * 64;   // K | V (attention.py:134)
-                const bf16* vbase = kbase + d;
-                for (int j = tid; j < kv_len; j += MG_THREADS) {      // thread per key
-                    const bf16* krow = kbase + (size_t)j * (2 * d);
-                    float kf[64];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(krow + 8 * i);
-                        const float2 k0 = unpack_bf16(u.x), k1 = unpack_bf16(u.y), k2 = unpack_bf16(u.z), k3 = unpack_bf16(u.w);
-                        kf[8 * i] = k0.x; kf[8 * i + 1] = k0.y; kf[8 * i + 2] = k1.x; kf[8 * i + 3] = k1.y;
-                        kf[8 * i + 4] = k2.x; kf[8 * i + 5] = k2.y; kf[8 * i + 6] = k3.x; kf[8 * i + 7] = k3.y;
-                    }
-                    for (int r = 0; r < beam; ++r) {
+                mg_cp_async_wait_all();
+                __syncthreads();
+                for (int j = tid; j < kv_len; j += MG_THREADS) {
+                    const uint8_t* krow = sKx + j * 128;
+                    const int sw = j & 7;
+                    for (int r = 0; r < beam; ++r) {          // rows outer: few live registers, the K row is re-read from smem
                         float dot = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 64; i += 4) {
-                            const float4 q = *reinterpret_cast<const float4*>(qs + r * 64 + i);   // broadcast
-                            dot += q.x * kf[i] + q.y * kf[i + 1] + q.z * kf[i + 2] + q.w * kf[i + 3];
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(krow + ((i ^ sw) << 4));
+                            const float2 k0 = unpack_bf16(u.x), k1 = unpack_bf16(u.y), k2 = unpack_bf16(u.z), k3 = unpack_bf16(u.w);
+                            const float4 q0 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i);       // broadcast
+                            const float4 q1 = *reinterpret_cast<const float4*>(qs + r * 64 + 8 * i + 4);
+                            dot += q0.x * k0.x + q0.y * k0.y + q0.z * k1.x + q0.w * k1.y + q1.x * k2.x + q1.y * k2.y + q1.z * k3.x + q1.w * k3.y;
                         }
                         sc[r * scp + j] = dot * 0.125f;
                     }
@@ -422,7 +462,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) { ax[r] = 0.f; ay[r] = 0.f; }
                 for (int j = warp; j < kv_len; j += 8) {
-                    const float2 vv = unpack_bf16(*reinterpret_cast<const uint32_t*>(vbase + (size_t)j * (2 * d) + 2 * lane));
+                    const float2 vv = unpack_bf16(*reinterpret_cast<const uint32_t*>(sVx + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4));
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
                         if (r < beam) {
@@ -432,6 +472,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
                         }
                     }
                 }
+                // the K tile is dead since the scores: its region now holds the partials of the 8 key groups
 #pragma unroll
                 for (int r = 0; r < 16; ++r)
                     if (r < beam) *reinterpret_cast<float2*>(red + (warp * 16 + r) * 64 + 2 * lane) = make_float2(ax[r], ay[r]);
@@ -463,7 +504,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
                 const int fpc = dff / MG_C;                 // hidden features per CTA
                 const int pairs = fpc / 8 / 8;              // (value, gate) tile pairs per warp
                 float va[4] = {0.f, 0.f, 0.f, 0.f};
-                stream_tiles(xs, MG_XP, d, ly.w1, d, 2 * dff, 2 * pairs,
+                stream_tiles(xs, MG_XP, d, ly.w1, d, 2 * dff, 2 * pairs, 2 * (b % pairs),
                              [&](int i) { return ((i & 1) ? dff : 0) + c * fpc + (warp + 8 * (i >> 1)) * 8; },
                              [&](int i, const float(&acc)[4]) {
                                  const int feat = c * fpc + (warp + 8 * (i >> 1)) * 8 + 2 * t;
@@ -499,7 +540,7 @@ decode_mega_kernel(const __grid_constant__ MegaParams p) {
         // ---- S9: logits of this CTA's vocabulary slice (decoder/transformer.py:181) -> lg (fp32, local)
         {
             const int mine = (my_t1 - my_t0 - warp + 7) / 8;      // tiles warp, warp+8, ... of the slice
-            stream_tiles(xs, MG_XP, d, p.wout, d, V, mine > 0 ? mine : 0, [&](int i) { return (my_t0 + warp + 8 * i) * 8; },
+            stream_tiles(xs, MG_XP, d, p.wout, d, V, mine > 0 ? mine : 0, b, [&](int i) { return (my_t0 + warp + 8 * i) * 8; },
                          [&](int i, const float(&acc)[4]) {
                              const int lc = (warp + 8 * i) * 8 + 2 * t;
                              const int gc = my_t0 * 8 + lc;
@@ -659,7 +700,7 @@ const char* decode_mega_launch(cudaStream_t st, const MegaParams& p) {
     if (p.n_layers < 1 || p.n_layers > OTB_MEGA_MAX_LAYERS_INT) return "decode_mega: too many layers";
     if (p.B < 1 || p.T < 1 || p.st.N != p.B * p.st.beam) return "decode_mega: bad batch geometry";
     if (p.V < 8) return "decode_mega: vocabulary too small";
-    const MegaSmem L = mega_layout(p.dff, p.V, p.T);
+    const MegaSmem L = mega_layout(p.dff, p.V, p.T, p.st.Lmax);
     if (L.total > 227 * 1024) return "decode_mega: shared-memory budget exceeded (memory too long / d_ff too large)";
     static bool attr_set = false;
     if (!attr_set) {
