@@ -61,3 +61,21 @@ def test_shard_range_partitions_exactly():
                 assert 0 <= hi - lo <= n // w + 1
                 cover += list(range(lo, hi))
             assert cover == list(range(n))
+
+
+def test_transformer_lr_schedule_matches_oracle_and_reference_quirk():
+    """train.transformer_lr == TransformerScheduler.get_step_lr (scheduler.py:137-138); the first optimizer step uses
+    lr(3) because BaseScheduler.__init__ already steps once (pinned by tests/golden/train_step_postnorm_glu.pt)."""
+    import importlib
+    import sys
+    import types
+    from oracle import train_step as ot
+    # train.py imports the CUDA bindings lazily through ops; the schedule itself is plain Python
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'opentransformer_b200', 'train.py')).read()
+    ns = {}
+    start = src.index('def transformer_lr')
+    end = src.index('class FusedTrainer')
+    exec(src[start:end], ns)
+    for step in (1, 2, 3, 100, 11999, 12000, 12001, 50000):
+        assert abs(ns['transformer_lr'](step, 256, 12000) - ot.transformer_lr(step, 256, 12000)) < 1e-15
+    assert ot.first_step_index() == 3
