@@ -347,7 +347,8 @@ def attention_bwd(q, k, v, out, dout, lse, B, H, Tq, Tk, dq, dk, dv, kv_len=None
                   v_col0=0, dq_col0=0, dk_col0=0, dv_col0=0):
     """Gradients of otb_attention written into dq/dk/dv (bf16 matrices, column offsets d*_col0)."""
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v'), (out, 'out'), (dout, 'dout'), (dq, 'dq'), (dk, 'dk'), (dv, 'dv')):
-        _need(t, BF16, n) if t.is_contiguous() else None
+        if not t.is_cuda or t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError(f'{n} must be a 2-D bf16 CUDA tensor with unit column stride (no CPU fallback)')
     dsum = torch.empty(B, H, Tq, dtype=torch.float32, device=q.device)
     check(_lib.lib().otb_attention_bwd(_p(q), q.stride(0), q.shape[0], _p(k), k.stride(0), k.shape[0], _p(v), v.stride(0),
                                        _p(out), out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(dsum),

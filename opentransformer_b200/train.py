@@ -31,10 +31,6 @@ def _bf(t):
     return t.detach().to(BF16).contiguous()
 
 
-def _bft(t):
-    return t.detach().to(BF16).t().contiguous()
-
-
 def _f(t):
     return t.detach().float().contiguous()
 
