@@ -241,6 +241,15 @@ int otb_sumsq(const float* g, long long n, float* out, int zero_first, void* str
 int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* otb_adam_step with the step counters and the LR schedule on the DEVICE (no host sync, CUDA-graph friendly):
+ * counters i32 [3] = {optimizer steps, scheduler global_step, skipped steps}; when sqrt(*sumsq) is finite both counts
+ * advance and lr = factor * model_size^-0.5 * min(s^-0.5, s * warmup^-1.5) (TransformerScheduler, train/scheduler.py:137-138;
+ * warmup_steps <= 0: lr = base_lr), else only `skipped` advances and nothing is updated -- the reference skips
+ * scheduler.step() and optimizer.step() together (trainer.py:229-233).  hyper f32 [4] receives {lr, 1-b1^t, 1-b2^t, applied}. */
+int otb_adam_step_sched(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm,
+                        float base_lr, float model_size, float warmup_steps, float factor, float beta1, float beta2, float eps,
+                        float weight_decay, int32_t* counters, float* hyper, void* stream);
+
 /* Conv2d front end backward (frontend/conv.py:50-76 under autograd).  h1 = conv1 activation buffer (layout of
  * otb_conv1_relu).  col bf16 [B*T2*F2, 9*C1] = im2col of h1 for conv2 (k = (kh*3+kw)*C1 + c): conv2's weight gradient is
  * otb_linear_wgrad(dpre2, col) and its input gradient dcol = otb_linear(dpre2, W2^T).  otb_conv_col2im_relu folds dcol

@@ -252,12 +252,16 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
         atomicAdd(out, t);
     }
 }
+// hyper (optional, device f32 [4] = {lr, 1 - b1^t, 1 - b2^t, apply}) overrides lr / bc1 / bc2: written by adam_prepare_kernel,
+// which owns the step counters on the device so that a skipped (non-finite) step advances neither the LR schedule nor
+// Adam's bias-correction count -- exactly what trainer.py:229-233 does on the host.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, size_t n, const float* __restrict__ sumsq,
                                                    float max_norm, float lr, float b1, float b2, float eps, float wd,
-                                                   float bc1, float bc2) {
+                                                   float bc1, float bc2, const float* __restrict__ hyper) {
     const float total = sqrtf(*sumsq);
     if (!isfinite(total)) return;                      // NaN / Inf gradients: skip the step (trainer.py:229-230)
+    if (hyper != nullptr) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }
     float coef = 1.0f;
     if (max_norm > 0.f) coef = fminf(1.0f, max_norm / (total + 1e-6f));
     const float step = lr / bc1, rs2 = rsqrtf(bc2);
@@ -270,6 +274,27 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         v[i] = vi;
         p[i] = pi - step * mi / (sqrtf(vi) * rs2 + eps);
     }
+}
+// counters i32 [3] = {optimizer steps taken, scheduler global_step, skipped steps}.  One thread: advance them only when
+// the gradient norm is finite, then evaluate TransformerScheduler.get_step_lr (scheduler.py:137-138; warmup <= 0: constant
+// base_lr) and Adam's bias corrections for the step about to be taken.
+__global__ void adam_prepare_kernel(const float* __restrict__ sumsq, int* __restrict__ counters, float* __restrict__ hyper,
+                                    float base_lr, float model_size, float warmup, float factor, float b1, float b2) {
+    const float total = sqrtf(*sumsq);
+    if (!isfinite(total)) {
+        counters[2] += 1;
+        hyper[3] = 0.f;
+        return;
+    }
+    const int t = counters[0] + 1, s = counters[1] + 1;
+    counters[0] = t;
+    counters[1] = s;
+    double lr = (double)base_lr;
+    if (warmup > 0.f) lr = (double)factor * pow((double)model_size, -0.5) * fmin(pow((double)s, -0.5), (double)s * pow((double)warmup, -1.5));
+    hyper[0] = (float)lr;
+    hyper[1] = (float)(1.0 - pow((double)b1, (double)t));
+    hyper[2] = (float)(1.0 - pow((double)b2, (double)t));
+    hyper[3] = 1.f;
 }
 const char* sumsq_launch(cudaStream_t st, const float* g, size_t n, float* out, int zero_first) {
     if (zero_first) {
@@ -290,7 +315,18 @@ const char* adam_launch(cudaStream_t st, float* p, const float* g, float* m, flo
     size_t blocks = (n + 1023) / 1024;
     if (blocks > (size_t)(8 * num_sms())) blocks = 8 * num_sms();
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps, wd, bc1, bc2);
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, sumsq, max_norm, lr, b1, b2, eps, wd, bc1, bc2, nullptr);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+const char* adam_sched_launch(cudaStream_t st, float* p, const float* g, float* m, float* v, size_t n, const float* sumsq,
+                              float max_norm, float base_lr, float model_size, float warmup, float factor, float b1, float b2,
+                              float eps, float wd, int* counters, float* hyper) {
+    adam_prepare_kernel<<<1, 1, 0, st>>>(sumsq, counters, hyper, base_lr, model_size, warmup, factor, b1, b2);
+    size_t blocks = (n + 1023) / 1024;
+    if (blocks > (size_t)(8 * num_sms())) blocks = 8 * num_sms();
+    if (blocks < 1) blocks = 1;
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, sumsq, max_norm, 0.f, b1, b2, eps, wd, 1.f, 1.f, hyper);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

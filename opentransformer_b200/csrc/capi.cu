@@ -384,6 +384,14 @@ int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, con
     RET("otb_adam_step", adam_launch(ST(stream), p, g, m, v, (size_t)n, sumsq, max_norm, lr, beta1, beta2, eps, weight_decay, step));
 }
 
+int otb_adam_step_sched(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm,
+                        float base_lr, float model_size, float warmup_steps, float factor, float beta1, float beta2, float eps,
+                        float weight_decay, int32_t* counters, float* hyper, void* stream) {
+    if (!p || !g || !m || !v || !sumsq || !counters || !hyper || n < 1) return fail("otb_adam_step_sched", "bad arguments");
+    RET("otb_adam_step_sched", adam_sched_launch(ST(stream), p, g, m, v, (size_t)n, sumsq, max_norm, base_lr, model_size, warmup_steps,
+                                                 factor, beta1, beta2, eps, weight_decay, counters, hyper));
+}
+
 int otb_conv_im2col(const void* h1, void* col, int B, int T, int F, int C1, void* stream) {
     int T1, F1, T2, F2;
     if (otb_conv_geometry(T, F, &T1, &F1, &T2, &F2)) return 1;

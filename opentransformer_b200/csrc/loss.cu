@@ -30,8 +30,10 @@ __global__ void __launch_bounds__(256) ls_ce_kernel(const float* __restrict__ lo
     __shared__ float red[8];
     const int row = blockIdx.x;
     const float* x = logits + (size_t)row * ldl;
-    const long long t = tgt[row];
-    const bool is_pad = (t == pad_id);
+    long long t = tgt[row];
+    // a target outside [0, V) has no logit to read: treat the row like PAD (contributes nothing) instead of reading out of bounds
+    const bool is_pad = (t == pad_id) || t < 0 || t >= V;
+    if (t < 0 || t >= V) t = 0;
     float m = -INFINITY, s = 0.f;
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
         const float v = x[i];
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(256) ls_ce_kernel(const float* __restrict__ lo
     if (threadIdx.x == 0) {
         float l = 0.f;
         if (!is_pad) {
-            const float c = (float)(V - 1) * lo * logf(lo) + hi * logf(hi);
+            // sum_v conf_v log conf_v with xlogy semantics (0 log 0 = 0, what F.kl_div does): smoothing 0 or 1 stay finite
+            const float c = (lo > 0.f ? (float)(V - 1) * lo * logf(lo) : 0.f) + (hi > 0.f ? hi * logf(hi) : 0.f);
             l = c - lo * (s - (float)V * lse) - (hi - lo) * (x[t] - lse);
         }
         tok_loss[row] = l;

@@ -268,6 +268,9 @@ class TransformerEncoderLayer(nn.Module):
             raise NotImplementedError('relative_positional TransformerEncoder: use the Conformer encoder path')
         self.n_heads = n_heads
         self.normalize_before = normalize_before
+        # dropout is a training-time op (encoder/transformer.py:32-33,54,61); inference ignores it, train.py checks it
+        self.dropout_rates = {'slf_attn_dropout': slf_attn_dropout, 'ffn_dropout': ffn_dropout,
+                              'residual_dropout': residual_dropout}
         self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
         self.feed_forward = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation)
         self.norm1 = nn.LayerNorm(d_model)
@@ -547,6 +550,8 @@ class TransformerDecoderLayer(nn.Module):
             raise NotImplementedError('concat_after / relative_positional decoder')
         self.n_heads = n_heads
         self.normalize_before = normalize_before
+        self.dropout_rates = {'slf_attn_dropout': slf_attn_dropout, 'src_attn_dropout': src_attn_dropout,
+                              'ffn_dropout': ffn_dropout, 'residual_dropout': residual_dropout}
         self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
         self.src_attn = MultiHeadedCrossAttention(n_heads, d_model, memory_dim, src_attn_dropout)
         self.feed_forward = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation)

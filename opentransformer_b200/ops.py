@@ -463,6 +463,18 @@ def adam_step(p, g, m, v, sumsq_buf, max_norm, lr, betas, eps, weight_decay, ste
     _count()
 
 
+def adam_step_sched(p, g, m, v, sumsq_buf, max_norm, base_lr, model_size, warmup_steps, factor, betas, eps, weight_decay,
+                    counters, hyper):
+    """clip + Adam with the step counters / Noam schedule evaluated on the device (otb_adam_step_sched)."""
+    for t, n in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v'), (hyper, 'hyper')):
+        _need(t, torch.float32, n)
+    _need(counters, torch.int32, 'counters')
+    check(_lib.lib().otb_adam_step_sched(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq_buf), max_norm, base_lr,
+                                         float(model_size), float(warmup_steps or 0), factor, betas[0], betas[1], eps,
+                                         weight_decay, _p(counters), _p(hyper), _stream()), 'otb_adam_step_sched')
+    _count(2)
+
+
 def conv_im2col(h1, B, T, F, C1):
     _, _, T2, F2 = conv_geometry(T, F)
     col = torch.empty(B * T2 * F2, 9 * C1, dtype=BF16, device=h1.device)

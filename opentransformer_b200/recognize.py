@@ -81,7 +81,7 @@ class BeamDecoder:
     kernel) is captured into a CUDA graph on first use and replayed for every step.
     """
 
-    def __init__(self, decoder, batch, beam, T, max_len, device, use_graph=True, persistent=False):
+    def __init__(self, decoder, batch, beam, T, max_len, device, use_graph=True, persistent=False, keep_logp=None):
         self.dec = decoder
         self.B, self.beam, self.T, self.Lmax = batch, beam, T, max_len
         self.N = batch * beam
@@ -97,9 +97,11 @@ class BeamDecoder:
         self.logp = torch.zeros(self.N, decoder.vocab_size, dtype=torch.float32, device=device)
         self.topk_val = torch.zeros(self.N, beam, dtype=torch.float32, device=device)
         self.topk_idx = torch.zeros(self.N, beam, dtype=torch.int32, device=device)
-        self.keep_logp = not use_graph      # eager (test / debug) mode also materialises the full log-probs
+        # eager (test / debug) mode also materialises the full log-probs; keep_logp=True does so on the graph path (parity traces)
+        self.keep_logp = (not use_graph) if keep_logp is None else bool(keep_logp)
         self.use_graph = use_graph
         self.graph = None
+        self._graph_pk = None      # the bf16 weight pack whose device pointers the captured graph bakes in (kept alive with it)
         self.lm_logp = None
         self.lm_weight = 0.0
         if decoder.pos_emb.scale_learnable:
@@ -194,7 +196,12 @@ class BeamDecoder:
     def step(self):
         if not self.use_graph:
             return self._step_kernels()
+        if self.graph is not None and self._graph_pk is not self.dec.packed():
+            # parameters changed (load_state_dict / optimizer step): the pack was rebuilt at new addresses, the captured
+            # kernels would read the old (stale or recycled) weights -- drop the graph and capture again
+            self.graph = None
         if self.graph is None:
+            self._graph_pk = self.dec.packed()
             # warm-up outside capture (lazy func attributes, caches), then restore the state it advanced
             snap = [t.clone() for t in (self.state.tok_hist, self.state.par_hist, self.state.last_tok,
                                         self.state.scores, self.state.flag, self.state.anc, self.state.ctrl)]

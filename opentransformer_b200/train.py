@@ -52,6 +52,13 @@ class TrainPack:
         for blk in list(enc.blocks) + list(dec.blocks):
             if blk.feed_forward.activation != 'glu':
                 raise NotImplementedError('training path: GLU feed-forward only (round 1)')
+            rates = getattr(blk, 'dropout_rates', {})
+            if any(float(v) > 0.0 for v in rates.values()):
+                # the reference applies these in train mode (encoder/transformer.py:32-33,54,61; decoder/transformer.py:36-38);
+                # training WITHOUT them would be a different network, so refuse instead of silently dropping the regulariser
+                raise NotImplementedError(
+                    f'training path: dropout is not implemented on the sm_100a backward yet, got {rates}; '
+                    'set residual_dropout / slf_attn_dropout / src_attn_dropout / ffn_dropout to 0.0')
         self.fe = self._frontend(fe)
         self.enc = [self._enc_layer(b) for b in enc.blocks]
         self.dec = [self._dec_layer(b) for b in dec.blocks]
@@ -344,11 +351,29 @@ class FusedTrainer:
         self.group = process_group
         # BaseScheduler starts at global_step 1 and its constructor already calls step() once (scheduler.py:22,42-46);
         # the trainer steps it again before every optimizer.step() (trainer.py:232): the first update uses lr(3)
-        self.global_step = 2
-        self.opt_steps = 0
+        # The counts live on the DEVICE ({optimizer steps, scheduler global_step, skipped}): the fused Adam launch advances them
+        # only when the gradient norm is finite, as the reference skips scheduler.step() together with optimizer.step()
+        # (trainer.py:229-233) -- no host sync, and a skipped step cannot desynchronise the LR schedule / bias correction.
+        self.counters = torch.tensor([0, 2, 0], dtype=torch.int32, device=dev)
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
         self.micro = 0
         self.use_graph = use_graph
-        self._graphs = {}
+        self.graph_after = 2          # capture a CUDA graph for an input geometry once it has been seen this many times
+        self.max_graphs = 8           # LRU bound: every graph owns a private pool with the whole activation tape
+        self._graphs = {}             # key -> (graph, inputs, mask, truth, loss, launches), most recently used last
+        self._seen = {}
+
+    @property
+    def opt_steps(self):
+        return int(self.counters[0].item())
+
+    @property
+    def global_step(self):
+        return int(self.counters[1].item())
+
+    @property
+    def skipped_steps(self):
+        return int(self.counters[2].item())
 
     def lr(self):
         if self.warmup:
@@ -369,10 +394,22 @@ class FusedTrainer:
 
     def _graph_for(self, inputs, mask, truth):
         """The ~870 launches of one micro-batch captured once per input geometry and replayed: launched one by one from
-        Python the step is host-bound (14.6 ms against 10.2 ms of kernel time, profiles/r1_launches_train_v0.csv)."""
+        Python the step is host-bound (14.6 ms against 10.2 ms of kernel time, profiles/r1_launches_train_v0.csv).
+        Real ASR batches have a new (T, L) almost every step, so a geometry runs EAGERLY until it has recurred
+        `graph_after` times, and at most `max_graphs` graphs are kept (least recently used first out): use_graph pays off
+        with bucketed / padded batches (otrans/data/bucket.py), it must not grow memory without bound otherwise.
+        Returns None when this call should run eagerly."""
         key = (tuple(inputs.shape), tuple(truth.shape), inputs.device.index)
-        ent = self._graphs.get(key)
+        ent = self._graphs.pop(key, None)
         if ent is None:
+            n = self._seen.get(key, 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            self._seen[key] = n
+            if n < self.graph_after:
+                return None
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))        # drops the graph and its memory pool
             sx, sm, st = inputs.clone(), mask.clone(), truth.clone()
             snap = self.flat_g.clone()
             cur = torch.cuda.current_stream()
@@ -389,14 +426,15 @@ class FusedTrainer:
             launches = ops.COUNTERS['launches'] - n0
             ops.COUNTERS['launches'] = n0           # capture records, it does not launch
             ent = (graph, sx, sm, st, loss, launches)
-            self._graphs[key] = ent
+        self._graphs[key] = ent       # (re-)insert as most recently used
         return ent
 
     def step(self, inputs, mask, truth):
         """One micro-batch; every `accum_steps` calls an optimizer step.  Returns the (un-scaled) loss tensor."""
         with torch.no_grad():
-            if self.use_graph:
-                graph, sx, sm, st, loss, launches = self._graph_for(inputs, mask, truth)
+            ent = self._graph_for(inputs, mask, truth) if self.use_graph else None
+            if ent is not None:
+                graph, sx, sm, st, loss, launches = ent
                 sx.copy_(inputs)
                 sm.copy_(mask)
                 st.copy_(truth)
@@ -410,10 +448,8 @@ class FusedTrainer:
                 # ONE NCCL all-reduce per optimizer step (the reference's DDP reduces on every micro-batch)
                 allreduce_mean_(self.flat_g, self.group)
                 ops.sumsq(self.flat_g, self.sumsq)
-                self.global_step += 1
-                self.opt_steps += 1
-                ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.sumsq, self.clip, self.lr(), self.betas, self.eps,
-                              self.wd, self.opt_steps)
+                ops.adam_step_sched(self.flat_p, self.flat_g, self.m, self.v, self.sumsq, self.clip, self.base_lr, self.model_size,
+                                    self.warmup, self.factor, self.betas, self.eps, self.wd, self.counters, self.hyper)
                 self.flat_g.zero_()
                 modules.bump_param_generation()     # bf16 shadow copies (modules._Packed) must be rebuilt
         return loss

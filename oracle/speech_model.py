@@ -408,7 +408,8 @@ def label_smoothing_loss(logits, target, smoothing=0.1):
     conf = torch.full_like(flat, smoothing / (v - 1))
     conf.scatter_(1, tgt.unsqueeze(1), 1 - smoothing)
     logp = F.log_softmax(flat, dim=-1)
-    per_tok = torch.sum(conf * (torch.log(conf) - logp), dim=-1)
+    # F.kl_div(logp, conf, 'none') = xlogy(conf, conf) - conf * logp  (0 log 0 = 0: loss.py:43 stays finite at smoothing 0 / 1)
+    per_tok = torch.sum(torch.xlogy(conf, conf) - conf * logp, dim=-1)
     pad = tgt == PAD
     return torch.sum(per_tok.masked_fill(pad, 0.0)) / torch.sum(~pad)
 

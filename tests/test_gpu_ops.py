@@ -311,17 +311,21 @@ def test_logsoftmax_topk_fused(rows, V, k, lm):
     assert torch.equal(idx2, idx) and torch.equal(val2, val)
 
 
-def test_label_smoothing_cross_entropy_forward_and_grad():
+@pytest.mark.parametrize('smoothing', [0.1, 0.0, 1.0])
+def test_label_smoothing_cross_entropy_forward_and_grad(smoothing):
+    """smoothing 0 / 1: the constant sum_v conf_v log conf_v has 0*log(0) terms, which F.kl_div (xlogy) treats as 0
+    (otrans/module/loss.py:43); the loss must stay finite."""
     from oracle import speech_model as om
     rows, V = 93, 4234
     g = torch.Generator().manual_seed(5)
     logits = (torch.randn(rows, 4240, generator=g) * 3).to(DEV)
     tgt = torch.randint(1, V, (rows,), generator=g)
     tgt[::7] = 0                                                   # PAD rows
-    loss, dl = ops.ls_cross_entropy(logits, tgt.to(DEV), V, 0.1, want_grad=True)
+    loss, dl = ops.ls_cross_entropy(logits, tgt.to(DEV), V, smoothing, want_grad=True)
     x = logits[:, :V].detach().cpu().double().requires_grad_(True)
-    ref = om.label_smoothing_loss(x.unsqueeze(0), tgt.unsqueeze(0), 0.1)
+    ref = om.label_smoothing_loss(x.unsqueeze(0), tgt.unsqueeze(0), smoothing)
     ref.backward()
+    assert math.isfinite(float(loss))
     assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref))), (float(loss), float(ref))
     print(_report('ls-ce dlogits', dl.cpu(), x.grad.float(), 1e-5, 1e-7))
 
