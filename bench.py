@@ -157,11 +157,42 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def quiet_nccl():
-    """NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION/INFO (the GPU image sets it); rank 0's stdout must
-    carry exactly one JSON line."""
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE', ''):
-        os.environ['NCCL_DEBUG'] = 'WARN'
+def nccl_logging():
+    """NCCL writes its debug output to STDOUT unless NCCL_DEBUG_FILE is set; rank 0's stdout must carry exactly one JSON
+    line.  Round 1 forced NCCL_DEBUG=WARN, which also hid the communicator's rank count from the driver.  Now every rank
+    logs INIT-level INFO into a file; rank 0 parses it (ranks of the communicator, NVLS) into the JSON line and echoes the
+    init lines to stderr."""
+    os.environ['NCCL_DEBUG'] = 'INFO'
+    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+    path = '/tmp/otb_nccl_%s_r%s.log' % (os.environ.get('MASTER_PORT', '0'), os.environ.get('RANK', '0'))
+    os.environ['NCCL_DEBUG_FILE'] = path
+    try:
+        os.remove(path)
+    except OSError:
+        pass
+    return path
+
+
+def nccl_summary(path, world):
+    """{'nranks': N seen in the 'Init COMPLETE' line, 'nvls': bool, ...} from rank 0's NCCL INFO log."""
+    import re
+    out = {'log': path, 'nranks': None, 'nvls': None, 'version': None}
+    try:
+        txt = open(path, errors='replace').read()
+    except OSError:
+        return out
+    m = re.search(r'nranks (\d+)[^\n]*Init COMPLETE', txt) or re.search(r'nranks (\d+)', txt)
+    if m:
+        out['nranks'] = int(m.group(1))
+    out['nvls'] = bool(re.search(r'NVLS', txt))
+    m = re.search(r'NCCL version ([0-9.+a-z]+)', txt)
+    if m:
+        out['version'] = m.group(1)
+    out['nranks_ok'] = (out['nranks'] == world) if out['nranks'] is not None else None
+    for ln in txt.splitlines():
+        if 'Init COMPLETE' in ln or 'NCCL version' in ln or ('NVLS' in ln and 'comm' in ln):
+            sys.stderr.write('[nccl] ' + ln.strip()[:240] + '\n')
+    return out
 
 
 def measured_peaks():
@@ -251,10 +282,10 @@ def run_reference(args):
     return 0
 
 
-def time_gemm_shape(tag, dev, reps=50):
-    """Average duration (ms) of one otb_linear launch of shape `tag` = (epilogue, M, weight rows, K, out_f32): `reps`
-    back-to-back launches on synthetic operands between two CUDA events (per-launch events around 8 us kernels mostly
-    measure the gap between launches)."""
+def time_gemm_shape(tag, dev, reps=200):
+    """Average DEVICE duration (ms) of one otb_linear launch of shape `tag` = (epilogue, M, weight rows, K, out_f32): a CUDA
+    graph of `reps` launches on synthetic operands, replayed between two CUDA events (round 1 launched them eagerly through
+    ctypes, which measured the host's launch rate, VERDICT r1 weak #6)."""
     from opentransformer_b200 import ops
     epi, M, Nw, K, of32 = tag
     g = torch.Generator().manual_seed(3)
@@ -271,16 +302,53 @@ def time_gemm_shape(tag, dev, reps=50):
         kw['table'], kw['period'] = torch.zeros(M, n_out, device=dev), M
     ld = (n_out + 7) // 8 * 8
     out = torch.empty(M, ld, dtype=torch.float32 if of32 else torch.bfloat16, device=dev)
-    for _ in range(5):
-        ops.linear(a, w, bias, epi, out=out, **kw)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            ops.linear(a, w, bias, epi, out=out, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    n0 = ops.COUNTERS['launches']
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            ops.linear(a, w, bias, epi, out=out, **kw)
+    ops.COUNTERS['launches'] = n0
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        ops.linear(a, w, bias, epi, out=out, **kw)
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+
+
+def init_dist():
+    """(rank, world, local, device, nccl log path): one process per GPU, NCCL over NVLink for N > 1."""
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    log = None
+    if world > 1 and not dist.is_initialized():
+        log = nccl_logging()
+        dist.init_process_group('nccl', device_id=dev)
+    return rank, world, local, dev, log
+
+
+def dist_barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def ids_digest(ids):
+    import hashlib
+    return hashlib.sha1(ids.detach().to('cpu', torch.int64).contiguous().numpy().tobytes()).hexdigest()
 
 
 def workload_config(args, batch):
@@ -295,23 +363,31 @@ def workload_config(args, batch):
 
 
 # ------------------------------------------------------------------------------------------------
+DEC_FLOP = 540.0e9     # KV-cached beam decode, 32 utt x beam 10 x 60 steps
+ENC_FLOP = 410.0e9     # frontend + 12-layer encoder forward, 32 x 1000 frames
+
+
+def decode_step_bytes(model, batch, T2):
+    """Algorithmic HBM/L2 bytes of ONE beam step of one utterance batch: every decoder weight read once
+    (bf16; the cross-attention K/V projection is not part of the step) + the per-utterance cross-attention K/V cache."""
+    dec = model.decoder
+    w = 0
+    for n, p in dec.named_parameters():
+        if 'vk_proj' in n or n.startswith('output_layer.weight') and dec.output_layer.weight is dec.embedding.weight:
+            continue
+        w += p.numel() * 2
+    kv = len(dec.blocks) * batch * T2 * 2 * dec.d_model * 2
+    return w, kv
+
+
 def run_b200(args):
     import torch.distributed as dist
     from opentransformer_b200 import ops
-    from opentransformer_b200.recognize import SpeechToTextRecognizer
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        quiet_nccl()
-        dist.init_process_group('nccl', device_id=dev)
+    from opentransformer_b200.recognize import SpeechToTextRecognizer, BeamDecoder
+    rank, world, local, dev, nccl_log = init_dist()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        dist_barrier(world)
 
     model = build_model().to(dev)
     # Distinct resident input batches, rotated by step index, so consecutive steps never re-read the same input
@@ -321,24 +397,33 @@ def run_b200(args):
     ring_pin = [(x.pin_memory(), m.pin_memory()) for x, m in ring_cpu]
     ring_dev = [(x.to(dev), m.to(dev)) for x, m in ring_cpu]
 
-    # L independent "lanes" (stream + recogniser state + captured decode graph): the decode loop is a chain of
-    # small latency-bound kernels that leaves most SMs idle, so several utterance batches are kept in flight.
-    L = max(1, args.lanes)
-    # single-lane diagnostics run on their own recogniser captured under the latency policy; the concurrent lanes use
-    # the throughput policy (least SM-time per decode step) -- the policy is baked into each captured decode graph
+    def make_rec(persistent):
+        return SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA, ngpu=1,
+                                      persistent=persistent)
+
+    # decode path: 'persistent' = the whole 60-step loop in one launch per batch (csrc/decode_group.cu, 48 SMs per batch of
+    # 32 utterances x beam 10), 'graph' = one CUDA-graph replay of ~52 kernels per step (round 1)
     ops.set_tile_policy('latency')
-    rec_lat = SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA, ngpu=1)
+    probe = make_rec(True)
+    with torch.no_grad():
+        probe.recognize_ids(*ring_dev[0])
+    persist_ok = next(iter(probe._decoders.values())).persistent
+    use_persist = persist_ok if args.decode == 'auto' else (args.decode == 'persistent')
+    if use_persist and not persist_ok:
+        raise SystemExit('bench.py: --decode persistent, but the persistent kernel does not support this configuration')
+    L = args.lanes if args.lanes > 0 else (3 if use_persist else 16)
+    L = max(1, L)
+    # lone-batch diagnostics: one recogniser per decode path (graph path captured under the latency tile policy)
+    rec_graph, rec_pers = make_rec(False), (probe if persist_ok else None)
     with torch.no_grad():
         for i in range(3):
-            rec_lat.recognize_ids(*ring_dev[i])
+            rec_graph.recognize_ids(*ring_dev[i])
+            if rec_pers is not None:
+                rec_pers.recognize_ids(*ring_dev[i])
     torch.cuda.synchronize()
-    policy = args.tile_policy if args.tile_policy != 'auto' else ('throughput' if L > 1 else 'latency')
+    policy = args.tile_policy if args.tile_policy != 'auto' else ('throughput' if (L > 1 and not use_persist) else 'latency')
     ops.set_tile_policy(policy)
-    lanes = []
-    for j in range(L):
-        rec = SpeechToTextRecognizer(model, beam_width=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA,
-                                     ngpu=1)
-        lanes.append((torch.cuda.Stream(device=dev), rec))
+    lanes = [(torch.cuda.Stream(device=dev), make_rec(use_persist)) for _ in range(L)]
 
     def step_resident(rec, i):
         x, m = ring_dev[i % RING]
@@ -362,7 +447,7 @@ def run_b200(args):
         bufs[2].synchronize()
         return bufs
 
-    def timed(fn, steps, n_lanes):
+    def timed(fn, steps, n_lanes, recs=None):
         """K steps spread round-robin over n_lanes host threads / CUDA streams; device time by CUDA events."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,6 +458,8 @@ def run_b200(args):
             try:
                 torch.cuda.set_device(local)
                 st, rec = lanes[j]
+                if recs is not None:
+                    rec = recs[j]
                 st.wait_event(e0)
                 with torch.cuda.stream(st):
                     for i in range(j, steps, n_lanes):
@@ -404,35 +491,36 @@ def run_b200(args):
             step_e2e(rec, 0)
         st.synchronize()
 
-    # ---- diagnostics outside the headline region: single-lane latency and encoder-only time
+    # ---- diagnostics outside the headline region: encoder-only time and lone-batch latency of both decode paths
     def enc_only(rec, i):
         with torch.no_grad():
             return rec._encode_bf16(*ring_dev[i % RING])
     timed(enc_only, 8, 1)                           # untimed: first pass after the graph captures
-    ms_enc = timed(enc_only, 8, 1) / 8
-    ops.PROFILE = []            # records the eager GEMM launches (shapes, counts) of the single-lane passes
-    ms_lat_tp = timed(step_resident, 4, 1) / 4      # lane 0 alone, under the lanes' own tile policy
-    prof, ops.PROFILE = ops.PROFILE, None
-    keep = lanes[0]
-    lanes[0] = (keep[0], rec_lat)
-    ms_lat = timed(step_resident, 4, 1) / 4         # lone batch, latency policy
-    lanes[0] = keep
-    # the same decode-step kernels, eager (outside the CUDA graph) so that each GEMM launch can be bracketed by events
-    from opentransformer_b200.recognize import BeamDecoder
+    ms_enc = timed(enc_only, 16, 1) / 16
+    ms_lat_graph = timed(step_resident, 4, 1, [rec_graph]) / 4
+    ms_lat_pers = timed(step_resident, 8, 1, [rec_pers]) / 8 if rec_pers is not None else float('nan')
+    ms_lat = ms_lat_pers if use_persist else ms_lat_graph
+    # device duration of the persistent kernel alone (events on its own stream around the single launch)
+    dec_kernel_ms = float('nan')
+    if rec_pers is not None:
+        with torch.no_grad():
+            mem0, len0, B0, T20 = rec_pers._encode_bf16(*ring_dev[0])
+            bd0 = rec_pers._decoder_for(B0, T20, dev)
+            ts = []
+            for _ in range(6):
+                bd0.setup(mem0, len0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                bd0.run_persistent(MAX_LEN)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            dec_kernel_ms = sorted(ts)[len(ts) // 2]
+    # reference ids of batch 0 for the output check (resident pass on lane 0)
     with torch.no_grad():
-        mem0, len0, B0, T20 = lanes[0][1]._encode_bf16(*ring_dev[0])
-        bd0 = BeamDecoder(model.decoder, B0, BEAM, T20, MAX_LEN, dev, use_graph=False)
-        bd0.keep_logp = False
-        bd0.setup(mem0, len0)
-        for _ in range(4):
-            bd0.step()
-        torch.cuda.synchronize()
-        ops.PROFILE = []
-        for _ in range(8):
-            bd0.step()
-        torch.cuda.synchronize()
-    prof_dec, ops.PROFILE = ops.PROFILE, None
-    del bd0
+        ids0, scores0, steps0 = lanes[0][1].recognize_ids(*ring_dev[0])
+        ids0 = ids0.clone()
+    torch.cuda.synchronize()
 
     # K steps over L lanes run in ceil(K/L) rounds; when the last round would be mostly empty (K = 20, L = 16), fewer lanes
     # with full rounds finish sooner (K = 20 -> 2 rounds of 10)
@@ -440,103 +528,188 @@ def run_b200(args):
     L_eff = min(L, -(-args.steps // rounds))
     if L > 1:
         timed(step_resident, 2 * L, L)      # untimed multi-lane pass: thread start-up, allocator growth per stream
+    # The timed region is EXACTLY `steps` steps between barrier + synchronize; it is repeated until ~1 s of device time has
+    # been measured so that the per-step cost does not depend on the driver's step count.
+    probe_ms = timed(step_resident, args.steps, L_eff)
+    repeats = int(min(64, max(1, -(-args.min_ms // max(probe_ms, 1e-3)))))
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     n0 = ops.COUNTERS['launches']
-    ms_total = timed(step_resident, args.steps, L_eff)
-    launches = ops.COUNTERS['launches'] - n0
+    res_ms = [timed(step_resident, args.steps, L_eff) for _ in range(repeats)]
+    launches = (ops.COUNTERS['launches'] - n0) // repeats
     if L > 1:
         timed(step_e2e, 2 * L, L)           # untimed: per-stream allocator pools and pinned result buffers of the e2e path
-    ms_e2e = timed(step_e2e, args.steps, L_eff)
+    e2e_ms = [timed(step_e2e, args.steps, L_eff) for _ in range(repeats)]
     clocks = sampler.stop() if sampler else None
+    ms_total, ms_e2e = sum(res_ms) / repeats, sum(e2e_ms) / repeats
 
-    t = torch.tensor([ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_tp], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_graph, dec_kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_tp = t.tolist()
+    ms_total, ms_e2e, ms_enc, ms_lat, ms_lat_graph, dec_kernel_ms = t.tolist()
 
+    line = None
     if rank == 0:
         peaks, src = measured_peaks()
-        # Dominant kernel = the GEMM launch shape with the largest device time per recognize pass.  The decode loop runs
-        # inside a CUDA graph (no per-launch events), so its GEMM shapes are timed in `prof_dec`: 8 eager decode steps of
-        # the same kernels on the same shapes, x MAX_LEN steps per pass.  Encoder / setup shapes come from the 4 eager
-        # single-lane passes in `prof`.
-        epi_names = ['bias', 'relu', 'glu', 'posenc-table', 'residual', 'residual+layernorm', 'swish', 'gelu', 'tanh']
-        shapes = {}
-        for records, per_pass in ((prof, 1.0 / 4), (prof_dec, MAX_LEN / 8.0)):
-            for k, f, a, b, tag in records:
-                if k == 'gemm':
-                    e = shapes.setdefault(tag, {'launches_per_pass': 0.0})
-                    e['launches_per_pass'] += per_pass
-        for tag, e in shapes.items():       # launch counts from the recorded passes, durations from back-to-back launches
-            e['avg_ms'] = time_gemm_shape(tag, dev)
-            e['ms_per_pass'] = e['avg_ms'] * e['launches_per_pass']
-        tag, e = max(shapes.items(), key=lambda kv: kv[1]['ms_per_pass'])
-        epi, M_, Nw_, K_, _of32 = tag
-        avg_ms = e['avg_ms']
-        flops = 2.0 * M_ * Nw_ * K_
-        n_out = Nw_ // 2 if epi == 2 else Nw_
-        nbytes = 2.0 * (M_ * K_ + Nw_ * K_ + M_ * n_out) + (2.0 * M_ * n_out if epi in (4, 5) else 0.0)
-        tf, gbs = flops / (avg_ms * 1e-3) / 1e12, nbytes / (avg_ms * 1e-3) / 1e9
-        peak_tf, peak_bw = peaks.get('bf16_tflops_sustained', 1400.0), peaks.get('hbm_gbs', 6650.0)
-        use_hbm = gbs / peak_bw > tf / peak_tf
-        ach, peak = (gbs, peak_bw) if use_hbm else (tf, peak_tf)
-        all_ms = sum(v['ms_per_pass'] for v in shapes.values())
+        peak_tf, peak_tf_burst, peak_bw = peaks.get('bf16_tflops_sustained', 1400.0), peaks.get('bf16_tflops', 1590.0), peaks.get('hbm_gbs', 6650.0)
+        T2 = ops.conv_geometry(T_FRAMES, F_BINS)[2]
+        w_bytes, kv_bytes = decode_step_bytes(model, B_PER_GPU, T2)
+        ms_step = ms_total / args.steps
+        dec_bytes = MAX_LEN * (w_bytes + kv_bytes)
+        enc_bytes = 0.15e9                          # weights + input + 12 x (read + write [M,256] bf16)
+        def fr(flop, nbytes, ms, tf_peak):
+            return {'tflops': flop / (ms * 1e-3) / 1e12, 'frac_tensor': flop / (ms * 1e-3) / 1e12 / tf_peak,
+                    'gbs': nbytes / (ms * 1e-3) / 1e9, 'frac_hbm': nbytes / (ms * 1e-3) / 1e9 / peak_bw}
         traffic = None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-                traffic = json.load(f).get('%s_M%d_N%d_K%d' % (epi_names[epi], M_, Nw_, K_))
+            with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
+                traffic = json.load(f).get('decode_group_kernel' if use_persist else 'gemm_tc_kernel')
         except Exception:
             pass
-        roofline = {'bound': 'hbm' if use_hbm else 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'GB/s' if use_hbm else 'TFLOP/s',
-                    'frac': ach / peak if peak else None, 'traffic': traffic,
-                    'kernel': f'gemm_tc_kernel, epilogue {epi_names[epi]}, M={M_} N={Nw_} K={K_}: {e["launches_per_pass"]:.0f} launches and '
-                              f'{e["ms_per_pass"]:.2f} ms per recognize pass (largest share of {all_ms:.2f} ms of GEMM time per pass), '
-                              f'avg {avg_ms * 1e3:.1f} us per launch (50 back-to-back launches between CUDA events); algorithmic {flops / 1e9:.3f} GFLOP (2MNK) and '
-                              f'{nbytes / 1e6:.2f} MB (A + W + out [+ resid]) per launch = {tf:.1f} TFLOP/s, {gbs:.0f} GB/s: a '
-                              f'latency-bound launch (few CTAs, {K_ // 64} dependent k-blocks), far from either roof',
-                    'alt': {'tflops': tf, 'frac_tensor': tf / peak_tf, 'gbs': gbs, 'frac_hbm': gbs / peak_bw},
-                    'all_gemm_shapes_ms_per_pass': {('%s_M%d_N%d_K%d' % (epi_names[t[0]], t[1], t[2], t[3])): round(v['ms_per_pass'], 3)
-                                                    for t, v in sorted(shapes.items(), key=lambda kv: -kv[1]['ms_per_pass'])[:8]},
-                    'peak_source': f'MEASURED_PEAKS.json ({src})'}
+        if use_persist:
+            # dominant kernel = the persistent decode kernel: one launch per batch, ~90 % of the device time of a pass
+            ach = dec_bytes / (dec_kernel_ms * 1e-3) / 1e9
+            roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak_bw, 'unit': 'GB/s', 'frac': ach / peak_bw, 'traffic': traffic,
+                        'kernel': f'decode_group_kernel (csrc/decode_group.cu): ONE launch = the whole {MAX_LEN}-step beam-{BEAM} decode of {B_PER_GPU} '
+                                  f'utterances on 3 row groups x 16 CTAs; {dec_kernel_ms:.2f} ms per launch (CUDA events on its stream, lone batch, '
+                                  f'median of 6); algorithmic bytes per launch = {MAX_LEN} steps x ({w_bytes / 1e6:.1f} MB decoder weights + '
+                                  f'{kv_bytes / 1e6:.1f} MB cross-attention K/V) = {dec_bytes / 1e9:.2f} GB (SURVEY.md 8d), {DEC_FLOP / 1e9:.0f} GFLOP; '
+                                  'latency-bound (58 dependent phases per step behind group barriers), the working set is L2-resident',
+                        'alt': fr(DEC_FLOP, dec_bytes, dec_kernel_ms, peak_tf_burst),
+                        'peak_source': f'MEASURED_PEAKS.json ({src}); burst bf16 figure for the lone kernel, sustained for whole steps'}
+        else:
+            roofline = graph_path_roofline(model, lanes, ring_dev, dev, peaks, src, traffic)
+        roofline['whole_step'] = dict(fr(ENC_FLOP + DEC_FLOP, enc_bytes + dec_bytes, ms_step, peak_tf),
+                                      note=f'(410 + 540) GFLOP and {(enc_bytes + dec_bytes) / 1e9:.2f} GB algorithmic per 32-utterance pass over '
+                                           f'ms_per_step = {ms_step:.3f} ms ({L_eff} batches in flight)')
+        roofline['lone_batch'] = dict(fr(ENC_FLOP + DEC_FLOP, enc_bytes + dec_bytes, ms_lat, peak_tf), ms=ms_lat)
+        roofline['encoder_forward'] = dict(fr(ENC_FLOP, enc_bytes, ms_enc, peak_tf), ms=ms_enc)
         utt = B_PER_GPU * world * args.steps
         value = utt / (ms_total * 1e-3)
         e2e = utt / (ms_e2e * 1e-3)
         cfg = workload_config(args, B_PER_GPU)
         cfg['lanes'] = L_eff
+        cfg['decode_path'] = 'persistent (one launch per batch)' if use_persist else 'per-step CUDA graph'
         cfg['tile_policy'] = policy
+        cfg['repeats'] = repeats
+        # output check: digest of the n-best ids of input batch 0 against the committed one (tools/make_bench_digest.py runs
+        # the bf16-policy oracle on the same inputs / weights in the build container)
+        digest = ids_digest(ids0)
+        expected = None
+        try:
+            with open(os.path.join(ROOT, 'tests', 'golden', 'bench_digest.json')) as f:
+                expected = json.load(f).get('ids_sha1')
+        except Exception:
+            pass
         line = {
             'metric': 'utterances/sec (encoder-fwd + beam-10 decode, 60 steps)', 'value': value, 'unit': 'utt/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic', 'config': cfg,
             'e2e': {'value': e2e, 'unit': 'utt/s', 'h2d_bytes_per_step': ring_cpu[0][0].numel() * 4 + ring_cpu[0][1].numel(),
                     'd2h_bytes_per_step': B_PER_GPU * MAX_LEN * 8 + B_PER_GPU * 4},
             'gpu_launches': launches,
             'breakdown': {'single_lane_step_ms': ms_lat, 'single_lane_utt_per_s': B_PER_GPU * world / (ms_lat * 1e-3),
                           'encoder_fwd_ms': ms_enc, 'encoder_fwd_utt_per_s': B_PER_GPU * world / (ms_enc * 1e-3),
-                          'single_lane_step_ms_under_lane_policy': ms_lat_tp,
                           'beam_decode_ms': ms_lat - ms_enc,
-                          'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3)},
+                          'beam_decode_utt_per_s': B_PER_GPU * world / ((ms_lat - ms_enc) * 1e-3),
+                          'persistent_decode_kernel_ms': dec_kernel_ms,
+                          'graph_path_single_lane_step_ms': ms_lat_graph,
+                          'timed_region_ms': {'mean': ms_total, 'min': min(res_ms), 'max': max(res_ms), 'repeats': repeats}},
             'roofline': roofline,
+            'validation': {'ids_sha1': digest, 'expected_sha1': expected, 'match': (digest == expected) if expected else None,
+                           'steps_executed': int(steps0)},
             'clocks': clocks,
         }
+        if nccl_log:
+            line['comm'] = nccl_summary(nccl_log, world)
         if args.cpu_baseline and world == 1:
             threads, cores = pick_cpu_threads()
             sd, params = flat_state_dict(model), model_params()
-            xs, ms_ = synthetic_batch(args.ref_sample, 0)
+            xs, ms_ = ring_cpu[0][0][:args.ref_sample], ring_cpu[0][1][:args.ref_sample]
             t0 = time.perf_counter()
-            cpu_reference_pass(sd, params, xs, ms_)
+            nb_ref, _, _, _ = cpu_reference_pass(sd, params, xs, ms_)
             dt = time.perf_counter() - t0
+            same = sum(int(torch.equal(ids0[b, 0].cpu(), nb_ref[b, 0])) for b in range(args.ref_sample)) \
+                if nb_ref.shape[2] == ids0.shape[2] else 0
             line['cpu_baseline'] = {'value': args.ref_sample / dt, 'unit': 'utt/s', 'cores': threads,
                                     'visible_cores': cores, 'kind': 'port',
-                                    'sample': f'{args.ref_sample} utterances, one full pass (encoder-fwd + 60-step '
-                                              f'beam-10 decode) of the oracle port in {dt:.1f} s'}
+                                    'sample': f'{args.ref_sample} utterances (the first of input batch 0), one full pass '
+                                              f'(encoder-fwd + 60-step beam-10 decode) of the oracle port in {dt:.1f} s'}
+            line['validation']['oracle_check'] = {'utterances': args.ref_sample, 'one_best_ids_equal': same,
+                                                  'note': 'fp32 oracle port vs the CUDA path on the same utterances'}
+    del lanes, rec_graph, rec_pers, probe
+    torch.cuda.empty_cache()
+    if args.extras:
+        # BASELINE configs 4 and 5 ride along so that the driver's N = 1/2/4/8 runs also cover the Conformer path and the
+        # only NCCL collective of the north star (the gradient all-reduce of the training step)
+        ex = {}
+        for name, fn in (('conformer_cfg4', measure_conformer), ('train_cfg5', measure_train)):
+            try:
+                r = fn(args, min(args.steps, 12))
+                if rank == 0:
+                    ex[name] = r
+            except Exception as exn:  # an extra must never cost the headline line
+                if rank == 0:
+                    ex[name] = {'error': repr(exn)[:300]}
+        if rank == 0:
+            line['extras'] = ex
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def graph_path_roofline(model, lanes, ring_dev, dev, peaks, src, traffic):
+    """Per-step CUDA-graph decode path: dominant kernel = the GEMM launch shape with the largest device time per recognize
+    pass; launch counts from recorded eager passes, durations from a CUDA graph of 200 launches (device-measured)."""
+    from opentransformer_b200 import ops
+    from opentransformer_b200.recognize import BeamDecoder
+    rec = lanes[0][1]
+    ops.PROFILE = []
+    with torch.no_grad():
+        for i in range(2):
+            rec._encode_bf16(*ring_dev[i])
+        mem0, len0, B0, T20 = rec._encode_bf16(*ring_dev[0])
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, []
+        bd0 = BeamDecoder(model.decoder, B0, BEAM, T20, MAX_LEN, dev, use_graph=False, keep_logp=False)
+        bd0.setup(mem0, len0)
+        for _ in range(8):
+            bd0.step()
+        torch.cuda.synchronize()
+    prof_dec, ops.PROFILE = ops.PROFILE, None
+    epi_names = ['bias', 'relu', 'glu', 'posenc-table', 'residual', 'residual+layernorm', 'swish', 'gelu', 'tanh']
+    shapes = {}
+    for records, per_pass in ((prof, 1.0 / 3), (prof_dec, MAX_LEN / 8.0)):
+        for k, f, a, b, tag in records:
+            if k == 'gemm':
+                e = shapes.setdefault(tag, {'launches_per_pass': 0.0})
+                e['launches_per_pass'] += per_pass
+    for tag, e in shapes.items():
+        e['avg_ms'] = time_gemm_shape(tag, dev)
+        e['ms_per_pass'] = e['avg_ms'] * e['launches_per_pass']
+    tag, e = max(shapes.items(), key=lambda kv: kv[1]['ms_per_pass'])
+    epi, M_, Nw_, K_, _of32 = tag
+    avg_ms = e['avg_ms']
+    flops = 2.0 * M_ * Nw_ * K_
+    n_out = Nw_ // 2 if epi == 2 else Nw_
+    nbytes = 2.0 * (M_ * K_ + Nw_ * K_ + M_ * n_out) + (2.0 * M_ * n_out if epi in (4, 5) else 0.0)
+    tf, gbs = flops / (avg_ms * 1e-3) / 1e12, nbytes / (avg_ms * 1e-3) / 1e9
+    peak_tf, peak_bw = peaks.get('bf16_tflops', 1590.0), peaks.get('hbm_gbs', 6650.0)
+    use_hbm = gbs / peak_bw > tf / peak_tf
+    ach, peak = (gbs, peak_bw) if use_hbm else (tf, peak_tf)
+    return {'bound': 'hbm' if use_hbm else 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'GB/s' if use_hbm else 'TFLOP/s',
+            'frac': ach / peak if peak else None, 'traffic': traffic,
+            'kernel': f'gemm_tc_kernel, epilogue {epi_names[epi]}, M={M_} N={Nw_} K={K_}: {e["launches_per_pass"]:.0f} launches and '
+                      f'{e["ms_per_pass"]:.2f} ms per recognize pass, avg {avg_ms * 1e3:.1f} us per launch (CUDA graph of 200 launches '
+                      f'between events); algorithmic {flops / 1e9:.3f} GFLOP and {nbytes / 1e6:.2f} MB per launch',
+            'alt': {'tflops': tf, 'frac_tensor': tf / peak_tf, 'gbs': gbs, 'frac_hbm': gbs / peak_bw},
+            'all_gemm_shapes_ms_per_pass': {('%s_M%d_N%d_K%d' % (epi_names[t[0]], t[1], t[2], t[3])): round(v['ms_per_pass'], 3)
+                                            for t, v in sorted(shapes.items(), key=lambda kv: -kv[1]['ms_per_pass'])[:8]},
+            'peak_source': f'MEASURED_PEAKS.json ({src})'}
 
 
 def conformer_params():
@@ -553,28 +726,16 @@ def conformer_params():
     return p
 
 
-def run_conformer(args):
-    """BASELINE config 4: Conformer encoder forward, 64 x 1000 frames per GPU, utterance-sharded over ranks."""
+def measure_conformer(args, steps):
+    """BASELINE config 4: Conformer encoder forward, 64 x 1000 frames per GPU, utterance-sharded over ranks.
+    Returns the result line (rank 0) -- used both as the main line of --workload conformer and as an extra of the default run."""
     import torch.distributed as dist
     from opentransformer_b200.model import SpeechToText
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        quiet_nccl()
-        dist.init_process_group('nccl', device_id=dev)
+    rank, world, local, dev, nccl_log = init_dist()
     torch.manual_seed(1234)
     model = SpeechToText(conformer_params()).eval().to(dev)
     B = 64
     ring = [tuple(t.to(dev) for t in synthetic_batch(B, 1000 * rank + i)) for i in range(8)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     with torch.no_grad():
         # ~400 launches per pass: replayed from a CUDA graph (launched one by one from Python the pass is host-bound as soon
         # as several ranks share the host's cores), inputs copied into the graph's static buffers every step
@@ -596,34 +757,45 @@ def run_conformer(args):
             return out
         for i in range(3):
             one_pass(i)
-        barrier()
+        dist_barrier(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             one_pass(i)
         e1.record()
-        barrier()
+        dist_barrier(world)
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.destroy_process_group()
     ms = float(t[0])
-    if rank == 0:
-        peaks, src = measured_peaks()
-        flop = 898.0e9      # ~898 GFLOP per 64-utterance batch
-        ach = flop * args.steps / (ms * 1e-3) / 1e12
-        emit({'metric': 'utterances/sec (Conformer encoder forward)', 'value': B * world * args.steps / (ms * 1e-3),
-                          'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-                          'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                          'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-                          'config': {'workload': 'Conformer encoder 12L d_model=256 d_ff=768 k=5 rel-pos, frontend 1->256->256, '
-                                                 f'{B} utt x {T_FRAMES} frames per GPU (BASELINE config 4)',
-                                     'parallelism': f'dp{world}'},
-                          'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks.get('bf16_tflops_sustained'),
-                                       'unit': 'TFLOP/s', 'frac': ach / peaks.get('bf16_tflops_sustained', 1400.0),
-                                       'traffic': None, 'kernel': 'whole encoder pass (898 GFLOP algorithmic per batch)',
-                                       'peak_source': src}})
+    del graph, model, ring
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peaks, src = measured_peaks()
+    flop = 898.0e9      # ~898 GFLOP per 64-utterance batch
+    ach = flop * steps / (ms * 1e-3) / 1e12
+    return {'metric': 'utterances/sec (Conformer encoder forward)', 'value': B * world * steps / (ms * 1e-3),
+            'unit': 'utt/s', 'n_gpus': world, 'steps': steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'Conformer encoder 12L d_model=256 d_ff=768 k=5 rel-pos, frontend 1->256->256, '
+                                   f'{B} utt x {T_FRAMES} frames per GPU (BASELINE config 4)',
+                       'parallelism': f'dp{world} (utterance sharding, no data-path collective)'},
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peaks.get('bf16_tflops_sustained'),
+                         'unit': 'TFLOP/s', 'frac': ach / peaks.get('bf16_tflops_sustained', 1400.0),
+                         'traffic': None, 'kernel': 'whole encoder pass (898 GFLOP algorithmic per batch)',
+                         'peak_source': src}}
+
+
+def run_conformer(args):
+    import torch.distributed as dist
+    line = measure_conformer(args, args.steps)
+    if line is not None:
+        emit(line)
+    if dist.is_initialized():
+        dist.destroy_process_group()
     return 0
 
 
@@ -652,7 +824,7 @@ def synthetic_targets(batch, seed):
     return t
 
 
-def run_train(args):
+def measure_train(args, steps):
     """BASELINE config 5: one optimizer step per `step` -- SpecAugment (device) -> forward -> hand-written backward ->
     gradient all-reduce over NCCL (N > 1) -> global-norm clip + Adam.  32 utterances x 1000 frames per GPU (weak scaling:
     global batch 32 N; N = 8 is the reference's 256)."""
@@ -663,14 +835,7 @@ def run_train(args):
     from opentransformer_b200.augment import spec_augment_
     from opentransformer_b200.model import SpeechToText
     from opentransformer_b200.train import FusedTrainer
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        quiet_nccl()
-        dist.init_process_group('nccl', device_id=dev)
+    rank, world, local, dev, nccl_log = init_dist()
     torch.manual_seed(1234)                       # identical initial weights on every rank (run.py:23-33)
     model = SpeechToText(train_params()).to(dev).train()
     trainer = FusedTrainer(model, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, clip_grad=5.0, model_size=256,
@@ -686,9 +851,7 @@ def run_train(args):
     lens = [T_FRAMES] * B_PER_GPU
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        dist_barrier(world)
 
     def step_resident(i):
         x, m, t = ring_dev[i % RING]
@@ -720,27 +883,28 @@ def run_train(args):
     if sampler:
         sampler.start()
     n0 = ops.COUNTERS['launches']
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, steps)
     launches = ops.COUNTERS['launches'] - n0
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
     clocks = sampler.stop() if sampler else None
     final_loss = float(step_resident(0))
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.destroy_process_group()
     ms, ms_e2e = t.tolist()
+    del trainer, model, ring_dev
+    torch.cuda.empty_cache()
     if rank == 0:
         peaks, src = measured_peaks()
         # encoder-fwd 410.0 + teacher-forced decoder ~38.9 GFLOP per 32-utt batch; backward = 2x forward
         flop = 3.0 * (410.0e9 + 38.9e9)
-        ach = flop * args.steps / (ms * 1e-3) / 1e12
-        utt = B_PER_GPU * world * args.steps
+        ach = flop * steps / (ms * 1e-3) / 1e12
+        utt = B_PER_GPU * world * steps
         item = ring[0]
-        emit({
+        line = {
             'metric': 'utterances/sec (training step: SpecAugment + fwd + bwd + grad all-reduce + clip + Adam)',
-            'value': utt / (ms * 1e-3), 'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'value': utt / (ms * 1e-3), 'unit': 'utt/s', 'n_gpus': world, 'steps': steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
             'config': {'workload': 'BASELINE config 5: training step, Speech-Transformer 12-enc/6-dec d_model=256, '
                                    f'{B_PER_GPU} utt x {T_FRAMES} frames per GPU, targets 20-30 tokens, label smoothing 0.1, '
@@ -755,7 +919,20 @@ def run_train(args):
                          'frac': ach / peaks.get('bf16_tflops_sustained', 1400.0), 'traffic': None,
                          'kernel': 'whole training step (3 x 448.9 GFLOP algorithmic per 32-utterance batch)',
                          'peak_source': src},
-            'clocks': clocks})
+            'clocks': clocks}
+        if nccl_log:
+            line['comm'] = nccl_summary(nccl_log, world)
+        return line
+    return None
+
+
+def run_train(args):
+    import torch.distributed as dist
+    line = measure_train(args, args.steps)
+    if line is not None:
+        emit(line)
+    if dist.is_initialized():
+        dist.destroy_process_group()
     return 0
 
 
@@ -769,7 +946,13 @@ def main():
     ap.add_argument('--workload', default='transformer', choices=['transformer', 'conformer', 'train'],
                     help="'conformer' = BASELINE config 4 (encoder forward only), 'train' = config 5 (training step); "
                          "default is the headline workload")
-    ap.add_argument('--lanes', type=int, default=16, help='utterance batches kept in flight per GPU (streams)')
+    ap.add_argument('--lanes', type=int, default=0, help='utterance batches kept in flight per GPU (streams); 0 = auto: 3 for the '
+                                                       'persistent decode kernel (48 SMs per batch), 16 for the per-step graph')
+    ap.add_argument('--decode', default='auto', choices=['auto', 'persistent', 'graph'],
+                    help='decode path: one persistent launch per batch (csrc/decode_group.cu) or one CUDA-graph replay per step')
+    ap.add_argument('--min-ms', type=float, default=1000.0, help='repeat the timed K-step region until this much device time is measured')
+    ap.add_argument('--no-extras', dest='extras', action='store_false',
+                    help='skip the BASELINE config 4 / 5 measurements appended to the default run')
     ap.add_argument('--tile-policy', default='auto', choices=['auto', 'latency', 'throughput'],
                     help='tiling of the decode-step GEMMs (otb_set_tile_policy); auto = throughput when lanes > 1')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')

@@ -51,9 +51,9 @@ int otb_set_tile_policy(int policy);
 int otb_debug_gemm_timing(unsigned long long* buf);
 /* Profiling aid: 0 = normal, 1 = GEMM mainloop without TMA traffic, 2 = without MMAs (results are garbage). */
 int otb_debug_gemm_mode(int mode);
-/* Profiling aid: buf (device, u64 [>= 256]) receives clock64 stamps at every stage boundary of decode step `step`
- * of the next otb_decode_mega launches (cluster 0, rank 0); NULL disables. */
-int otb_debug_mega_timing(unsigned long long* buf, int step);
+/* Profiling aid: buf (device, u64 [>= 256]) receives clock64 stamps at every phase boundary of decode step `step`
+ * of the next otb_decode_persistent launches (group 0, CTA 0); NULL disables. */
+int otb_debug_decode_timing(unsigned long long* buf, int step);
 
 /* Conv2dLayer output geometry, kernel 3, stride 2, padding (0,1)  (frontend/conv.py:10-11,27):
  * T1 = (T-3)/2+1, F1 = (F-1)/2+1, T2 = (T1-3)/2+1, F2 = (F1-1)/2+1.  The conv1 activation buffer is
@@ -167,11 +167,13 @@ int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int 
 
 /* ---- Persistent decode loop --------------------------------------------------------------------------------
  * The whole loop of SpeechToTextRecognizer.recognize (recognize/speech2text.py:60-68: decode_step :95-153 ->
- * TransformerDecoder.inference, decoder/transformer.py:185-208) for ALL steps in one launch: one thread-block
- * cluster of 4 CTAs per utterance (rank == attention head), weights streamed from L2 by mma.sync, search state in
- * shared memory, no kernel launch or host round trip inside the loop.  Post-norm GLU decoder, d_model 256, 4 heads,
- * d_ff % 512 == 0, beam <= 16, max_steps <= st->Lmax <= 128 (other configurations: per-step calls above).
- * All pointers are device pointers; weights bf16 [N,K] row-major exactly as nn.Linear stores them. */
+ * TransformerDecoder.inference, decoder/transformer.py:185-208) for ALL steps in one launch (csrc/decode_group.cu):
+ * the hypotheses of up to 128 / beam utterances form one 128-row tcgen05 tile owned by a group of 16 co-operating CTAs
+ * (projections split by output column / contraction slice, weights streamed from L2 by TMA, accumulators in TMEM,
+ * activations exchanged through L2 behind a group-local barrier), search state on the device, no kernel launch or host
+ * round trip inside the loop.  Post-norm GLU decoder, d_model 256, 4 heads, d_ff 2048, beam <= 16, T <= 256 memory
+ * frames, max_steps <= st->Lmax <= 128, ceil(B / (128 / beam)) * 16 <= number of SMs (other configurations: per-step
+ * calls above).  All pointers are device pointers; weights bf16 [N,K] row-major exactly as nn.Linear stores them. */
 #define OTB_MEGA_MAX_LAYERS 8
 typedef struct {
     const void *wqkv, *wo, *wq, *wo2, *w1, *w2;                 /* slf_attn.qvk_proj, .output_proj, src_attn.q_proj, .output_proj, feed_forward.w_1, .w_2 */
@@ -187,17 +189,20 @@ typedef struct {
     otb_mega_layer layers[OTB_MEGA_MAX_LAYERS];
     float ln_eps;
 } otb_mega_model;
+/* Scratch the launch needs (activations, partial sums, barrier counters, TMA descriptors), in bytes; -1 on bad arguments. */
+long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam);
 /* kvx bf16 [n_layers, B*T, 2d]: src_attn.vk_proj(memory) per layer (K | V, attention.py:134), projected once per
  * utterance by otb_linear; mem_len i32 [B]; kc/vc bf16 [n_layers, st->Lmax, N, d] self-attention cache (scratch);
- * st: search state, initialised by otb_beam_init (ctrl zeroed).  On return tok_hist / par_hist hold max_steps steps
- * (an utterance that ended early is padded with EOS / identity parents, exactly what the reference's finished-
- * hypothesis masking produces), scores / flag / last_tok the final state, ctrl[0] the reference's executed step
- * count (first step at which every hypothesis of every utterance has ended, else max_steps).
+ * st: search state, initialised by otb_beam_init (ctrl zeroed); workspace: 256-byte aligned device scratch of at least
+ * otb_decode_persistent_workspace() bytes.  On return tok_hist / par_hist hold max_steps steps (a group of utterances
+ * that ended early is padded with EOS / identity parents, exactly what the reference's finished-hypothesis masking
+ * produces), scores / flag / last_tok the final state, ctrl[0] the reference's executed step count (first step at which
+ * every hypothesis of every utterance has ended, else max_steps).
  * dbg_logp (optional, f32 [max_steps, N, vocab]) receives every step's log-probs, dbg_scores (optional, f32
  * [max_steps, N]) every step's hypothesis scores -- parity traces. */
-int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,
-                    const otb_beam_state* st, int B, int T, int max_steps, float* dbg_logp, float* dbg_scores,
-                    void* stream);
+int otb_decode_persistent(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,
+                          const otb_beam_state* st, int B, int T, int max_steps, void* workspace, long long workspace_bytes,
+                          float* dbg_logp, float* dbg_scores, void* stream);
 
 /* ---- Training step (SpeechToText.forward + loss.backward() + clip + Adam, model/speech2text.py:39-64,
  * train/trainer.py:206-234).  The reference differentiates through torch autograd; the entry points below are the

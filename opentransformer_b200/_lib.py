@@ -43,7 +43,7 @@ _SIGS = {
     'otb_debug_gemm_timing': (c_int, [_P]),
     'otb_debug_gemm_mode': (c_int, [c_int]),
     'otb_set_tile_policy': (c_int, [c_int]),
-    'otb_debug_mega_timing': (c_int, [_P, c_int]),
+    'otb_debug_decode_timing': (c_int, [_P, c_int]),
     'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_conv2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -85,7 +85,9 @@ _SIGS = {
     'otb_conv_col2im_relu': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_conv1_wgrad': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_spec_augment': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    'otb_decode_mega': (c_int, [POINTER(MegaModelC), _P, _P, _P, _P, POINTER(BeamStateC), c_int, c_int, c_int, _P, _P, _P]),
+    'otb_decode_persistent_workspace': (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    'otb_decode_persistent': (c_int, [POINTER(MegaModelC), _P, _P, _P, _P, POINTER(BeamStateC), c_int, c_int, c_int, _P, c_int64,
+                                      _P, _P, _P]),
 }
 
 

@@ -60,9 +60,9 @@ int otb_debug_gemm_mode(int mode) {
     return 0;
 }
 
-int otb_debug_mega_timing(unsigned long long* buf, int step) {
-    g_mega_dbg = buf;
-    g_mega_dbg_step = step;
+int otb_debug_decode_timing(unsigned long long* buf, int step) {
+    g_dg_dbg = buf;
+    g_dg_dbg_step = step;
     return 0;
 }
 
@@ -266,11 +266,16 @@ int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int 
                                                   reinterpret_cast<long long*>(out_preds), out_scores));
 }
 
-int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,
-                    const otb_beam_state* st, int B, int T, int max_steps, float* dbg_logp, float* dbg_scores,
-                    void* stream) {
-    if (!model || !kvx || !mem_len || !kc || !vc || !st) return fail("otb_decode_mega", "null operand");
-    if (model->n_layers < 1 || model->n_layers > OTB_MEGA_MAX_LAYERS) return fail("otb_decode_mega", "1..8 decoder layers");
+long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam) {
+    if (N < 1 || n_layers < 1 || Lmax < 1 || B < 1 || beam < 1 || beam > 16) return -1;
+    return (long long)decode_group_workspace_bytes(N, n_layers, Lmax, B, beam);
+}
+
+int otb_decode_persistent(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,
+                          const otb_beam_state* st, int B, int T, int max_steps, void* workspace, long long workspace_bytes,
+                          float* dbg_logp, float* dbg_scores, void* stream) {
+    if (!model || !kvx || !mem_len || !kc || !vc || !st || !workspace) return fail("otb_decode_persistent", "null operand");
+    if (model->n_layers < 1 || model->n_layers > OTB_MEGA_MAX_LAYERS) return fail("otb_decode_persistent", "1..8 decoder layers");
     MegaParams p;
     memset(&p, 0, sizeof(p));
     p.n_layers = model->n_layers; p.d = model->d_model; p.H = model->n_heads; p.dff = model->d_ff; p.V = model->vocab;
@@ -278,7 +283,7 @@ int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t*
     p.wout = reinterpret_cast<const bf16*>(model->wout);
     p.bout = model->bout;
     p.pe = model->pe;
-    if (!p.emb || !p.wout || !p.pe) return fail("otb_decode_mega", "null model tensor");
+    if (!p.emb || !p.wout || !p.pe) return fail("otb_decode_persistent", "null model tensor");
     for (int l = 0; l < model->n_layers; ++l) {
         const otb_mega_layer& s = model->layers[l];
         MegaLayer& d = p.layers[l];
@@ -289,7 +294,7 @@ int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t*
         const void* need[18] = {s.wqkv, s.wo, s.wq, s.wo2, s.w1, s.w2, s.bqkv, s.bo, s.bq, s.bo2, s.b1, s.b2,
                                 s.g1, s.be1, s.g2, s.be2, s.g3, s.be3};
         for (int i = 0; i < 18; ++i)
-            if (!need[i]) return fail("otb_decode_mega", "null layer tensor (biases are required)");
+            if (!need[i]) return fail("otb_decode_persistent", "null layer tensor (biases are required)");
     }
     p.kvx = reinterpret_cast<const bf16*>(kvx);
     p.mem_len = mem_len;
@@ -299,7 +304,7 @@ int otb_decode_mega(const otb_mega_model* model, const void* kvx, const int32_t*
     p.B = B; p.T = T; p.max_steps = max_steps;
     p.eps = model->ln_eps;
     p.dbg_logp = dbg_logp; p.dbg_scores = dbg_scores;
-    RET("otb_decode_mega", decode_mega_launch(ST(stream), p));
+    RET("otb_decode_persistent", decode_group_launch(ST(stream), p, workspace, (size_t)workspace_bytes));
 }
 
 int otb_attention_bwd(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,

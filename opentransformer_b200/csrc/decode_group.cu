@@ -1,0 +1,1087 @@
+// Persistent beam-search decode kernel for sm_100a, round 2: the WHOLE decode loop of SpeechToTextRecognizer.recognize
+// (otrans/recognize/speech2text.py:60-68 -> decode_step :95-153 -> TransformerDecoder.inference,
+// otrans/decoder/transformer.py:185-208) in ONE launch, GEMMs on tcgen05 tensor cores.
+//
+// Round 1 ran a decode step as 52 dependent kernels (7-13 us each for 2-4 us of work: 0.50 ms per beam step) or as one
+// cluster of 4 CTAs per utterance streaming ALL decoder weights through mma.sync for its 10 rows (830 MB of L2 traffic per
+// step).  This kernel keeps the rows of up to 12 utterances (beam 10 -> 120 hypotheses) together as ONE 128-row tcgen05
+// tile and gives each such ROW GROUP to P = 16 co-operating CTAs:
+//
+//   * every projection is split over the group's CTAs by OUTPUT column (QKV 48, out / q projections 16, GLU 128 hidden
+//     features per CTA) or, for w_2, by CONTRACTION slice (the CTA's own 128 hidden features, partial sums reduced through
+//     L2) -- so the 25.8 MB of decoder weights are read once per group-step (3 groups for 32 utterances x beam 10), straight
+//     from L2 by TMA into the UMMA shared-memory layout, accumulators in TMEM;
+//   * activations move between the phases through L2 (a [rows, 256] matrix is 64 KB) and a group-local software barrier
+//     (one atomic + an acquire poll, ~1 us) replaces the kernel boundary (7-13 us) -- groups never synchronise with each
+//     other, utterances are independent;
+//   * LayerNorm is applied by the CONSUMER while it builds its A operand (fp32 pre-norm rows -> bf16 swizzled tile), so a
+//     post-norm layer costs 9 barriers: QKV | self-attention | out-proj | LN+q-proj | cross-attention | out-proj | LN+GLU+w_2
+//     partial | reduce | (next layer);
+//   * self-attention over the per-hypothesis KV cache is SIMT (lanes over cached positions, ancestry table, as round 1);
+//     cross-attention of the <= 16 hypotheses of an utterance against its 249 encoder frames is one m16 problem per (utterance,
+//     head): mma.sync on K / V tiles that TMA prefetches during the preceding phase (tcgen05 has no M < 64 shape);
+//   * the tail -- logits, log-softmax statistics and per-row top-k candidates in the logits GEMM's epilogue (the [N, V]
+//     log-prob matrix is never written), candidate merge + finished masking + beam^2 pruning + ancestry update per utterance --
+//     follows beam.cu exactly (ties -> lower index), so ids / parents are bit-exact with the oracle's beam_step driven by this
+//     kernel's log-probs.
+//
+// Supported: post-norm decoder, GLU feed-forward with d_ff = 2048, d_model 256, 4 heads, beam <= 16, memory length <= 256
+// frames, max_len <= 128.  Anything else runs on the per-step graph path (recognize.BeamDecoder.step).
+#include <string.h>
+
+#include "beam_common.cuh"
+#include "otb_internal.h"
+#include "ptx.cuh"
+
+namespace otb {
+
+static constexpr int DG_THREADS = 512;
+static constexpr int DG_P = 16;            // CTAs per row group
+static constexpr int DG_D = 256;           // d_model
+static constexpr int DG_H = 4;
+static constexpr int DG_DFF = 2048;
+static constexpr int DG_A_BYTES = 65536;   // A operand tile: 4 k-blocks of [128 rows x 64] bf16, SWIZZLE_128B
+static constexpr int DG_STAGE = 65536;     // two big stages: weight chunks / cross-attention K|V tiles / self-attention V staging
+static constexpr int DG_SB = 24576;        // small B operand (<= 48 weight rows x 256) | cross-attention scratch
+static constexpr int DG_MISC = 12288;
+static constexpr int DG_SMEM = DG_A_BYTES + 2 * DG_STAGE + DG_SB + DG_MISC + 1024;
+static constexpr int DG_PP = 528;          // cross-attention probability row pitch (bytes): 512 + 16 -> conflict-free ldmatrix
+
+unsigned long long* g_dg_dbg = nullptr;
+int g_dg_dbg_step = 0;
+
+struct DgMisc {
+    uint64_t kb_full[4];      // k-block operands landed (TMA) -- one use per GEMM
+    uint64_t st_full[2];      // big stage landed
+    uint64_t st_empty[2];     // big stage consumed (tcgen05.commit)
+    uint64_t acc_full[2];     // accumulator complete (tcgen05.commit)
+    uint64_t acc_empty[2];    // accumulator drained by the 128 epilogue threads
+    uint32_t tmem_slot;
+    int flag;                 // broadcast scratch
+    alignas(16) uint32_t rs[128 * 8];     // residual slice of this CTA: rows x 16 columns, bf16 pairs
+    alignas(16) float bias[512];          // per-phase bias slice
+    float c_val[KMAX * KMAX];
+    int c_tok[KMAX * KMAX];
+    float sel_v[KMAX];
+    int sel_i[KMAX];
+    float row_v[KMAX][KMAX];
+    int row_i[KMAX][KMAX];
+};
+static_assert(sizeof(DgMisc) <= DG_MISC, "DgMisc must fit its shared-memory slot");
+
+// ---------------------------------------------------------------------------------------------- small PTX helpers
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void dg_mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                            uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ float dg_sigmoid(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// byte offset of the 16-byte chunk (row r, chunk c of 8) inside a [rows x 64] bf16 k-block in the SWIZZLE_128B K-major layout
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __grid_constant__ DgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sST = smem + DG_A_BYTES;                 // [2][DG_STAGE]
+    uint8_t* sSB = sST + 2 * DG_STAGE;
+    DgMisc& ms = *reinterpret_cast<DgMisc*>(sSB + DG_SB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / DG_P, j = blockIdx.x % DG_P;
+    const int beam = p.st.beam, N = p.st.N, Lmax = p.st.Lmax, V = p.V;
+    const int u0 = g * p.utts_per_group;
+    const int nutt = min(p.utts_per_group, p.B - u0);
+    const int row0 = u0 * beam, nrows = nutt * beam;
+    const int nl = p.n_layers;
+    const CUtensorMap* maps = p.maps;
+    const CUtensorMap* map_wout = maps + nl * 6;
+    const CUtensorMap* map_ctx = maps + nl * 6 + 1;
+    const CUtensorMap* map_kvx = maps + nl * 6 + 2;
+    int* bar = p.bar + g * 32;                        // 128-byte separated counters
+    const bool is_tma = (warp == 0 && lane == 0), is_mma = (warp == 1 && lane == 0);
+    const bool is_epi = (warp >= 4 && warp < 8);
+    const int erow = (warp & 3) * 32 + lane;          // TMEM lane == tile row of an epilogue thread
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&ms.kb_full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&ms.st_full[i], 1);
+            mbar_init(&ms.st_empty[i], 1);
+            mbar_init(&ms.acc_full[i], 1);
+            mbar_init(&ms.acc_empty[i], 128);
+        }
+        ms.flag = 0;
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&ms.tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ms.tmem_slot;
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+
+    // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
+    uint32_t par_kb = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_acce = 0;   // bit i = barrier i
+    int bar_target = 0;
+
+    const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x == 0 && tid == 0);
+    int dbg_n = 0;
+    bool dbg_on = false;
+#define DG_STAMP() do { if (dbg_on) p.dbg_clk[dbg_n++] = clock64(); } while (0)
+
+    // group barrier: every CTA of the group has finished the phase (its global writes are visible); `pre` runs on the TMA
+    // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles)
+    auto gsync = [&](auto pre) {
+        __syncthreads();
+        bar_target += DG_P;
+        if (tid == 0) {
+            __threadfence();
+            fence_proxy_async_all();
+            red_release_gpu_add(bar, 1);
+            pre();
+            const long long t0 = clock64();
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(bar) < bar_target) {
+                if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 20000000000LL) __trap();   // a protocol bug traps instead of hanging
+            }
+            fence_proxy_async_all();
+        }
+        __syncthreads();
+    };
+    auto nop = [] {};
+
+    // ---- A operand builders (all 512 threads; rows >= nrows are zero) ------------------------------------------
+    // writes x (8 consecutive columns c8*8.. of tile row r) into the swizzled A tile and, for this CTA's 16 residual columns, rs
+    auto put_a8 = [&](int r, int c8, const float (&v)[8]) {
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]);
+        o.y = pack_bf16(v[2], v[3]);
+        o.z = pack_bf16(v[4], v[5]);
+        o.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(sA + (c8 >> 3) * 16384 + sw128(r, c8 & 7)) = o;
+        if ((c8 >> 1) == j) *reinterpret_cast<uint4*>(&ms.rs[r * 8 + (c8 & 1) * 4]) = o;
+    };
+    // embedding + positional encoding (decoder/transformer.py:163,169; pos.py:56): A = emb[last_tok] * sqrt(d) + PE[step]
+    auto build_a_embed = [&](int step) {
+        for (int r = warp; r < 128; r += 16) {
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (r < nrows) {
+                long long tok = p.st.last_tok[row0 + r];
+                if (tok < 0 || tok >= V) tok = 0;
+                const uint4 u = *reinterpret_cast<const uint4*>(p.emb + (size_t)tok * DG_D + lane * 8);
+                const float* pe = p.pe + (size_t)step * DG_D + lane * 8;
+                const float4 p0 = *reinterpret_cast<const float4*>(pe), p1 = *reinterpret_cast<const float4*>(pe + 4);
+                const float2 e0 = unpack_bf16(u.x), e1 = unpack_bf16(u.y), e2 = unpack_bf16(u.z), e3 = unpack_bf16(u.w);
+                const float xs = 16.0f;   // sqrt(256)
+                v[0] = e0.x * xs + p0.x; v[1] = e0.y * xs + p0.y; v[2] = e1.x * xs + p0.z; v[3] = e1.y * xs + p0.w;
+                v[4] = e2.x * xs + p1.x; v[5] = e2.y * xs + p1.y; v[6] = e3.x * xs + p1.z; v[7] = e3.y * xs + p1.w;
+            }
+            put_a8(r, lane, v);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+    };
+    // LayerNorm of the gathered pre-norm rows (fp32, resid + projection + bias) -> bf16 A tile (transformer.py:54-56 etc.)
+    auto build_a_ln = [&](const float* gamma, const float* beta) {
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
+#pragma unroll 1
+        for (int rb = warp * 8; rb < warp * 8 + 8; rb += 4) {
+            float4 y0[4], y1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rb + i;
+                if (r < nrows) {
+                    const float* src = p.pre + (size_t)(row0 + r) * DG_D + lane * 8;
+                    y0[i] = *reinterpret_cast<const float4*>(src);
+                    y1[i] = *reinterpret_cast<const float4*>(src + 4);
+                } else {
+                    y0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    y1[i] = y0[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rb + i;
+                float v[8] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w, y1[i].x, y1[i].y, y1[i].z, y1[i].w};
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s += v[q];
+                const float mean = warp_sum(s) * (1.0f / DG_D);
+                float q2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const float dd = v[q] - mean; q2 += dd * dd; }
+                const float rstd = rsqrtf(warp_sum(q2) * (1.0f / DG_D) + p.eps);
+                float o[8];
+                o[0] = (v[0] - mean) * rstd * g0.x + b0.x; o[1] = (v[1] - mean) * rstd * g0.y + b0.y;
+                o[2] = (v[2] - mean) * rstd * g0.z + b0.z; o[3] = (v[3] - mean) * rstd * g0.w + b0.w;
+                o[4] = (v[4] - mean) * rstd * g1.x + b1.x; o[5] = (v[5] - mean) * rstd * g1.y + b1.y;
+                o[6] = (v[6] - mean) * rstd * g1.z + b1.z; o[7] = (v[7] - mean) * rstd * g1.w + b1.w;
+                if (r >= nrows) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = 0.f;
+                }
+                put_a8(r, lane, o);
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+    };
+
+    // ---- small GEMM: acc[128 x nB] = A[128 x 256] * W[b_row0 .. b_row0 + nB, 256]^T, B slice in sSB ----------------------
+    // a_tma: A is fetched from the ctx matrix by TMA (else it was built in shared memory by the CTA).  epi(c, r16) is called by
+    // the 128 epilogue threads for every 16-column chunk of their row.  Ends with a CTA barrier.
+    auto gemm_small = [&](const CUtensorMap* mb, int b_row0, int nB, bool a_tma, const float* bias, auto epi) {
+        if (tid < nB) ms.bias[tid] = bias[b_row0 + tid];
+        if (is_tma) {
+            for (int kb = 0; kb < 4; ++kb) {
+                mbar_arrive_expect_tx(&ms.kb_full[kb], (uint32_t)(nB * 128 + (a_tma ? 16384 : 0)));
+                if (a_tma) tma_load_2d(sA + kb * 16384, map_ctx, &ms.kb_full[kb], kb * 64, row0);
+                tma_load_2d(sSB + kb * nB * 128, mb, &ms.kb_full[kb], kb * 64, b_row0);
+            }
+        } else if (is_mma) {
+            const uint32_t idesc = umma_idesc_bf16(nB);
+            for (int kb = 0; kb < 4; ++kb) {
+                mbar_wait(&ms.kb_full[kb], (par_kb >> kb) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sSB + kb * nB * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(&ms.acc_full[0]);
+        }
+        __syncthreads();   // bias slice visible to the epilogue threads
+        if (is_epi) {
+            mbar_wait(&ms.acc_full[0], par_accf & 1);
+            tc_fence_after();
+            for (int c = 0; c < nB; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_row + c, r);
+                tmem_ld_wait();
+                epi(c, r);
+            }
+            tc_fence_before();
+        }
+        par_kb ^= 0xF;
+        par_accf ^= 1;
+        __syncthreads();
+    };
+
+    // big-stage loads issued by the TMA thread
+    auto load_w1 = [&](int l) {   // both stages: k-block kb -> stage kb/2, [value rows | gate rows] of this CTA's 128 hidden features
+        const CUtensorMap* m = maps + l * 6 + 4;
+        for (int kb = 0; kb < 4; ++kb) {
+            uint8_t* dst = sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768;
+            mbar_arrive_expect_tx(&ms.kb_full[kb], 32768);
+            tma_load_2d(dst, m, &ms.kb_full[kb], kb * 64, j * 128);
+            tma_load_2d(dst + 16384, m, &ms.kb_full[kb], kb * 64, DG_DFF + j * 128);
+        }
+    };
+    auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
+        const int u = u0 + task / DG_H, h = task % DG_H;
+        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
+        tma_load_2d(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T);
+        tma_load_2d(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T);
+    };
+    const int n_vchunks = (V + 127) / 128;
+    auto load_wout = [&](int chunk, int s) {
+        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sST + s * DG_STAGE + kb * 16384, map_wout, &ms.st_full[s], kb * 64, chunk * 128);
+    };
+    const int n_tasks = nutt * DG_H;   // cross-attention problems of this group; CTA j takes j, j + P, ...
+
+    int steps_done = 0;
+    bool group_done = false;
+    for (int step = 0; step < p.max_steps; ++step) {
+        dbg_on = dbg_cta && step == p.dbg_step;
+        dbg_n = 0;
+        DG_STAMP();
+        build_a_embed(step);
+        DG_STAMP();   // 1 embed
+        for (int l = 0; l < nl; ++l) {
+            const DgLayer& ly = p.layers[l];
+            // ---------------- QKV projection of the newest token (attention.py:68-73): 48 of the 768 columns per CTA
+            gemm_small(maps + l * 6 + 0, j * 48, 48, false, ly.bqkv, [&](int c, const uint32_t (&r)[16]) {
+                if (erow >= nrows) return;
+                const int col = j * 48 + c;               // 16-column chunks never straddle the q | k | v boundaries
+                uint4 o[2];
+                uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    ow[i] = pack_bf16(__uint_as_float(r[2 * i]) + ms.bias[c + 2 * i], __uint_as_float(r[2 * i + 1]) + ms.bias[c + 2 * i + 1]);
+                bf16* dst;
+                if (col < DG_D) dst = p.qbuf + (size_t)(row0 + erow) * DG_D + col;
+                else if (col < 2 * DG_D) dst = p.kc + (((size_t)l * Lmax + step) * N + row0 + erow) * DG_D + (col - DG_D);
+                else dst = p.vc + (((size_t)l * Lmax + step) * N + row0 + erow) * DG_D + (col - 2 * DG_D);
+                reinterpret_cast<uint4*>(dst)[0] = o[0];
+                reinterpret_cast<uint4*>(dst)[1] = o[1];
+            });
+            DG_STAMP();   // QKV
+            gsync(nop);
+            DG_STAMP();
+            // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
+            {
+                const int nkeys = step + 1;
+                const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
+                uint8_t* stage = sST + (size_t)warp * 8192;          // 64 cached positions x 128 B of V per warp
+                float* sq = reinterpret_cast<float*>(sSB) + warp * 64;
+                for (int task = j * 16 + warp; task < nrows * DG_H; task += DG_P * 16) {
+                    const int r = task / DG_H, h = task % DG_H;
+                    const int n = row0 + r;
+                    const int* an = an_base + (size_t)n * Lmax;
+                    {
+                        const float2 qq = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.qbuf + (size_t)n * DG_D + h * 64 + 2 * lane));
+                        __syncwarp();
+                        sq[2 * lane] = qq.x;
+                        sq[2 * lane + 1] = qq.y;
+                        __syncwarp();
+                    }
+                    float sc[4];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int s = lane + 32 * q;
+                        sc[q] = -INFINITY;
+                        if (s < nkeys) {
+                            const int slot = (s < step) ? an[s] : n;
+                            const size_t off = (((size_t)l * Lmax + s) * N + slot) * DG_D + h * 64;
+                            uint4 ku[8], vu[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) ku[i] = *reinterpret_cast<const uint4*>(p.kc + off + 8 * i);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) vu[i] = *reinterpret_cast<const uint4*>(p.vc + off + 8 * i);
+                            float dot = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 a = unpack_bf16(ku[i].x), b = unpack_bf16(ku[i].y), c2 = unpack_bf16(ku[i].z), e = unpack_bf16(ku[i].w);
+                                const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * i);
+                                const float4 q1 = *reinterpret_cast<const float4*>(sq + 8 * i + 4);
+                                dot += q0.x * a.x + q0.y * a.y + q0.z * b.x + q0.w * b.y + q1.x * c2.x + q1.y * c2.y + q1.z * e.x + q1.w * e.y;
+                            }
+                            sc[q] = dot * 0.125f;
+                            mx = fmaxf(mx, sc[q]);
+                            if (s < 64) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage + s * 128 + (((i + s) & 7) << 4)) = vu[i];
+                            }
+                        }
+                    }
+                    mx = warp_max(mx);
+                    float lsum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sc[q] = (lane + 32 * q < nkeys) ? __expf(sc[q] - mx) : 0.f;
+                        lsum += sc[q];
+                    }
+                    lsum = warp_sum(lsum);
+                    __syncwarp();
+                    float ax = 0.f, ay = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cnt = min(32, nkeys - 32 * q);
+                        if (cnt <= 0) break;
+                        for (int t = 0; t < cnt; ++t) {
+                            const int s = t + 32 * q;
+                            const float pw = __shfl_sync(0xffffffffu, sc[q], t);
+                            uint32_t vv;
+                            if (s < 64) {
+                                vv = *reinterpret_cast<const uint32_t*>(stage + s * 128 + ((((lane >> 2) + s) & 7) << 4) + (lane & 3) * 4);
+                            } else {   // prefixes longer than the staging area: straight from the cache (L2)
+                                const int slot = (s < step) ? an[s] : n;
+                                vv = *reinterpret_cast<const uint32_t*>(p.vc + (((size_t)l * Lmax + s) * N + slot) * DG_D + h * 64 + 2 * lane);
+                            }
+                            const float2 vf = unpack_bf16(vv);
+                            ax = fmaf(pw, vf.x, ax);
+                            ay = fmaf(pw, vf.y, ay);
+                        }
+                    }
+                    const float inv = 1.0f / lsum;
+                    *reinterpret_cast<uint32_t*>(p.ctx + (size_t)n * DG_D + h * 64 + 2 * lane) = pack_bf16(ax * inv, ay * inv);
+                    __syncwarp();
+                }
+            }
+            DG_STAMP();   // self-attention
+            gsync(nop);
+            DG_STAMP();
+            // ---------------- out-projection + residual -> pre-norm rows (attention.py:44, transformer.py:54)
+            auto epi_pre = [&](int c, const uint32_t (&r)[16]) {
+                if (erow >= nrows) return;
+                float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 r0 = unpack_bf16(ms.rs[erow * 8 + 2 * i]), r1 = unpack_bf16(ms.rs[erow * 8 + 2 * i + 1]);
+                    dst[i] = make_float4(__uint_as_float(r[4 * i]) + ms.bias[4 * i] + r0.x, __uint_as_float(r[4 * i + 1]) + ms.bias[4 * i + 1] + r0.y,
+                                         __uint_as_float(r[4 * i + 2]) + ms.bias[4 * i + 2] + r1.x, __uint_as_float(r[4 * i + 3]) + ms.bias[4 * i + 3] + r1.y);
+                }
+            };
+            gemm_small(maps + l * 6 + 1, j * 16, 16, true, ly.bo, epi_pre);
+            DG_STAMP();   // out-proj
+            gsync(nop);
+            DG_STAMP();
+            // ---------------- LayerNorm 1 + cross-attention query projection (attention.py:128)
+            build_a_ln(ly.g1, ly.be1);
+            DG_STAMP();   // LN1
+            gemm_small(maps + l * 6 + 2, j * 16, 16, false, ly.bq, [&](int c, const uint32_t (&r)[16]) {
+                if (erow >= nrows) return;
+                uint4 o[2];
+                uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    ow[i] = pack_bf16(__uint_as_float(r[2 * i]) + ms.bias[2 * i], __uint_as_float(r[2 * i + 1]) + ms.bias[2 * i + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(p.q2 + (size_t)(row0 + erow) * DG_D + j * 16);
+                dst[0] = o[0];
+                dst[1] = o[1];
+            });
+            DG_STAMP();   // q-proj
+            gsync([&] {   // encoder K / V tiles of this CTA's first two (utterance, head) problems arrive during the barrier
+                if (j < n_tasks) load_kv(l, j, 0);
+                if (j + DG_P < n_tasks) load_kv(l, j + DG_P, 1);
+            });
+            DG_STAMP();
+            // ---------------- cross-attention (attention.py:129-141,34-41): one m16 problem per (utterance, head)
+            {
+                float* wmax = reinterpret_cast<float*>(sSB);                  // [16 warps][16 rows]
+                float* wsum = wmax + 256;
+                float* red = wsum + 256;                                       // [16 warps][16 rows][8] PV partials
+                uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
+                const int gq = lane >> 2, tq = lane & 3;
+                int it = 0;
+                for (int task = j; task < n_tasks; task += DG_P, ++it) {
+                    const int s = it & 1;
+                    const int u = u0 + task / DG_H, h = task % DG_H;
+                    const int kv_len = min(p.mem_len[u], p.T);
+                    const uint8_t* sK = sST + s * DG_STAGE;
+                    const uint8_t* sV = sK + 32768;
+                    // Q fragments (rows = hypotheses of the utterance) straight from L2
+                    uint32_t qa[4][4];
+                    {
+                        const bf16* qb = p.q2 + (size_t)(u * beam) * DG_D + h * 64;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const int d0 = ks * 16 + 2 * tq;
+                            qa[ks][0] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0) : 0u;
+                            qa[ks][1] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0) : 0u;
+                            qa[ks][2] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0 + 8) : 0u;
+                            qa[ks][3] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0 + 8) : 0u;
+                        }
+                    }
+                    mbar_wait(&ms.st_full[s], (par_stf >> s) & 1);
+                    par_stf ^= (1u << s);
+                    // S = Q K^T for this warp's 16 keys
+                    float sc[2][4];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+                    {
+                        const int m = lane >> 3, rr = lane & 7;
+                        const int key = warp * 16 + (m >> 1) * 8 + rr;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            uint32_t b0, b1, b2, b3;
+                            ldmatrix_x4(smem_u32(sK) + sw128(key, 2 * ks + (m & 1)), b0, b1, b2, b3);
+                            dg_mma16816(sc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                            dg_mma16816(sc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                        }
+                    }
+                    const float sl2 = 0.125f * 1.4426950408889634f;
+                    float mlo = -INFINITY, mhi = -INFINITY;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int k0 = warp * 16 + nt * 8 + 2 * tq;
+                        sc[nt][0] = (k0 < kv_len) ? sc[nt][0] * sl2 : -INFINITY;
+                        sc[nt][1] = (k0 + 1 < kv_len) ? sc[nt][1] * sl2 : -INFINITY;
+                        sc[nt][2] = (k0 < kv_len) ? sc[nt][2] * sl2 : -INFINITY;
+                        sc[nt][3] = (k0 + 1 < kv_len) ? sc[nt][3] * sl2 : -INFINITY;
+                        mlo = fmaxf(mlo, fmaxf(sc[nt][0], sc[nt][1]));
+                        mhi = fmaxf(mhi, fmaxf(sc[nt][2], sc[nt][3]));
+                    }
+                    mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 1));
+                    mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 2));
+                    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
+                    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+                    if (tq == 0) {
+                        wmax[warp * 16 + gq] = mlo;
+                        wmax[warp * 16 + gq + 8] = mhi;
+                    }
+                    __syncthreads();
+                    float Mlo = -INFINITY, Mhi = -INFINITY;
+#pragma unroll
+                    for (int w = 0; w < 16; ++w) {
+                        Mlo = fmaxf(Mlo, wmax[w * 16 + gq]);
+                        Mhi = fmaxf(Mhi, wmax[w * 16 + gq + 8]);
+                    }
+                    float slo = 0.f, shi = 0.f;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const float p0 = ex2f(sc[nt][0] - Mlo), p1 = ex2f(sc[nt][1] - Mlo);     // exp2(-inf) = 0 for masked keys
+                        const float p2 = ex2f(sc[nt][2] - Mhi), p3 = ex2f(sc[nt][3] - Mhi);
+                        slo += p0 + p1;
+                        shi += p2 + p3;
+                        const int kc = warp * 16 + nt * 8 + 2 * tq;
+                        *reinterpret_cast<uint32_t*>(sP + gq * DG_PP + kc * 2) = pack_bf16(p0, p1);
+                        *reinterpret_cast<uint32_t*>(sP + (gq + 8) * DG_PP + kc * 2) = pack_bf16(p2, p3);
+                    }
+                    slo += __shfl_xor_sync(0xffffffffu, slo, 1);
+                    slo += __shfl_xor_sync(0xffffffffu, slo, 2);
+                    shi += __shfl_xor_sync(0xffffffffu, shi, 1);
+                    shi += __shfl_xor_sync(0xffffffffu, shi, 2);
+                    if (tq == 0) {
+                        wsum[warp * 16 + gq] = slo;
+                        wsum[warp * 16 + gq + 8] = shi;
+                    }
+                    __syncthreads();
+                    // O = P V: warp = (8 output dims, half of the keys)
+                    const int nt8 = warp & 7, kh = warp >> 3;
+                    float oc[4] = {0.f, 0.f, 0.f, 0.f};
+                    {
+                        const int m = lane >> 3, rr = lane & 7;
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk += 2) {
+                            const int key0 = kh * 128 + kk * 16;
+                            uint32_t a0, a1, a2, a3, c0, c1, c2, c3, v0, v1, v2, v3;
+                            ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + (m >> 1) * 8) * 2), a0, a1, a2, a3);
+                            ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + 16 + (m >> 1) * 8) * 2), c0, c1, c2, c3);
+                            ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, nt8), v0, v1, v2, v3);   // keys key0 .. key0+31
+                            dg_mma16816(oc, a0, a1, a2, a3, v0, v1);
+                            dg_mma16816(oc, c0, c1, c2, c3, v2, v3);
+                        }
+                    }
+                    red[(warp * 16 + gq) * 8 + 2 * tq] = oc[0];
+                    red[(warp * 16 + gq) * 8 + 2 * tq + 1] = oc[1];
+                    red[(warp * 16 + gq + 8) * 8 + 2 * tq] = oc[2];
+                    red[(warp * 16 + gq + 8) * 8 + 2 * tq + 1] = oc[3];
+                    __syncthreads();
+                    // the stage is free: fetch the K / V tiles of the task after next
+                    if (is_tma && task + 2 * DG_P < n_tasks) load_kv(l, task + 2 * DG_P, s);
+                    if (tid < 16 * 32) {
+                        const int r = tid >> 5, dp = tid & 31;     // row, output dim pair
+                        if (r < beam) {
+                            const int w0 = dp >> 2, e = (dp & 3) * 2;
+                            float L = 0.f;
+#pragma unroll
+                            for (int w = 0; w < 16; ++w) L += wsum[w * 16 + r];
+                            const float inv = 1.0f / L;
+                            const float ox = red[(w0 * 16 + r) * 8 + e] + red[((w0 + 8) * 16 + r) * 8 + e];
+                            const float oy = red[(w0 * 16 + r) * 8 + e + 1] + red[((w0 + 8) * 16 + r) * 8 + e + 1];
+                            *reinterpret_cast<uint32_t*>(p.ctx + (size_t)(u * beam + r) * DG_D + h * 64 + 2 * dp) = pack_bf16(ox * inv, oy * inv);
+                        }
+                    }
+                    __syncthreads();
+                }
+                // every thread advanced par_stf by its own waits: all threads waited on the same tasks, so the words agree
+            }
+            DG_STAMP();   // cross-attention
+            gsync([&] { load_w1(l); });    // W1 slice (128 KB) streams in while the out-projection and LayerNorm run
+            DG_STAMP();
+            // ---------------- cross-attention out-projection + residual -> pre-norm rows
+            // (kb_full barriers are busy with the W1 prefetch: this small GEMM uses the st_full pair instead)
+            {
+                if (tid < 16) ms.bias[tid] = ly.bo2[j * 16 + tid];
+                if (is_tma) {
+                    mbar_arrive_expect_tx(&ms.st_full[0], (uint32_t)(4 * (16 * 128 + 16384)));
+                    for (int kb = 0; kb < 4; ++kb) {
+                        tma_load_2d(sA + kb * 16384, map_ctx, &ms.st_full[0], kb * 64, row0);
+                        tma_load_2d(sSB + kb * 2048, maps + l * 6 + 3, &ms.st_full[0], kb * 64, j * 16);
+                    }
+                } else if (is_mma) {
+                    const uint32_t idesc = umma_idesc_bf16(16);
+                    mbar_wait(&ms.st_full[0], par_stf & 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sSB + kb * 2048);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&ms.acc_full[0]);
+                }
+                __syncthreads();
+                if (is_epi) {
+                    mbar_wait(&ms.acc_full[0], par_accf & 1);
+                    tc_fence_after();
+                    uint32_t r[16];
+                    tmem_ld16(t_row, r);
+                    tmem_ld_wait();
+                    epi_pre(0, r);
+                    tc_fence_before();
+                }
+                par_stf ^= 1;
+                par_accf ^= 1;
+                __syncthreads();
+            }
+            DG_STAMP();   // out-proj 2
+            gsync(nop);
+            DG_STAMP();
+            // ---------------- LayerNorm 2 + GLU feed-forward: hidden features [128 j, 128 j + 128) (ffn.py:18,39-41)
+            build_a_ln(ly.g2, ly.be2);
+            DG_STAMP();   // LN2
+            {
+                if (tid < 256) ms.bias[tid] = ly.b1[(tid < 128 ? 0 : DG_DFF - 128) + j * 128 + tid];
+                if (is_mma) {
+                    const uint32_t idesc = umma_idesc_bf16(256);
+                    for (int kb = 0; kb < 4; ++kb) {
+                        mbar_wait(&ms.kb_full[kb], (par_kb >> kb) & 1);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + kb * 16384);
+                        const uint32_t b_addr = smem_u32(sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&ms.acc_full[0]);
+                } else if (is_tma) {
+                    // W2[:, 128 j .. 128 j + 128) (this CTA's contraction slice) follows into stage 0 as soon as W1 has been consumed
+                    mbar_wait(&ms.acc_full[0], par_accf & 1);
+                    mbar_arrive_expect_tx(&ms.st_full[0], 65536);
+                    tma_load_2d(sST, maps + l * 6 + 5, &ms.st_full[0], j * 128, 0);
+                    tma_load_2d(sST + 32768, maps + l * 6 + 5, &ms.st_full[0], j * 128 + 64, 0);
+                }
+                __syncthreads();
+                if (is_epi) {
+                    mbar_wait(&ms.acc_full[0], par_accf & 1);
+                    tc_fence_after();
+                    // h = (a + b_a) * sigmoid(g + b_g) -> bf16, written over the (dead) A tile as a [128 x 128] K-major operand
+#pragma unroll 1
+                    for (int c = 0; c < 128; c += 16) {
+                        uint32_t ra[16], rg[16];
+                        tmem_ld16(t_row + c, ra);
+                        tmem_ld16(t_row + 128 + c, rg);
+                        tmem_ld_wait();
+                        uint4 o[2];
+                        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float a0 = __uint_as_float(ra[2 * i]) + ms.bias[c + 2 * i], a1 = __uint_as_float(ra[2 * i + 1]) + ms.bias[c + 2 * i + 1];
+                            const float g0 = __uint_as_float(rg[2 * i]) + ms.bias[128 + c + 2 * i], g1 = __uint_as_float(rg[2 * i + 1]) + ms.bias[128 + c + 2 * i + 1];
+                            ow[i] = pack_bf16(a0 * dg_sigmoid(g0), a1 * dg_sigmoid(g1));
+                        }
+                        const int c8 = c >> 3;
+                        *reinterpret_cast<uint4*>(sA + (c8 >> 3) * 16384 + sw128(erow, c8 & 7)) = o[0];
+                        *reinterpret_cast<uint4*>(sA + ((c8 + 1) >> 3) * 16384 + sw128(erow, (c8 + 1) & 7)) = o[1];
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                }
+                par_kb ^= 0xF;
+                par_accf ^= 1;
+                __syncthreads();
+                DG_STAMP();   // W1 + GLU
+                // w_2 partial: acc2[128 x 256] = h[128 x 128] * W2[:, slice]^T   (TMEM columns 256..511)
+                if (is_mma) {
+                    const uint32_t idesc = umma_idesc_bf16(256);
+                    mbar_wait(&ms.st_full[0], par_stf & 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sST + kb * 32768);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem + 256, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&ms.acc_full[1]);
+                }
+                if (is_epi) {
+                    mbar_wait(&ms.acc_full[1], (par_accf >> 1) & 1);
+                    tc_fence_after();
+                    float* dst = p.part + ((size_t)j * N + row0 + erow) * DG_D;
+#pragma unroll 1
+                    for (int c = 0; c < 256; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(t_row + 256 + c, r);
+                        tmem_ld_wait();
+                        if (erow < nrows) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                *reinterpret_cast<uint4*>(dst + c + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                        }
+                    }
+                    tc_fence_before();
+                }
+                par_stf ^= 1;
+                par_accf ^= 2;
+            }
+            DG_STAMP();   // W2 partial
+            const bool last_layer = (l + 1 == nl);
+            gsync([&] {
+                if (last_layer) {   // output-layer chunks of this CTA: the first two stream in during the reduction
+                    if (j < n_vchunks) load_wout(j, 0);
+                    if (j + DG_P < n_vchunks) load_wout(j + DG_P, 1);
+                }
+            });
+            DG_STAMP();
+            // ---------------- reduce the 16 partial sums of this CTA's 16 output columns + bias + residual -> pre-norm rows
+            {
+                const int r = tid >> 2, q4 = tid & 3;
+                if (r < nrows) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* src = p.part + ((size_t)(row0 + r)) * DG_D + j * 16 + q4 * 4;
+                    float4 v[DG_P];
+#pragma unroll
+                    for (int pp = 0; pp < DG_P; ++pp) v[pp] = *reinterpret_cast<const float4*>(src + (size_t)pp * N * DG_D);
+#pragma unroll
+                    for (int pp = 0; pp < DG_P; ++pp) { acc.x += v[pp].x; acc.y += v[pp].y; acc.z += v[pp].z; acc.w += v[pp].w; }
+                    const float4 b = *reinterpret_cast<const float4*>(ly.b2 + j * 16 + q4 * 4);
+                    const float2 r0 = unpack_bf16(ms.rs[r * 8 + 2 * q4]), r1 = unpack_bf16(ms.rs[r * 8 + 2 * q4 + 1]);
+                    *reinterpret_cast<float4*>(p.pre + (size_t)(row0 + r) * DG_D + j * 16 + q4 * 4) =
+                        make_float4(acc.x + b.x + r0.x, acc.y + b.y + r0.y, acc.z + b.z + r1.x, acc.w + b.w + r1.y);
+                }
+            }
+            DG_STAMP();   // reduce
+            gsync(nop);
+            DG_STAMP();
+            build_a_ln(ly.g3, ly.be3);   // LayerNorm 3 = input of the next layer (or of the output layer)
+            DG_STAMP();   // LN3
+        }
+
+        // ---------------- output layer (decoder/transformer.py:181) in 128-column chunks; log-softmax statistics and the per-row
+        // top-`beam` candidates are formed in the epilogue (transformer.py:206 + speech2text.py:112), the logits are never stored
+        {
+            int my_chunks = 0;
+            for (int c = j; c < n_vchunks; c += DG_P) ++my_chunks;
+            if (is_tma) {
+                for (int i = 2; i < my_chunks; ++i) {        // chunks 0 and 1 were prefetched
+                    const int s = i & 1;
+                    mbar_wait(&ms.st_empty[s], ((par_ste >> s) & 1) ^ (uint32_t)(((i - 2) >> 1) & 1));
+                    load_wout(j + i * DG_P, s);
+                }
+            } else if (is_mma) {
+                const uint32_t idesc = umma_idesc_bf16(128);
+                for (int i = 0; i < my_chunks; ++i) {
+                    const int s = i & 1;
+                    const uint32_t use = (uint32_t)((i >> 1) & 1);
+                    if (i >= 2) {
+                        mbar_wait(&ms.acc_empty[s], ((par_acce >> s) & 1) ^ (uint32_t)(((i - 2) >> 1) & 1));
+                        tc_fence_after();
+                    }
+                    mbar_wait(&ms.st_full[s], ((par_stf >> s) & 1) ^ use);
+                    tc_fence_after();
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sST + s * DG_STAGE + kb * 16384);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem + s * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&ms.st_empty[s]);
+                    umma_commit(&ms.acc_full[s]);
+                }
+            } else if (is_epi) {
+                float m = -INFINITY, ssum = 0.f;
+                TopList tl;
+                tl.init();
+                float* dump = p.dbg_logp ? p.dbg_logp + ((size_t)step * N + row0 + erow) * V : nullptr;
+                for (int i = 0; i < my_chunks; ++i) {
+                    const int s = i & 1;
+                    const int col0 = (j + i * DG_P) * 128;
+                    mbar_wait(&ms.acc_full[s], ((par_accf >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < 128; c += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(t_row + s * 128 + c, r);
+                        tmem_ld_wait();
+                        if (col0 + c >= V) continue;
+                        float x[16];
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int col = col0 + c + q;
+                            x[q] = (col < V) ? __uint_as_float(r[q]) + (p.bout ? __ldg(p.bout + col) : 0.f) : -INFINITY;
+                            cm = fmaxf(cm, x[q]);
+                        }
+                        if (erow < nrows) {
+                            const float mn = fmaxf(m, cm);
+                            float acc = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) acc += __expf(x[q] - mn);
+                            ssum = ssum * __expf(m - mn) + acc;
+                            m = mn;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (col0 + c + q < V) {
+                                    tl.push(x[q], col0 + c + q);
+                                    if (dump) dump[col0 + c + q] = x[q];
+                                }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&ms.acc_empty[s]);
+                }
+                if (erow < nrows) {
+                    p.stats[(size_t)(row0 + erow) * DG_P + j] = make_float2(m, ssum);
+                    float* cv = p.cand_v + ((size_t)(row0 + erow) * DG_P + j) * KMAX;
+                    int* ci = p.cand_i + ((size_t)(row0 + erow) * DG_P + j) * KMAX;
+#pragma unroll
+                    for (int q = 0; q < KMAX; ++q) {
+                        cv[q] = tl.v[q];
+                        ci[q] = tl.i[q];
+                    }
+                }
+            }
+            // parity bookkeeping: barrier pair s was used ceil((my_chunks - s) / 2) times
+            const uint32_t u0n = (uint32_t)((my_chunks + 1) >> 1), u1n = (uint32_t)(my_chunks >> 1);
+            par_stf ^= (u0n & 1) | ((u1n & 1) << 1);
+            par_ste ^= (u0n & 1) | ((u1n & 1) << 1);
+            par_accf ^= (u0n & 1) | ((u1n & 1) << 1);
+            par_acce ^= (u0n & 1) | ((u1n & 1) << 1);
+        }
+        DG_STAMP();   // logits + stats + candidates
+        gsync(nop);
+        DG_STAMP();
+        // ---------------- per utterance: merge candidates, finished masking, beam^2 pruning, ancestry (speech2text.py:102-153)
+        int ended_here = 0;
+        for (int ul = j; ul < nutt; ul += DG_P) {
+            const int u = u0 + ul;
+            for (int r = warp; r < beam; r += 16) {
+                const int n = u * beam + r;
+                // log-sum-exp of the row from the 16 partial (max, sum) pairs
+                float2 stt = (lane < DG_P) ? p.stats[(size_t)n * DG_P + lane] : make_float2(-INFINITY, 0.f);
+                const float M = warp_max(stt.x);
+                const float S = warp_sum(stt.y * __expf(stt.x - M));
+                const float lse = M + logf(S);
+                if (p.dbg_logp) {
+                    float* dump = p.dbg_logp + ((size_t)step * N + n) * V;
+                    for (int c = lane; c < V; c += 32) dump[c] = dump[c] - lse;
+                }
+                if (p.st.flag[n]) {                      // mask_finished_scores / mask_finished_preds (speech2text.py:156-192)
+                    if (lane < beam) {
+                        ms.row_v[r][lane] = (lane == 0) ? 0.f : -INFINITY;
+                        ms.row_i[r][lane] = (int)EOS_ID;
+                    }
+                } else {
+                    // 16 sorted lists of `beam` candidates -> top-`beam` of (log-prob, token id), ties -> lower token id
+                    float cvv[(DG_P * KMAX + 31) / 32];
+                    int cii[(DG_P * KMAX + 31) / 32];
+                    const int ncand = DG_P * beam;
+#pragma unroll
+                    for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q) {
+                        const int idx = lane + 32 * q;
+                        cvv[q] = -INFINITY;
+                        cii[q] = 0x7fffffff;
+                        if (idx < ncand) {
+                            const int cj = idx / beam, ck = idx % beam;
+                            const float xv = p.cand_v[((size_t)n * DG_P + cj) * KMAX + ck];
+                            cii[q] = p.cand_i[((size_t)n * DG_P + cj) * KMAX + ck];
+                            cvv[q] = (cii[q] != 0x7fffffff) ? xv - lse : -INFINITY;
+                        }
+                    }
+                    for (int k = 0; k < beam; ++k) {
+                        float bv = -INFINITY;
+                        int bi = 0x7fffffff;
+#pragma unroll
+                        for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q)
+                            if (better(cvv[q], cii[q], bv, bi)) { bv = cvv[q]; bi = cii[q]; }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q)
+                            if (cii[q] == bi && bi != 0x7fffffff) { cvv[q] = -INFINITY; cii[q] = 0x7fffffff; }   // token ids are unique per row
+                        if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
+                    }
+                }
+                __syncwarp();
+                const float base = p.st.scores[n];
+                if (lane < beam) {
+                    ms.c_val[r * beam + lane] = base + ms.row_v[r][lane];      // scores + last_k_scores (:118)
+                    ms.c_tok[r * beam + lane] = ms.row_i[r][lane];
+                }
+            }
+            __syncthreads();
+            if (warp == 0) warp_topk([&](int idx) { return ms.c_val[idx]; }, beam * beam, beam, ms.sel_v, ms.sel_i);   // (:119-122)
+            __syncthreads();
+            const int cur = step & 1, nxt = cur ^ 1;
+            for (int r = warp; r < beam; r += 16) {      // ancestry of the surviving hypotheses (:126-140)
+                const int off = ms.sel_i[r];
+                const int parent = u * beam + off / beam;
+                const int nn = u * beam + r;
+                const int* a_old = p.st.anc + ((size_t)cur * N + parent) * Lmax;
+                int* a_new = p.st.anc + ((size_t)nxt * N + nn) * Lmax;
+                for (int s = lane; s < step; s += 32) a_new[s] = a_old[s];
+                if (lane == 0) {
+                    a_new[step] = parent;
+                    p.st.tok_hist[(size_t)step * N + nn] = ms.c_tok[off];
+                    p.st.par_hist[(size_t)step * N + nn] = parent;
+                }
+            }
+            __syncthreads();   // every read of the old scores / flags of this utterance is done
+            if (tid < beam) {
+                const int nn = u * beam + tid;
+                const int tok = ms.c_tok[ms.sel_i[tid]];
+                p.st.scores[nn] = ms.sel_v[tid];
+                p.st.last_tok[nn] = tok;
+                p.st.flag[nn] = (tok == (int)EOS_ID) ? 1 : 0;
+                if (p.dbg_scores) p.dbg_scores[(size_t)step * N + nn] = ms.sel_v[tid];
+                if (tok == (int)EOS_ID) atomicAdd(&ms.flag, 1);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            ended_here = ms.flag;
+            ms.flag = 0;
+            if (ended_here) atomicAdd(&p.gstate[(size_t)g * Lmax + step], ended_here);
+        }
+        DG_STAMP();   // beam step
+        gsync(nop);
+        DG_STAMP();
+        steps_done = step + 1;
+        if (tid == 0) ms.flag = (ld_acquire_gpu(&p.gstate[(size_t)g * Lmax + step]) == nrows) ? 1 : 0;
+        __syncthreads();
+        group_done = ms.flag != 0;
+        __syncthreads();
+        if (tid == 0) ms.flag = 0;
+        if (group_done) break;      // every hypothesis of every utterance of this group ended (uniform across the group)
+    }
+
+    // A group that ended early keeps emitting EOS from its (sorted) hypotheses with identity parents while the reference loops
+    // on for the other utterances (speech2text.py:62-68): fill the rest of its history so that any global step count >= its own
+    // gives the reference's tokens.  Global step count = max over groups (the reference breaks when EVERY hypothesis ended).
+    if (j == 0) {
+        for (int i = tid; i < (p.max_steps - steps_done) * nrows; i += DG_THREADS) {
+            const int s = steps_done + i / nrows, r = i % nrows;
+            p.st.tok_hist[(size_t)s * N + row0 + r] = (int)EOS_ID;
+            p.st.par_hist[(size_t)s * N + row0 + r] = row0 + r;
+            if (p.dbg_scores) p.dbg_scores[(size_t)s * N + row0 + r] = p.st.scores[row0 + r];
+        }
+        if (tid == 0) {
+            atomicMax(&p.st.ctrl[0], group_done ? steps_done : p.max_steps);
+            if (!group_done) atomicAdd(&p.st.ctrl[2], 1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+#undef DG_STAMP
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam) {
+    const int upg = 128 / beam;
+    const int G = (B + upg - 1) / upg;
+    size_t b = 0;
+    auto take = [&](size_t n) { b += (n + 255) & ~(size_t)255; };
+    take((size_t)(n_layers * 6 + 3) * sizeof(CUtensorMap));   // maps
+    take((size_t)N * DG_D * 2);                                // qbuf
+    take((size_t)(N + 128) * DG_D * 2);                        // ctx (+ one tile of slack rows for the last group's TMA box)
+    take((size_t)N * DG_D * 4);                                // pre
+    take((size_t)N * DG_D * 2);                                // q2
+    take((size_t)DG_P * N * DG_D * 4);                         // part
+    take((size_t)N * DG_P * 8);                                // stats
+    take((size_t)N * DG_P * KMAX * 4);                         // cand_v
+    take((size_t)N * DG_P * KMAX * 4);                         // cand_i
+    take((size_t)G * 128);                                     // bar
+    take((size_t)G * Lmax * 4);                                // gstate
+    return b + 1024;
+}
+
+const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* workspace, size_t workspace_bytes) {
+    if (mp.d != DG_D || mp.H != DG_H) return "decode_persistent: needs d_model 256 with 4 heads";
+    if (mp.dff != DG_DFF) return "decode_persistent: d_ff must be 2048 (128 hidden features per CTA of a 16-CTA group)";
+    if (mp.st.beam < 1 || mp.st.beam > KMAX) return "decode_persistent: beam must be in [1,16]";
+    if (mp.st.Lmax > 128 || mp.max_steps > mp.st.Lmax || mp.max_steps < 1) return "decode_persistent: max_steps <= Lmax <= 128";
+    if (mp.n_layers < 1 || mp.n_layers > OTB_MEGA_MAX_LAYERS_INT) return "decode_persistent: too many layers";
+    if (mp.B < 1 || mp.T < 1 || mp.T > 256 || mp.st.N != mp.B * mp.st.beam) return "decode_persistent: bad batch geometry (memory length <= 256)";
+    if (mp.V < 16) return "decode_persistent: vocabulary too small";
+    const int beam = mp.st.beam, N = mp.st.N;
+    const int upg = 128 / beam;
+    const int G = (mp.B + upg - 1) / upg;
+    if (G * DG_P > num_sms()) return "decode_persistent: batch needs more co-resident CTAs than the GPU has SMs";
+    if (workspace_bytes < decode_group_workspace_bytes(N, mp.n_layers, mp.st.Lmax, mp.B, beam)) return "decode_persistent: workspace too small";
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return "decode_persistent: workspace must be 256-byte aligned";
+
+    DgParams p;
+    memset(&p, 0, sizeof(p));
+    uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+    auto take = [&](size_t n) { uint8_t* r = w; w += (n + 255) & ~(size_t)255; return r; };
+    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 3) * sizeof(CUtensorMap)));
+    p.qbuf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
+    p.ctx = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
+    p.pre = reinterpret_cast<float*>(take((size_t)N * DG_D * 4));
+    p.q2 = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
+    p.part = reinterpret_cast<float*>(take((size_t)DG_P * N * DG_D * 4));
+    p.stats = reinterpret_cast<float2*>(take((size_t)N * DG_P * 8));
+    p.cand_v = reinterpret_cast<float*>(take((size_t)N * DG_P * KMAX * 4));
+    p.cand_i = reinterpret_cast<int*>(take((size_t)N * DG_P * KMAX * 4));
+    p.bar = reinterpret_cast<int*>(take((size_t)G * 128));
+    p.gstate = reinterpret_cast<int*>(take((size_t)G * mp.st.Lmax * 4));
+
+    // tensor maps (host encode -> device array).  Weights [rows, K] bf16 row-major, box = (64 columns) x (rows of one slice).
+    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 3];
+    const char* err;
+    for (int l = 0; l < mp.n_layers; ++l) {
+        const MegaLayer& ly = mp.layers[l];
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 0], ly.wqkv, DG_D, 3 * DG_D, DG_D, 64, 48))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 1], ly.wo, DG_D, DG_D, DG_D, 64, 16))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 2], ly.wq, DG_D, DG_D, DG_D, 64, 16))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 3], ly.wo2, DG_D, DG_D, DG_D, 64, 16))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 4], ly.w1, DG_D, 2 * DG_DFF, DG_D, 64, 128))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 5], ly.w2, DG_DFF, DG_D, DG_DFF, 64, 256))) return err;
+        DgLayer& d = p.layers[l];
+        d.bqkv = ly.bqkv; d.bo = ly.bo; d.bq = ly.bq; d.bo2 = ly.bo2; d.b1 = ly.b1; d.b2 = ly.b2;
+        d.g1 = ly.g1; d.be1 = ly.be1; d.g2 = ly.g2; d.be2 = ly.be2; d.g3 = ly.g3; d.be3 = ly.be3;
+    }
+    const int nm = mp.n_layers * 6;
+    if ((err = encode_tmap_2d(&h_maps[nm + 0], mp.wout, DG_D, (uint64_t)mp.V, DG_D, 64, 128))) return err;
+    if ((err = encode_tmap_2d(&h_maps[nm + 1], p.ctx, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
+    if ((err = encode_tmap_2d(&h_maps[nm + 2], mp.kvx, 2 * DG_D, (uint64_t)mp.n_layers * mp.B * mp.T, 2 * DG_D, 64, 256))) return err;
+    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 3) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    if ((e = cudaMemsetAsync(p.bar, 0, (size_t)G * 128, st)) != cudaSuccess) return cudaGetErrorString(e);
+    if ((e = cudaMemsetAsync(p.gstate, 0, (size_t)G * mp.st.Lmax * 4, st)) != cudaSuccess) return cudaGetErrorString(e);
+
+    p.n_layers = mp.n_layers; p.V = mp.V; p.G = G; p.utts_per_group = upg;
+    p.emb = mp.emb; p.bout = mp.bout; p.pe = mp.pe;
+    p.maps = d_maps;
+    p.mem_len = mp.mem_len; p.kc = mp.kc; p.vc = mp.vc;
+    p.st = mp.st; p.B = mp.B; p.T = mp.T; p.max_steps = mp.max_steps; p.eps = mp.eps;
+    p.dbg_logp = mp.dbg_logp; p.dbg_scores = mp.dbg_scores;
+    p.dbg_clk = g_dg_dbg; p.dbg_step = g_dg_dbg_step;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM) != cudaSuccess)
+            return "cudaFuncSetAttribute(decode_persistent) failed";
+        attr_set = true;
+    }
+    decode_group_kernel<<<G * DG_P, DG_THREADS, DG_SMEM, st>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace otb

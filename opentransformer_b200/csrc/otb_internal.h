@@ -150,12 +150,44 @@ struct MegaParams {
     float eps;
     float* dbg_logp;      // optional [max_steps, N, V]
     float* dbg_scores;    // optional [max_steps, N]
-    unsigned long long* dbg_clk;   // optional clock64 stamps of cluster 0 / rank 0 at step dbg_step (otb_debug_mega_timing)
+};
+// ---- persistent decode kernel, round 2 (decode_group.cu): row groups of <= 128 hypotheses x 16 CTAs, tcgen05 GEMMs
+struct DgLayer {
+    const float *bqkv, *bo, *bq, *bo2, *b1, *b2;
+    const float *g1, *be1, *g2, *be2, *g3, *be3;
+};
+struct DgParams {
+    int n_layers, V, G, utts_per_group;
+    const bf16* emb;
+    const float* bout;
+    const float* pe;
+    DgLayer layers[OTB_MEGA_MAX_LAYERS_INT];
+    const CUtensorMap* maps;   // device array: per layer {wqkv, wo, wq, wo2, w1, w2}, then wout, ctx, kvx
+    const int* mem_len;
+    bf16* kc;
+    bf16* vc;
+    BeamState st;
+    int B, T, max_steps;
+    float eps;
+    bf16* qbuf;                // [N, d]   self-attention queries of the newest token
+    bf16* ctx;                 // [N + 128, d] attention context (self, then cross)
+    float* pre;                // [N, d]   pre-LayerNorm rows (residual + projection + bias), fp32
+    bf16* q2;                  // [N, d]   cross-attention queries
+    float* part;               // [16, N, d] w_2 partial sums of the 16 contraction slices
+    float2* stats;             // [N, 16]  (max, sum exp) of each CTA's vocabulary columns
+    float* cand_v;             // [N, 16, 16] per-CTA top-k logits
+    int* cand_i;               //           and their token ids
+    int* bar;                  // [G, 32]  group barrier counters
+    int* gstate;               // [G, Lmax] ended-hypothesis count per step
+    float* dbg_logp;
+    float* dbg_scores;
+    unsigned long long* dbg_clk;
     int dbg_step;
 };
-extern unsigned long long* g_mega_dbg;
-extern int g_mega_dbg_step;
-const char* decode_mega_launch(cudaStream_t st, const MegaParams& p);
+extern unsigned long long* g_dg_dbg;
+extern int g_dg_dbg_step;
+size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam);
+const char* decode_group_launch(cudaStream_t st, const MegaParams& p, void* workspace, size_t workspace_bytes);
 
 const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,
                         const void* v, int ldv, const AttnParams& p);

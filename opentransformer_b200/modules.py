@@ -541,6 +541,57 @@ class ConformerEncoder(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # decoder
 # ------------------------------------------------------------------------------------------------
+class DecoderCache:
+    """The decoder cache the reference stubbed out (decoder/transformer.py:92-126,188-203; README TODO), as the opaque
+    `cache` object of ``TransformerDecoder.inference(preds, memory, memory_mask, cache)``:
+
+      * cross-attention K/V of the memory, projected ONCE (the reference re-runs vk_proj on the beam-tiled memory at every
+        step, attention.py:129).  When the memory rows are the beam-tiled copies of `batch` utterances
+        (recognize/speech2text.py:51-52) pass ``beam`` so that each utterance is projected once and shared by its beams;
+      * self-attention K/V of every decoded position [layer, position, row, d]; beam pruning never moves K/V rows, it
+        rewrites a 4-byte ancestry entry per (row, position) -- ``reorder(parent_rows)`` is what `decode_step` calls where
+        the reference intended reselect_hidden* (recognize/speech2text.py:195-218).
+
+    Build it with ``TransformerDecoder.init_cache``.  One `inference` call consumes exactly one new token per row."""
+
+    def __init__(self, decoder, memory, memory_mask, max_len, beam=1):
+        n, T, D = memory.shape
+        if n % beam:
+            raise ValueError('DecoderCache: memory rows must be a multiple of beam')
+        dev = memory.device
+        self.N, self.T, self.beam, self.Lmax, self.step = n, T, beam, max_len, 0
+        self.batch = n // beam
+        nl, d = len(decoder.blocks), decoder.d_model
+        pk = decoder.packed()
+        self._pk = pk            # the cache is tied to this weight pack (K/V were projected with it)
+        mem = memory.contiguous().view(self.batch, beam, T, D)[:, 0]                 # one copy per utterance
+        msk = memory_mask.contiguous().view(self.batch, beam, T)[:, 0]
+        mem_bf16 = ops.scale_add_table(mem.contiguous().view(self.batch * T, D).float())
+        self.mem_len = _lengths(msk)
+        self.kvx = torch.empty(nl, self.batch * T, 2 * d, dtype=BF16, device=dev)
+        for l, p in enumerate(pk['blocks']):
+            ops.linear(mem_bf16, p['wkv'], p['bkv'], out=self.kvx[l])
+        self.kc = torch.zeros(nl, max_len, n, d, dtype=BF16, device=dev)
+        self.vc = torch.zeros(nl, max_len, n, d, dtype=BF16, device=dev)
+        self.anc = torch.zeros(2, n, max_len, dtype=torch.int32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.table = ops.sinusoid_table(max_len + 1, d, 0, dev)
+
+    def reorder(self, parent_rows):
+        """Row n of the next step continues row parent_rows[n] (i64/i32 [N], global row indices)."""
+        if self.step == 0:
+            raise RuntimeError('DecoderCache.reorder before the first inference step')
+        s = self.step - 1                     # the position that was just decoded
+        cur, nxt = s & 1, (s & 1) ^ 1
+        par = parent_rows.view(-1).long()
+        self.anc[nxt] = self.anc[cur].index_select(0, par)
+        self.anc[nxt, :, s] = par.to(torch.int32)
+
+    def advance_without_reorder(self):
+        """Greedy / teacher-forced use (no pruning): every row continues itself."""
+        self.reorder(torch.arange(self.N, device=self.anc.device))
+
+
 class TransformerDecoderLayer(nn.Module):
     def __init__(self, n_heads, d_model, d_ff, memory_dim, slf_attn_dropout=0.0, src_attn_dropout=0.0,
                  ffn_dropout=0.0, residual_dropout=0.1, normalize_before=False, concat_after=False,
@@ -647,8 +698,56 @@ class TransformerDecoder(nn.Module):
                 for i in range(len(self.blocks))}
         return logits.view(B, L, -1)[:, :, :self.vocab_size], attn
 
+    def init_cache(self, memory, memory_mask, max_len, beam=1):
+        """KV cache for `inference` (see DecoderCache).  memory f32 [N,T,D] (beam-tiled or not), memory_mask bool [N,T]."""
+        _no_train(self)
+        return DecoderCache(self, memory, memory_mask, max_len, beam)
+
     def inference(self, preds, memory, memory_mask=None, cache=None):
+        """decoder/transformer.py:185-208.  cache None (the reference's only working mode): the whole prefix is recomputed.
+        cache = DecoderCache (``init_cache``): only the newest token preds[:, -1] is run through the layers against the cached
+        keys / values -- O(l) instead of O(l^2) per step -- and the same object is returned; the caller reorders it after
+        pruning (SpeechToTextRecognizer.decode_step does)."""
         assert preds.dim() == 2
+        if isinstance(cache, DecoderCache):
+            return self._inference_cached(preds, cache)
         logits, attn = self.forward(preds, memory, memory_mask)       # full recompute, as transformer.py:204
         last = logits[:, -1, :].contiguous()
         return ops.log_softmax(last, self.vocab_size), cache, attn
+
+    def _inference_cached(self, preds, c):
+        _no_train(self)
+        pk = self._pack.get()
+        if pk is not c._pk:
+            raise RuntimeError('DecoderCache was built with different decoder weights (parameters changed since init_cache)')
+        if preds.shape[0] != c.N or preds.shape[1] != c.step + 1:
+            raise ValueError(f'cached inference expects preds [N={c.N}, {c.step + 1}] (one new token per call), got {tuple(preds.shape)}')
+        if c.step >= c.Lmax:
+            raise ValueError('DecoderCache is full (max_len reached)')
+        if self.pos_emb.scale_learnable:
+            raise NotImplementedError('decoder with learnable positional scale')
+        d, H, N = self.d_model, self.n_heads, c.N
+        c.step_dev.fill_(c.step)
+        tok = preds[:, -1].contiguous()
+        x = ops.embed_posenc(tok, pk['emb'], c.table, N, d, step_ptr=c.step_dev)
+        for l, (blk, p) in enumerate(zip(self.blocks, pk['blocks'])):
+            nb = blk.normalize_before
+            if nb:
+                x = ops.layernorm(x, *p['ln1'])
+            qkv = ops.linear(x, p['wqkv'], p['bqkv'])
+            ctx = ops.decode_self_attn(qkv, c.kc[l], c.vc[l], c.anc, c.step_dev, N, H, c.Lmax)
+            x = _proj_resid_ln(ctx, p['wo'], p['bo'], x, None if nb else p['ln1'])
+            if nb:
+                x = ops.layernorm(x, *p['ln2'])
+            q = ops.linear(x, p['wq'], p['bq'])
+            ctx = ops.attention(q, c.kvx[l], c.kvx[l], c.batch, H, c.beam, c.T, kv_len=c.mem_len, k_col0=0, v_col0=d)
+            x = _proj_resid_ln(ctx, p['wo2'], p['bo2'], x, None if nb else p['ln2'])
+            if nb:
+                x = ops.layernorm(x, *p['ln3'])
+            x = _ffn(x, p['ffn'], x, None if nb else p['ln3'])
+        if self.normalize_before:
+            x = ops.layernorm(x, *pk['after'])
+        logits = ops.linear(x, pk['wout'], pk['bout'], EPI_BIAS, out_f32=True, n_out=self.ld_logits)
+        c.step += 1
+        attn = {'dec_block_%d' % i: {'slf_attn_weights': None, 'src_attn_weights': None} for i in range(len(self.blocks))}
+        return ops.log_softmax(logits, self.vocab_size), c, attn

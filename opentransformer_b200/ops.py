@@ -70,6 +70,10 @@ def set_tile_policy(policy):
     check(_lib.lib().otb_set_tile_policy({'latency': 0, 'throughput': 1}[policy]), 'otb_set_tile_policy')
 
 
+def num_sms():
+    return int(_lib.lib().otb_num_sms())
+
+
 def conv_geometry(T, F):
     t1, f1, t2, f2 = (ctypes.c_int() for _ in range(4))
     check(_lib.lib().otb_conv_geometry(T, F, t1, f1, t2, f2), 'otb_conv_geometry')
@@ -319,11 +323,19 @@ class BeamState:
         return out_preds, out_scores
 
 
-def decode_mega(model_c, kvx, mem_len, kc, vc, state, B, T, max_steps, dbg_logp=None, dbg_scores=None):
-    """The whole beam-search decode loop in one persistent cluster kernel (otb_decode_mega)."""
+def decode_persistent_workspace(N, n_layers, Lmax, B, beam, device):
+    n = int(_lib.lib().otb_decode_persistent_workspace(N, n_layers, Lmax, B, beam))
+    if n < 0:
+        raise ValueError('otb_decode_persistent_workspace: bad geometry')
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def decode_persistent(model_c, kvx, mem_len, kc, vc, state, B, T, max_steps, workspace, dbg_logp=None, dbg_scores=None):
+    """The whole beam-search decode loop in one persistent kernel (otb_decode_persistent, csrc/decode_group.cu)."""
     _need(kvx, BF16, 'kvx'); _need(kc, BF16, 'kc'); _need(vc, BF16, 'vc'); _need(mem_len, torch.int32, 'mem_len')
-    check(_lib.lib().otb_decode_mega(ctypes.byref(model_c), _p(kvx), _p(mem_len), _p(kc), _p(vc), ctypes.byref(state.c),
-                                     B, T, max_steps, _p(dbg_logp), _p(dbg_scores), _stream()), 'otb_decode_mega')
+    check(_lib.lib().otb_decode_persistent(ctypes.byref(model_c), _p(kvx), _p(mem_len), _p(kc), _p(vc), ctypes.byref(state.c),
+                                           B, T, max_steps, _p(workspace), workspace.numel(), _p(dbg_logp), _p(dbg_scores),
+                                           _stream()), 'otb_decode_persistent')
     _count()
 
 

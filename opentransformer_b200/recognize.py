@@ -106,21 +106,23 @@ class BeamDecoder:
         self.lm_weight = 0.0
         if decoder.pos_emb.scale_learnable:
             raise NotImplementedError('decoder with learnable positional scale')
-        # persistent path (opt-in): the whole loop in one cluster kernel (csrc/decode_mega.cu) when the configuration is
-        # the shipped one (post-norm GLU decoder, d_model 256, 4 heads).  Round-1 measurement (profiles/r1_mega_phases.txt):
-        # bit-exact and launch-free, but 28.7 ms per 60 steps -- no faster than the per-step graph, and it occupies 128 SMs
-        # so batches cannot overlap -- hence the per-step graph stays the default until its stage costs are fixed.
+        # persistent path: the whole loop in ONE launch (csrc/decode_group.cu: row groups of <= 128 hypotheses x 16 CTAs,
+        # tcgen05 GEMMs, group-local barriers) when the configuration is the shipped one (post-norm GLU decoder, d_model 256,
+        # 4 heads, d_ff 2048, <= 256 memory frames); anything else takes the per-step graph.
         self.persistent = bool(persistent) and self.mega_supported()
         self._mega_model = None
         self._mega_sig = None
+        self._ws = None
 
     def mega_supported(self):
         dec = self.dec
+        groups = -(-self.B // max(1, 128 // self.beam))
         ok = (dec.d_model == 256 and dec.n_heads == 4 and not dec.normalize_before and 1 <= len(dec.blocks) <= 8
-              and self.beam <= 16 and self.Lmax <= 128 and dec.vocab_size >= 8)
+              and self.beam <= 16 and self.Lmax <= 128 and dec.vocab_size >= 16 and self.T <= 256
+              and groups * 16 <= ops.num_sms())
         for blk in dec.blocks:
             ff = blk.feed_forward
-            ok = ok and ff.activation == 'glu' and ff.w_2.in_features % 512 == 0 and not blk.normalize_before
+            ok = ok and ff.activation == 'glu' and ff.w_2.in_features == 2048 and not blk.normalize_before
             ok = ok and all(m.bias is not None for m in (blk.slf_attn.qvk_proj, blk.slf_attn.output_proj, blk.src_attn.q_proj,
                                                          blk.src_attn.output_proj, ff.w_1, ff.w_2))
         return bool(ok)
@@ -150,8 +152,10 @@ class BeamDecoder:
 
     def run_persistent(self, max_steps, dbg_logp=None, dbg_scores=None):
         """All steps in ONE launch; no host round trip (ctrl[0] = executed steps is read by the caller)."""
-        ops.decode_mega(self._mega(), self.kvx, self.mem_len, self.kc, self.vc, self.state, self.B, self.T, max_steps,
-                        dbg_logp, dbg_scores)
+        if self._ws is None:
+            self._ws = ops.decode_persistent_workspace(self.N, len(self.dec.blocks), self.Lmax, self.B, self.beam, self.device)
+        ops.decode_persistent(self._mega(), self.kvx, self.mem_len, self.kc, self.vc, self.state, self.B, self.T, max_steps,
+                              self._ws, dbg_logp, dbg_scores)
 
     def setup(self, memory_bf16, mem_len):
         """Project cross-attention K/V once per utterance and reset the search state."""
@@ -297,18 +301,29 @@ class SpeechToTextRecognizer(Recognizer):
         return self.model.decoder.inference(preds, memory, memory_mask, cache)
 
     def decode_step(self, preds, memory, memory_mask, cache, scores, flag):
-        """One reference-style step on caller-owned tensors (speech2text.py:95-153): full-prefix decoder
-        (as the reference) + the CUDA beam kernel.  The fast path used by recognize() is BeamDecoder."""
+        """One reference-style step on caller-owned tensors (speech2text.py:95-153): decoder.inference + the CUDA beam
+        kernel.  With cache['decoder'] = model.decoder.init_cache(memory, mask, max_len, beam) the decoder runs KV-cached
+        (one token per call) and the cache is reordered by the surviving hypotheses' parents -- the feature the reference
+        left as a stub (decoder/transformer.py:188-203, reselect_hidden* :195-218); with None it recomputes the full prefix
+        like the reference.  The fast path used by recognize() is BeamDecoder."""
+        from .modules import DecoderCache
         n = scores.size(0)
         batch = n // self.beam_width
-        log_probs, _, _ = self.decode(preds, memory, memory_mask, cache['decoder'] if cache else None)
+        dcache = cache.get('decoder') if isinstance(cache, dict) else None
+        log_probs, dcache, _ = self.decode(preds, memory, memory_mask, dcache)
         st = ops.BeamState(batch, self.beam_width, 1, scores.device)
         st.init()
         st.scores.copy_(scores.view(-1))
         st.flag.copy_(flag.view(-1).to(torch.uint8))
-        st.step(log_probs.contiguous(), log_probs.shape[-1])
+        lm_logp, lm_w = None, 0.0
+        if self.lm is not None and self.lm_weight:
+            lm_logp = self.lm.predict(preds, last_frame=True).squeeze(1).contiguous()
+            lm_w = float(self.lm_weight)
+        st.step(log_probs.contiguous(), log_probs.shape[-1], lm_logp, lm_w)
         parent = st.par_hist[0].long()
         tok = st.tok_hist[0].long()
+        if isinstance(dcache, DecoderCache):
+            dcache.reorder(parent)
         preds_symbol = torch.cat((preds.index_select(0, parent), tok.view(-1, 1)), dim=1)
         return preds_symbol, cache, st.scores.view(-1, 1).clone(), (tok == EOS).view(-1, 1)
 

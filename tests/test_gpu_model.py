@@ -401,3 +401,56 @@ def test_end_to_end_best_hypothesis_vs_fp32_oracle():
     same = sum(int(torch.equal(p[b, 0].cpu(), nb_ref[b, 0])) for b in range(B))
     print(f'1-best identical to fp32 oracle for {same}/{B} utterances; scores gpu {s.view(-1).tolist()} ref {ns_ref.view(-1).tolist()}')
     torch.testing.assert_close(s.cpu(), ns_ref, rtol=3e-2, atol=0.3)
+
+
+def test_decoder_kv_cache_through_the_reference_seam():
+    """The cache the reference stubbed out (decoder/transformer.py:92-126,188-203), through its own seam:
+    decoder.inference(preds, memory, mask, cache) with cache = decoder.init_cache(...) runs one token per call, and
+    SpeechToTextRecognizer.decode_step reorders it by the surviving parents.  Must agree with the full-prefix recompute
+    (cache None, the reference's behaviour) and with the oracle in lock-step."""
+    params = _params(n_enc=1, n_dec=3)
+    model, sd = _build(params)
+    B, beam, max_len = 3, 4, 8
+    x, mask = _batch(B, 200, 80, [200, 150, 173])
+    rec = SpeechToTextRecognizer(model, beam_width=beam, nbest=1, max_len=max_len, penalty=0.6, lamda=5, ngpu=1)
+    memory, mmask, _, _ = rec.encode(x.to(DEV), mask.to(DEV))
+    T2 = memory.shape[1]
+    bm = memory.unsqueeze(1).repeat(1, beam, 1, 1).view(B * beam, T2, -1)
+    bmask = mmask.unsqueeze(1).repeat(1, beam, 1).view(B * beam, T2)
+    kw = om.decoder_kwargs(params)
+
+    def loop(cache):
+        preds = torch.ones(B * beam, 1, dtype=torch.long, device=DEV)
+        scores = torch.tensor([0.0] + [float('-inf')] * (beam - 1), device=DEV).repeat(B).unsqueeze(1)
+        flag = torch.zeros_like(scores, dtype=torch.bool)
+        with torch.no_grad():
+            for _ in range(max_len):
+                preds, cache, scores, flag = rec.decode_step(preds, bm, bmask, cache, scores, flag)
+        return preds, scores
+
+    with torch.no_grad():
+        dc = model.decoder.init_cache(bm, bmask, max_len, beam=beam)
+    p_c, s_c = loop({'decoder': dc})
+    p_f, s_f = loop({'decoder': None})
+    assert dc.step == max_len
+    same = int((p_c == p_f).all(dim=1).sum())
+    print(f'KV-cached seam vs full-prefix seam: {same}/{B * beam} hypotheses identical; 1-best scores {s_c.view(B, beam)[:, 0].tolist()} '
+          f'vs {s_f.view(B, beam)[:, 0].tolist()}')
+    torch.testing.assert_close(s_c, s_f, rtol=3e-2, atol=0.3)
+    assert torch.equal(p_c.view(B, beam, -1)[:, 0], p_f.view(B, beam, -1)[:, 0]), '1-best of the cached and the recomputing seam differ'
+    # lock-step with the oracle: cached log-probs of the seam drive the oracle's beam_step; ids must be bit-exact
+    with torch.no_grad():
+        dc = model.decoder.init_cache(bm, bmask, max_len, beam=beam)
+        preds = torch.ones(B * beam, 1, dtype=torch.long, device=DEV)
+        o_preds = preds.cpu()
+        o_scores = torch.tensor([0.0] + [float('-inf')] * (beam - 1)).repeat(B).unsqueeze(1)
+        o_flag = torch.zeros_like(o_scores, dtype=torch.bool)
+        for s in range(max_len):
+            lp, dc, _ = model.decoder.inference(preds, bm, bmask, dc)
+            lp_ref = om.decoder_inference(o_preds, bm.cpu(), bmask.cpu(), sd, 'decoder.', **kw)
+            alive = ~o_flag.view(-1)
+            assert _rel(lp.cpu()[alive][:, 2:], lp_ref[alive][:, 2:]) < REL_L2_LOGITS
+            tr = []
+            o_preds, o_scores, o_flag = obs.beam_step(lp.cpu(), o_preds, o_scores, o_flag, beam, trace=tr)
+            dc.reorder(tr[0]['parent'].to(DEV))        # rows the surviving hypotheses extend (speech2text.py:136)
+            preds = o_preds.to(DEV)

@@ -17,12 +17,12 @@ with torch.no_grad():
 x, mask = bench.synthetic_batch(32, 0)
 x, mask = x.to(dev), mask.to(dev)
 L = _lib.lib()
-names = ['start', 'S0 embed']
+names = ['start', 'embed']
 for l in range(6):
-    names += [f'L{l} ' + n for n in ('S1 qkv', 'S2 self-attn', 'bar1', 'S3 out-proj', 'bar2', 'LN1', 'S4 q-proj', 'S5 scores',
-                                     'S5 softmax', 'S5 PV', 'bar3', 'S6 out-proj2', 'bar4', 'LN2', 'S7 GLU', 'bar5', 'S8 w2',
-                                     'bar6', 'LN3')]
-names += ['S9 logits', 'partial lse', 'bar7', 'logp+topk', 'bar8', 'merge+beam']
+    names += [f'L{l} ' + n for n in ('qkv gemm', 'barrier', 'self-attn', 'barrier', 'out-proj', 'barrier', 'LN1 build', 'q-proj', 'barrier',
+                                     'cross-attn', 'barrier', 'out-proj2', 'barrier', 'LN2 build', 'w1+glu', 'w2 partial', 'barrier',
+                                     'reduce', 'barrier', 'LN3 build')]
+names += ['logits+topk', 'barrier', 'beam step', 'barrier']
 with torch.no_grad():
     mem, lens, B, T2 = model.encode_bf16(x, mask)
     bd = BeamDecoder(model.decoder, B, 10, T2, 60, dev, use_graph=False, persistent=True)
@@ -30,11 +30,11 @@ with torch.no_grad():
         buf = torch.zeros(512, dtype=torch.int64, device=dev)
         for rep in range(2):
             bd.setup(mem, lens)
-            L.otb_debug_mega_timing(ctypes.c_void_p(buf.data_ptr()) if rep == 1 else None, step)
+            L.otb_debug_decode_timing(ctypes.c_void_p(buf.data_ptr()) if rep == 1 else None, step)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); bd.run_persistent(60); e1.record()
             torch.cuda.synchronize()
-        L.otb_debug_mega_timing(None, 0)
+        L.otb_debug_decode_timing(None, 0)
         t = buf.cpu().tolist()
         n = len(names)
         print(f'=== step {step}: whole 60-step launch {e0.elapsed_time(e1):.2f} ms; step total {(t[n-1]-t[0])} cycles')
@@ -45,3 +45,4 @@ with torch.no_grad():
             agg[key] = agg.get(key, 0) + dt
         for k, v in agg.items():
             print(f'    {k:14s} {v:9d} cycles  {100.0 * v / (t[n-1]-t[0]):5.1f}%')
+        print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 22)])
