@@ -82,6 +82,19 @@ int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias
                float eps, float alpha, const float* table, int period, const int* row_len, int row_period,
                void* stream);
 
+/* Training-mode residual connection with nn.Dropout on the sub-layer output (encoder/transformer.py:32-33,54,61;
+ * decoder/transformer.py:36-38 `residual_dropout`): out bf16 = resid + alpha * keep * (a w^T + bias) / (1 - p), where
+ * keep(seed, site, row, col) is a counter-based Bernoulli(1-p) mask (csrc/dropout.cuh) -- a pure function of the per-step
+ * seed (*seed is read on the DEVICE at run time, so a captured CUDA graph draws a fresh mask per replay), the dropout
+ * site id and the element, so the backward replays it instead of storing it. */
+int otb_linear_dropout_resid(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldc, int M, int N,
+                             int K, const void* resid, int ldr, float alpha, float p, const uint32_t* seed, uint32_t site,
+                             void* stream);
+/* Backward of that dropout: out = dy * keep / (1 - p) (bf16 [M,N]); mask (optional, u8 [M,N]) receives keep -- with dy / out
+ * NULL this only exports the mask (parity tests replay it in the oracle). */
+int otb_dropout_bwd(const void* dy, int lddy, void* out, int ldo, uint8_t* mask, int M, int N, float p, const uint32_t* seed,
+                    uint32_t site, void* stream);
+
 /* Fused masked multi-head attention, d_k = 64 (attention.py:80,34-41): for batch b, head h
  *   out[b*Tq+i, h*64:(h+1)*64] = softmax_j((q_i . k_j + bd) / 8, j < kv_len[b], causal: j <= i) V
  * q/k/v are row-major bf16 matrices; batch b owns rows [b*Tq, (b+1)*Tq) of q and [b*Tk, (b+1)*Tk) of k,v;
@@ -254,6 +267,16 @@ int otb_adam_step(float* p, const float* g, float* m, float* v, long long n, con
 int otb_adam_step_sched(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float max_norm,
                         float base_lr, float model_size, float warmup_steps, float factor, float beta1, float beta2, float eps,
                         float weight_decay, int32_t* counters, float* hyper, void* stream);
+
+/* Joint-CTC loss of SpeechToText.forward (model/speech2text.py:60-72 -> CTCAssistor.compute_loss, model/ctc.py:48-52):
+ * nn.CTCLoss(blank, reduction 'mean', zero_infinity = True) and its gradient with respect to the LOGITS.
+ * logp f32 [B*T, ldl] = log_softmax of the assistor's logits (otb_log_softmax); in_len i32 [B] valid frames; targets i64
+ * [B, ldt] label rows (the first tgt_len[b] entries count); max_tgt >= every tgt_len (<= 64); nll f32 [B] per-utterance
+ * negative log-likelihood (+inf if infeasible); loss f32 [1]; ws f32 [B, T, 2 max_tgt + 1] scratch (alpha + beta);
+ * dlogits_bf16 (optional, bf16 [B*T, ldd]) = grad_scale * d loss / d logits (padded frames / infeasible utterances: 0). */
+int otb_ctc_loss(const float* logp, int ldl, int B, int T, int V, const int32_t* in_len, const int64_t* targets, int ldt,
+                 const int32_t* tgt_len, int max_tgt, int blank, float* nll, float* loss, float* ws, void* dlogits_bf16, int ldd,
+                 float grad_scale, void* stream);
 
 /* Conv2d front end backward (frontend/conv.py:50-76 under autograd).  h1 = conv1 activation buffer (layout of
  * otb_conv1_relu).  col bf16 [B*T2*F2, 9*C1] = im2col of h1 for conv2 (k = (kh*3+kw)*C1 + c): conv2's weight gradient is

@@ -3,6 +3,7 @@
 // (otrans/train/trainer.py:206-234: loss.backward(), clip_grad_norm_, optimizer.step()).
 #include <math.h>
 
+#include "dropout.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
 
@@ -198,6 +199,37 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const bf16* __restrict__ 
     for (int j = 0; j < 8; ++j) d[j] = v[j] > 0.f ? d[j] : 0.f;
     reinterpret_cast<uint4*>(dx)[i] = pack8(d);
 }
+// Backward of the residual dropout (and the mask export for tests): out[m,n] = dy[m,n] * keep(seed, site, m, n) / (1-p);
+// mask (optional, u8 [M,N]) receives keep.  Same pure function as the forward GEMM epilogue (dropout.cuh): nothing was stored.
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const bf16* __restrict__ dy, int lddy, bf16* __restrict__ out, int ldo,
+                                                          unsigned char* __restrict__ mask, int M, int N, unsigned thresh, float scale,
+                                                          const unsigned* __restrict__ seed_ptr, unsigned site) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(i / (N / 2)), cp = (int)(i % (N / 2));
+    if (row >= M) return;
+    const unsigned seed = *seed_ptr;
+    const bool k0 = drop_keep(seed, site, (uint32_t)row, (uint32_t)(2 * cp), thresh);
+    const bool k1 = drop_keep(seed, site, (uint32_t)row, (uint32_t)(2 * cp + 1), thresh);
+    if (mask) {
+        mask[(size_t)row * N + 2 * cp] = k0 ? 1 : 0;
+        mask[(size_t)row * N + 2 * cp + 1] = k1 ? 1 : 0;
+    }
+    if (dy) {
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (size_t)row * lddy + 2 * cp));
+        *reinterpret_cast<uint32_t*>(out + (size_t)row * ldo + 2 * cp) = pack_bf16(k0 ? v.x * scale : 0.f, k1 ? v.y * scale : 0.f);
+    }
+}
+const char* dropout_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, bf16* out, int ldo, unsigned char* mask, int M, int N, float p,
+                               const unsigned* seed, unsigned site) {
+    if (M < 1 || N < 2 || (N & 1) || (lddy & 1) || (ldo & 1)) return "dropout: N and the row pitches must be even";
+    if (!(p >= 0.f && p < 1.f)) return "dropout: p must be in [0, 1)";
+    if (!seed) return "dropout: null seed";
+    const size_t n = (size_t)M * (N / 2);
+    dropout_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, lddy, out, ldo, mask, M, N, drop_threshold(p), 1.0f / (1.0f - p), seed, site);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char* relu_bwd_launch(cudaStream_t st, const bf16* dy, const bf16* y, bf16* dx, size_t n) {
     if (n % 8) return "relu_bwd: n must be a multiple of 8";
     relu_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>(dy, y, dx, n / 8);

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "../../include/otb200.h"
+#include "dropout.cuh"
 #include "otb_internal.h"
 
 namespace otb {
@@ -142,6 +143,29 @@ int otb_linear(const void* a, int lda, const void* w, int ldw, const float* bias
     p.row_len = row_len; p.row_period = row_period;
     const int w_rows = (epilogue == EPI_GLU) ? 2 * N : N;
     RET("otb_linear", gemm_launch(ST(stream), a, lda, w, ldw, w_rows, epilogue, p, nullptr));
+}
+
+int otb_linear_dropout_resid(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
+                             const void* resid, int ldr, float alpha, float p_drop, const uint32_t* seed, uint32_t site, void* stream) {
+    if (!a || !w || !out || !resid || !seed) return fail("otb_linear_dropout_resid", "null operand");
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return fail("otb_linear_dropout_resid", "p must be in [0, 1)");
+    if (ldc < N) return fail("otb_linear_dropout_resid", "ldc < N");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.bias = bias;
+    p.out = out; p.ldc = ldc; p.out_f32 = 0;
+    p.resid = reinterpret_cast<const bf16*>(resid); p.ldr = ldr;
+    p.alpha = alpha;
+    p.drop_seed = seed; p.drop_site = site; p.drop_thresh = drop_threshold(p_drop); p.drop_scale = 1.0f / (1.0f - p_drop);
+    RET("otb_linear_dropout_resid", gemm_launch(ST(stream), a, lda, w, ldw, N, EPI_RESID, p, nullptr));
+}
+
+int otb_dropout_bwd(const void* dy, int lddy, void* out, int ldo, uint8_t* mask, int M, int N, float p, const uint32_t* seed,
+                    uint32_t site, void* stream) {
+    if ((!dy || !out) && !mask) return fail("otb_dropout_bwd", "nothing to do");
+    RET("otb_dropout_bwd", dropout_bwd_launch(ST(stream), reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<bf16*>(out), ldo, mask, M, N,
+                                              p, seed, site));
 }
 
 int otb_attention(const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows, const void* v, int ldv,
@@ -395,6 +419,15 @@ int otb_adam_step_sched(float* p, const float* g, float* m, float* v, long long 
     if (!p || !g || !m || !v || !sumsq || !counters || !hyper || n < 1) return fail("otb_adam_step_sched", "bad arguments");
     RET("otb_adam_step_sched", adam_sched_launch(ST(stream), p, g, m, v, (size_t)n, sumsq, max_norm, base_lr, model_size, warmup_steps,
                                                  factor, beta1, beta2, eps, weight_decay, counters, hyper));
+}
+
+int otb_ctc_loss(const float* logp, int ldl, int B, int T, int V, const int32_t* in_len, const int64_t* targets, int ldt,
+                 const int32_t* tgt_len, int max_tgt, int blank, float* nll, float* loss, float* ws, void* dlogits_bf16, int ldd,
+                 float grad_scale, void* stream) {
+    if (!logp || !in_len || !targets || !tgt_len || !nll || !loss || !ws) return fail("otb_ctc_loss", "null operand");
+    if (ldl < V || (dlogits_bf16 && ldd < V)) return fail("otb_ctc_loss", "row pitch < V");
+    RET("otb_ctc_loss", ctc_launch(ST(stream), logp, ldl, B, T, V, in_len, reinterpret_cast<const long long*>(targets), ldt, tgt_len, max_tgt,
+                                   blank, nll, loss, ws, reinterpret_cast<bf16*>(dlogits_bf16), ldd, grad_scale));
 }
 
 int otb_conv_im2col(const void* h1, void* col, int B, int T, int F, int C1, void* stream) {

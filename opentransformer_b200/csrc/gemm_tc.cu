@@ -25,6 +25,7 @@
 // round-robin tile scheduler, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <string.h>
 
+#include "dropout.cuh"
 #include "launch.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
@@ -500,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float* trow = nullptr;
                     if (EPI == EPI_TABLE)
                         trow = p.table + (size_t)((out_row >= 0 ? out_row : 0) % p.period) * p.N + col_base + c;
+                    const uint32_t dseed = (EPI == EPI_RESID && p.drop_seed != nullptr) ? *p.drop_seed : 0u;
                     float bv[16];
                     {
                         const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
@@ -518,6 +520,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (EPI == EPI_TANH) x = tanhf(x);
                         if (EPI == EPI_TABLE) x = x * p.alpha + ((c + i < ncols) ? __ldg(trow + i) : 0.f);
                         if (!row_live) x = 0.f;
+                        if (EPI == EPI_RESID && p.drop_seed != nullptr)   // nn.Dropout on the sub-layer output (transformer.py:54,61)
+                            x = drop_keep(dseed, p.drop_site, (uint32_t)out_row, (uint32_t)(col_base + c + i), p.drop_thresh) ? x * p.drop_scale : 0.f;
                         if (EPI == EPI_RESID) x = res[i] + p.alpha * x;
                         v[i] = x;
                     }

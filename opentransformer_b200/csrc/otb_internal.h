@@ -48,6 +48,10 @@ struct GemmParams {
     int conv_cchunks;  // C_in / 64
     int splitk;        // TN (weight-gradient) mode: number of contraction splits (fp32 atomics when > 1)
     int accum;         // TN mode: add into `out` instead of overwriting it
+    // training-mode dropout of the projection BEFORE the residual add (EPI_RESID only): out = resid + alpha * keep * (.) / (1-p)
+    const unsigned* drop_seed;    // device scalar, null = no dropout
+    unsigned drop_site, drop_thresh;
+    float drop_scale;
     unsigned long long* dbg;  // optional [grid][8] clock64 phase stamps (otb_debug_gemm_timing)
     int dbg_mode;             // 0 normal; 1 = no TMA traffic (MMA-only cadence); 2 = no MMA (TMA-only cadence)
 };
@@ -102,6 +106,8 @@ const char* layernorm_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, cons
                                  bf16* dz, int lddz, float* dgamma, float* dbeta, float eps, int M, int N, int accumulate);
 const char* glu_launch(cudaStream_t st, const bf16* u, const bf16* dh, bf16* out, int M, int F);
 const char* relu_bwd_launch(cudaStream_t st, const bf16* dy, const bf16* y, bf16* dx, size_t n);
+const char* dropout_bwd_launch(cudaStream_t st, const bf16* dy, int lddy, bf16* out, int ldo, unsigned char* mask, int M, int N, float p,
+                               const unsigned* seed, unsigned site);
 const char* embed_bwd_launch(cudaStream_t st, const long long* tok, const bf16* dx, float* dE, int N, int d, int vocab, float scale);
 const char* im2col_s2_launch(cudaStream_t st, const bf16* h1, bf16* col, int B, int T2, int F2, int C);
 const char* col2im_s2_relu_launch(cudaStream_t st, const bf16* dcol, const bf16* h1, bf16* dpre1, int B, int T1, int F1, int T2,
@@ -220,6 +226,10 @@ const char* beam_finalize_launch(cudaStream_t stream, BeamState st, float penalt
 const char* ls_ce_launch(cudaStream_t st, const float* logits, int ldl, const long long* tgt, int rows, int V, float eps,
                          int pad_id, float* tok_loss, float* loss, int* n_valid, float* dlogits, int ldd,
                          bf16* dlogits_bf16 = nullptr);
+
+const char* ctc_launch(cudaStream_t st, const float* logp, int ldl, int B, int T, int V, const int* in_len, const long long* targets,
+                       int ldt, const int* tgt_len, int max_tgt, int blank, float* nll, float* loss, float* ws, bf16* dlogits, int ldd,
+                       float grad_scale);
 
 int num_sms();
 extern unsigned long long* g_gemm_dbg;

@@ -134,6 +134,43 @@ def linear(a, w, bias=None, epilogue=EPI_BIAS, out=None, out_f32=False, resid=No
     return out
 
 
+def linear_dropout_resid(a, w, bias, resid, p, seed, site, alpha=1.0, out=None):
+    """out = resid + alpha * dropout_p(a @ w^T + bias): training-mode residual connection (otb_linear_dropout_resid).
+    seed: int32/uint32 device tensor [1] (read at run time), site: dropout site id."""
+    for t, n in ((a, 'a'), (w, 'w'), (resid, 'resid')):
+        if not t.is_cuda or t.dtype != BF16 or t.dim() != 2 or t.stride(1) != 1:
+            raise TypeError(f'{n} must be a 2-D bf16 CUDA tensor with unit column stride')
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    check(_lib.lib().otb_linear_dropout_resid(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), M, N, K,
+                                              _p(resid), resid.stride(0), alpha, float(p), _p(seed), int(site), _stream()),
+          'otb_linear_dropout_resid')
+    _count()
+    return out
+
+
+def dropout_bwd(dy, p, seed, site):
+    """dy * keep / (1 - p) with the mask of dropout site `site` replayed from (seed, site)."""
+    _need(dy, BF16, 'dy')
+    M, N = dy.shape
+    out = torch.empty_like(dy)
+    check(_lib.lib().otb_dropout_bwd(_p(dy), dy.stride(0), _p(out), out.stride(0), None, M, N, float(p), _p(seed), int(site),
+                                     _stream()), 'otb_dropout_bwd')
+    _count()
+    return out
+
+
+def dropout_mask(M, N, p, seed, site):
+    """u8 [M,N] keep mask of a dropout site (parity tests replay it in the oracle)."""
+    mask = torch.empty(M, N, dtype=torch.uint8, device=seed.device)
+    check(_lib.lib().otb_dropout_bwd(None, 0, None, 0, _p(mask), M, N, float(p), _p(seed), int(site), _stream()),
+          'otb_dropout_bwd')
+    _count()
+    return mask
+
+
 def attention(q, k, v, B, H, Tq, Tk, kv_len=None, causal=False, q_col0=0, k_col0=0, v_col0=0, out=None, bd=None,
               resid=None):
     """q/k/v: bf16 2-D matrices (may be the same [M,3d] buffer with different column offsets)."""
@@ -485,6 +522,27 @@ def adam_step_sched(p, g, m, v, sumsq_buf, max_norm, base_lr, model_size, warmup
                                          float(model_size), float(warmup_steps or 0), factor, betas[0], betas[1], eps,
                                          weight_decay, _p(counters), _p(hyper), _stream()), 'otb_adam_step_sched')
     _count(2)
+
+
+def ctc_loss(logits, B, T, V, in_len, targets, tgt_len, blank=0, want_grad=False, grad_scale=1.0):
+    """nn.CTCLoss(blank, 'mean', zero_infinity=True) on logits f32 [B*T, ld] (model/ctc.py:48-52).
+    -> (loss 0-d, nll f32 [B], dlogits bf16 [B*T, ld] or None)."""
+    _need(logits, torch.float32, 'logits'); _need(in_len, torch.int32, 'in_len'); _need(tgt_len, torch.int32, 'tgt_len')
+    targets = targets.contiguous()
+    dev = logits.device
+    ld = logits.stride(0)
+    logp = torch.empty(B * T, ld, dtype=torch.float32, device=dev)
+    check(_lib.lib().otb_log_softmax(_p(logits), ld, _p(logp), ld, B * T, V, _stream()), 'otb_log_softmax')
+    max_tgt = targets.shape[1]
+    nll = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = torch.empty(B, T, 2 * max_tgt + 1, dtype=torch.float32, device=dev)
+    dl = torch.empty(B * T, ld, dtype=BF16, device=dev) if want_grad else None
+    check(_lib.lib().otb_ctc_loss(_p(logp), ld, B, T, V, _p(in_len), _p(targets), targets.stride(0), _p(tgt_len), max_tgt, blank,
+                                  _p(nll), _p(loss), _p(ws), _p(dl), ld if want_grad else 0, float(grad_scale), _stream()),
+          'otb_ctc_loss')
+    _count(4 if want_grad else 3)
+    return loss[0], nll, dl
 
 
 def conv_im2col(h1, B, T, F, C1):

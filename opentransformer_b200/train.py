@@ -11,10 +11,10 @@ otb_attention_bwd) and everything else on the HBM-bound backward kernels (csrc/b
 node is `_SpeechToTextLoss`, which makes `model(inputs, targets)[0].backward()` populate `.grad` of the fp32 master
 parameters exactly like the reference module.
 
-Scope (round 1): the shipped Speech-Transformer configuration -- conv front end, post-norm Transformer encoder /
-decoder with GLU feed-forward, tied or untied output layer, all dropout rates 0 (the reference's residual_dropout is
-stochastic; gradient parity is defined without it).  Conformer / pre-norm training is not
-built yet and raises.
+Scope: the shipped Speech-Transformer configuration -- conv front end, post-norm Transformer encoder / decoder with GLU
+feed-forward, tied or untied output layer, `residual_dropout` as shipped (0.1: counter-based masks in the residual GEMM's
+epilogue, replayed in the backward; csrc/dropout.cuh); the other dropout rates must be 0 (as shipped) and raise
+otherwise.  Conformer / pre-norm training is not built yet and raises.
 """
 import math
 
@@ -53,12 +53,14 @@ class TrainPack:
             if blk.feed_forward.activation != 'glu':
                 raise NotImplementedError('training path: GLU feed-forward only (round 1)')
             rates = getattr(blk, 'dropout_rates', {})
-            if any(float(v) > 0.0 for v in rates.values()):
-                # the reference applies these in train mode (encoder/transformer.py:32-33,54,61; decoder/transformer.py:36-38);
-                # training WITHOUT them would be a different network, so refuse instead of silently dropping the regulariser
-                raise NotImplementedError(
-                    f'training path: dropout is not implemented on the sm_100a backward yet, got {rates}; '
-                    'set residual_dropout / slf_attn_dropout / src_attn_dropout / ffn_dropout to 0.0')
+            other = {k: v for k, v in rates.items() if k != 'residual_dropout' and float(v) > 0.0}
+            if other:
+                # the reference applies these in train mode (attention.py:45, ffn.py:40); training WITHOUT them would be a
+                # different network, so refuse instead of silently dropping the regulariser.  residual_dropout -- the only
+                # non-zero rate of the shipped configs -- IS implemented (otb_linear_dropout_resid / otb_dropout_bwd).
+                raise NotImplementedError(f'training path: only residual_dropout is implemented, got {other}; set them to 0.0')
+            if not (0.0 <= float(rates.get('residual_dropout', 0.0)) < 1.0):
+                raise ValueError('residual_dropout must be in [0, 1)')
         self.fe = self._frontend(fe)
         self.enc = [self._enc_layer(b) for b in enc.blocks]
         self.dec = [self._dec_layer(b) for b in dec.blocks]
@@ -140,14 +142,49 @@ def _linear_bwd(dy, x, wt, grads, wname, bname, resid=None):
     return ops.linear(dy, wt)
 
 
+ENC_SITE, DEC_SITE = 0, 1000      # dropout site ids: encoder layer i -> 2 i + {0, 1}; decoder layer i -> 1000 + 3 i + {0, 1, 2}
+
+
+def dropout_sites(model):
+    """[(site id, 'encoder' | 'decoder', rate)] of every residual-dropout site (what a parity test must replay)."""
+    out = []
+    for i, b in enumerate(model.encoder.blocks):
+        out += [(ENC_SITE + 2 * i + k, 'encoder', float(b.dropout_rates['residual_dropout'])) for k in range(2)]
+    for i, b in enumerate(model.decoder.blocks):
+        out += [(DEC_SITE + 3 * i + k, 'decoder', float(b.dropout_rates['residual_dropout'])) for k in range(3)]
+    return out
+
+
+def _resid(ctx, w, b, x, rate, seed, site):
+    """x + dropout(ctx W^T + b): the residual connection of a sub-layer in training mode (transformer.py:54,61)."""
+    if rate > 0.0:
+        return ops.linear_dropout_resid(ctx, w, b, x, rate, seed, site)
+    return ops.linear(ctx, w, b, EPI_RESID, resid=x)
+
+
+def _drop_bwd(dz, rate, seed, site):
+    return ops.dropout_bwd(dz, rate, seed, site) if rate > 0.0 else dz
+
+
 def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True, grad_sink=None, grad_scale=1.0,
-                     bf16_of=None):
+                     bf16_of=None, drop_seed=None, truth_length=None, return_ctc=False):
     """One forward (+ backward) pass.  inputs f32 [B,T,F], mask bool [B,T], truth i64 [B,L+1] (BOS ... EOS PAD*).
     Returns (loss 0-d f32 tensor, {parameter name -> fp32 gradient}) with names as in model.named_parameters().
-    grad_sink: name -> fp32 tensor the gradients (x grad_scale) are ADDED into (gradient accumulation buffer)."""
+    grad_sink: name -> fp32 tensor the gradients (x grad_scale) are ADDED into (gradient accumulation buffer).
+    drop_seed: int32 device tensor [1], the dropout seed of THIS pass (read on the device); required when any
+    residual_dropout rate is non-zero.  truth_length: i32/i64 [B] label counts incl. <S/E> (targets['targets_length'],
+    data/loader.py:94) -- required when model.ctc_weight > 0: the loss is then (1 - w) * attention + w * CTC
+    (model/speech2text.py:60-62) and the CTC head's gradients flow into the encoder through the memory."""
     fe, enc, dec = model.frontend, model.encoder, model.decoder
+    ctc_w = float(getattr(model, 'ctc_weight', 0.0) or 0.0)
+    if ctc_w > 0.0 and truth_length is None:
+        raise ValueError('forward_backward: ctc_weight > 0 needs truth_length')
     pk = TrainPack(model, bf16_of)
     dev = inputs.device
+    e_rates = [float(b.dropout_rates['residual_dropout']) for b in enc.blocks]
+    d_rates = [float(b.dropout_rates['residual_dropout']) for b in dec.blocks]
+    if drop_seed is None and any(r > 0.0 for r in e_rates + d_rates):
+        raise ValueError('forward_backward: residual_dropout > 0 needs a drop_seed tensor')
     B, T, F = inputs.shape
     H, d = enc.blocks[0].n_heads, enc.d_model
     x_in = inputs.contiguous().float()
@@ -163,14 +200,14 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     scale, table = enc.pos_emb.scale_and_table(T2, dev)
     x = ops.linear(h2, fpk['wo'], fpk['bo'], EPI_TABLE, alpha=scale, table=table, period=T2)
     enc_tape = []
-    for p in pk.enc:
+    for i, p in enumerate(pk.enc):
         qkv = ops.linear(x, p['qkv'][0], p['qkv'][2])
         ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
-        z1 = ops.linear(ctx, p['o'][0], p['o'][2], EPI_RESID, resid=x)
+        z1 = _resid(ctx, p['o'][0], p['o'][2], x, e_rates[i], drop_seed, ENC_SITE + 2 * i)
         x1 = ops.layernorm(z1, *p['ln1'])
         u = ops.linear(x1, p['w1'][0], p['w1'][2])
         h = ops.glu_fwd(u)
-        z2 = ops.linear(h, p['w2'][0], p['w2'][2], EPI_RESID, resid=x1)
+        z2 = _resid(h, p['w2'][0], p['w2'][2], x1, e_rates[i], drop_seed, ENC_SITE + 2 * i + 1)
         enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, z2))
         x = ops.layernorm(z2, *p['ln2'])
     mem = x
@@ -182,30 +219,41 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     _, dtable = dec.pos_emb.scale_and_table(L, dev)
     y = ops.embed_posenc(tgt_in, pk.out['emb'], dtable, B * L, d, period=L)
     dec_tape = []
-    for p in pk.dec:
+    for i, p in enumerate(pk.dec):
         qkv = ops.linear(y, p['qkv'][0], p['qkv'][2])
         ctx, lse = ops.attention_train(qkv, qkv, qkv, B, Hd, L, L, causal=True, q_col0=0, k_col0=d, v_col0=2 * d)
-        z1 = ops.linear(ctx, p['o'][0], p['o'][2], EPI_RESID, resid=y)
+        z1 = _resid(ctx, p['o'][0], p['o'][2], y, d_rates[i], drop_seed, DEC_SITE + 3 * i)
         y1 = ops.layernorm(z1, *p['ln1'])
         q = ops.linear(y1, p['q'][0], p['q'][2])
         kv = ops.linear(mem, p['kv'][0], p['kv'][2])
         ctx2, lse2 = ops.attention_train(q, kv, kv, B, Hd, L, T2, kv_len=lengths, k_col0=0, v_col0=d)
-        z2 = ops.linear(ctx2, p['o2'][0], p['o2'][2], EPI_RESID, resid=y1)
+        z2 = _resid(ctx2, p['o2'][0], p['o2'][2], y1, d_rates[i], drop_seed, DEC_SITE + 3 * i + 1)
         y2 = ops.layernorm(z2, *p['ln2'])
         u = ops.linear(y2, p['w1'][0], p['w1'][2])
         h = ops.glu_fwd(u)
-        z3 = ops.linear(h, p['w2'][0], p['w2'][2], EPI_RESID, resid=y2)
+        z3 = _resid(h, p['w2'][0], p['w2'][2], y2, d_rates[i], drop_seed, DEC_SITE + 3 * i + 2)
         dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3))
         y = ops.layernorm(z3, *p['ln3'])
     V = dec.vocab_size
     logits = ops.linear(y, pk.out['wout'], pk.out['bout'], EPI_BIAS, out_f32=True, n_out=pk.ld_logits)
     sm = model.smoothing if smoothing is None else smoothing
+    loss_ctc, dctc = None, None
+    if ctc_w > 0.0:     # CTCAssistor on the encoder states (model/ctc.py:33-52)
+        wc = pk._w(model.assistor.output_layer.weight)
+        ctc_logits = ops.linear(mem, wc, _f(model.assistor.output_layer.bias), EPI_BIAS, out_f32=True, n_out=model.assistor.ld_logits)
+        loss_ctc, _, dctc = ops.ctc_loss(ctc_logits, B, T2, V, lengths, tgt_out, truth_length.to(torch.int32).to(dev).contiguous(),
+                                         model.assistor.blank, want_grad=want_grads, grad_scale=ctc_w * grad_scale)
     if not want_grads:
         loss, _ = ops.ls_cross_entropy(logits, tgt_out, V, sm)
-        return loss, None
+        if ctc_w > 0.0:
+            loss = (1.0 - ctc_w) * loss + ctc_w * loss_ctc
+        return (loss, None, loss_ctc) if return_ctc else (loss, None)
     loss, dlogits = ops.ls_cross_entropy_train(logits, tgt_out, V, sm)
-    if grad_scale != 1.0:
-        dlogits = ops.scale_add_table(dlogits, grad_scale)                       # loss / accum_steps (trainer.py:216)
+    att_scale = grad_scale * (1.0 - ctc_w)
+    if att_scale != 1.0:
+        dlogits = ops.scale_add_table(dlogits, att_scale)                        # loss / accum_steps (trainer.py:216), x (1 - w)
+    if ctc_w > 0.0:
+        loss = (1.0 - ctc_w) * loss + ctc_w * loss_ctc
 
     # ------------------------------------------------------------------ backward
     g = _Grads(grad_sink)
@@ -219,12 +267,14 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     for i in reversed(range(len(pk.dec))):
         p, pre = pk.dec[i], f'decoder.blocks.{i}.'
         (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3) = dec_tape[i]
+        rt, st0 = d_rates[i], DEC_SITE + 3 * i
         dz3 = _ln_bwd(dy, z3, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
-        dh = _linear_bwd(dz3, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+        # the sub-layer branch sees the replayed dropout mask, the residual branch (resid= below) the plain gradient
+        dh = _linear_bwd(_drop_bwd(dz3, rt, drop_seed, st0 + 2), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
         du = ops.glu_bwd(dh, u)
         dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz3)
         dz2 = _ln_bwd(dy2, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
-        dctx2 = _linear_bwd(dz2, ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
+        dctx2 = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         ops.attention_bwd(q, kv, kv, ctx2, dctx2, lse2, B, Hd, L, T2, dq, dkv, dkv, kv_len=lengths, k_col0=0, v_col0=d,
@@ -232,7 +282,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         dmem = _linear_bwd(dkv, mem, p['kv'][1], g, pre + 'src_attn.vk_proj.weight', pre + 'src_attn.vk_proj.bias', resid=dmem)
         dy1 = _linear_bwd(dq, y1, p['q'][1], g, pre + 'src_attn.q_proj.weight', pre + 'src_attn.q_proj.bias', resid=dz2)
         dz1 = _ln_bwd(dy1, z1, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
-        dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+        dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, Hd, L, L, dqkv, dqkv, dqkv, causal=True, q_col0=0, k_col0=d,
                           v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
@@ -250,15 +300,23 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         g['decoder.embedding.weight'] = demb
 
     dx = dmem
+    if ctc_w > 0.0:     # CTC head: parameter gradients, and its gradient with respect to the memory joins the decoder's
+        wname_c = 'assistor.output_layer.weight'
+        g[wname_c] = ops.linear_wgrad(dctc[:, :V], mem, out=g.out(wname_c), accumulate=acc)
+        g.put('assistor.output_layer.bias', ops.colsum(dctc)[:V])
+        wc_t = torch.zeros(d, dctc.shape[1], dtype=BF16, device=dev)
+        wc_t[:, :V] = wc.t()
+        dx = ops.linear(dctc, wc_t, None, EPI_RESID, resid=dmem)
     for i in reversed(range(len(pk.enc))):
         p, pre = pk.enc[i], f'encoder.blocks.{i}.'
         (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
+        rt, st0 = e_rates[i], ENC_SITE + 2 * i
         dz2 = _ln_bwd(dx, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
-        dh = _linear_bwd(dz2, h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+        dh = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
         du = ops.glu_bwd(dh, u)
         dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz2)
         dz1 = _ln_bwd(dx1, z1, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
-        dctx = _linear_bwd(dz1, ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+        dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, H, T2, T2, dqkv, dqkv, dqkv, kv_len=lengths, q_col0=0, k_col0=d,
                           v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
@@ -283,18 +341,24 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     g1 = ops.conv1_wgrad(dpre1, x_in, B, T, F, C1p)                               # [C1p, 9 taps + bias]
     g.put('frontend.conv1.conv_layer.weight', g1[:C1, :9].reshape(C1, 1, 3, 3))
     g.put('frontend.conv1.conv_layer.bias', g1[:C1, 9])
-    return loss, g
+    return (loss, g, loss_ctc) if return_ctc else (loss, g)
 
 
 class _SpeechToTextLoss(torch.autograd.Function):
     """loss = SpeechToText.forward(...) as ONE autograd node over the fp32 master parameters."""
 
     @staticmethod
-    def forward(ctx, model, inputs, mask, truth, names, *params):
+    def forward(ctx, model, inputs, mask, truth, tlen, names, *params):
         with torch.no_grad():
-            loss, grads = forward_backward(model, inputs, mask, truth)
+            seed = getattr(model, '_drop_seed', None)
+            if seed is None or seed.device != inputs.device:      # a fresh dropout mask per training forward
+                seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(inputs.device)
+                model._drop_seed = seed
+            seed.add_(1)
+            loss, grads, ctc = forward_backward(model, inputs, mask, truth, drop_seed=seed, truth_length=tlen, return_ctc=True)
         ctx.grads = [grads.get(n) for n in names]
         ctx.shapes = [p.shape for p in params]
+        model._last_ctc_loss = ctc
         return loss.clone()
 
     @staticmethod
@@ -302,14 +366,15 @@ class _SpeechToTextLoss(torch.autograd.Function):
         out = []
         for gr, shp in zip(ctx.grads, ctx.shapes):
             out.append(None if gr is None else (gr.view(shp) * gloss))
-        return (None, None, None, None, None) + tuple(out)
+        return (None, None, None, None, None, None) + tuple(out)
 
 
-def loss_with_grad(model, inputs, mask, truth):
-    """Training-mode SpeechToText.forward: a loss tensor whose .backward() fills `.grad` of every parameter."""
+def loss_with_grad(model, inputs, mask, truth, truth_length=None):
+    """Training-mode SpeechToText.forward: (loss tensor whose .backward() fills `.grad` of every parameter, CTC loss or None)."""
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
     names = [n for n, _ in named]
-    return _SpeechToTextLoss.apply(model, inputs, mask, truth, names, *[p for _, p in named])
+    loss = _SpeechToTextLoss.apply(model, inputs, mask, truth, truth_length, names, *[p for _, p in named])
+    return loss, getattr(model, '_last_ctc_loss', None)
 
 
 def transformer_lr(step, model_size, warmup_steps, factor=1.0):
@@ -357,6 +422,9 @@ class FusedTrainer:
         self.counters = torch.tensor([0, 2, 0], dtype=torch.int32, device=dev)
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
         self.micro = 0
+        # dropout seed of the current micro-step, on the device: incremented inside the (captured) micro-step, so every
+        # CUDA-graph replay draws fresh masks (a seed passed by value would be frozen into the graph)
+        self.drop_seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32).to(dev)
         self.use_graph = use_graph
         self.graph_after = 2          # capture a CUDA graph for an input geometry once it has been seen this many times
         self.max_graphs = 8           # LRU bound: every graph owns a private pool with the whole activation tape
@@ -384,15 +452,16 @@ class FusedTrainer:
         (o, k), shape = self._by_ptr[param.data_ptr()]
         return self.flat_bf16[o:o + k].view(shape)
 
-    def _micro(self, inputs, mask, truth):
+    def _micro(self, inputs, mask, truth, tlen=None):
         """forward + backward of one micro-batch; gradients / accum_steps are ADDED into the flat buffer by the backward
         kernels themselves (no per-parameter add)."""
         self.flat_bf16.copy_(self.flat_p)
+        self.drop_seed.add_(1)
         loss, _ = forward_backward(self.model, inputs, mask, truth, grad_sink=self.sink, grad_scale=1.0 / self.accum_steps,
-                                   bf16_of=self._bf16_of)
+                                   bf16_of=self._bf16_of, drop_seed=self.drop_seed, truth_length=tlen)
         return loss
 
-    def _graph_for(self, inputs, mask, truth):
+    def _graph_for(self, inputs, mask, truth, tlen=None):
         """The ~870 launches of one micro-batch captured once per input geometry and replayed: launched one by one from
         Python the step is host-bound (14.6 ms against 10.2 ms of kernel time, profiles/r1_launches_train_v0.csv).
         Real ASR batches have a new (T, L) almost every step, so a geometry runs EAGERLY until it has recurred
@@ -411,37 +480,41 @@ class FusedTrainer:
             while len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))        # drops the graph and its memory pool
             sx, sm, st = inputs.clone(), mask.clone(), truth.clone()
+            stl = tlen.to(torch.int32).to(inputs.device).clone() if tlen is not None else None
             snap = self.flat_g.clone()
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):          # warm-up outside capture: lazy kernel attributes, cached tables
-                self._micro(sx, sm, st)
+                self._micro(sx, sm, st, stl)
             cur.wait_stream(side)
             self.flat_g.copy_(snap)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.COUNTERS['launches']
             with torch.cuda.graph(graph):
-                loss = self._micro(sx, sm, st)
+                loss = self._micro(sx, sm, st, stl)
             launches = ops.COUNTERS['launches'] - n0
             ops.COUNTERS['launches'] = n0           # capture records, it does not launch
-            ent = (graph, sx, sm, st, loss, launches)
+            ent = (graph, sx, sm, st, loss, launches, stl)
         self._graphs[key] = ent       # (re-)insert as most recently used
         return ent
 
-    def step(self, inputs, mask, truth):
-        """One micro-batch; every `accum_steps` calls an optimizer step.  Returns the (un-scaled) loss tensor."""
+    def step(self, inputs, mask, truth, truth_length=None):
+        """One micro-batch; every `accum_steps` calls an optimizer step.  Returns the (un-scaled) loss tensor.
+        truth_length (targets['targets_length']) is needed by joint-CTC models only."""
         with torch.no_grad():
-            ent = self._graph_for(inputs, mask, truth) if self.use_graph else None
+            ent = self._graph_for(inputs, mask, truth, truth_length) if self.use_graph else None
             if ent is not None:
-                graph, sx, sm, st, loss, launches = ent
+                graph, sx, sm, st, loss, launches, stl = ent
                 sx.copy_(inputs)
                 sm.copy_(mask)
                 st.copy_(truth)
+                if stl is not None:
+                    stl.copy_(truth_length)
                 graph.replay()
                 ops.COUNTERS['launches'] += launches
             else:
-                loss = self._micro(inputs, mask, truth)
+                loss = self._micro(inputs, mask, truth, truth_length)
             self.micro += 1
             if self.micro % self.accum_steps == 0:
                 # the one exchange step of data-parallel training (SURVEY.md 8e): mean of the flat gradient over ranks,

@@ -37,6 +37,22 @@ def _r(x, policy):
     return x
 
 
+# Training-mode residual dropout (encoder/transformer.py:32-33,54,61; decoder/transformer.py:36-38).  torch's own Philox
+# masks cannot be reproduced by another implementation, so parity tests REPLAY the product's masks: set_dropout(fn) installs
+# fn(site, tensor) -> tensor (e.g. tensor * keep / (1 - p)); None (default) = eval mode / rate 0.  Sites: 'encoder.blocks.i'
+# x {0: after self-attention, 1: after the feed-forward}, 'decoder.blocks.i' x {0, 1, 2} (self, cross, feed-forward).
+_DROP = None
+
+
+def set_dropout(fn):
+    global _DROP
+    _DROP = fn
+
+
+def _drop(prefix, k, t):
+    return t if _DROP is None else _DROP((prefix, k), t)
+
+
 def linear(x, sd, prefix, policy=None, bias=True):
     """nn.Linear: x @ W^T + b (operands optionally bf16-rounded, fp32 accumulate)."""
     w = sd[prefix + '.weight']
@@ -231,13 +247,13 @@ def transformer_encoder_layer(x, mask, pos, sd, prefix, n_heads, activation, nor
         a, _ = mha_self_relpos(_r(x, policy), mask, pos, sd, prefix + '.slf_attn', n_heads, policy)
     else:
         a, _ = mha_self(_r(x, policy), mask, sd, prefix + '.slf_attn', n_heads, policy)
-    x = res + a
+    x = res + _drop(prefix, 0, a)
     if not normalize_before:
         x = layer_norm(x, sd, prefix + '.norm1')
     if normalize_before:
         x = layer_norm(x, sd, prefix + '.norm2')
     res = x
-    x = res + ffn(_r(x, policy), sd, prefix + '.feed_forward', activation, policy)
+    x = res + _drop(prefix, 1, ffn(_r(x, policy), sd, prefix + '.feed_forward', activation, policy))
     if not normalize_before:
         x = layer_norm(x, sd, prefix + '.norm2')
     return _r(x, policy)
@@ -352,20 +368,20 @@ def transformer_decoder(targets, memory, memory_mask, sd, prefix, n_blocks, n_he
             x = layer_norm(x, sd, p + '.norm1')
         res = x
         a, _ = mha_self(_r(x, policy), causal, sd, p + '.slf_attn', n_heads, policy)
-        x = res + a
+        x = res + _drop(p, 0, a)
         if not normalize_before:
             x = layer_norm(x, sd, p + '.norm1')
         if normalize_before:
             x = layer_norm(x, sd, p + '.norm2')
         res = x
         a, _ = mha_cross(_r(x, policy), memory, mm, sd, p + '.src_attn', n_heads, policy)
-        x = res + a
+        x = res + _drop(p, 1, a)
         if not normalize_before:
             x = layer_norm(x, sd, p + '.norm2')
         if normalize_before:
             x = layer_norm(x, sd, p + '.norm3')
         res = x
-        x = res + ffn(_r(x, policy), sd, p + '.feed_forward', activation, policy)
+        x = res + _drop(p, 2, ffn(_r(x, policy), sd, p + '.feed_forward', activation, policy))
         if not normalize_before:
             x = layer_norm(x, sd, p + '.norm3')
         x = _r(x, policy)
@@ -447,9 +463,26 @@ def decoder_kwargs(params):
                 normalize_before=dp.get('normalize_before', True))
 
 
-def model_forward_loss(inputs, mask, truth, sd, params, policy=None):
-    """SpeechToText.forward (model/speech2text.py:39-58): loss of decoder(truth[:, :-1]) vs truth[:, 1:]."""
+def ctc_loss(memory, memory_mask, targets_out, targets_length, sd, prefix='assistor.', blank=0, policy=None):
+    """SpeechToText.compute_ctc_loss -> CTCAssistor.forward (model/speech2text.py:66-69, model/ctc.py:33-52):
+    nn.CTCLoss(blank, reduction 'mean', zero_infinity=True) on log_softmax(output_layer(memory)), lengths from the mask."""
+    logits = linear(memory, sd, prefix + 'output_layer', policy)
+    log_probs = F.log_softmax(logits, dim=-1)
+    mem_len = memory_mask.sum(dim=-1)
+    return F.ctc_loss(log_probs.transpose(0, 1), targets_out, mem_len, targets_length, blank=blank, reduction='mean',
+                      zero_infinity=True)
+
+
+def model_forward_loss(inputs, mask, truth, sd, params, policy=None, truth_length=None, return_parts=False):
+    """SpeechToText.forward (model/speech2text.py:39-64): loss of decoder(truth[:, :-1]) vs truth[:, 1:]; with
+    ctc_weight > 0 mixed with the joint-CTC loss of the encoder states, (1 - w) * att + w * ctc."""
     memory, mmask = encode(inputs, mask, sd, params, policy)
     logits = transformer_decoder(truth[:, :-1], memory, mmask, sd, 'decoder.', policy=policy,
                                  **decoder_kwargs(params))
-    return label_smoothing_loss(logits, truth[:, 1:], params.get('smoothing', 0.1)), logits
+    loss = label_smoothing_loss(logits, truth[:, 1:], params.get('smoothing', 0.1))
+    w = params.get('ctc_weight', 0.0)
+    if w > 0:
+        lc = ctc_loss(memory, mmask, truth[:, 1:], truth_length, sd, policy=policy)
+        total = (1 - w) * loss + w * lc
+        return (total, logits, lc) if return_parts else (total, logits)
+    return (loss, logits, None) if return_parts else (loss, logits)

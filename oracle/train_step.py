@@ -15,14 +15,14 @@ from . import speech_model as om
 TIED = ('decoder.embedding.weight', 'decoder.output_layer.weight')
 
 
-def loss_and_grads(x, mask, truth, sd, params):
+def loss_and_grads(x, mask, truth, sd, params, truth_length=None):
     """-> (loss, {name: grad}) with the reference's parameter names; a tied output layer contributes to
     'decoder.embedding.weight' (decoder/transformer.py:156-158) and has no entry of its own."""
     leaf = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
     tied = params['decoder'].get('share_embedding', False)
     if tied:
         leaf[TIED[1]] = leaf[TIED[0]]
-    loss, _ = om.model_forward_loss(x, mask, truth, leaf, params)
+    loss, _ = om.model_forward_loss(x, mask, truth, leaf, params, truth_length=truth_length)
     loss.backward()
     grads = {}
     for k, v in leaf.items():

@@ -226,9 +226,58 @@ def train_case():
     print('train_step', os.path.getsize(path) // 1024, 'KiB loss', float(loss), 'grad_norm', float(grad_norm), 'lr', sched.lr)
 
 
+def ctc_case():
+    """Joint-CTC training forward + backward through the REAL reference (model/speech2text.py:30-36,60-72 -> CTCAssistor,
+    model/ctc.py:12-52): loss = (1 - w) * attention loss + w * nn.CTCLoss(blank 0, zero_infinity) and every gradient."""
+    params = small_params('transformer')
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k in list(params[part]):
+            if 'dropout' in k:
+                params[part][k] = 0.0
+    params['ctc_weight'] = 0.3
+    params['encoder_output_size'] = params['encoder']['d_model']
+    torch.manual_seed(1234)
+    model = End2EndModel['speech2text'](params)
+    model.train()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'norm' in n:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith('.bias'):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        model.decoder.embedding.weight.mul_(0.12)
+    x, mask = make_batch(0, 3, 90, params['frontend']['input_size'], [90, 61, 74])
+    gt = torch.Generator().manual_seed(3)
+    tgt = torch.randint(3, params['decoder']['vocab_size'], (3, 9), generator=gt)
+    tgt[:, 0] = 1
+    tgt[0, 7:] = torch.tensor([1, 0])
+    tgt[1, 5:] = torch.tensor([1, 0, 0, 0])
+    tgt[2, 8] = 1
+    tgt[2, 3] = tgt[2, 2]                      # a repeated label: CTC must pass through the blank between them
+    tlen = torch.tensor([7, 5, 8], dtype=torch.int32)      # labels incl. <S/E> (collate: targets_length + 1, data/loader.py:94)
+    sd = {}
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k, v in getattr(model, part).state_dict().items():
+            sd[f'{part}.{k}'] = v.clone()
+    for k, v in model.assistor.state_dict().items():
+        sd[f'assistor.{k}'] = v.clone()
+    loss, aux = model({'inputs': x, 'mask': mask}, {'targets': tgt, 'targets_length': tlen})
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    out = {'params': params, 'state_dict': sd, 'x': x, 'mask': mask, 'targets': tgt, 'targets_length': tlen,
+           'loss': loss.detach(), 'ctc_loss': torch.as_tensor(aux['CTCLoss']), 'grads': grads}
+    path = os.path.join(HERE, 'joint_ctc_postnorm_glu.pt')
+    torch.save(out, path)
+    print('joint_ctc', os.path.getsize(path) // 1024, 'KiB loss', float(loss), 'ctc', aux['CTCLoss'])
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'train':
         train_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'ctc':
+        ctc_case()
         sys.exit(0)
     lm_case()
     run_case('small_transformer_postnorm_glu', small_params('transformer'))

@@ -151,3 +151,99 @@ def test_fused_trainer_step_matches_oracle_step(use_graph):
         assert (num / den) ** 0.5 < 0.3       # Adam normalises every coordinate to ~lr*sign(g): bf16 noise flips the sign of near-zero gradients only
     # parameters are views into the flat buffer; state_dict keys / shapes unchanged (checkpoint format, speech2text.py:71-87)
     assert set(k for k in model.state_dict()) >= set(names)
+
+
+def test_residual_dropout_gradients_with_replayed_masks():
+    """residual_dropout = 0.1 as shipped (egs/aishell/conf/transformer_baseline.yaml): the CUDA path draws counter-based
+    masks in the residual GEMM epilogues and replays them in the backward.  torch's Philox masks cannot be reproduced,
+    so the oracle is run with the PRODUCT's masks (exported per dropout site): loss and every gradient must then match
+    like in the deterministic case, the masks must have the right rate, differ between sites and between seeds, and a
+    shipped-config model must train through the public seam."""
+    from oracle import speech_model as om
+    from opentransformer_b200 import ops
+    params = _params(n_enc=2, n_dec=2)
+    params['encoder']['residual_dropout'] = 0.1
+    params['decoder']['residual_dropout'] = 0.1
+    model, sd = _build(params)
+    x, mask, tgt = _batch()
+    B, T2, L, p = x.shape[0], ops.conv_geometry(x.shape[1], 80)[2], tgt.shape[1] - 1, 0.1
+    seed = torch.tensor([12345], dtype=torch.int32, device=DEV)
+    masks = {}
+    for site, part, rate in train.dropout_sites(model):
+        assert rate == p
+        rows = B * T2 if part == 'encoder' else B * L
+        m = ops.dropout_mask(rows, 256, p, seed, site).cpu()
+        i = (site - train.ENC_SITE) // 2 if part == 'encoder' else (site - train.DEC_SITE) // 3
+        k = (site - train.ENC_SITE) % 2 if part == 'encoder' else (site - train.DEC_SITE) % 3
+        masks[(f'{part}.blocks.{i}', k)] = m.view(B, -1, 256).float()
+    keep = torch.stack([m.mean() for m in masks.values()])
+    assert float((keep - 0.9).abs().max()) < 0.01, keep.tolist()
+    ms = list(masks.values())
+    assert not torch.equal(ms[0], ms[1]), 'different sites must draw different masks'
+    seed2 = torch.tensor([12346], dtype=torch.int32, device=DEV)
+    assert not torch.equal(ops.dropout_mask(B * T2, 256, p, seed2, 0).cpu().view(B, -1, 256).float(), ms[0])
+    om.set_dropout(lambda site, t: t * masks[site] / (1.0 - p))
+    try:
+        loss_ref, g_ref = ot.loss_and_grads(x, mask, tgt, sd, params)
+    finally:
+        om.set_dropout(None)
+    loss_nodrop, _ = ot.loss_and_grads(x, mask, tgt, sd, params)
+    with torch.no_grad():
+        loss, g = train.forward_backward(model.train(), x.to(DEV), mask.to(DEV), tgt.to(DEV), drop_seed=seed)
+    names = [n for n, _ in model.named_parameters()]
+    worst = sorted(((_rel(g[n], g_ref[n]), n) for n in names), reverse=True)
+    r_all = _rel(torch.cat([g[n].reshape(-1).cpu() for n in names]), torch.cat([g_ref[n].reshape(-1) for n in names]))
+    print(f'residual dropout 0.1, replayed masks: loss gpu {float(loss):.5f} oracle {float(loss_ref):.5f} (without dropout '
+          f'{float(loss_nodrop):.5f}); all grads rel_l2 {r_all:.3e}; worst ' + ', '.join(f'{n} {r:.2e}' for r, n in worst[:3]))
+    assert abs(float(loss_ref) - float(loss_nodrop)) > 1e-4, 'the replayed masks must actually change the network'
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    assert r_all < REL_L2_GRAD_ALL and worst[0][0] < REL_L2_GRAD, worst[:3]
+    # public seam: model.train(); loss.backward() -- two calls draw different masks (the seed advances on the device)
+    l1, _ = model({'inputs': x.to(DEV), 'mask': mask.to(DEV)}, {'targets': tgt.to(DEV), 'targets_length': None})
+    l2, _ = model({'inputs': x.to(DEV), 'mask': mask.to(DEV)}, {'targets': tgt.to(DEV), 'targets_length': None})
+    l1.backward()
+    assert float(l1) != float(l2) and all(p_.grad is not None for p_ in model.parameters())
+    # FusedTrainer with the CUDA graph: replays must not freeze the mask
+    tr = train.FusedTrainer(model, accum_steps=1, use_graph=True)
+    losses = [float(tr.step(x.to(DEV), mask.to(DEV), tgt.to(DEV))) for _ in range(4)]
+    print('FusedTrainer losses with dropout (graph from the 2nd step on):', losses)
+    assert len(set(losses)) == 4
+
+
+def test_other_dropout_rates_raise_in_training():
+    params = _params(n_enc=1, n_dec=1)
+    params['encoder']['ffn_dropout'] = 0.1
+    model, _ = _build(params)
+    x, mask, tgt = _batch()
+    with pytest.raises(NotImplementedError):
+        train.forward_backward(model.train(), x.to(DEV), mask.to(DEV), tgt.to(DEV))
+
+
+def test_joint_ctc_loss_and_gradients_match_oracle():
+    """ctc_weight 0.3 (model/speech2text.py:30-36,60-72): (1 - w) * attention + w * CTC; the CTC head's gradients and its
+    contribution to the encoder's, against the oracle (pinned to the reference by tests/golden/joint_ctc_postnorm_glu.pt)."""
+    params = _params(n_enc=2, n_dec=1)
+    params['ctc_weight'] = 0.3
+    params['encoder_output_size'] = 256
+    model, sd = _build(params)
+    for k, v in model.assistor.state_dict().items():
+        sd[f'assistor.{k}'] = v.detach().clone().float().cpu()
+    x, mask, tgt = _batch()
+    tlen = torch.tensor([(int((tgt[b, 1:] != 0).sum())) for b in range(tgt.shape[0])], dtype=torch.int32)
+    loss_ref, g_ref = ot.loss_and_grads(x, mask, tgt, sd, params, truth_length=tlen)
+    with torch.no_grad():
+        loss, g, lc = train.forward_backward(model.train(), x.to(DEV), mask.to(DEV), tgt.to(DEV), truth_length=tlen.to(DEV),
+                                             return_ctc=True)
+    names = [n for n, _ in model.named_parameters()]
+    assert set(names) == set(g_ref) == set(g), (set(names) ^ set(g_ref), set(names) ^ set(g))
+    worst = sorted(((_rel(g[n], g_ref[n]), n) for n in names), reverse=True)
+    r_all = _rel(torch.cat([g[n].reshape(-1).cpu() for n in names]), torch.cat([g_ref[n].reshape(-1) for n in names]))
+    print(f'joint CTC: loss gpu {float(loss):.5f} oracle {float(loss_ref):.5f} (ctc part {float(lc):.5f}); all grads rel_l2 {r_all:.3e}; '
+          'worst ' + ', '.join(f'{n} {r:.2e}' for r, n in worst[:3]))
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    assert r_all < REL_L2_GRAD_ALL and worst[0][0] < REL_L2_GRAD, worst[:3]
+    # public seam, eval mode: (loss, {'CTCLoss': ..}) like the reference
+    model.eval()
+    with torch.no_grad():
+        l2, aux = model({'inputs': x.to(DEV), 'mask': mask.to(DEV)}, {'targets': tgt.to(DEV), 'targets_length': tlen})
+    assert abs(float(l2) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) and 'CTCLoss' in aux

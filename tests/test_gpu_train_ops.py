@@ -3,6 +3,7 @@ import math
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -206,3 +207,34 @@ def test_spec_augment_kernel_matches_numpy_slicing():
     random.seed(5); np.random.seed(6)
     got = spec_augment_(x.to(DEV).clone(), lens)
     assert torch.equal(got.cpu(), ref)
+
+
+def test_ctc_loss_and_logit_gradient_vs_torch():
+    """otb_ctc_loss = nn.CTCLoss(blank 0, 'mean', zero_infinity=True) (model/ctc.py:31,48-52) and its gradient w.r.t. the
+    logits: ragged input lengths, repeated labels, an empty target and an INFEASIBLE utterance (more labels than frames,
+    which zero_infinity turns into loss 0 / gradient 0)."""
+    B, T, V, L = 6, 37, 50, 9
+    g = torch.Generator().manual_seed(21)
+    logits = (torch.randn(B * T, 56, generator=g) * 2).to(DEV)
+    in_len = torch.tensor([37, 30, 12, 37, 5, 20], dtype=torch.int32)
+    tgt = torch.randint(1, V, (B, L), generator=g)
+    tgt[0, 3] = tgt[0, 2]                                 # repeated label
+    tgt[3, :] = tgt[3, 0]                                 # all labels equal
+    tlen = torch.tensor([9, 6, 4, 9, 8, 0], dtype=torch.int32)     # utterance 4: 8 labels in 5 frames -> infeasible; 5: empty
+    loss, nll, dl = ops.ctc_loss(logits, B, T, V, in_len.to(DEV), tgt.to(DEV), tlen.to(DEV), 0, want_grad=True)
+    x = logits[:, :V].detach().cpu().double().view(B, T, V).requires_grad_(True)
+    lp = torch.log_softmax(x, -1).transpose(0, 1)
+    ref = F.ctc_loss(lp, tgt, in_len.long(), tlen.long(), blank=0, reduction='mean', zero_infinity=True)
+    ref.backward()
+    ref_nll = F.ctc_loss(lp.detach(), tgt, in_len.long(), tlen.long(), blank=0, reduction='none', zero_infinity=False)
+    print(f'ctc loss gpu {float(loss):.6f} torch {float(ref):.6f}; nll gpu {nll.cpu().tolist()} torch {ref_nll.tolist()}')
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    fin = torch.isfinite(ref_nll)
+    assert torch.equal(torch.isfinite(nll.cpu()), fin)
+    torch.testing.assert_close(nll.cpu()[fin].double(), ref_nll[fin], rtol=1e-4, atol=1e-4)
+    got = dl.float().cpu().view(B, T, -1)
+    assert float(got[:, :, V:].abs().max()) == 0.0
+    assert float(got[4].abs().max()) == 0.0, 'infeasible utterance: zero gradient (zero_infinity)'
+    r = _rel(got[:, :, :V], x.grad.float())
+    print(f'ctc dlogits rel_l2 {r:.3e}')
+    assert r < 6e-3
