@@ -264,29 +264,44 @@ class TransformerEncoderLayer(nn.Module):
         super().__init__()
         if concat_after:
             raise NotImplementedError('concat_after is not used by any shipped config')
-        if relative_positional:
-            raise NotImplementedError('relative_positional TransformerEncoder: use the Conformer encoder path')
         self.n_heads = n_heads
         self.normalize_before = normalize_before
+        self.relative_positional = relative_positional
         # dropout is a training-time op (encoder/transformer.py:32-33,54,61); inference ignores it, train.py checks it
         self.dropout_rates = {'slf_attn_dropout': slf_attn_dropout, 'ffn_dropout': ffn_dropout,
                               'residual_dropout': residual_dropout}
-        self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
+        if relative_positional:     # encoder/transformer.py:23-24: Transformer-XL style attention, NO output projection
+            self.slf_attn = MultiHeadedSelfAttentionWithRelPos(n_heads, d_model, slf_attn_dropout)
+        else:
+            self.slf_attn = MultiHeadedSelfAttention(n_heads, d_model, slf_attn_dropout)
         self.feed_forward = PositionwiseFeedForward(d_model, d_ff, ffn_dropout, activation)
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
 
     def pack(self):
         a = self.slf_attn
-        return {'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj),
-                'ffn': _ffn_pack(self.feed_forward), 'ln1': _ln(self.norm1), 'ln2': _ln(self.norm2)}
+        pk = {'ffn': _ffn_pack(self.feed_forward), 'ln1': _ln(self.norm1), 'ln2': _ln(self.norm2)}
+        if self.relative_positional:
+            pk['rel'] = a.pack()
+        else:
+            pk.update({'wqkv': _w(a.qvk_proj), 'bqkv': _b(a.qvk_proj), 'wo': _w(a.output_proj), 'bo': _b(a.output_proj)})
+        return pk
 
-    def run(self, x, pk, B, T, lengths, causal=False):
+    def run(self, x, pk, B, T, lengths, causal=False, pos_bf16=None):
         """x bf16 [B*T, d] -> bf16 [B*T, d]   (encoder/transformer.py:41-65); causal=True is the tril mask the
         Transformer LM feeds to the same layer (model/lm.py:14-18,148-151)."""
         d, H = x.shape[1], self.n_heads
         if self.normalize_before:
             x = ops.layernorm(x, *pk['ln1'])          # residual is taken AFTER the norm (transformer.py:42-44)
+        if self.relative_positional:
+            if causal:
+                raise NotImplementedError('causal rel-pos attention')
+            x = self.slf_attn.run(x, x, pk['rel'], B, T, lengths, pos_bf16)       # x + attention (no output projection)
+            if not self.normalize_before:
+                x = ops.layernorm(x, *pk['ln1'])
+            if self.normalize_before:
+                x = ops.layernorm(x, *pk['ln2'])
+            return _ffn(x, pk['ffn'], x, None if self.normalize_before else pk['ln2'])
         qkv = ops.linear(x, pk['wqkv'], pk['bqkv'])
         ctx = ops.attention(qkv, qkv, qkv, B, H, T, T, kv_len=lengths, causal=causal, q_col0=0, k_col0=d,
                             v_col0=2 * d)
@@ -319,13 +334,23 @@ class TransformerEncoder(nn.Module):
             self.norm = nn.LayerNorm(d_model)
         self._pack = _Packed(self, lambda: {'blocks': [b.pack() for b in self.blocks],
                                             'norm': _ln(self.norm) if normalize_before else None})
+        self._pos_cache = {}
+
+    def _rel_pos(self, T, device):
+        key = (T, device.index)
+        p = self._pos_cache.get(key)
+        if p is None:   # PE[-(T-1) .. T-1] (encoder/transformer.py:117-119), bf16 GEMM operand of pos_proj
+            p = ops.scale_add_table(ops.sinusoid_table(2 * T - 1, self.d_model, -(T - 1), device))
+            self._pos_cache[key] = p
+        return p
 
     def forward_bf16(self, x, B, T, lengths):
-        """x bf16 [B*T, d] with the positional encoding already applied."""
+        """x bf16 [B*T, d] with the positional encoding already applied (abs-pos) / the raw front-end output (rel-pos)."""
         _no_train(self)
         pk = self._pack.get()
+        pos = self._rel_pos(T, x.device) if self.relative_positional else None
         for blk, bpk in zip(self.blocks, pk['blocks']):
-            x = blk.run(x, bpk, B, T, lengths)
+            x = blk.run(x, bpk, B, T, lengths, pos_bf16=pos)
         if self.normalize_before:
             x = ops.layernorm(x, *pk['norm'])
         return x
@@ -335,6 +360,8 @@ class TransformerEncoder(nn.Module):
         return not self.relative_positional
 
     def apply_posenc_bf16(self, x, B, T):
+        if self.relative_positional:       # enc_output = inputs (encoder/transformer.py:116): no x*sqrt(d)+PE
+            return x if x.dtype == BF16 else ops.scale_add_table(x)
         scale, table = self.pos_emb.scale_and_table(T, x.device)
         return ops.scale_add_table(x, scale, table, T)
 

@@ -95,6 +95,34 @@ def test_frontend_encoder_states_match_oracle(pre_norm, act):
     assert set(attn) == {f'enc_block_{i}' for i in range(3)}
 
 
+def test_transformer_encoder_relative_positional_matches_oracle():
+    """TransformerEncoder(relative_positional=True) (encoder/transformer.py:23-24,46,116-119): Transformer-XL style
+    attention without output projection inside the post-norm layer; the oracle path is pinned to the reference by
+    tests/golden/small_transformer_relpos.pt."""
+    params = _params(n_enc=2, n_dec=1)
+    params['encoder'].update(relative_positional=True)
+    model, sd = _build(params)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith('posu') or n.endswith('posv'):
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+    sd = {}
+    for part in ('frontend', 'encoder', 'decoder'):
+        for k, v in getattr(model, part).state_dict().items():
+            sd[f'{part}.{k}'] = v.detach().clone().float().cpu()
+    x, mask = _batch(3, 400, 80, [400, 300, 255])
+    mem_ref, mmask = om.encode(x, mask, sd, params)
+    with torch.no_grad():
+        fe, fmask = model.frontend(x.to(DEV), mask.to(DEV))
+        mem, _, _ = model.encoder(fe, fmask)
+        fused, lens, B, T2 = model.encode_bf16(x.to(DEV), mask.to(DEV))
+    r1 = _rel(_valid(mem.cpu(), mmask), _valid(mem_ref, mmask))
+    r2 = _rel(_valid(fused.float().view(B, T2, -1).cpu(), mmask), _valid(mem_ref, mmask))
+    print(f'rel-pos TransformerEncoder rel_l2 module-API={r1:.3e} fused={r2:.3e}')
+    assert r1 < REL_L2_STATES and r2 < REL_L2_STATES
+
+
 def _conformer_params(n_enc=2, relpos=True):
     p = _params(n_enc=1, n_dec=1)
     p['encoder_type'] = 'conformer'
