@@ -231,6 +231,11 @@ const char* ctc_launch(cudaStream_t st, const float* logp, int ldl, int B, int T
                        int ldt, const int* tgt_len, int max_tgt, int blank, float* nll, float* loss, float* ws, bf16* dlogits, int ldd,
                        float grad_scale);
 
+const char* fbank_launch(cudaStream_t st, const float* wave, int ld_wave, const int* n_samples, int B, const float* window,
+                         const float* bank, const int* bank_range, float* out, int Tmax, int F, int frame_len, int frame_shift,
+                         float preemph);
+const char* utt_cmvn_launch(cudaStream_t st, float* x, int B, int Tmax, int F, const int* n_frames, const float* gmean, const float* gstd);
+
 int num_sms();
 extern unsigned long long* g_gemm_dbg;
 extern int g_gemm_dbg_mode;
