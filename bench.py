@@ -402,19 +402,21 @@ def run_b200(args):
                                       persistent=persistent)
 
     # decode path: 'persistent' = the whole 60-step loop in one launch per batch (csrc/decode_group.cu, 48 SMs per batch of
-    # 32 utterances x beam 10), 'graph' = one CUDA-graph replay of ~52 kernels per step (round 1)
+    # 32 utterances x beam 10), 'graph' = one CUDA-graph replay of ~52 kernels per step (round 1).  'auto' takes the
+    # persistent kernel only after a probe in a CHILD process produced exactly the graph path's hypotheses on input batch 0:
+    # a device-side fault there (a trap poisons the CUDA context) must not cost the benchmark line.
     ops.set_tile_policy('latency')
-    probe = make_rec(True)
-    with torch.no_grad():
-        probe.recognize_ids(*ring_dev[0])
-    persist_ok = next(iter(probe._decoders.values())).persistent
+    persist_ok, probe_note = False, 'not probed'
+    if args.decode in ('auto', 'persistent'):
+        persist_ok, probe_note = probe_persistent(local)
     use_persist = persist_ok if args.decode == 'auto' else (args.decode == 'persistent')
     if use_persist and not persist_ok:
-        raise SystemExit('bench.py: --decode persistent, but the persistent kernel does not support this configuration')
+        raise SystemExit(f'bench.py: --decode persistent, but the probe failed: {probe_note}')
+    probe = make_rec(True) if use_persist else None
     L = args.lanes if args.lanes > 0 else (3 if use_persist else 16)
     L = max(1, L)
     # lone-batch diagnostics: one recogniser per decode path (graph path captured under the latency tile policy)
-    rec_graph, rec_pers = make_rec(False), (probe if persist_ok else None)
+    rec_graph, rec_pers = make_rec(False), probe
     with torch.no_grad():
         for i in range(3):
             rec_graph.recognize_ids(*ring_dev[i])
@@ -591,6 +593,7 @@ def run_b200(args):
         cfg = workload_config(args, B_PER_GPU)
         cfg['lanes'] = L_eff
         cfg['decode_path'] = 'persistent (one launch per batch)' if use_persist else 'per-step CUDA graph'
+        cfg['persistent_probe'] = probe_note
         cfg['tile_policy'] = policy
         cfg['repeats'] = repeats
         # output check: digest of the n-best ids of input batch 0 against the committed one (tools/make_bench_digest.py runs
@@ -660,6 +663,46 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def probe_persistent(local):
+    """Run `bench.py --probe-persistent` in a child process: (ok, note).  ok = the persistent decode kernel supports the
+    benchmark configuration AND returned the same n-best ids / step count as the per-step graph path on input batch 0."""
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'TORCHELASTIC_RUN_ID'):
+        env.pop(k, None)
+    env['OTB_PROBE_DEVICE'] = str(local)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--probe-persistent'], env=env, capture_output=True, text=True,
+                           timeout=300)
+    except subprocess.TimeoutExpired:
+        return False, 'probe timed out'
+    last = (r.stdout.strip().splitlines() or [''])[-1]
+    if r.returncode == 0 and last.startswith('PROBE OK'):
+        return True, last
+    return False, ('rc %d: ' % r.returncode) + (last or r.stderr.strip()[-200:])
+
+
+def run_probe_persistent():
+    from opentransformer_b200.recognize import SpeechToTextRecognizer
+    dev = torch.device('cuda', int(os.environ.get('OTB_PROBE_DEVICE', '0')))
+    torch.cuda.set_device(dev)
+    model = build_model().to(dev)
+    x, m = synthetic_batch(B_PER_GPU, 0)
+    x, m = x.to(dev), m.to(dev)
+    kw = dict(beam_width=BEAM, nbest=BEAM, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA, ngpu=1)
+    rp, rg = SpeechToTextRecognizer(model, persistent=True, **kw), SpeechToTextRecognizer(model, persistent=False, **kw)
+    pp, sp, n_p = rp.recognize_ids(x, m)
+    if not next(iter(rp._decoders.values())).persistent:
+        print('PROBE FAIL persistent kernel does not support this configuration')
+        return 1
+    pg, sg, n_g = rg.recognize_ids(x, m)
+    pp2, _, _ = rp.recognize_ids(x, m)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(pp, pg)) and n_p == n_g and bool(torch.equal(pp, pp2))
+    print(('PROBE OK' if same else 'PROBE FAIL') + f' steps {n_p}/{n_g}, n-best ids equal to the graph path: {bool(torch.equal(pp, pg))}, '
+          f'deterministic: {bool(torch.equal(pp, pp2))}, max |score diff| {float((sp - sg).abs().max()):.3e}')
+    return 0 if same else 1
 
 
 def graph_path_roofline(model, lanes, ring_dev, dev, peaks, src, traffic):
@@ -956,7 +999,10 @@ def main():
     ap.add_argument('--tile-policy', default='auto', choices=['auto', 'latency', 'throughput'],
                     help='tiling of the decode-step GEMMs (otb_set_tile_policy); auto = throughput when lanes > 1')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    ap.add_argument('--probe-persistent', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.probe_persistent:
+        return run_probe_persistent()
     guard_stdout()
     if args.impl == 'reference':
         return run_reference(args)

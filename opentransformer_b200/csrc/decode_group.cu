@@ -43,8 +43,9 @@ static constexpr int DG_DFF = 2048;
 static constexpr int DG_A_BYTES = 65536;   // A operand tile: 4 k-blocks of [128 rows x 64] bf16, SWIZZLE_128B
 static constexpr int DG_STAGE = 65536;     // two big stages: weight chunks / cross-attention K|V tiles / self-attention V staging
 static constexpr int DG_SB = 24576;        // small B operand (<= 48 weight rows x 256) | cross-attention scratch
-static constexpr int DG_MISC = 12288;
+static constexpr int DG_MISC = 9728;
 static constexpr int DG_SMEM = DG_A_BYTES + 2 * DG_STAGE + DG_SB + DG_MISC + 1024;
+static_assert(DG_SMEM <= 227 * 1024, "decode_group_kernel: shared-memory budget (227 KB per CTA)");
 static constexpr int DG_PP = 528;          // cross-attention probability row pitch (bytes): 512 + 16 -> conflict-free ldmatrix
 
 unsigned long long* g_dg_dbg = nullptr;
@@ -59,7 +60,7 @@ struct DgMisc {
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
     alignas(16) uint32_t rs[128 * 8];     // residual slice of this CTA: rows x 16 columns, bf16 pairs
-    alignas(16) float bias[512];          // per-phase bias slice
+    alignas(16) float bias[256];          // per-phase bias slice
     float c_val[KMAX * KMAX];
     int c_tok[KMAX * KMAX];
     float sel_v[KMAX];

@@ -23,6 +23,7 @@
 // than a one-CTA-per-row-block tiling would (63 -> 252 CTAs at cfg 2, 3 -> 12 in the decode loop).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static
 // round-robin tile scheduler, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
 #include <string.h>
 
 #include "dropout.cuh"
@@ -117,7 +118,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // LN partial statistics [2 tile parities][cluster ranks * 4 quarters <= 16][128 rows]: in the upper part of the
     // staging buffer when the LN tile is 64 wide (staging needs 128 x 144 B), else (one CTA per row block, at most
     // 4 partials per parity) in the pipeline-stage area's tail
-    float2* s_stats = (BN == 64) ? reinterpret_cast<float2*>(stg + 32768) : reinterpret_cast<float2*>(aux + 6144);
+    float2* s_stats = (BN == 64) ? reinterpret_cast<float2*>(stg + 32768)
+                                 : (BN == 128 ? reinterpret_cast<float2*>(stg + 36864) : reinterpret_cast<float2*>(aux + 6144));   // BN 128: 2 x 8 x 128 partials = 16 KB above the 34 KB of staged rows
     const uint32_t cl_rank = (EPI == EPI_RESID_LN) ? cluster_ctarank() : 0;
     const uint32_t cl_size = (EPI == EPI_RESID_LN) ? cluster_nctarank() : 1;
 
@@ -740,6 +742,12 @@ static int choose_bn(int m_tiles, int n_cols, int epi, int out_f32) {
         // 256-wide tile does the same main loop as four 64-wide ones: with enough row blocks to occupy the SMs (or under
         // the throughput policy) keep the whole row in one CTA; a lone small problem (decode, M = 320) is split over a
         // cluster of N/64 CTAs with DSMEM statistics, which shortens its launch by 2-4 us.
+        // OTB_LN_BN = 64 | 128 | 256 overrides the column tile of the large-M case (tuning aid: the row is then split over
+        // a cluster of N / BN CTAs with DSMEM statistics; 63 -> 126 -> 252 CTAs at cfg 2)
+        static const int forced = [] { const char* e = getenv("OTB_LN_BN"); return e ? atoi(e) : 0; }();
+        if (forced == 64 || forced == 128 || forced == 256) {
+            if (m_tiles >= 32 && forced <= n_cols && n_cols % forced == 0) return forced;
+        }
         return (m_tiles >= 32 || decode) ? n_cols : 64;
     }
     const int sms = num_sms();
