@@ -27,6 +27,7 @@
 //
 // Supported: post-norm decoder, GLU feed-forward with d_ff = 2048, d_model 256, 4 heads, beam <= 16, memory length <= 256
 // frames, max_len <= 128.  Anything else runs on the per-step graph path (recognize.BeamDecoder.step).
+#include <stdlib.h>
 #include <string.h>
 
 #include "beam_common.cuh"
@@ -161,9 +162,25 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #define DG_STAMP() do { if (dbg_on) p.dbg_clk[dbg_n++] = clock64(); } while (0)
 
     // group barrier: every CTA of the group has finished the phase (its global writes are visible); `pre` runs on the TMA
-    // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles)
+    // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles).
+    // Launched as thread-block clusters of 16 (p.cluster) the group IS the cluster: hardware barrier.cluster with
+    // release / acquire semantics; otherwise one atomic + an acquire poll on a counter in L2.
     auto gsync = [&](auto pre) {
+        if (p.cluster) {
+            if (p.dbg_clk != nullptr) __syncthreads();   // profiling runs: attribute the other warps' tail to the phase, not to the barrier
+            if (tid == 0) fence_proxy_async_all();
+            DG_STAMP();
+            __syncwarp();
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            if (tid == 0) pre();
+            __syncwarp();
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (tid == 0) fence_proxy_async_all();
+            __syncthreads();
+            return;
+        }
         __syncthreads();
+        DG_STAMP();
         bar_target += DG_P;
         if (tid == 0) {
             __threadfence();
@@ -216,11 +233,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     auto build_a_ln = [&](const float* gamma, const float* beta) {
         const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
-#pragma unroll 1
-        for (int rb = warp * 8; rb < warp * 8 + 8; rb += 4) {
-            float4 y0[4], y1[4];
+        {
+            const int rb = warp * 8;
+            float4 y0[8], y1[8];      // all 8 rows of the warp in flight at once: one L2 round trip instead of two
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const int r = rb + i;
                 if (r < nrows) {
                     const float* src = p.pre + (size_t)(row0 + r) * DG_D + lane * 8;
@@ -232,7 +249,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const int r = rb + i;
                 float v[8] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w, y1[i].x, y1[i].y, y1[i].z, y1[i].w};
                 float s = 0.f;
@@ -348,91 +365,104 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 reinterpret_cast<uint4*>(dst)[0] = o[0];
                 reinterpret_cast<uint4*>(dst)[1] = o[1];
             });
-            DG_STAMP();   // QKV
-            gsync(nop);
+            gsync(nop);   // stamps: phase end (inside), barrier end (below)
             DG_STAMP();
             // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
+            // One warp per (hypothesis, head).  v1 gave every lane a whole key (8 x 16-byte loads of a 128-byte row per lane =
+            // 32 cache lines per load instruction) and was bound by the L1 wavefront rate: 66 k cycles per layer at step 50.
+            // Now 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V row: one 128-byte line per
+            // 8 lanes, 4 keys per load instruction), the partial dot products meet through 3 shuffles, and each of the 4 lane
+            // groups keeps an online-softmax (m, l, o[8]) over its keys; the groups are merged at the end.
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
-                uint8_t* stage = sST + (size_t)warp * 8192;          // 64 cached positions x 128 B of V per warp
-                float* sq = reinterpret_cast<float*>(sSB) + warp * 64;
+                int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                const int g4 = lane >> 3, c8 = lane & 7;
                 for (int task = j * 16 + warp; task < nrows * DG_H; task += DG_P * 16) {
                     const int r = task / DG_H, h = task % DG_H;
                     const int n = row0 + r;
-                    const int* an = an_base + (size_t)n * Lmax;
+                    __syncwarp();
+                    for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
+                    float qf[8];
                     {
-                        const float2 qq = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.qbuf + (size_t)n * DG_D + h * 64 + 2 * lane));
-                        __syncwarp();
-                        sq[2 * lane] = qq.x;
-                        sq[2 * lane + 1] = qq.y;
-                        __syncwarp();
+                        const uint4 qu = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n * DG_D + h * 64 + c8 * 8);
+                        const float2 q0 = unpack_bf16(qu.x), q1 = unpack_bf16(qu.y), q2 = unpack_bf16(qu.z), q3 = unpack_bf16(qu.w);
+                        qf[0] = q0.x * 0.125f; qf[1] = q0.y * 0.125f; qf[2] = q1.x * 0.125f; qf[3] = q1.y * 0.125f;
+                        qf[4] = q2.x * 0.125f; qf[5] = q2.y * 0.125f; qf[6] = q3.x * 0.125f; qf[7] = q3.y * 0.125f;
                     }
-                    float sc[4];
-                    float mx = -INFINITY;
+                    __syncwarp();
+                    float m = -INFINITY, lsum = 0.f;
+                    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const size_t col = (size_t)h * 64 + c8 * 8;
+                    for (int k0 = 0; k0 < nkeys; k0 += 16) {          // 4 keys per lane group per iteration, 8 loads in flight per lane
+                        uint4 ku[4], vu[4];
+                        bool ok[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int s = lane + 32 * q;
-                        sc[q] = -INFINITY;
-                        if (s < nkeys) {
-                            const int slot = (s < step) ? an[s] : n;
-                            const size_t off = (((size_t)l * Lmax + s) * N + slot) * DG_D + h * 64;
-                            uint4 ku[8], vu[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) ku[i] = *reinterpret_cast<const uint4*>(p.kc + off + 8 * i);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) vu[i] = *reinterpret_cast<const uint4*>(p.vc + off + 8 * i);
-                            float dot = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float2 a = unpack_bf16(ku[i].x), b = unpack_bf16(ku[i].y), c2 = unpack_bf16(ku[i].z), e = unpack_bf16(ku[i].w);
-                                const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * i);
-                                const float4 q1 = *reinterpret_cast<const float4*>(sq + 8 * i + 4);
-                                dot += q0.x * a.x + q0.y * a.y + q0.z * b.x + q0.w * b.y + q1.x * c2.x + q1.y * c2.y + q1.z * e.x + q1.w * e.y;
-                            }
-                            sc[q] = dot * 0.125f;
-                            mx = fmaxf(mx, sc[q]);
-                            if (s < 64) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage + s * 128 + (((i + s) & 7) << 4)) = vu[i];
+                        for (int u = 0; u < 4; ++u) {
+                            const int sidx = k0 + 4 * u + g4;
+                            ok[u] = sidx < nkeys;
+                            const int slot = (sidx < step) ? an_s[sidx] : n;
+                            const size_t off = (((size_t)l * Lmax + (ok[u] ? sidx : 0)) * N + slot) * DG_D + col;
+                            if (ok[u]) {
+                                ku[u] = *reinterpret_cast<const uint4*>(p.kc + off);
+                                vu[u] = *reinterpret_cast<const uint4*>(p.vc + off);
+                            } else {
+                                ku[u] = make_uint4(0, 0, 0, 0);
+                                vu[u] = ku[u];
                             }
                         }
-                    }
-                    mx = warp_max(mx);
-                    float lsum = 0.f;
+                        float sc[4];
+                        float mb = m;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        sc[q] = (lane + 32 * q < nkeys) ? __expf(sc[q] - mx) : 0.f;
-                        lsum += sc[q];
-                    }
-                    lsum = warp_sum(lsum);
-                    __syncwarp();
-                    float ax = 0.f, ay = 0.f;
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 a = unpack_bf16(ku[u].x), b2 = unpack_bf16(ku[u].y), c2 = unpack_bf16(ku[u].z), e = unpack_bf16(ku[u].w);
+                            float d = qf[0] * a.x + qf[1] * a.y + qf[2] * b2.x + qf[3] * b2.y + qf[4] * c2.x + qf[5] * c2.y + qf[6] * e.x + qf[7] * e.y;
+                            d += __shfl_xor_sync(0xffffffffu, d, 1);
+                            d += __shfl_xor_sync(0xffffffffu, d, 2);
+                            d += __shfl_xor_sync(0xffffffffu, d, 4);
+                            sc[u] = ok[u] ? d : -INFINITY;
+                            mb = fmaxf(mb, sc[u]);
+                        }
+                        if (mb != -INFINITY) {
+                            const float alpha = (m == -INFINITY) ? 0.f : __expf(m - mb);
+                            lsum *= alpha;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int cnt = min(32, nkeys - 32 * q);
-                        if (cnt <= 0) break;
-                        for (int t = 0; t < cnt; ++t) {
-                            const int s = t + 32 * q;
-                            const float pw = __shfl_sync(0xffffffffu, sc[q], t);
-                            uint32_t vv;
-                            if (s < 64) {
-                                vv = *reinterpret_cast<const uint32_t*>(stage + s * 128 + ((((lane >> 2) + s) & 7) << 4) + (lane & 3) * 4);
-                            } else {   // prefixes longer than the staging area: straight from the cache (L2)
-                                const int slot = (s < step) ? an[s] : n;
-                                vv = *reinterpret_cast<const uint32_t*>(p.vc + (((size_t)l * Lmax + s) * N + slot) * DG_D + h * 64 + 2 * lane);
+                            for (int q = 0; q < 8; ++q) o[q] *= alpha;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float pw = ok[u] ? __expf(sc[u] - mb) : 0.f;
+                                lsum += pw;
+                                const float2 a = unpack_bf16(vu[u].x), b2 = unpack_bf16(vu[u].y), c2 = unpack_bf16(vu[u].z), e = unpack_bf16(vu[u].w);
+                                o[0] = fmaf(pw, a.x, o[0]); o[1] = fmaf(pw, a.y, o[1]); o[2] = fmaf(pw, b2.x, o[2]); o[3] = fmaf(pw, b2.y, o[3]);
+                                o[4] = fmaf(pw, c2.x, o[4]); o[5] = fmaf(pw, c2.y, o[5]); o[6] = fmaf(pw, e.x, o[6]); o[7] = fmaf(pw, e.y, o[7]);
                             }
-                            const float2 vf = unpack_bf16(vv);
-                            ax = fmaf(pw, vf.x, ax);
-                            ay = fmaf(pw, vf.y, ay);
+                            m = mb;
                         }
                     }
-                    const float inv = 1.0f / lsum;
-                    *reinterpret_cast<uint32_t*>(p.ctx + (size_t)n * DG_D + h * 64 + 2 * lane) = pack_bf16(ax * inv, ay * inv);
-                    __syncwarp();
+                    // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
+                    float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+                    const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
+                    lsum *= w;
+                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[q] *= w;
+                        o[q] += __shfl_xor_sync(0xffffffffu, o[q], 8);
+                        o[q] += __shfl_xor_sync(0xffffffffu, o[q], 16);
+                    }
+                    if (g4 == 0) {
+                        const float inv = 1.0f / lsum;
+                        uint4 ou;
+                        ou.x = pack_bf16(o[0] * inv, o[1] * inv);
+                        ou.y = pack_bf16(o[2] * inv, o[3] * inv);
+                        ou.z = pack_bf16(o[4] * inv, o[5] * inv);
+                        ou.w = pack_bf16(o[6] * inv, o[7] * inv);
+                        *reinterpret_cast<uint4*>(p.ctx + (size_t)n * DG_D + h * 64 + c8 * 8) = ou;
+                    }
                 }
             }
-            DG_STAMP();   // self-attention
             gsync(nop);
             DG_STAMP();
             // ---------------- out-projection + residual -> pre-norm rows (attention.py:44, transformer.py:54)
@@ -447,7 +477,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
             };
             gemm_small(maps + l * 6 + 1, j * 16, 16, true, ly.bo, epi_pre);
-            DG_STAMP();   // out-proj
             gsync(nop);
             DG_STAMP();
             // ---------------- LayerNorm 1 + cross-attention query projection (attention.py:128)
@@ -464,7 +493,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 dst[0] = o[0];
                 dst[1] = o[1];
             });
-            DG_STAMP();   // q-proj
             gsync([&] {   // encoder K / V tiles of this CTA's first two (utterance, head) problems arrive during the barrier
                 if (j < n_tasks) load_kv(l, j, 0);
                 if (j + DG_P < n_tasks) load_kv(l, j + DG_P, 1);
@@ -603,7 +631,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
                 // every thread advanced par_stf by its own waits: all threads waited on the same tasks, so the words agree
             }
-            DG_STAMP();   // cross-attention
             gsync([&] { load_w1(l); });    // W1 slice (128 KB) streams in while the out-projection and LayerNorm run
             DG_STAMP();
             // ---------------- cross-attention out-projection + residual -> pre-norm rows
@@ -642,7 +669,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 par_accf ^= 1;
                 __syncthreads();
             }
-            DG_STAMP();   // out-proj 2
             gsync(nop);
             DG_STAMP();
             // ---------------- LayerNorm 2 + GLU feed-forward: hidden features [128 j, 128 j + 128) (ffn.py:18,39-41)
@@ -732,7 +758,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 par_stf ^= 1;
                 par_accf ^= 2;
             }
-            DG_STAMP();   // W2 partial
             const bool last_layer = (l + 1 == nl);
             gsync([&] {
                 if (last_layer) {   // output-layer chunks of this CTA: the first two stream in during the reduction
@@ -758,7 +783,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         make_float4(acc.x + b.x + r0.x, acc.y + b.y + r0.y, acc.z + b.z + r1.x, acc.w + b.w + r1.y);
                 }
             }
-            DG_STAMP();   // reduce
             gsync(nop);
             DG_STAMP();
             build_a_ln(ly.g3, ly.be3);   // LayerNorm 3 = input of the next layer (or of the output layer)
@@ -856,7 +880,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             par_accf ^= (u0n & 1) | ((u1n & 1) << 1);
             par_acce ^= (u0n & 1) | ((u1n & 1) << 1);
         }
-        DG_STAMP();   // logits + stats + candidates
         gsync(nop);
         DG_STAMP();
         // ---------------- per utterance: merge candidates, finished masking, beam^2 pruning, ancestry (speech2text.py:102-153)
@@ -955,7 +978,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             ms.flag = 0;
             if (ended_here) atomicAdd(&p.gstate[(size_t)g * Lmax + step], ended_here);
         }
-        DG_STAMP();   // beam step
         gsync(nop);
         DG_STAMP();
         steps_done = step + 1;
@@ -1075,10 +1097,52 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.dbg_clk = g_dg_dbg; p.dbg_step = g_dg_dbg_step;
 
     static bool attr_set = false;
+    static int cluster_ok = -1;     // -1 unknown, 0 clusters of 16 unavailable, 1 available
     if (!attr_set) {
-        if (cudaFuncSetAttribute(decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(decode_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM) != cudaSuccess) {
+            (void)cudaGetLastError();
             return "cudaFuncSetAttribute(decode_persistent) failed";
+        }
         attr_set = true;
+    }
+    // Preferred launch: one thread-block CLUSTER of 16 CTAs per row group (non-portable cluster size; a B200 GPC holds 16-20
+    // SMs, so up to 8 such clusters are co-resident): the group barrier becomes barrier.cluster (hardware, ~0.3 us, and the
+    // CTAs of a group are co-scheduled by construction).  OTB_DG_CLUSTER=0, or a device that refuses the cluster shape, falls
+    // back to the software barrier on a counter in L2 (plain launch; needs G * 16 <= #SMs co-resident CTAs).
+    if (cluster_ok < 0) {
+        const char* e_ = getenv("OTB_DG_CLUSTER");
+        cluster_ok = (e_ && e_[0] == '0') ? 0 : 1;
+        if (cluster_ok && cudaFuncSetAttribute(decode_group_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cluster_ok = 0;
+        }
+        if (cluster_ok) {
+            cudaLaunchConfig_t q;
+            memset(&q, 0, sizeof(q));
+            q.gridDim = dim3(DG_P); q.blockDim = dim3(DG_THREADS); q.dynamicSmemBytes = DG_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = DG_P; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int nclus = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclus, decode_group_kernel, &q) != cudaSuccess || nclus < 1) {
+                (void)cudaGetLastError();
+                cluster_ok = 0;
+            }
+        }
+    }
+    p.cluster = cluster_ok;
+    if (cluster_ok) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(G * DG_P); cfg.blockDim = dim3(DG_THREADS); cfg.dynamicSmemBytes = DG_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = DG_P; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, decode_group_kernel, p);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
     decode_group_kernel<<<G * DG_P, DG_THREADS, DG_SMEM, st>>>(p);
     e = cudaGetLastError();

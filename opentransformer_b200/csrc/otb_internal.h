@@ -164,6 +164,7 @@ struct DgLayer {
 };
 struct DgParams {
     int n_layers, V, G, utts_per_group;
+    int cluster;               // 1: launched as thread-block clusters of 16 (group == cluster, hardware barrier)
     const bf16* emb;
     const float* bout;
     const float* pe;

@@ -31,8 +31,14 @@ with torch.no_grad():
         ids.append(nb)
         print('utterances', b0, '..', b0 + 3, 'distinct tokens in 1-best', [len(set(r.tolist())) for r in nb[:, 0]], flush=True)
 ids = torch.cat(ids, 0).to(torch.int64).contiguous()
-out = {'ids_sha1': hashlib.sha1(ids.numpy().tobytes()).hexdigest(), 'shape': list(ids.shape),
-       'generator': 'tools/make_bench_digest.py (oracle, policy bf16)', 'first_row': ids[0, 0, :8].tolist()}
-with open(os.path.join(ROOT, 'tests', 'golden', 'bench_digest.json'), 'w') as f:
-    json.dump(out, f, indent=1)
-print(out)
+path = os.path.join(ROOT, 'tests', 'golden', 'bench_digest.json')
+try:
+    out = json.load(open(path))
+except Exception:
+    out = {}
+out.update({'oracle_sha1': hashlib.sha1(ids.numpy().tobytes()).hexdigest(), 'shape': list(ids.shape),
+            'generator': 'tools/make_bench_digest.py (oracle, policy bf16); gpu_* keys: tools/gpu_r2_digest.sh on a B200',
+            'oracle_ids': ids[:, 0].tolist()})
+with open(path, 'w') as f:
+    json.dump(out, f)
+print({k: v for k, v in out.items() if k != 'oracle_ids'})
