@@ -203,7 +203,7 @@ typedef struct {
     float ln_eps;
 } otb_mega_model;
 /* Scratch the launch needs (activations, partial sums, barrier counters, TMA descriptors), in bytes; -1 on bad arguments. */
-long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam);
+long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam, int vocab);
 /* kvx bf16 [n_layers, B*T, 2d]: src_attn.vk_proj(memory) per layer (K | V, attention.py:134), projected once per
  * utterance by otb_linear; mem_len i32 [B]; kc/vc bf16 [n_layers, st->Lmax, N, d] self-attention cache (scratch);
  * st: search state, initialised by otb_beam_init (ctrl zeroed); workspace: 256-byte aligned device scratch of at least

@@ -290,9 +290,9 @@ int otb_beam_finalize(const otb_beam_state* st, float penalty, float lamda, int 
                                                   reinterpret_cast<long long*>(out_preds), out_scores));
 }
 
-long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam) {
-    if (N < 1 || n_layers < 1 || Lmax < 1 || B < 1 || beam < 1 || beam > 16) return -1;
-    return (long long)decode_group_workspace_bytes(N, n_layers, Lmax, B, beam);
+long long otb_decode_persistent_workspace(int N, int n_layers, int Lmax, int B, int beam, int vocab) {
+    if (N < 1 || n_layers < 1 || Lmax < 1 || B < 1 || beam < 1 || beam > 16 || vocab < 1) return -1;
+    return (long long)decode_group_workspace_bytes(N, n_layers, Lmax, B, beam, vocab);
 }
 
 int otb_decode_persistent(const otb_mega_model* model, const void* kvx, const int32_t* mem_len, void* kc, void* vc,

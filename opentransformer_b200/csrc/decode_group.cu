@@ -8,22 +8,24 @@
 // tile and gives each such ROW GROUP to P = 16 co-operating CTAs:
 //
 //   * every projection is split over the group's CTAs by OUTPUT column (QKV 48, out / q projections 16, GLU 128 hidden
-//     features per CTA) or, for w_2, by CONTRACTION slice (the CTA's own 128 hidden features, partial sums reduced through
-//     L2) -- so the 25.8 MB of decoder weights are read once per group-step (3 groups for 32 utterances x beam 10), straight
-//     from L2 by TMA into the UMMA shared-memory layout, accumulators in TMEM;
-//   * activations move between the phases through L2 (a [rows, 256] matrix is 64 KB) and a group-local software barrier
-//     (one atomic + an acquire poll, ~1 us) replaces the kernel boundary (7-13 us) -- groups never synchronise with each
-//     other, utterances are independent;
-//   * LayerNorm is applied by the CONSUMER while it builds its A operand (fp32 pre-norm rows -> bf16 swizzled tile), so a
-//     post-norm layer costs 9 barriers: QKV | self-attention | out-proj | LN+q-proj | cross-attention | out-proj | LN+GLU+w_2
-//     partial | reduce | (next layer);
-//   * self-attention over the per-hypothesis KV cache is SIMT (lanes over cached positions, ancestry table, as round 1);
-//     cross-attention of the <= 16 hypotheses of an utterance against its 249 encoder frames is one m16 problem per (utterance,
-//     head): mma.sync on K / V tiles that TMA prefetches during the preceding phase (tcgen05 has no M < 64 shape);
-//   * the tail -- logits, log-softmax statistics and per-row top-k candidates in the logits GEMM's epilogue (the [N, V]
-//     log-prob matrix is never written), candidate merge + finished masking + beam^2 pruning + ancestry update per utterance --
-//     follows beam.cu exactly (ties -> lower index), so ids / parents are bit-exact with the oracle's beam_step driven by this
-//     kernel's log-probs.
+//     features per CTA) or, for w_2, by CONTRACTION slice (the CTA's own 128 hidden features; the 16 partial products are
+//     summed by a row-partitioned pass that also applies the residual and LayerNorm 3) -- so the 25.8 MB of decoder weights
+//     are read once per group-step (3 groups for 32 utterances x beam 10), straight from L2 by TMA into the UMMA
+//     shared-memory layout, accumulators in TMEM; every weight slice is prefetched during the barrier in front of its phase;
+//   * activations move between the phases through L2 (a [rows, 256] matrix is 64 KB).  The group is launched as ONE
+//     thread-block cluster of 16 CTAs: the phase boundary is barrier.cluster (release / acquire, 1-3 k cycles measured)
+//     instead of a kernel boundary (7-13 us); groups never synchronise with each other, utterances are independent.  A
+//     software barrier (atomic + acquire poll in L2) is kept for devices that refuse the non-portable cluster size;
+//   * LayerNorm 1 / 2 are applied by the CONSUMER while it builds its A operand (fp32 pre-norm rows -> bf16 swizzled tile),
+//     so a post-norm layer costs 7 barriers: QKV | self-attention | out-proj | LN+q-proj | cross-attention | out-proj |
+//     LN+GLU+w_2 partial | reduce+LN (= input of the next layer);
+//   * self-attention over the per-hypothesis KV cache is SIMT: a warp per (hypothesis, head), 8 lanes per cached position
+//     (coalesced 128-byte rows through the ancestry table), online softmax per lane group;
+//     cross-attention of the <= 16 hypotheses of an utterance against its <= 256 encoder frames is one m16 problem per
+//     (utterance, head): mma.sync on K / V tiles that TMA prefetches during the preceding phase (tcgen05 has no M < 64 shape);
+//   * the tail -- logits (coalesced fp32 rows in L2), then per utterance log-softmax + per-row top-k + finished masking +
+//     beam^2 pruning + ancestry update -- follows beam.cu exactly (ties -> lower index), so ids / parents are bit-exact with
+//     the oracle's beam_step driven by this kernel's log-probs.
 //
 // Supported: post-norm decoder, GLU feed-forward with d_ff = 2048, d_model 256, 4 heads, beam <= 16, memory length <= 256
 // frames, max_len <= 128.  Anything else runs on the per-step graph path (recognize.BeamDecoder.step).
@@ -42,8 +44,8 @@ static constexpr int DG_D = 256;           // d_model
 static constexpr int DG_H = 4;
 static constexpr int DG_DFF = 2048;
 static constexpr int DG_A_BYTES = 65536;   // A operand tile: 4 k-blocks of [128 rows x 64] bf16, SWIZZLE_128B
-static constexpr int DG_STAGE = 65536;     // two big stages: weight chunks / cross-attention K|V tiles / self-attention V staging
-static constexpr int DG_SB = 24576;        // small B operand (<= 48 weight rows x 256) | cross-attention scratch
+static constexpr int DG_STAGE = 65536;     // two big stages: weight chunks / cross-attention K|V tiles / logit rows of the beam step
+static constexpr int DG_SB = 24576;        // small B operand (<= 48 weight rows x 256) | cross-attention scratch | store staging
 static constexpr int DG_MISC = 9728;
 static constexpr int DG_SMEM = DG_A_BYTES + 2 * DG_STAGE + DG_SB + DG_MISC + 1024;
 static_assert(DG_SMEM <= 227 * 1024, "decode_group_kernel: shared-memory budget (227 KB per CTA)");
@@ -53,7 +55,9 @@ unsigned long long* g_dg_dbg = nullptr;
 int g_dg_dbg_step = 0;
 
 struct DgMisc {
-    uint64_t kb_full[4];      // k-block operands landed (TMA) -- one use per GEMM
+    uint64_t kb_full[4];      // small B operand k-blocks landed (TMA, prefetched one phase ahead)
+    uint64_t a_full[4];       // A operand k-blocks landed (TMA from ctx / xbuf)
+    uint64_t w1_full[4];      // W1 k-blocks landed
     uint64_t st_full[2];      // big stage landed
     uint64_t st_empty[2];     // big stage consumed (tcgen05.commit)
     uint64_t acc_full[2];     // accumulator complete (tcgen05.commit)
@@ -129,13 +133,19 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const CUtensorMap* map_wout = maps + nl * 6;
     const CUtensorMap* map_ctx = maps + nl * 6 + 1;
     const CUtensorMap* map_kvx = maps + nl * 6 + 2;
+    const CUtensorMap* map_x = maps + nl * 6 + 3;
     int* bar = p.bar + g * 32;                        // 128-byte separated counters
     const bool is_tma = (warp == 0 && lane == 0), is_mma = (warp == 1 && lane == 0);
     const bool is_epi = (warp >= 4 && warp < 8);
-    const int erow = (warp & 3) * 32 + lane;          // TMEM lane == tile row of an epilogue thread
+    const int equad = warp & 3;                       // TMEM lane quadrant of an epilogue warp
+    const int erow = equad * 32 + lane;               // TMEM lane == tile row of an epilogue thread
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&ms.kb_full[i], 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&ms.kb_full[i], 1);
+            mbar_init(&ms.a_full[i], 1);
+            mbar_init(&ms.w1_full[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&ms.st_full[i], 1);
             mbar_init(&ms.st_empty[i], 1);
@@ -150,10 +160,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ms.tmem_slot;
-    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_acce = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_acce = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x == 0 && tid == 0);
@@ -161,15 +171,17 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     bool dbg_on = false;
 #define DG_STAMP() do { if (dbg_on) p.dbg_clk[dbg_n++] = clock64(); } while (0)
 
-    // group barrier: every CTA of the group has finished the phase (its global writes are visible); `pre` runs on the TMA
-    // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles).
-    // Launched as thread-block clusters of 16 (p.cluster) the group IS the cluster: hardware barrier.cluster with
-    // release / acquire semantics; otherwise one atomic + an acquire poll on a counter in L2.
+    // Group barrier: every CTA of the group has finished the phase (its global writes are visible).  `pre` runs on the TMA
+    // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles); the
+    // leading CTA barrier guarantees that every warp of THIS CTA is done with the shared memory those prefetches overwrite.
+    // Launched as thread-block clusters of 16 (p.cluster) the group IS the cluster: hardware barrier.cluster with release /
+    // acquire semantics (~1-3 k cycles measured, profiles/r2_decode_phases_*.txt); otherwise one atomic + an acquire poll on a
+    // counter in L2 (~4 k cycles).
     auto gsync = [&](auto pre) {
+        __syncthreads();
+        DG_STAMP();
         if (p.cluster) {
-            if (p.dbg_clk != nullptr) __syncthreads();   // profiling runs: attribute the other warps' tail to the phase, not to the barrier
             if (tid == 0) fence_proxy_async_all();
-            DG_STAMP();
             __syncwarp();
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
             if (tid == 0) pre();
@@ -179,8 +191,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             __syncthreads();
             return;
         }
-        __syncthreads();
-        DG_STAMP();
         bar_target += DG_P;
         if (tid == 0) {
             __threadfence();
@@ -198,21 +208,50 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     };
     auto nop = [] {};
 
-    // ---- A operand builders (all 512 threads; rows >= nrows are zero) ------------------------------------------
-    // writes x (8 consecutive columns c8*8.. of tile row r) into the swizzled A tile and, for this CTA's 16 residual columns, rs
-    auto put_a8 = [&](int r, int c8, const float (&v)[8]) {
-        uint4 o;
-        o.x = pack_bf16(v[0], v[1]);
-        o.y = pack_bf16(v[2], v[3]);
-        o.z = pack_bf16(v[4], v[5]);
-        o.w = pack_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(sA + (c8 >> 3) * 16384 + sw128(r, c8 & 7)) = o;
-        if ((c8 >> 1) == j) *reinterpret_cast<uint4*>(&ms.rs[r * 8 + (c8 & 1) * 4]) = o;
+    // ---- operand loads issued by the TMA thread ------------------------------------------------------------------
+    // small B operand: nB weight rows [b_row0, b_row0 + nB) x 256, k-block kb at sSB + kb * nB * 128 (prefetched at the
+    // barrier in front of the phase that consumes it)
+    auto load_small_b = [&](const CUtensorMap* mb, int b_row0, int nB) {
+        for (int kb = 0; kb < 4; ++kb) {
+            mbar_arrive_expect_tx(&ms.kb_full[kb], (uint32_t)(nB * 128));
+            tma_load_2d(sSB + kb * nB * 128, mb, &ms.kb_full[kb], kb * 64, b_row0);
+        }
     };
-    // embedding + positional encoding (decoder/transformer.py:163,169; pos.py:56): A = emb[last_tok] * sqrt(d) + PE[step]
+    auto load_a = [&](const CUtensorMap* ma) {        // A tile: rows [row0, row0 + 128) of ctx / x
+        for (int kb = 0; kb < 4; ++kb) {
+            mbar_arrive_expect_tx(&ms.a_full[kb], 16384);
+            tma_load_2d(sA + kb * 16384, ma, &ms.a_full[kb], kb * 64, row0);
+        }
+    };
+    auto load_w1 = [&](int l) {   // both stages: k-block kb -> stage kb/2, [value rows | gate rows] of this CTA's 128 hidden features
+        const CUtensorMap* m = maps + l * 6 + 4;
+        for (int kb = 0; kb < 4; ++kb) {
+            uint8_t* dst = sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768;
+            mbar_arrive_expect_tx(&ms.w1_full[kb], 32768);
+            tma_load_2d(dst, m, &ms.w1_full[kb], kb * 64, j * 128);
+            tma_load_2d(dst + 16384, m, &ms.w1_full[kb], kb * 64, DG_DFF + j * 128);
+        }
+    };
+    auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
+        const int u = u0 + task / DG_H, h = task % DG_H;
+        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
+        tma_load_2d(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T);
+        tma_load_2d(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T);
+    };
+    const int n_vchunks = (V + 127) / 128;
+    auto load_wout = [&](int chunk, int s) {
+        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sST + s * DG_STAGE + kb * 16384, map_wout, &ms.st_full[s], kb * 64, chunk * 128);
+    };
+    const int n_tasks = nutt * DG_H;   // cross-attention problems of this group; CTA j takes j, j + P, ...
+
+    // ---- A operand builders -------------------------------------------------------------------------------------
+    // embedding + positional encoding (decoder/transformer.py:163,169; pos.py:56): x = emb[last_tok] * sqrt(d) + PE[step].
+    // Every CTA builds the whole tile (the QKV projection of layer 0 reads it from shared memory); rows [8 j, 8 j + 8) are also
+    // written to xbuf, where the out-projection epilogues fetch their residual slice.
     auto build_a_embed = [&](int step) {
         for (int r = warp; r < 128; r += 16) {
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint4 o = make_uint4(0, 0, 0, 0);
             if (r < nrows) {
                 long long tok = p.st.last_tok[row0 + r];
                 if (tok < 0 || tok >= V) tok = 0;
@@ -221,76 +260,83 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const float4 p0 = *reinterpret_cast<const float4*>(pe), p1 = *reinterpret_cast<const float4*>(pe + 4);
                 const float2 e0 = unpack_bf16(u.x), e1 = unpack_bf16(u.y), e2 = unpack_bf16(u.z), e3 = unpack_bf16(u.w);
                 const float xs = 16.0f;   // sqrt(256)
-                v[0] = e0.x * xs + p0.x; v[1] = e0.y * xs + p0.y; v[2] = e1.x * xs + p0.z; v[3] = e1.y * xs + p0.w;
-                v[4] = e2.x * xs + p1.x; v[5] = e2.y * xs + p1.y; v[6] = e3.x * xs + p1.z; v[7] = e3.y * xs + p1.w;
+                o.x = pack_bf16(e0.x * xs + p0.x, e0.y * xs + p0.y);
+                o.y = pack_bf16(e1.x * xs + p0.z, e1.y * xs + p0.w);
+                o.z = pack_bf16(e2.x * xs + p1.x, e2.y * xs + p1.y);
+                o.w = pack_bf16(e3.x * xs + p1.z, e3.y * xs + p1.w);
+                if ((r >> 3) == j) *reinterpret_cast<uint4*>(p.xbuf + (size_t)(row0 + r) * DG_D + lane * 8) = o;
             }
-            put_a8(r, lane, v);
+            *reinterpret_cast<uint4*>(sA + (lane >> 3) * 16384 + sw128(r, lane & 7)) = o;
         }
         fence_proxy_async_smem();
         __syncthreads();
     };
-    // LayerNorm of the gathered pre-norm rows (fp32, resid + projection + bias) -> bf16 A tile (transformer.py:54-56 etc.)
-    auto build_a_ln = [&](const float* gamma, const float* beta) {
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
-        {
-            const int rb = warp * 8;
-            float4 y0[8], y1[8];      // all 8 rows of the warp in flight at once: one L2 round trip instead of two
+    // LayerNorm of the gathered pre-norm rows (fp32: residual + projection + bias) -> bf16 A tile (transformer.py:54-56 ...).
+    // 8 lanes per row (4 rows per warp instruction; lane c of a row owns columns 32 k + 4 c .. + 3, k = 0..7: every load
+    // instruction reads 128 contiguous bytes per row), statistics through 3 shuffles.  v2 gave a row to a whole warp (5-level
+    // shuffles, 16-byte swizzled stores): 7.5 k cycles per build, three per layer.  The 16 columns of this CTA go to the
+    // residual stash rs; with x2_out the rows [8 j, 8 j + 8) are also written to global memory (residual of the w_2 reduction).
+    auto build_a_ln = [&](const float* gamma, const float* beta, bf16* x_out) {
+        const int g4 = lane >> 3, c = lane & 7;
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            const int r = warp * 8 + it * 4 + g4;
+            float4 v[8];
+            if (r < nrows) {
+                const float* src = p.pre + (size_t)(row0 + r) * DG_D + 4 * c;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rb + i;
-                if (r < nrows) {
-                    const float* src = p.pre + (size_t)(row0 + r) * DG_D + lane * 8;
-                    y0[i] = *reinterpret_cast<const float4*>(src);
-                    y1[i] = *reinterpret_cast<const float4*>(src + 4);
-                } else {
-                    y0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    y1[i] = y0[i];
-                }
+                for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(src + 32 * k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rb + i;
-                float v[8] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w, y1[i].x, y1[i].y, y1[i].z, y1[i].w};
-                float s = 0.f;
+            for (int k = 0; k < 8; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            const float mean = s * (1.0f / DG_D);
+            float q = 0.f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) s += v[q];
-                const float mean = warp_sum(s) * (1.0f / DG_D);
-                float q2 = 0.f;
+            for (int k = 0; k < 8; ++k) {
+                const float a = v[k].x - mean, b = v[k].y - mean, cc = v[k].z - mean, d = v[k].w - mean;
+                q += (a * a + b * b) + (cc * cc + d * d);
+            }
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            q += __shfl_xor_sync(0xffffffffu, q, 4);
+            const float rstd = rsqrtf(q * (1.0f / DG_D) + p.eps);
+            const bool live = r < nrows;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { const float dd = v[q] - mean; q2 += dd * dd; }
-                const float rstd = rsqrtf(warp_sum(q2) * (1.0f / DG_D) + p.eps);
-                float o[8];
-                o[0] = (v[0] - mean) * rstd * g0.x + b0.x; o[1] = (v[1] - mean) * rstd * g0.y + b0.y;
-                o[2] = (v[2] - mean) * rstd * g0.z + b0.z; o[3] = (v[3] - mean) * rstd * g0.w + b0.w;
-                o[4] = (v[4] - mean) * rstd * g1.x + b1.x; o[5] = (v[5] - mean) * rstd * g1.y + b1.y;
-                o[6] = (v[6] - mean) * rstd * g1.z + b1.z; o[7] = (v[7] - mean) * rstd * g1.w + b1.w;
-                if (r >= nrows) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = 0.f;
-                }
-                put_a8(r, lane, o);
+            for (int k = 0; k < 8; ++k) {
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + 32 * k + 4 * c));     // L1-resident after the first row
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + 32 * k + 4 * c));
+                uint2 o;
+                o.x = live ? pack_bf16((v[k].x - mean) * rstd * gm.x + bt.x, (v[k].y - mean) * rstd * gm.y + bt.y) : 0u;
+                o.y = live ? pack_bf16((v[k].z - mean) * rstd * gm.z + bt.z, (v[k].w - mean) * rstd * gm.w + bt.w) : 0u;
+                const int col = 32 * k + 4 * c;           // 4 consecutive columns = half of a 16-byte chunk
+                *reinterpret_cast<uint2*>(sA + (col >> 6) * 16384 + sw128(r, (col & 63) >> 3) + (col & 4) * 2) = o;
+                if ((col >> 4) == j) *reinterpret_cast<uint2*>(&ms.rs[r * 8 + ((col & 15) >> 1)]) = o;
+                if (x_out != nullptr && live && (r >> 3) == j) *reinterpret_cast<uint2*>(x_out + (size_t)(row0 + r) * DG_D + col) = o;
             }
         }
         fence_proxy_async_smem();
         __syncthreads();
     };
 
-    // ---- small GEMM: acc[128 x nB] = A[128 x 256] * W[b_row0 .. b_row0 + nB, 256]^T, B slice in sSB ----------------------
-    // a_tma: A is fetched from the ctx matrix by TMA (else it was built in shared memory by the CTA).  epi(c, r16) is called by
-    // the 128 epilogue threads for every 16-column chunk of their row.  Ends with a CTA barrier.
-    auto gemm_small = [&](const CUtensorMap* mb, int b_row0, int nB, bool a_tma, const float* bias, auto epi) {
+    // ---- small GEMM: acc[128 x nB] = A[128 x 256] * Bslice^T, B slice prefetched into sSB (kb_full).  a_map != null: A is fetched
+    // here by TMA (a_full), else it was built in shared memory by the CTA.  epi(c, r16) is called by the 128 epilogue threads for
+    // every 16-column chunk of their row.  Ends with a CTA barrier.
+    auto gemm_small = [&](int nB, const CUtensorMap* a_map, const float* bias, int b_row0, auto epi) {
         if (tid < nB) ms.bias[tid] = bias[b_row0 + tid];
         if (is_tma) {
-            for (int kb = 0; kb < 4; ++kb) {
-                mbar_arrive_expect_tx(&ms.kb_full[kb], (uint32_t)(nB * 128 + (a_tma ? 16384 : 0)));
-                if (a_tma) tma_load_2d(sA + kb * 16384, map_ctx, &ms.kb_full[kb], kb * 64, row0);
-                tma_load_2d(sSB + kb * nB * 128, mb, &ms.kb_full[kb], kb * 64, b_row0);
-            }
+            if (a_map != nullptr) load_a(a_map);
         } else if (is_mma) {
             const uint32_t idesc = umma_idesc_bf16(nB);
             for (int kb = 0; kb < 4; ++kb) {
                 mbar_wait(&ms.kb_full[kb], (par_kb >> kb) & 1);
+                if (a_map != nullptr) mbar_wait(&ms.a_full[kb], (par_a >> kb) & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sSB + kb * nB * 128);
 #pragma unroll
@@ -312,35 +358,32 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             tc_fence_before();
         }
         par_kb ^= 0xF;
+        if (a_map != nullptr) par_a ^= 0xF;
         par_accf ^= 1;
         __syncthreads();
     };
-
-    // big-stage loads issued by the TMA thread
-    auto load_w1 = [&](int l) {   // both stages: k-block kb -> stage kb/2, [value rows | gate rows] of this CTA's 128 hidden features
-        const CUtensorMap* m = maps + l * 6 + 4;
-        for (int kb = 0; kb < 4; ++kb) {
-            uint8_t* dst = sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768;
-            mbar_arrive_expect_tx(&ms.kb_full[kb], 32768);
-            tma_load_2d(dst, m, &ms.kb_full[kb], kb * 64, j * 128);
-            tma_load_2d(dst + 16384, m, &ms.kb_full[kb], kb * 64, DG_DFF + j * 128);
+    // [32 rows of this epilogue warp] x [32 fp32 columns] from TMEM -> coalesced 128-byte global stores through a padded
+    // shared-memory tile (each lane owns a ROW in TMEM; storing its 32 floats directly costs 32 cache lines per instruction)
+    float* tstage = reinterpret_cast<float*>(sSB) + equad * (32 * 33);
+    auto store_tile32 = [&](uint32_t taddr, float* gbase, int ld, const float* bias32, int ncols_ok) {
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tstage[lane * 33 + i] = __uint_as_float(r[i]) + (bias32 ? bias32[i] : 0.f);
+        __syncwarp();
+        if (lane < ncols_ok) {
+            for (int rr = 0; rr < 32; ++rr) {
+                const int row = equad * 32 + rr;
+                if (row < nrows) gbase[(size_t)row * ld + lane] = tstage[rr * 33 + lane];
+            }
         }
+        __syncwarp();
     };
-    auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
-        const int u = u0 + task / DG_H, h = task % DG_H;
-        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
-        tma_load_2d(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T);
-        tma_load_2d(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T);
-    };
-    const int n_vchunks = (V + 127) / 128;
-    auto load_wout = [&](int chunk, int s) {
-        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sST + s * DG_STAGE + kb * 16384, map_wout, &ms.st_full[s], kb * 64, chunk * 128);
-    };
-    const int n_tasks = nutt * DG_H;   // cross-attention problems of this group; CTA j takes j, j + P, ...
 
     int steps_done = 0;
     bool group_done = false;
+    if (is_tma) load_small_b(maps + 0, j * 48, 48);          // QKV weights of layer 0 for the first step
     for (int step = 0; step < p.max_steps; ++step) {
         dbg_on = dbg_cta && step == p.dbg_step;
         dbg_n = 0;
@@ -350,7 +393,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         for (int l = 0; l < nl; ++l) {
             const DgLayer& ly = p.layers[l];
             // ---------------- QKV projection of the newest token (attention.py:68-73): 48 of the 768 columns per CTA
-            gemm_small(maps + l * 6 + 0, j * 48, 48, false, ly.bqkv, [&](int c, const uint32_t (&r)[16]) {
+            gemm_small(48, l == 0 ? nullptr : map_x, ly.bqkv, j * 48, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
                 const int col = j * 48 + c;               // 16-column chunks never straddle the q | k | v boundaries
                 uint4 o[2];
@@ -365,18 +408,17 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 reinterpret_cast<uint4*>(dst)[0] = o[0];
                 reinterpret_cast<uint4*>(dst)[1] = o[1];
             });
-            gsync(nop);   // stamps: phase end (inside), barrier end (below)
+            gsync([&] { load_small_b(maps + l * 6 + 1, j * 16, 16); });      // out-projection weights arrive during the barrier
             DG_STAMP();
             // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
-            // One warp per (hypothesis, head).  v1 gave every lane a whole key (8 x 16-byte loads of a 128-byte row per lane =
-            // 32 cache lines per load instruction) and was bound by the L1 wavefront rate: 66 k cycles per layer at step 50.
-            // Now 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V row: one 128-byte line per
-            // 8 lanes, 4 keys per load instruction), the partial dot products meet through 3 shuffles, and each of the 4 lane
-            // groups keeps an online-softmax (m, l, o[8]) over its keys; the groups are merged at the end.
+            // One warp per (hypothesis, head); 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V
+            // row: one 128-byte line per 8 lanes, 4 keys per load instruction), the partial dot products meet through 3
+            // shuffles, each of the 4 lane groups keeps an online softmax (m, l, o[8]) over its keys, merged at the end.
+            // The K / V chunks of the next 16 keys are in flight while the current 16 are reduced.
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
-                int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                int* an_s = reinterpret_cast<int*>(sST) + warp * 128;          // this warp's ancestry row (<= 128 positions)
                 const int g4 = lane >> 3, c8 = lane & 7;
                 for (int task = j * 16 + warp; task < nrows * DG_H; task += DG_P * 16) {
                     const int r = task / DG_H, h = task % DG_H;
@@ -394,23 +436,25 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     float m = -INFINITY, lsum = 0.f;
                     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     const size_t col = (size_t)h * 64 + c8 * 8;
-                    for (int k0 = 0; k0 < nkeys; k0 += 16) {          // 4 keys per lane group per iteration, 8 loads in flight per lane
-                        uint4 ku[4], vu[4];
-                        bool ok[4];
+                    uint4 ku[4], vu[4], kn[4], vn[4];
+                    auto fetch = [&](int k0, uint4 (&kk)[4], uint4 (&vv)[4]) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int sidx = k0 + 4 * u + g4;
-                            ok[u] = sidx < nkeys;
-                            const int slot = (sidx < step) ? an_s[sidx] : n;
-                            const size_t off = (((size_t)l * Lmax + (ok[u] ? sidx : 0)) * N + slot) * DG_D + col;
-                            if (ok[u]) {
-                                ku[u] = *reinterpret_cast<const uint4*>(p.kc + off);
-                                vu[u] = *reinterpret_cast<const uint4*>(p.vc + off);
+                            if (sidx < nkeys) {
+                                const int slot = (sidx < step) ? an_s[sidx] : n;
+                                const size_t off = (((size_t)l * Lmax + sidx) * N + slot) * DG_D + col;
+                                kk[u] = *reinterpret_cast<const uint4*>(p.kc + off);
+                                vv[u] = *reinterpret_cast<const uint4*>(p.vc + off);
                             } else {
-                                ku[u] = make_uint4(0, 0, 0, 0);
-                                vu[u] = ku[u];
+                                kk[u] = make_uint4(0, 0, 0, 0);
+                                vv[u] = kk[u];
                             }
                         }
+                    };
+                    fetch(0, ku, vu);
+                    for (int k0 = 0; k0 < nkeys; k0 += 16) {
+                        if (k0 + 16 < nkeys) fetch(k0 + 16, kn, vn);
                         float sc[4];
                         float mb = m;
 #pragma unroll
@@ -420,7 +464,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             d += __shfl_xor_sync(0xffffffffu, d, 1);
                             d += __shfl_xor_sync(0xffffffffu, d, 2);
                             d += __shfl_xor_sync(0xffffffffu, d, 4);
-                            sc[u] = ok[u] ? d : -INFINITY;
+                            sc[u] = (k0 + 4 * u + g4 < nkeys) ? d : -INFINITY;
                             mb = fmaxf(mb, sc[u]);
                         }
                         if (mb != -INFINITY) {
@@ -430,7 +474,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             for (int q = 0; q < 8; ++q) o[q] *= alpha;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float pw = ok[u] ? __expf(sc[u] - mb) : 0.f;
+                                const float pw = (sc[u] == -INFINITY) ? 0.f : __expf(sc[u] - mb);
                                 lsum += pw;
                                 const float2 a = unpack_bf16(vu[u].x), b2 = unpack_bf16(vu[u].y), c2 = unpack_bf16(vu[u].z), e = unpack_bf16(vu[u].w);
                                 o[0] = fmaf(pw, a.x, o[0]); o[1] = fmaf(pw, a.y, o[1]); o[2] = fmaf(pw, b2.x, o[2]); o[3] = fmaf(pw, b2.y, o[3]);
@@ -438,6 +482,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             }
                             m = mb;
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { ku[u] = kn[u]; vu[u] = vn[u]; }
                     }
                     // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
                     float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
@@ -465,24 +511,26 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             }
             gsync(nop);
             DG_STAMP();
-            // ---------------- out-projection + residual -> pre-norm rows (attention.py:44, transformer.py:54)
-            auto epi_pre = [&](int c, const uint32_t (&r)[16]) {
+            // ---------------- out-projection + residual (the layer input, xbuf) -> pre-norm rows (attention.py:44, transformer.py:54)
+            gemm_small(16, map_ctx, ly.bo, j * 16, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
+                const uint4* rsrc = reinterpret_cast<const uint4*>(p.xbuf + (size_t)(row0 + erow) * DG_D + j * 16);
+                const uint4 ra = rsrc[0], rb = rsrc[1];
+                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                 float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 r0 = unpack_bf16(ms.rs[erow * 8 + 2 * i]), r1 = unpack_bf16(ms.rs[erow * 8 + 2 * i + 1]);
+                    const float2 r0 = unpack_bf16(rw[2 * i]), r1 = unpack_bf16(rw[2 * i + 1]);
                     dst[i] = make_float4(__uint_as_float(r[4 * i]) + ms.bias[4 * i] + r0.x, __uint_as_float(r[4 * i + 1]) + ms.bias[4 * i + 1] + r0.y,
                                          __uint_as_float(r[4 * i + 2]) + ms.bias[4 * i + 2] + r1.x, __uint_as_float(r[4 * i + 3]) + ms.bias[4 * i + 3] + r1.y);
                 }
-            };
-            gemm_small(maps + l * 6 + 1, j * 16, 16, true, ly.bo, epi_pre);
-            gsync(nop);
+            });
+            gsync([&] { load_small_b(maps + l * 6 + 2, j * 16, 16); });      // q-projection weights
             DG_STAMP();
             // ---------------- LayerNorm 1 + cross-attention query projection (attention.py:128)
-            build_a_ln(ly.g1, ly.be1);
+            build_a_ln(ly.g1, ly.be1, nullptr);
             DG_STAMP();   // LN1
-            gemm_small(maps + l * 6 + 2, j * 16, 16, false, ly.bq, [&](int c, const uint32_t (&r)[16]) {
+            gemm_small(16, nullptr, ly.bq, j * 16, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
                 uint4 o[2];
                 uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -614,7 +662,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     __syncthreads();
                     // the stage is free: fetch the K / V tiles of the task after next
                     if (is_tma && task + 2 * DG_P < n_tasks) load_kv(l, task + 2 * DG_P, s);
-                    if (tid < 16 * 32) {
+                    {
                         const int r = tid >> 5, dp = tid & 31;     // row, output dim pair
                         if (r < beam) {
                             const int w0 = dp >> 2, e = (dp & 3) * 2;
@@ -629,57 +677,34 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     }
                     __syncthreads();
                 }
-                // every thread advanced par_stf by its own waits: all threads waited on the same tasks, so the words agree
             }
-            gsync([&] { load_w1(l); });    // W1 slice (128 KB) streams in while the out-projection and LayerNorm run
+            gsync([&] {    // W1 slice (128 KB) and the out-projection weights stream in while the other CTAs finish
+                load_w1(l);
+                load_small_b(maps + l * 6 + 3, j * 16, 16);
+            });
             DG_STAMP();
-            // ---------------- cross-attention out-projection + residual -> pre-norm rows
-            // (kb_full barriers are busy with the W1 prefetch: this small GEMM uses the st_full pair instead)
-            {
-                if (tid < 16) ms.bias[tid] = ly.bo2[j * 16 + tid];
-                if (is_tma) {
-                    mbar_arrive_expect_tx(&ms.st_full[0], (uint32_t)(4 * (16 * 128 + 16384)));
-                    for (int kb = 0; kb < 4; ++kb) {
-                        tma_load_2d(sA + kb * 16384, map_ctx, &ms.st_full[0], kb * 64, row0);
-                        tma_load_2d(sSB + kb * 2048, maps + l * 6 + 3, &ms.st_full[0], kb * 64, j * 16);
-                    }
-                } else if (is_mma) {
-                    const uint32_t idesc = umma_idesc_bf16(16);
-                    mbar_wait(&ms.st_full[0], par_stf & 1);
-                    tc_fence_after();
-                    for (int kb = 0; kb < 4; ++kb) {
-                        const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sSB + kb * 2048);
+            // ---------------- cross-attention out-projection + residual (x1, the stash of LayerNorm 1) -> pre-norm rows
+            gemm_small(16, map_ctx, ly.bo2, j * 16, [&](int c, const uint32_t (&r)[16]) {
+                if (erow >= nrows) return;
+                float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
-                    }
-                    umma_commit(&ms.acc_full[0]);
+                for (int i = 0; i < 4; ++i) {
+                    const float2 r0 = unpack_bf16(ms.rs[erow * 8 + 2 * i]), r1 = unpack_bf16(ms.rs[erow * 8 + 2 * i + 1]);
+                    dst[i] = make_float4(__uint_as_float(r[4 * i]) + ms.bias[4 * i] + r0.x, __uint_as_float(r[4 * i + 1]) + ms.bias[4 * i + 1] + r0.y,
+                                         __uint_as_float(r[4 * i + 2]) + ms.bias[4 * i + 2] + r1.x, __uint_as_float(r[4 * i + 3]) + ms.bias[4 * i + 3] + r1.y);
                 }
-                __syncthreads();
-                if (is_epi) {
-                    mbar_wait(&ms.acc_full[0], par_accf & 1);
-                    tc_fence_after();
-                    uint32_t r[16];
-                    tmem_ld16(t_row, r);
-                    tmem_ld_wait();
-                    epi_pre(0, r);
-                    tc_fence_before();
-                }
-                par_stf ^= 1;
-                par_accf ^= 1;
-                __syncthreads();
-            }
+            });
             gsync(nop);
             DG_STAMP();
             // ---------------- LayerNorm 2 + GLU feed-forward: hidden features [128 j, 128 j + 128) (ffn.py:18,39-41)
-            build_a_ln(ly.g2, ly.be2);
+            build_a_ln(ly.g2, ly.be2, p.x2buf);
             DG_STAMP();   // LN2
             {
                 if (tid < 256) ms.bias[tid] = ly.b1[(tid < 128 ? 0 : DG_DFF - 128) + j * 128 + tid];
                 if (is_mma) {
                     const uint32_t idesc = umma_idesc_bf16(256);
                     for (int kb = 0; kb < 4; ++kb) {
-                        mbar_wait(&ms.kb_full[kb], (par_kb >> kb) & 1);
+                        mbar_wait(&ms.w1_full[kb], (par_w1 >> kb) & 1);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(sA + kb * 16384);
                         const uint32_t b_addr = smem_u32(sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768);
@@ -721,7 +746,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     tc_fence_before();
                     fence_proxy_async_smem();
                 }
-                par_kb ^= 0xF;
+                par_w1 ^= 0xF;
                 par_accf ^= 1;
                 __syncthreads();
                 DG_STAMP();   // W1 + GLU
@@ -741,18 +766,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 if (is_epi) {
                     mbar_wait(&ms.acc_full[1], (par_accf >> 1) & 1);
                     tc_fence_after();
-                    float* dst = p.part + ((size_t)j * N + row0 + erow) * DG_D;
+                    float* dst = p.part + ((size_t)j * N + row0) * DG_D;
 #pragma unroll 1
-                    for (int c = 0; c < 256; c += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(t_row + 256 + c, r);
-                        tmem_ld_wait();
-                        if (erow < nrows) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                *reinterpret_cast<uint4*>(dst + c + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-                        }
-                    }
+                    for (int c = 0; c < 256; c += 32) store_tile32(t_row + 256 + c, dst + c, DG_D, nullptr, 32);
                     tc_fence_before();
                 }
                 par_stf ^= 1;
@@ -763,38 +779,66 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 if (last_layer) {   // output-layer chunks of this CTA: the first two stream in during the reduction
                     if (j < n_vchunks) load_wout(j, 0);
                     if (j + DG_P < n_vchunks) load_wout(j + DG_P, 1);
+                } else {
+                    load_small_b(maps + (l + 1) * 6 + 0, j * 48, 48);      // QKV weights of the next layer
                 }
             });
             DG_STAMP();
-            // ---------------- reduce the 16 partial sums of this CTA's 16 output columns + bias + residual -> pre-norm rows
+            // ---------------- sum of the 16 partial products + bias + residual (x2) + LayerNorm 3, rows [8 j, 8 j + 8) of the
+            // tile: every load is a contiguous 512-byte half row, the row statistics stay inside the CTA, and the result is the
+            // bf16 input of the next layer (or of the output layer) in xbuf -- no separate LayerNorm pass, no fp32 round trip
             {
-                const int r = tid >> 2, q4 = tid & 3;
-                if (r < nrows) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float* src = p.part + ((size_t)(row0 + r)) * DG_D + j * 16 + q4 * 4;
-                    float4 v[DG_P];
+                float* rsum = ms.c_val;      // [16 warps] partial sums, then squared deviations (sSB is receiving the next QKV weights)
+                const int rr = warp >> 1, half = warp & 1;
+                const int r = j * 8 + rr;
+                const int c0 = half * 128 + lane * 4;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool live = r < nrows;
+                if (live) {
+                    const float* src = p.part + ((size_t)(row0 + r)) * DG_D + c0;
 #pragma unroll
-                    for (int pp = 0; pp < DG_P; ++pp) v[pp] = *reinterpret_cast<const float4*>(src + (size_t)pp * N * DG_D);
+                    for (int h8 = 0; h8 < DG_P; h8 += 8) {
+                        float4 v[8];
 #pragma unroll
-                    for (int pp = 0; pp < DG_P; ++pp) { acc.x += v[pp].x; acc.y += v[pp].y; acc.z += v[pp].z; acc.w += v[pp].w; }
-                    const float4 b = *reinterpret_cast<const float4*>(ly.b2 + j * 16 + q4 * 4);
-                    const float2 r0 = unpack_bf16(ms.rs[r * 8 + 2 * q4]), r1 = unpack_bf16(ms.rs[r * 8 + 2 * q4 + 1]);
-                    *reinterpret_cast<float4*>(p.pre + (size_t)(row0 + r) * DG_D + j * 16 + q4 * 4) =
-                        make_float4(acc.x + b.x + r0.x, acc.y + b.y + r0.y, acc.z + b.z + r1.x, acc.w + b.w + r1.y);
+                        for (int pp = 0; pp < 8; ++pp) v[pp] = *reinterpret_cast<const float4*>(src + (size_t)(h8 + pp) * N * DG_D);
+#pragma unroll
+                        for (int pp = 0; pp < 8; ++pp) { acc.x += v[pp].x; acc.y += v[pp].y; acc.z += v[pp].z; acc.w += v[pp].w; }
+                    }
+                    const float4 b = *reinterpret_cast<const float4*>(ly.b2 + c0);
+                    const uint2 xr = *reinterpret_cast<const uint2*>(p.x2buf + (size_t)(row0 + r) * DG_D + c0);
+                    const float2 r0 = unpack_bf16(xr.x), r1 = unpack_bf16(xr.y);
+                    acc.x += b.x + r0.x; acc.y += b.y + r0.y; acc.z += b.z + r1.x; acc.w += b.w + r1.y;
+                }
+                float s = warp_sum((acc.x + acc.y) + (acc.z + acc.w));
+                if (lane == 0) rsum[warp] = s;
+                __syncthreads();
+                const float mean = (rsum[rr * 2] + rsum[rr * 2 + 1]) * (1.0f / DG_D);
+                const float a = acc.x - mean, b = acc.y - mean, cc = acc.z - mean, d = acc.w - mean;
+                float q = warp_sum((a * a + b * b) + (cc * cc + d * d));
+                __syncthreads();
+                if (lane == 0) rsum[warp] = q;
+                __syncthreads();
+                const float rstd = rsqrtf((rsum[rr * 2] + rsum[rr * 2 + 1]) * (1.0f / DG_D) + p.eps);
+                if (live) {
+                    const float4 gm = *reinterpret_cast<const float4*>(ly.g3 + c0), bt = *reinterpret_cast<const float4*>(ly.be3 + c0);
+                    uint2 o;
+                    o.x = pack_bf16(a * rstd * gm.x + bt.x, b * rstd * gm.y + bt.y);
+                    o.y = pack_bf16(cc * rstd * gm.z + bt.z, d * rstd * gm.w + bt.w);
+                    *reinterpret_cast<uint2*>(p.xbuf + (size_t)(row0 + r) * DG_D + c0) = o;
                 }
             }
             gsync(nop);
             DG_STAMP();
-            build_a_ln(ly.g3, ly.be3);   // LayerNorm 3 = input of the next layer (or of the output layer)
-            DG_STAMP();   // LN3
         }
 
-        // ---------------- output layer (decoder/transformer.py:181) in 128-column chunks; log-softmax statistics and the per-row
-        // top-`beam` candidates are formed in the epilogue (transformer.py:206 + speech2text.py:112), the logits are never stored
+        // ---------------- output layer (decoder/transformer.py:181) in 128-column chunks: logits (+ bias) to global memory with
+        // coalesced stores.  (v2 formed the log-softmax statistics and a per-row top-k in registers in this epilogue: one
+        // sorted insertion per element per lane with all 32 rows of a warp diverging = 300 k cycles per step.)
         {
             int my_chunks = 0;
             for (int c = j; c < n_vchunks; c += DG_P) ++my_chunks;
             if (is_tma) {
+                load_a(map_x);
                 for (int i = 2; i < my_chunks; ++i) {        // chunks 0 and 1 were prefetched
                     const int s = i & 1;
                     mbar_wait(&ms.st_empty[s], ((par_ste >> s) & 1) ^ (uint32_t)(((i - 2) >> 1) & 1));
@@ -802,6 +846,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
             } else if (is_mma) {
                 const uint32_t idesc = umma_idesc_bf16(128);
+                for (int kb = 0; kb < 4; ++kb) mbar_wait(&ms.a_full[kb], (par_a >> kb) & 1);
                 for (int i = 0; i < my_chunks; ++i) {
                     const int s = i & 1;
                     const uint32_t use = (uint32_t)((i >> 1) & 1);
@@ -821,60 +866,28 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     umma_commit(&ms.acc_full[s]);
                 }
             } else if (is_epi) {
-                float m = -INFINITY, ssum = 0.f;
-                TopList tl;
-                tl.init();
-                float* dump = p.dbg_logp ? p.dbg_logp + ((size_t)step * N + row0 + erow) * V : nullptr;
+                float* biasw = reinterpret_cast<float*>(sSB) + 4 * 32 * 33 + equad * 32;     // this warp's 32 bias values
                 for (int i = 0; i < my_chunks; ++i) {
                     const int s = i & 1;
                     const int col0 = (j + i * DG_P) * 128;
                     mbar_wait(&ms.acc_full[s], ((par_accf >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
                     tc_fence_after();
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(t_row + s * 128 + c, r);
-                        tmem_ld_wait();
-                        if (col0 + c >= V) continue;
-                        float x[16];
-                        float cm = -INFINITY;
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const int col = col0 + c + q;
-                            x[q] = (col < V) ? __uint_as_float(r[q]) + (p.bout ? __ldg(p.bout + col) : 0.f) : -INFINITY;
-                            cm = fmaxf(cm, x[q]);
-                        }
-                        if (erow < nrows) {
-                            const float mn = fmaxf(m, cm);
-                            float acc = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) acc += __expf(x[q] - mn);
-                            ssum = ssum * __expf(m - mn) + acc;
-                            m = mn;
-#pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                if (col0 + c + q < V) {
-                                    tl.push(x[q], col0 + c + q);
-                                    if (dump) dump[col0 + c + q] = x[q];
-                                }
-                        }
+                    for (int c = 0; c < 128; c += 32) {
+                        const int cc0 = col0 + c;
+                        if (cc0 >= V) break;      // warp-uniform
+                        __syncwarp();
+                        biasw[lane] = (p.bout != nullptr && cc0 + lane < V) ? p.bout[cc0 + lane] : 0.f;
+                        __syncwarp();
+                        store_tile32(t_row + s * 128 + c, p.logits + (size_t)row0 * p.ldv + cc0, p.ldv, biasw, min(32, V - cc0));
                     }
                     tc_fence_before();
                     mbar_arrive(&ms.acc_empty[s]);
                 }
-                if (erow < nrows) {
-                    p.stats[(size_t)(row0 + erow) * DG_P + j] = make_float2(m, ssum);
-                    float* cv = p.cand_v + ((size_t)(row0 + erow) * DG_P + j) * KMAX;
-                    int* ci = p.cand_i + ((size_t)(row0 + erow) * DG_P + j) * KMAX;
-#pragma unroll
-                    for (int q = 0; q < KMAX; ++q) {
-                        cv[q] = tl.v[q];
-                        ci[q] = tl.i[q];
-                    }
-                }
             }
             // parity bookkeeping: barrier pair s was used ceil((my_chunks - s) / 2) times
             const uint32_t u0n = (uint32_t)((my_chunks + 1) >> 1), u1n = (uint32_t)(my_chunks >> 1);
+            par_a ^= 0xF;
             par_stf ^= (u0n & 1) | ((u1n & 1) << 1);
             par_ste ^= (u0n & 1) | ((u1n & 1) << 1);
             par_accf ^= (u0n & 1) | ((u1n & 1) << 1);
@@ -882,59 +895,107 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         }
         gsync(nop);
         DG_STAMP();
-        // ---------------- per utterance: merge candidates, finished masking, beam^2 pruning, ancestry (speech2text.py:102-153)
+        // ---------------- per utterance: log-softmax + top-`beam` of every hypothesis row (decoder/transformer.py:206,
+        // speech2text.py:112: 8 warps per row, two rows at a time, rows staged in the free weight stages), finished masking,
+        // beam^2 pruning, ancestry (speech2text.py:102-153) -- beam.cu's algorithm, ties -> lower index
         int ended_here = 0;
         for (int ul = j; ul < nutt; ul += DG_P) {
             const int u = u0 + ul;
+            {
+                const int hb = warp >> 3, hw = warp & 7, ht = tid & 255;      // half block (row slot), warp / thread inside it
+                float* srow = reinterpret_cast<float*>(sST + hb * DG_STAGE);  // [V] this half's row
+                float* hred = reinterpret_cast<float*>(sSB) + hb * 16;        // [8] reduction scratch + [1] broadcast
+                float* cand_v = reinterpret_cast<float*>(sSB) + 64 + hb * (8 * KMAX);
+                int* cand_i = reinterpret_cast<int*>(sSB) + 64 + 2 * 8 * KMAX + hb * (8 * KMAX);
+                for (int r0 = 0; r0 < beam; r0 += 2) {
+                    const int r = r0 + hb;
+                    const bool have = r < beam;
+                    const int n = u * beam + (have ? r : 0);
+                    const float* x = p.logits + (size_t)n * p.ldv;
+                    float mx = -INFINITY;
+                    if (have) {
+                        for (int i = ht; i < V; i += 256) {
+                            const float v = x[i];
+                            srow[i] = v;
+                            mx = fmaxf(mx, v);
+                        }
+                    }
+                    mx = warp_max(mx);
+                    if (lane == 0) hred[hw] = mx;
+                    __syncthreads();
+                    mx = hred[0];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, hred[i]);
+                    float sum = 0.f;
+                    if (have)
+                        for (int i = ht; i < V; i += 256) sum += expf(srow[i] - mx);
+                    sum = warp_sum(sum);
+                    __syncthreads();
+                    if (lane == 0) hred[hw] = sum;
+                    __syncthreads();
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) tsum += hred[i];
+                    const float lse = mx + logf(tsum);
+                    if (have) {
+                        float* dump = p.dbg_logp ? p.dbg_logp + ((size_t)step * N + n) * V : nullptr;
+                        for (int i = ht; i < V; i += 256) {
+                            const float v = srow[i] - lse;
+                            srow[i] = v;
+                            if (dump) dump[i] = v;
+                        }
+                    }
+                    __syncthreads();
+                    // per-warp top-k over a contiguous slice: k rounds of (lane-local scan, warp arg-max, knock out)
+                    const int per = (V + 7) / 8;
+                    const int lo = hw * per, hi = min(V, lo + per);
+                    if (have) {
+                        for (int k = 0; k < beam; ++k) {
+                            float bv = -INFINITY;
+                            int bi = 0x7fffffff;
+                            for (int idx = lo + lane; idx < hi; idx += 32) {
+                                const float v = srow[idx];
+                                if (v > bv) { bv = v; bi = idx; }      // ascending scan + strict '>' keeps the lower index on ties
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                            }
+                            if (bi != 0x7fffffff && ((bi - lo) & 31) == lane) srow[bi] = -INFINITY;
+                            if (lane == 0) { cand_v[hw * KMAX + k] = bv; cand_i[hw * KMAX + k] = bi; }
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                    if (have && hw == 0) {
+                        // merge: 8 sorted lists of `beam` -> the row's top-`beam` (lane w < 8 walks list w)
+                        int pos = 0;
+                        for (int k = 0; k < beam; ++k) {
+                            float bv = (lane < 8 && pos < beam) ? cand_v[lane * KMAX + pos] : -INFINITY;
+                            int bi = (lane < 8 && pos < beam) ? cand_i[lane * KMAX + pos] : 0x7fffffff;
+                            const float mv = bv;
+                            const int mi = bi;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                            }
+                            if (mi == bi && mv == bv && lane < 8) ++pos;
+                            if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
             for (int r = warp; r < beam; r += 16) {
                 const int n = u * beam + r;
-                // log-sum-exp of the row from the 16 partial (max, sum) pairs
-                float2 stt = (lane < DG_P) ? p.stats[(size_t)n * DG_P + lane] : make_float2(-INFINITY, 0.f);
-                const float M = warp_max(stt.x);
-                const float S = warp_sum(stt.y * __expf(stt.x - M));
-                const float lse = M + logf(S);
-                if (p.dbg_logp) {
-                    float* dump = p.dbg_logp + ((size_t)step * N + n) * V;
-                    for (int c = lane; c < V; c += 32) dump[c] = dump[c] - lse;
-                }
                 if (p.st.flag[n]) {                      // mask_finished_scores / mask_finished_preds (speech2text.py:156-192)
                     if (lane < beam) {
                         ms.row_v[r][lane] = (lane == 0) ? 0.f : -INFINITY;
                         ms.row_i[r][lane] = (int)EOS_ID;
-                    }
-                } else {
-                    // 16 sorted lists of `beam` candidates -> top-`beam` of (log-prob, token id), ties -> lower token id
-                    float cvv[(DG_P * KMAX + 31) / 32];
-                    int cii[(DG_P * KMAX + 31) / 32];
-                    const int ncand = DG_P * beam;
-#pragma unroll
-                    for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q) {
-                        const int idx = lane + 32 * q;
-                        cvv[q] = -INFINITY;
-                        cii[q] = 0x7fffffff;
-                        if (idx < ncand) {
-                            const int cj = idx / beam, ck = idx % beam;
-                            const float xv = p.cand_v[((size_t)n * DG_P + cj) * KMAX + ck];
-                            cii[q] = p.cand_i[((size_t)n * DG_P + cj) * KMAX + ck];
-                            cvv[q] = (cii[q] != 0x7fffffff) ? xv - lse : -INFINITY;
-                        }
-                    }
-                    for (int k = 0; k < beam; ++k) {
-                        float bv = -INFINITY;
-                        int bi = 0x7fffffff;
-#pragma unroll
-                        for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q)
-                            if (better(cvv[q], cii[q], bv, bi)) { bv = cvv[q]; bi = cii[q]; }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-                        }
-#pragma unroll
-                        for (int q = 0; q < (DG_P * KMAX + 31) / 32; ++q)
-                            if (cii[q] == bi && bi != 0x7fffffff) { cvv[q] = -INFINITY; cii[q] = 0x7fffffff; }   // token ids are unique per row
-                        if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
                     }
                 }
                 __syncwarp();
@@ -978,7 +1039,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             ms.flag = 0;
             if (ended_here) atomicAdd(&p.gstate[(size_t)g * Lmax + step], ended_here);
         }
-        gsync(nop);
+        gsync([&] { load_small_b(maps + 0, j * 48, 48); });     // QKV weights of layer 0 for the next step
         DG_STAMP();
         steps_done = step + 1;
         if (tid == 0) ms.flag = (ld_acquire_gpu(&p.gstate[(size_t)g * Lmax + step]) == nrows) ? 1 : 0;
@@ -988,6 +1049,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         if (tid == 0) ms.flag = 0;
         if (group_done) break;      // every hypothesis of every utterance of this group ended (uniform across the group)
     }
+    // drain the QKV-weight prefetch that was issued for a step that will not run
+    if (is_mma)
+        for (int kb = 0; kb < 4; ++kb) mbar_wait(&ms.kb_full[kb], (par_kb >> kb) & 1);
 
     // A group that ended early keeps emitting EOS from its (sorted) hypotheses with identity parents while the reference loops
     // on for the other utterances (speech2text.py:62-68): fill the rest of its history so that any global step count >= its own
@@ -1014,20 +1078,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam) {
+static int dg_ldv(int V) { return (V + 31) / 32 * 32; }
+
+size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam, int V) {
     const int upg = 128 / beam;
     const int G = (B + upg - 1) / upg;
     size_t b = 0;
     auto take = [&](size_t n) { b += (n + 255) & ~(size_t)255; };
-    take((size_t)(n_layers * 6 + 3) * sizeof(CUtensorMap));   // maps
+    take((size_t)(n_layers * 6 + 4) * sizeof(CUtensorMap));   // maps
     take((size_t)N * DG_D * 2);                                // qbuf
     take((size_t)(N + 128) * DG_D * 2);                        // ctx (+ one tile of slack rows for the last group's TMA box)
+    take((size_t)(N + 128) * DG_D * 2);                        // xbuf
+    take((size_t)N * DG_D * 2);                                // x2buf
     take((size_t)N * DG_D * 4);                                // pre
     take((size_t)N * DG_D * 2);                                // q2
     take((size_t)DG_P * N * DG_D * 4);                         // part
-    take((size_t)N * DG_P * 8);                                // stats
-    take((size_t)N * DG_P * KMAX * 4);                         // cand_v
-    take((size_t)N * DG_P * KMAX * 4);                         // cand_i
+    take((size_t)N * dg_ldv(V) * 4);                           // logits
     take((size_t)G * 128);                                     // bar
     take((size_t)G * Lmax * 4);                                // gstate
     return b + 1024;
@@ -1045,27 +1111,28 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     const int upg = 128 / beam;
     const int G = (mp.B + upg - 1) / upg;
     if (G * DG_P > num_sms()) return "decode_persistent: batch needs more co-resident CTAs than the GPU has SMs";
-    if (workspace_bytes < decode_group_workspace_bytes(N, mp.n_layers, mp.st.Lmax, mp.B, beam)) return "decode_persistent: workspace too small";
+    if (workspace_bytes < decode_group_workspace_bytes(N, mp.n_layers, mp.st.Lmax, mp.B, beam, mp.V)) return "decode_persistent: workspace too small";
     if (reinterpret_cast<uintptr_t>(workspace) & 255) return "decode_persistent: workspace must be 256-byte aligned";
 
     DgParams p;
     memset(&p, 0, sizeof(p));
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
     auto take = [&](size_t n) { uint8_t* r = w; w += (n + 255) & ~(size_t)255; return r; };
-    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 3) * sizeof(CUtensorMap)));
+    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 4) * sizeof(CUtensorMap)));
     p.qbuf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.ctx = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
+    p.xbuf = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
+    p.x2buf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.pre = reinterpret_cast<float*>(take((size_t)N * DG_D * 4));
     p.q2 = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.part = reinterpret_cast<float*>(take((size_t)DG_P * N * DG_D * 4));
-    p.stats = reinterpret_cast<float2*>(take((size_t)N * DG_P * 8));
-    p.cand_v = reinterpret_cast<float*>(take((size_t)N * DG_P * KMAX * 4));
-    p.cand_i = reinterpret_cast<int*>(take((size_t)N * DG_P * KMAX * 4));
+    p.ldv = dg_ldv(mp.V);
+    p.logits = reinterpret_cast<float*>(take((size_t)N * p.ldv * 4));
     p.bar = reinterpret_cast<int*>(take((size_t)G * 128));
     p.gstate = reinterpret_cast<int*>(take((size_t)G * mp.st.Lmax * 4));
 
     // tensor maps (host encode -> device array).  Weights [rows, K] bf16 row-major, box = (64 columns) x (rows of one slice).
-    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 3];
+    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 4];
     const char* err;
     for (int l = 0; l < mp.n_layers; ++l) {
         const MegaLayer& ly = mp.layers[l];
@@ -1083,7 +1150,8 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     if ((err = encode_tmap_2d(&h_maps[nm + 0], mp.wout, DG_D, (uint64_t)mp.V, DG_D, 64, 128))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 1], p.ctx, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 2], mp.kvx, 2 * DG_D, (uint64_t)mp.n_layers * mp.B * mp.T, 2 * DG_D, 64, 256))) return err;
-    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 3) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+    if ((err = encode_tmap_2d(&h_maps[nm + 3], p.xbuf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
+    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 4) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.bar, 0, (size_t)G * 128, st)) != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.gstate, 0, (size_t)G * mp.st.Lmax * 4, st)) != cudaSuccess) return cudaGetErrorString(e);

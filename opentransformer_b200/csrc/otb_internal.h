@@ -178,12 +178,13 @@ struct DgParams {
     float eps;
     bf16* qbuf;                // [N, d]   self-attention queries of the newest token
     bf16* ctx;                 // [N + 128, d] attention context (self, then cross)
+    bf16* xbuf;                // [N + 128, d] layer input x (embedding / LayerNorm 3 of the previous layer)
+    bf16* x2buf;               // [N, d]   LayerNorm 2 output (residual of the feed-forward)
     float* pre;                // [N, d]   pre-LayerNorm rows (residual + projection + bias), fp32
     bf16* q2;                  // [N, d]   cross-attention queries
     float* part;               // [16, N, d] w_2 partial sums of the 16 contraction slices
-    float2* stats;             // [N, 16]  (max, sum exp) of each CTA's vocabulary columns
-    float* cand_v;             // [N, 16, 16] per-CTA top-k logits
-    int* cand_i;               //           and their token ids
+    float* logits;             // [N, ldv] output-layer logits of the step
+    int ldv;
     int* bar;                  // [G, 32]  group barrier counters
     int* gstate;               // [G, Lmax] ended-hypothesis count per step
     float* dbg_logp;
@@ -193,7 +194,7 @@ struct DgParams {
 };
 extern unsigned long long* g_dg_dbg;
 extern int g_dg_dbg_step;
-size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam);
+size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam, int V);
 const char* decode_group_launch(cudaStream_t st, const MegaParams& p, void* workspace, size_t workspace_bytes);
 
 const char* attn_launch(cudaStream_t st, const void* q, int ldq, int q_rows, const void* k, int ldk, int k_rows,

@@ -360,8 +360,8 @@ class BeamState:
         return out_preds, out_scores
 
 
-def decode_persistent_workspace(N, n_layers, Lmax, B, beam, device):
-    n = int(_lib.lib().otb_decode_persistent_workspace(N, n_layers, Lmax, B, beam))
+def decode_persistent_workspace(N, n_layers, Lmax, B, beam, vocab, device):
+    n = int(_lib.lib().otb_decode_persistent_workspace(N, n_layers, Lmax, B, beam, vocab))
     if n < 0:
         raise ValueError('otb_decode_persistent_workspace: bad geometry')
     return torch.zeros(n, dtype=torch.uint8, device=device)

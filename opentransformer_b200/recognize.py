@@ -153,7 +153,8 @@ class BeamDecoder:
     def run_persistent(self, max_steps, dbg_logp=None, dbg_scores=None):
         """All steps in ONE launch; no host round trip (ctrl[0] = executed steps is read by the caller)."""
         if self._ws is None:
-            self._ws = ops.decode_persistent_workspace(self.N, len(self.dec.blocks), self.Lmax, self.B, self.beam, self.device)
+            self._ws = ops.decode_persistent_workspace(self.N, len(self.dec.blocks), self.Lmax, self.B, self.beam,
+                                                       self.dec.vocab_size, self.device)
         ops.decode_persistent(self._mega(), self.kvx, self.mem_len, self.kc, self.vc, self.state, self.B, self.T, max_steps,
                               self._ws, dbg_logp, dbg_scores)
 

@@ -21,8 +21,8 @@ names = ['start', 'embed']
 for l in range(6):
     names += [f'L{l} ' + n for n in ('qkv gemm', 'barrier', 'self-attn', 'barrier', 'out-proj', 'barrier', 'LN1 build', 'q-proj', 'barrier',
                                      'cross-attn', 'barrier', 'out-proj2', 'barrier', 'LN2 build', 'w1+glu', 'w2 partial', 'barrier',
-                                     'reduce', 'barrier', 'LN3 build')]
-names += ['logits+topk', 'barrier', 'beam step', 'barrier']
+                                     'reduce+LN3', 'barrier')]
+names += ['logits', 'barrier', 'lsm+topk+beam', 'barrier']
 with torch.no_grad():
     mem, lens, B, T2 = model.encode_bf16(x, mask)
     bd = BeamDecoder(model.decoder, B, 10, T2, 60, dev, use_graph=False, persistent=True)
@@ -45,4 +45,4 @@ with torch.no_grad():
             agg[key] = agg.get(key, 0) + dt
         for k, v in agg.items():
             print(f'    {k:14s} {v:9d} cycles  {100.0 * v / (t[n-1]-t[0]):5.1f}%')
-        print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 22)])
+        print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 21)])
