@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_acce = 0;   // bit i = barrier i
     int bar_target = 0;
 
-    const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x == 0 && tid == 0);
+    const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
     int dbg_n = 0;
     bool dbg_on = false;
-#define DG_STAMP() do { if (dbg_on) p.dbg_clk[dbg_n++] = clock64(); } while (0)
+#define DG_STAMP() do { if (dbg_on) p.dbg_clk[blockIdx.x * 256 + dbg_n++] = clock64(); } while (0)
 
     // Group barrier: every CTA of the group has finished the phase (its global writes are visible).  `pre` runs on the TMA
     // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles); the
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     auto load_small_b = [&](const CUtensorMap* mb, int b_row0, int nB) {
         for (int kb = 0; kb < 4; ++kb) {
             mbar_arrive_expect_tx(&ms.kb_full[kb], (uint32_t)(nB * 128));
-            tma_load_2d(sSB + kb * nB * 128, mb, &ms.kb_full[kb], kb * 64, b_row0);
+            tma_load_2d_hint(sSB + kb * nB * 128, mb, &ms.kb_full[kb], kb * 64, b_row0, TMA_EVICT_LAST);
         }
     };
     auto load_a = [&](const CUtensorMap* ma) {        // A tile: rows [row0, row0 + 128) of ctx / x
@@ -228,20 +228,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         for (int kb = 0; kb < 4; ++kb) {
             uint8_t* dst = sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768;
             mbar_arrive_expect_tx(&ms.w1_full[kb], 32768);
-            tma_load_2d(dst, m, &ms.w1_full[kb], kb * 64, j * 128);
-            tma_load_2d(dst + 16384, m, &ms.w1_full[kb], kb * 64, DG_DFF + j * 128);
+            tma_load_2d_hint(dst, m, &ms.w1_full[kb], kb * 64, j * 128, TMA_EVICT_LAST);
+            tma_load_2d_hint(dst + 16384, m, &ms.w1_full[kb], kb * 64, DG_DFF + j * 128, TMA_EVICT_LAST);
         }
     };
     auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
         const int u = u0 + task / DG_H, h = task % DG_H;
         mbar_arrive_expect_tx(&ms.st_full[s], 65536);
-        tma_load_2d(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T);
-        tma_load_2d(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T);
+        // the encoder K / V tiles are streamed once per step (49 MB per batch): evict-first, so that they do not push the
+        // decoder weights (re-read by every group, every step) out of L2
+        tma_load_2d_hint(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T, TMA_EVICT_FIRST);
+        tma_load_2d_hint(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T, TMA_EVICT_FIRST);
     };
     const int n_vchunks = (V + 127) / 128;
     auto load_wout = [&](int chunk, int s) {
         mbar_arrive_expect_tx(&ms.st_full[s], 65536);
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sST + s * DG_STAGE + kb * 16384, map_wout, &ms.st_full[s], kb * 64, chunk * 128);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_hint(sST + s * DG_STAGE + kb * 16384, map_wout, &ms.st_full[s], kb * 64, chunk * 128, TMA_EVICT_LAST);
     };
     const int n_tasks = nutt * DG_H;   // cross-attention problems of this group; CTA j takes j, j + P, ...
 
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     // ---- small GEMM: acc[128 x nB] = A[128 x 256] * Bslice^T, B slice prefetched into sSB (kb_full).  a_map != null: A is fetched
     // here by TMA (a_full), else it was built in shared memory by the CTA.  epi(c, r16) is called by the 128 epilogue threads for
     // every 16-column chunk of their row.  Ends with a CTA barrier.
-    auto gemm_small = [&](int nB, const CUtensorMap* a_map, const float* bias, int b_row0, auto epi) {
+    auto gemm_small = [&](int nB, const CUtensorMap* a_map, const float* bias, int b_row0, auto pre_epi, auto epi) {
         if (tid < nB) ms.bias[tid] = bias[b_row0 + tid];
         if (is_tma) {
             if (a_map != nullptr) load_a(a_map);
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         }
         __syncthreads();   // bias slice visible to the epilogue threads
         if (is_epi) {
+            pre_epi();      // e.g. the residual slice: its L2 round trip overlaps the operand loads and the MMAs
             mbar_wait(&ms.acc_full[0], par_accf & 1);
             tc_fence_after();
             for (int c = 0; c < nB; c += 16) {
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         for (int l = 0; l < nl; ++l) {
             const DgLayer& ly = p.layers[l];
             // ---------------- QKV projection of the newest token (attention.py:68-73): 48 of the 768 columns per CTA
-            gemm_small(48, l == 0 ? nullptr : map_x, ly.bqkv, j * 48, [&](int c, const uint32_t (&r)[16]) {
+            gemm_small(48, l == 0 ? nullptr : map_x, ly.bqkv, j * 48, nop, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
                 const int col = j * 48 + c;               // 16-column chunks never straddle the q | k | v boundaries
                 uint4 o[2];
@@ -414,7 +417,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // One warp per (hypothesis, head); 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V
             // row: one 128-byte line per 8 lanes, 4 keys per load instruction), the partial dot products meet through 3
             // shuffles, each of the 4 lane groups keeps an online softmax (m, l, o[8]) over its keys, merged at the end.
-            // The K / V chunks of the next 16 keys are in flight while the current 16 are reduced.
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
@@ -436,29 +438,27 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     float m = -INFINITY, lsum = 0.f;
                     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     const size_t col = (size_t)h * 64 + c8 * 8;
-                    uint4 ku[4], vu[4], kn[4], vn[4];
-                    auto fetch = [&](int k0, uint4 (&kk)[4], uint4 (&vv)[4]) {
+                    // 32 keys per iteration: 8 K and 8 V chunks of 16 bytes in flight per lane -- a 60-token prefix costs two exposed
+                    // HBM / L2 round trips (the K/V cache of a batch is ~100 MB: these gathers mostly miss L2)
+                    for (int k0 = 0; k0 < nkeys; k0 += 32) {
+                        uint4 ku[8], vu[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const int sidx = k0 + 4 * u + g4;
                             if (sidx < nkeys) {
                                 const int slot = (sidx < step) ? an_s[sidx] : n;
                                 const size_t off = (((size_t)l * Lmax + sidx) * N + slot) * DG_D + col;
-                                kk[u] = *reinterpret_cast<const uint4*>(p.kc + off);
-                                vv[u] = *reinterpret_cast<const uint4*>(p.vc + off);
+                                ku[u] = *reinterpret_cast<const uint4*>(p.kc + off);
+                                vu[u] = *reinterpret_cast<const uint4*>(p.vc + off);
                             } else {
-                                kk[u] = make_uint4(0, 0, 0, 0);
-                                vv[u] = kk[u];
+                                ku[u] = make_uint4(0, 0, 0, 0);
+                                vu[u] = ku[u];
                             }
                         }
-                    };
-                    fetch(0, ku, vu);
-                    for (int k0 = 0; k0 < nkeys; k0 += 16) {
-                        if (k0 + 16 < nkeys) fetch(k0 + 16, kn, vn);
-                        float sc[4];
+                        float sc[8];
                         float mb = m;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const float2 a = unpack_bf16(ku[u].x), b2 = unpack_bf16(ku[u].y), c2 = unpack_bf16(ku[u].z), e = unpack_bf16(ku[u].w);
                             float d = qf[0] * a.x + qf[1] * a.y + qf[2] * b2.x + qf[3] * b2.y + qf[4] * c2.x + qf[5] * c2.y + qf[6] * e.x + qf[7] * e.y;
                             d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #pragma unroll
                             for (int q = 0; q < 8; ++q) o[q] *= alpha;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
+                            for (int u = 0; u < 8; ++u) {
                                 const float pw = (sc[u] == -INFINITY) ? 0.f : __expf(sc[u] - mb);
                                 lsum += pw;
                                 const float2 a = unpack_bf16(vu[u].x), b2 = unpack_bf16(vu[u].y), c2 = unpack_bf16(vu[u].z), e = unpack_bf16(vu[u].w);
@@ -482,8 +482,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             }
                             m = mb;
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { ku[u] = kn[u]; vu[u] = vn[u]; }
                     }
                     // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
                     float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
@@ -512,11 +510,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             gsync(nop);
             DG_STAMP();
             // ---------------- out-projection + residual (the layer input, xbuf) -> pre-norm rows (attention.py:44, transformer.py:54)
-            gemm_small(16, map_ctx, ly.bo, j * 16, [&](int c, const uint32_t (&r)[16]) {
+            uint4 res_a = make_uint4(0, 0, 0, 0), res_b = res_a;
+            gemm_small(16, map_ctx, ly.bo, j * 16, [&] {
+                if (erow < nrows) {
+                    const uint4* rsrc = reinterpret_cast<const uint4*>(p.xbuf + (size_t)(row0 + erow) * DG_D + j * 16);
+                    res_a = rsrc[0];
+                    res_b = rsrc[1];
+                }
+            }, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
-                const uint4* rsrc = reinterpret_cast<const uint4*>(p.xbuf + (size_t)(row0 + erow) * DG_D + j * 16);
-                const uint4 ra = rsrc[0], rb = rsrc[1];
-                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                const uint32_t rw[8] = {res_a.x, res_a.y, res_a.z, res_a.w, res_b.x, res_b.y, res_b.z, res_b.w};
                 float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // ---------------- LayerNorm 1 + cross-attention query projection (attention.py:128)
             build_a_ln(ly.g1, ly.be1, nullptr);
             DG_STAMP();   // LN1
-            gemm_small(16, nullptr, ly.bq, j * 16, [&](int c, const uint32_t (&r)[16]) {
+            gemm_small(16, nullptr, ly.bq, j * 16, nop, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
                 uint4 o[2];
                 uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             });
             DG_STAMP();
             // ---------------- cross-attention out-projection + residual (x1, the stash of LayerNorm 1) -> pre-norm rows
-            gemm_small(16, map_ctx, ly.bo2, j * 16, [&](int c, const uint32_t (&r)[16]) {
+            gemm_small(16, map_ctx, ly.bo2, j * 16, nop, [&](int c, const uint32_t (&r)[16]) {
                 if (erow >= nrows) return;
                 float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
 #pragma unroll
@@ -717,8 +720,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     // W2[:, 128 j .. 128 j + 128) (this CTA's contraction slice) follows into stage 0 as soon as W1 has been consumed
                     mbar_wait(&ms.acc_full[0], par_accf & 1);
                     mbar_arrive_expect_tx(&ms.st_full[0], 65536);
-                    tma_load_2d(sST, maps + l * 6 + 5, &ms.st_full[0], j * 128, 0);
-                    tma_load_2d(sST + 32768, maps + l * 6 + 5, &ms.st_full[0], j * 128 + 64, 0);
+                    tma_load_2d_hint(sST, maps + l * 6 + 5, &ms.st_full[0], j * 128, 0, TMA_EVICT_LAST);
+                    tma_load_2d_hint(sST + 32768, maps + l * 6 + 5, &ms.st_full[0], j * 128 + 64, 0, TMA_EVICT_LAST);
                 }
                 __syncthreads();
                 if (is_epi) {
@@ -896,100 +899,137 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         gsync(nop);
         DG_STAMP();
         // ---------------- per utterance: log-softmax + top-`beam` of every hypothesis row (decoder/transformer.py:206,
-        // speech2text.py:112: 8 warps per row, two rows at a time, rows staged in the free weight stages), finished masking,
-        // beam^2 pruning, ancestry (speech2text.py:102-153) -- beam.cu's algorithm, ties -> lower index
+        // speech2text.py:112), finished masking, beam^2 pruning, ancestry (speech2text.py:102-153); ties -> lower index
         int ended_here = 0;
         for (int ul = j; ul < nutt; ul += DG_P) {
             const int u = u0 + ul;
-            {
-                const int hb = warp >> 3, hw = warp & 7, ht = tid & 255;      // half block (row slot), warp / thread inside it
-                float* srow = reinterpret_cast<float*>(sST + hb * DG_STAGE);  // [V] this half's row
-                float* hred = reinterpret_cast<float*>(sSB) + hb * 16;        // [8] reduction scratch + [1] broadcast
-                float* cand_v = reinterpret_cast<float*>(sSB) + 64 + hb * (8 * KMAX);
-                int* cand_i = reinterpret_cast<int*>(sSB) + 64 + 2 * 8 * KMAX + hb * (8 * KMAX);
-                for (int r0 = 0; r0 < beam; r0 += 2) {
-                    const int r = r0 + hb;
-                    const bool have = r < beam;
-                    const int n = u * beam + (have ? r : 0);
-                    const float* x = p.logits + (size_t)n * p.ldv;
-                    float mx = -INFINITY;
-                    if (have) {
-                        for (int i = ht; i < V; i += 256) {
-                            const float v = x[i];
-                            srow[i] = v;
-                            mx = fmaxf(mx, v);
-                        }
-                    }
-                    mx = warp_max(mx);
-                    if (lane == 0) hred[hw] = mx;
-                    __syncthreads();
-                    mx = hred[0];
+            // One warp per hypothesis row, all rows of the utterance at once, no shared-memory copy of the row:
+            //   pass 1 (float4 loads from L2): row maximum + each lane's own maximum; T = the beam-th largest of the 32 lane
+            //           maxima -- at least `beam` elements are >= T, so every element of the row's top-`beam` is >= T;
+            //   pass 2 (row is L2-hot): sum of exp(x - max) and the elements >= T compacted into a candidate list (<= 128;
+            //           typically 10-20); the list is ranked by (log-prob, lower token id) exactly like the reference path.
+            // A flat row (more than 128 elements >= T) takes the exact fallback: `beam` ordered arg-max scans of the row.
+            // (v3 staged each row in shared memory with scalar loads behind dependent stores and spent 30 k cycles per row.)
+            if (warp < beam) {
+                const int r = warp, n = u * beam + r;
+                const float4* x4 = reinterpret_cast<const float4*>(p.logits + (size_t)n * p.ldv);
+                const int nv4 = (V + 3) >> 2;
+                float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
+                float lmax = -INFINITY;
+                for (int base = 0; base < nv4; base += 32 * 8) {
+                    const int i0 = base + lane;
+                    float4 v[8];
 #pragma unroll
-                    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, hred[i]);
-                    float sum = 0.f;
-                    if (have)
-                        for (int i = ht; i < V; i += 256) sum += expf(srow[i] - mx);
-                    sum = warp_sum(sum);
-                    __syncthreads();
-                    if (lane == 0) hred[hw] = sum;
-                    __syncthreads();
-                    float tsum = 0.f;
+                    for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[i0 + 32 * q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tsum += hred[i];
-                    const float lse = mx + logf(tsum);
-                    if (have) {
-                        float* dump = p.dbg_logp ? p.dbg_logp + ((size_t)step * N + n) * V : nullptr;
-                        for (int i = ht; i < V; i += 256) {
-                            const float v = srow[i] - lse;
-                            srow[i] = v;
-                            if (dump) dump[i] = v;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const int c0 = (i0 + 32 * q) * 4;
+                        lmax = fmaxf(lmax, fmaxf(fmaxf(c0 < V ? v[q].x : -INFINITY, c0 + 1 < V ? v[q].y : -INFINITY),
+                                                 fmaxf(c0 + 2 < V ? v[q].z : -INFINITY, c0 + 3 < V ? v[q].w : -INFINITY)));
                     }
-                    __syncthreads();
-                    // per-warp top-k over a contiguous slice: k rounds of (lane-local scan, warp arg-max, knock out)
-                    const int per = (V + 7) / 8;
-                    const int lo = hw * per, hi = min(V, lo + per);
-                    if (have) {
-                        for (int k = 0; k < beam; ++k) {
-                            float bv = -INFINITY;
-                            int bi = 0x7fffffff;
-                            for (int idx = lo + lane; idx < hi; idx += 32) {
-                                const float v = srow[idx];
-                                if (v > bv) { bv = v; bi = idx; }      // ascending scan + strict '>' keeps the lower index on ties
+                }
+                const float rowmax = warp_max(lmax);
+                float T = -INFINITY;
+                {
+                    float t = lmax;
+                    for (int k = 0; k < beam; ++k) {
+                        const float mxk = warp_max(t);
+                        T = mxk;
+                        const unsigned who = __ballot_sync(0xffffffffu, t == mxk);
+                        if (mxk == -INFINITY) break;       // fewer than `beam` lanes hold anything: every element is a candidate
+                        if (lane == __ffs(who) - 1) t = -INFINITY;
+                    }
+                }
+                float sum = 0.f;
+                int ncand = 0;
+                for (int base = 0; base < nv4; base += 32 * 4) {      // warp-uniform trip count: whole warps take part in the ballots
+                    const int i0 = base + lane;
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[i0 + 32 * q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c0 = (i0 + 32 * q) * 4;
+                        const float xv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bool in = (i0 + 32 * q < nv4) && (c0 + e < V);
+                            if (in) sum += expf(xv[e] - rowmax);
+                            const bool hit = in && xv[e] >= T;
+                            const unsigned bm = __ballot_sync(0xffffffffu, hit);
+                            if (bm) {
+                                const int pos = ncand + __popc(bm & ((1u << lane) - 1));
+                                if (hit && pos < 128) cand[pos] = make_float2(xv[e], __int_as_float(c0 + e));
+                                ncand += __popc(bm);
                             }
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-                            }
-                            if (bi != 0x7fffffff && ((bi - lo) & 31) == lane) srow[bi] = -INFINITY;
-                            if (lane == 0) { cand_v[hw * KMAX + k] = bv; cand_i[hw * KMAX + k] = bi; }
-                            __syncwarp();
                         }
                     }
-                    __syncthreads();
-                    if (have && hw == 0) {
-                        // merge: 8 sorted lists of `beam` -> the row's top-`beam` (lane w < 8 walks list w)
-                        int pos = 0;
-                        for (int k = 0; k < beam; ++k) {
-                            float bv = (lane < 8 && pos < beam) ? cand_v[lane * KMAX + pos] : -INFINITY;
-                            int bi = (lane < 8 && pos < beam) ? cand_i[lane * KMAX + pos] : 0x7fffffff;
-                            const float mv = bv;
-                            const int mi = bi;
+                }
+                sum = warp_sum(sum);
+                const float lse = rowmax + logf(sum);
+                if (p.dbg_logp) {
+                    float* dump = p.dbg_logp + ((size_t)step * N + n) * V;
+                    const float* xs = p.logits + (size_t)n * p.ldv;
+                    for (int c = lane; c < V; c += 32) dump[c] = xs[c] - lse;
+                }
+                __syncwarp();
+                if (ncand <= 128) {
+                    float cv[4];
+                    int ci[4];
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-                            }
-                            if (mi == bi && mv == bv && lane < 8) ++pos;
-                            if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = lane + 32 * q;
+                        cv[q] = -INFINITY;
+                        ci[q] = 0x7fffffff;
+                        if (idx < ncand) {
+                            const float2 c2 = cand[idx];
+                            cv[q] = c2.x - lse;
+                            ci[q] = __float_as_int(c2.y);
                         }
                     }
-                    __syncthreads();
+                    for (int k = 0; k < beam; ++k) {
+                        float bv = -INFINITY;
+                        int bi = 0x7fffffff;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (better(cv[q], ci[q], bv, bi)) { bv = cv[q]; bi = ci[q]; }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (ci[q] == bi && bi != 0x7fffffff) { cv[q] = -INFINITY; ci[q] = 0x7fffffff; }   // token ids are unique in a row
+                        if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
+                    }
+                } else {
+                    // exact fallback: the next element after (pv, pi) in the order (log-prob descending, token id ascending)
+                    const float* xs = p.logits + (size_t)n * p.ldv;
+                    float pv = INFINITY;
+                    int pi = -1;
+                    for (int k = 0; k < beam; ++k) {
+                        float bv = -INFINITY;
+                        int bi = 0x7fffffff;
+                        for (int c = lane; c < V; c += 32) {
+                            const float v = xs[c] - lse;
+                            const bool after = (v < pv) || (v == pv && c > pi);
+                            if (after && better(v, c, bv, bi)) { bv = v; bi = c; }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                        }
+                        pv = bv;
+                        pi = bi;
+                        if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
+                    }
                 }
             }
+            __syncthreads();
             for (int r = warp; r < beam; r += 16) {
                 const int n = u * beam + r;
                 if (p.st.flag[n]) {                      // mask_finished_scores / mask_finished_preds (speech2text.py:156-192)

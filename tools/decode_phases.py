@@ -27,7 +27,7 @@ with torch.no_grad():
     mem, lens, B, T2 = model.encode_bf16(x, mask)
     bd = BeamDecoder(model.decoder, B, 10, T2, 60, dev, use_graph=False, persistent=True)
     for step in [int(a) for a in (sys.argv[1:] or ['5', '50'])]:
-        buf = torch.zeros(512, dtype=torch.int64, device=dev)
+        buf = torch.zeros(16 * 256, dtype=torch.int64, device=dev)
         for rep in range(2):
             bd.setup(mem, lens)
             L.otb_debug_decode_timing(ctypes.c_void_p(buf.data_ptr()) if rep == 1 else None, step)
@@ -35,7 +35,8 @@ with torch.no_grad():
             e0.record(); bd.run_persistent(60); e1.record()
             torch.cuda.synchronize()
         L.otb_debug_decode_timing(None, 0)
-        t = buf.cpu().tolist()
+        allt = buf.cpu().view(16, 256)
+        t = allt[0].tolist()
         n = len(names)
         print(f'=== step {step}: whole 60-step launch {e0.elapsed_time(e1):.2f} ms; step total {(t[n-1]-t[0])} cycles')
         agg = {}
@@ -46,3 +47,7 @@ with torch.no_grad():
         for k, v in agg.items():
             print(f'    {k:14s} {v:9d} cycles  {100.0 * v / (t[n-1]-t[0]):5.1f}%')
         print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 21)])
+        d = (allt[:, 1:n] - allt[:, :n - 1])                      # [cta, phase] durations of every CTA of group 0
+        print('    layer 2, per phase (min / max over the 16 CTAs):',
+              [(names[i].split(' ', 1)[1], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(2 + 2 * 19, 2 + 3 * 19)])
+        print('    tail, per phase (min / max over CTAs):', [(names[i], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(n - 4, n)])
