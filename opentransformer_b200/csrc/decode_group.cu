@@ -32,6 +32,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "beam_common.cuh"
 #include "otb_internal.h"
 #include "ptx.cuh"
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     auto build_a_ln = [&](const float* gamma, const float* beta, bf16* x_out) {
         const int g4 = lane >> 3, c = lane & 7;
 #pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
+        for (int it = 0; it < 2; ++it) {      // (unrolling the two row groups was tried: +200 B of spills in the attention loops)
             const int r = warp * 8 + it * 4 + g4;
             float4 v[8];
             if (r < nrows) {
@@ -367,7 +369,30 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     };
     // [32 rows of this epilogue warp] x [32 fp32 columns] from TMEM -> coalesced 128-byte global stores through a padded
     // shared-memory tile (each lane owns a ROW in TMEM; storing its 32 floats directly costs 32 cache lines per instruction)
+    // same idea for the w_2 partial products, stored as fp16 pairs (64 columns = one 128-byte line per row and instruction):
+    // the 16 partial sums of an output element are added in fp32 by the reduction pass; fp16 (11-bit significand, |partial| << 65504)
+    // halves the 128 KB every CTA has to push to L2 per layer -- measured 15 k cycles of store drain before the barrier
     float* tstage = reinterpret_cast<float*>(sSB) + equad * (32 * 33);
+    auto store_tile_half64 = [&](uint32_t taddr, __half* gbase, int ld) {
+        uint32_t* st32 = reinterpret_cast<uint32_t*>(tstage);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const __half2 a = __floats2half2_rn(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+            const __half2 b = __floats2half2_rn(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+            st32[lane * 33 + i] = *reinterpret_cast<const uint32_t*>(&a);
+            st32[lane * 33 + 16 + i] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 32; ++rr) {
+            const int row = equad * 32 + rr;
+            if (row < nrows) reinterpret_cast<uint32_t*>(gbase + (size_t)row * ld)[lane] = st32[rr * 33 + lane];
+        }
+        __syncwarp();
+    };
     auto store_tile32 = [&](uint32_t taddr, float* gbase, int ld, const float* bias32, int ncols_ok) {
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -769,9 +794,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 if (is_epi) {
                     mbar_wait(&ms.acc_full[1], (par_accf >> 1) & 1);
                     tc_fence_after();
-                    float* dst = p.part + ((size_t)j * N + row0) * DG_D;
+                    __half* dst = p.part + ((size_t)j * N + row0) * DG_D;
 #pragma unroll 1
-                    for (int c = 0; c < 256; c += 32) store_tile32(t_row + 256 + c, dst + c, DG_D, nullptr, 32);
+                    for (int c = 0; c < 256; c += 64) store_tile_half64(t_row + 256 + c, dst + c, DG_D);
                     tc_fence_before();
                 }
                 par_stf ^= 1;
@@ -798,14 +823,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 const bool live = r < nrows;
                 if (live) {
-                    const float* src = p.part + ((size_t)(row0 + r)) * DG_D + c0;
+                    const __half* src = p.part + ((size_t)(row0 + r)) * DG_D + c0;
+                    uint2 v[DG_P];
 #pragma unroll
-                    for (int h8 = 0; h8 < DG_P; h8 += 8) {
-                        float4 v[8];
+                    for (int pp = 0; pp < DG_P; ++pp) v[pp] = *reinterpret_cast<const uint2*>(src + (size_t)pp * N * DG_D);
 #pragma unroll
-                        for (int pp = 0; pp < 8; ++pp) v[pp] = *reinterpret_cast<const float4*>(src + (size_t)(h8 + pp) * N * DG_D);
-#pragma unroll
-                        for (int pp = 0; pp < 8; ++pp) { acc.x += v[pp].x; acc.y += v[pp].y; acc.z += v[pp].z; acc.w += v[pp].w; }
+                    for (int pp = 0; pp < DG_P; ++pp) {
+                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v[pp].x));
+                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v[pp].y));
+                        acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
                     }
                     const float4 b = *reinterpret_cast<const float4*>(ly.b2 + c0);
                     const uint2 xr = *reinterpret_cast<const uint2*>(p.x2buf + (size_t)(row0 + r) * DG_D + c0);
@@ -914,6 +940,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int r = warp, n = u * beam + r;
                 const float4* x4 = reinterpret_cast<const float4*>(p.logits + (size_t)n * p.ldv);
                 const int nv4 = (V + 3) >> 2;
+                if ((size_t)beam * p.ldv * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE)) {
+                    // the A tile and both weight stages are idle here: each warp copies ITS row with cp.async (every 16-byte piece
+                    // in flight at once: one L2 round trip) and makes its two passes over shared memory
+                    float4* srow4 = reinterpret_cast<float4*>(smem + (size_t)warp * p.ldv * 4);
+                    for (int i = lane; i < nv4; i += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(srow4 + i)), "l"(x4 + i) : "memory");
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();
+                    x4 = srow4;
+                }
                 float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
                 float lmax = -INFINITY;
                 for (int base = 0; base < nv4; base += 32 * 8) {
@@ -1132,7 +1168,7 @@ size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int be
     take((size_t)N * DG_D * 2);                                // x2buf
     take((size_t)N * DG_D * 4);                                // pre
     take((size_t)N * DG_D * 2);                                // q2
-    take((size_t)DG_P * N * DG_D * 4);                         // part
+    take((size_t)DG_P * N * DG_D * 2);                         // part (fp16)
     take((size_t)N * dg_ldv(V) * 4);                           // logits
     take((size_t)G * 128);                                     // bar
     take((size_t)G * Lmax * 4);                                // gstate
@@ -1165,7 +1201,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.x2buf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.pre = reinterpret_cast<float*>(take((size_t)N * DG_D * 4));
     p.q2 = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
-    p.part = reinterpret_cast<float*>(take((size_t)DG_P * N * DG_D * 4));
+    p.part = reinterpret_cast<__half*>(take((size_t)DG_P * N * DG_D * 2));
     p.ldv = dg_ldv(mp.V);
     p.logits = reinterpret_cast<float*>(take((size_t)N * p.ldv * 4));
     p.bar = reinterpret_cast<int*>(take((size_t)G * 128));
