@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const CUtensorMap* map_x = maps + nl * 6 + 3;
     int* bar = p.bar + g * 32;                        // 128-byte separated counters
     const bool is_tma = (warp == 0 && lane == 0), is_mma = (warp == 1 && lane == 0);
-    const bool is_epi = (warp >= 4 && warp < 8);
-    const int equad = warp & 3;                       // TMEM lane quadrant of an epilogue warp
+    const int equad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int ecg = warp >> 2;                        // column group of the warp in a 16-warp epilogue
     const int erow = equad * 32 + lane;               // TMEM lane == tile row of an epilogue thread
 
     if (tid == 0) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_acce = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
@@ -349,12 +349,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             }
             umma_commit(&ms.acc_full[0]);
         }
-        __syncthreads();   // bias slice visible to the epilogue threads
-        if (is_epi) {
+        __syncthreads();   // bias slice visible to the epilogue threads; the issuing lanes are back with their warps
+        // epilogue: warp w reads TMEM lanes [32 (w & 3), +32) (the hardware restriction) and the 16-column chunks w >> 2,
+        // (w >> 2) + 4, ...: the 48-column QKV slice is drained by 12 warps at once instead of 4 warps three times
+        if (ecg * 16 < nB) {
             pre_epi();      // e.g. the residual slice: its L2 round trip overlaps the operand loads and the MMAs
             mbar_wait(&ms.acc_full[0], par_accf & 1);
             tc_fence_after();
-            for (int c = 0; c < nB; c += 16) {
+            for (int c = ecg * 16; c < nB; c += 64) {
                 uint32_t r[16];
                 tmem_ld16(t_row + c, r);
                 tmem_ld_wait();
@@ -367,47 +369,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         par_accf ^= 1;
         __syncthreads();
     };
-    // [32 rows of this epilogue warp] x [32 fp32 columns] from TMEM -> coalesced 128-byte global stores through a padded
-    // shared-memory tile (each lane owns a ROW in TMEM; storing its 32 floats directly costs 32 cache lines per instruction)
-    // same idea for the w_2 partial products, stored as fp16 pairs (64 columns = one 128-byte line per row and instruction):
-    // the 16 partial sums of an output element are added in fp32 by the reduction pass; fp16 (11-bit significand, |partial| << 65504)
-    // halves the 128 KB every CTA has to push to L2 per layer -- measured 15 k cycles of store drain before the barrier
-    float* tstage = reinterpret_cast<float*>(sSB) + equad * (32 * 33);
-    auto store_tile_half64 = [&](uint32_t taddr, __half* gbase, int ld) {
-        uint32_t* st32 = reinterpret_cast<uint32_t*>(tstage);
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const __half2 a = __floats2half2_rn(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
-            const __half2 b = __floats2half2_rn(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
-            st32[lane * 33 + i] = *reinterpret_cast<const uint32_t*>(&a);
-            st32[lane * 33 + 16 + i] = *reinterpret_cast<const uint32_t*>(&b);
-        }
-        __syncwarp();
-        for (int rr = 0; rr < 32; ++rr) {
-            const int row = equad * 32 + rr;
-            if (row < nrows) reinterpret_cast<uint32_t*>(gbase + (size_t)row * ld)[lane] = st32[rr * 33 + lane];
-        }
-        __syncwarp();
-    };
-    auto store_tile32 = [&](uint32_t taddr, float* gbase, int ld, const float* bias32, int ncols_ok) {
-        uint32_t r[32];
-        tmem_ld32(taddr, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tstage[lane * 33 + i] = __uint_as_float(r[i]) + (bias32 ? bias32[i] : 0.f);
-        __syncwarp();
-        if (lane < ncols_ok) {
-            for (int rr = 0; rr < 32; ++rr) {
-                const int row = equad * 32 + rr;
-                if (row < nrows) gbase[(size_t)row * ld + lane] = tstage[rr * 33 + lane];
-            }
-        }
-        __syncwarp();
-    };
+    // Buffers that only this kernel reads back (w_2 partial products, logits) are stored in the order the TMEM epilogue produces
+    // them: [column group][row][16 bytes].  A thread owns a ROW of the accumulator, so its 16-byte pieces land next to the
+    // pieces of the neighbouring rows: every store instruction of a warp writes 512 contiguous bytes, with no shared-memory
+    // transpose (v4 staged 32 x 32 tiles through padded shared memory on 4 warps: 15 k cycles per layer for the partial
+    // products and 46 k per step for the logits before the barrier behind them opened).  The readers gather 16-byte pieces of
+    // consecutive rows, which are again contiguous.
+    const size_t part_slab = (size_t)64 * 128;          // uint4 per (contraction slice, group): 64 column groups x 128 rows
+    const int ldv4 = p.ldv >> 2;
+    uint4* lg4 = reinterpret_cast<uint4*>(p.logits) + (size_t)g * ldv4 * 128;     // this group's logits, [ldv / 4][128 rows] x 16 B
 
     int steps_done = 0;
     bool group_done = false;
@@ -749,12 +719,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     tma_load_2d_hint(sST + 32768, maps + l * 6 + 5, &ms.st_full[0], j * 128 + 64, 0, TMA_EVICT_LAST);
                 }
                 __syncthreads();
-                if (is_epi) {
+                {
                     mbar_wait(&ms.acc_full[0], par_accf & 1);
                     tc_fence_after();
-                    // h = (a + b_a) * sigmoid(g + b_g) -> bf16, written over the (dead) A tile as a [128 x 128] K-major operand
+                    // h = (a + b_a) * sigmoid(g + b_g) -> bf16, written over the (dead) A tile as a [128 x 128] K-major operand;
+                    // all 16 warps: warp w takes rows [32 (w & 3), +32) and hidden features [32 (w >> 2), +32)
 #pragma unroll 1
-                    for (int c = 0; c < 128; c += 16) {
+                    for (int c = ecg * 32; c < ecg * 32 + 32; c += 16) {
                         uint32_t ra[16], rg[16];
                         tmem_ld16(t_row + c, ra);
                         tmem_ld16(t_row + 128 + c, rg);
@@ -791,12 +762,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     }
                     umma_commit(&ms.acc_full[1]);
                 }
-                if (is_epi) {
+                __syncwarp();
+                {
+                    // fp32 partial products; warp w: rows [32 (w & 3), +32), columns [64 (w >> 2), +64) as 16 pieces of 4 columns
                     mbar_wait(&ms.acc_full[1], (par_accf >> 1) & 1);
                     tc_fence_after();
-                    __half* dst = p.part + ((size_t)j * N + row0) * DG_D;
+                    uint4* dst = reinterpret_cast<uint4*>(p.part) + ((size_t)j * p.G + g) * part_slab + (size_t)(ecg * 16) * 128 + erow;
 #pragma unroll 1
-                    for (int c = 0; c < 256; c += 64) store_tile_half64(t_row + 256 + c, dst + c, DG_D);
+                    for (int hq = 0; hq < 2; ++hq) {
+                        uint32_t r[32];
+                        tmem_ld32(t_row + 256 + ecg * 64 + hq * 32, r);
+                        tmem_ld_wait();
+                        if (erow < nrows) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) dst[(size_t)(hq * 8 + q) * 128] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                        }
+                    }
                     tc_fence_before();
                 }
                 par_stf ^= 1;
@@ -816,44 +797,54 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // tile: every load is a contiguous 512-byte half row, the row statistics stay inside the CTA, and the result is the
             // bf16 input of the next layer (or of the output layer) in xbuf -- no separate LayerNorm pass, no fp32 round trip
             {
-                float* rsum = ms.c_val;      // [16 warps] partial sums, then squared deviations (sSB is receiving the next QKV weights)
-                const int rr = warp >> 1, half = warp & 1;
+                // thread = (row 8 j + (tid & 7), 4-column group tid >> 3): a warp reads four full 128-byte lines per load (8
+                // consecutive rows x 16 bytes), the 16 slices in two batches of 8 loads, summed in slice order
+                float* rsum = ms.c_val;                                   // [16 warps][8 rows]
+                const int rr = tid & 7, c4 = tid >> 3;
                 const int r = j * 8 + rr;
-                const int c0 = half * 128 + lane * 4;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 const bool live = r < nrows;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (live) {
-                    const __half* src = p.part + ((size_t)(row0 + r)) * DG_D + c0;
-                    uint2 v[DG_P];
+                    const float4* src = reinterpret_cast<const float4*>(p.part) + (size_t)g * part_slab + (size_t)c4 * 128 + r;
 #pragma unroll
-                    for (int pp = 0; pp < DG_P; ++pp) v[pp] = *reinterpret_cast<const uint2*>(src + (size_t)pp * N * DG_D);
+                    for (int h8 = 0; h8 < DG_P; h8 += 8) {
+                        float4 v[8];
 #pragma unroll
-                    for (int pp = 0; pp < DG_P; ++pp) {
-                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v[pp].x));
-                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v[pp].y));
-                        acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+                        for (int pp = 0; pp < 8; ++pp) v[pp] = src[(size_t)(h8 + pp) * p.G * part_slab];
+#pragma unroll
+                        for (int pp = 0; pp < 8; ++pp) { acc.x += v[pp].x; acc.y += v[pp].y; acc.z += v[pp].z; acc.w += v[pp].w; }
                     }
-                    const float4 b = *reinterpret_cast<const float4*>(ly.b2 + c0);
-                    const uint2 xr = *reinterpret_cast<const uint2*>(p.x2buf + (size_t)(row0 + r) * DG_D + c0);
+                    const float4 b = *reinterpret_cast<const float4*>(ly.b2 + c4 * 4);
+                    const uint2 xr = *reinterpret_cast<const uint2*>(p.x2buf + (size_t)(row0 + r) * DG_D + c4 * 4);
                     const float2 r0 = unpack_bf16(xr.x), r1 = unpack_bf16(xr.y);
                     acc.x += b.x + r0.x; acc.y += b.y + r0.y; acc.z += b.z + r1.x; acc.w += b.w + r1.y;
                 }
-                float s = warp_sum((acc.x + acc.y) + (acc.z + acc.w));
-                if (lane == 0) rsum[warp] = s;
+                float s = (acc.x + acc.y) + (acc.z + acc.w);
+                s += __shfl_xor_sync(0xffffffffu, s, 8);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (lane < 8) rsum[warp * 8 + lane] = s;
                 __syncthreads();
-                const float mean = (rsum[rr * 2] + rsum[rr * 2 + 1]) * (1.0f / DG_D);
+                float mean = 0.f;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) mean += rsum[w * 8 + rr];
+                mean *= (1.0f / DG_D);
                 const float a = acc.x - mean, b = acc.y - mean, cc = acc.z - mean, d = acc.w - mean;
-                float q = warp_sum((a * a + b * b) + (cc * cc + d * d));
+                float q = (a * a + b * b) + (cc * cc + d * d);
+                q += __shfl_xor_sync(0xffffffffu, q, 8);
+                q += __shfl_xor_sync(0xffffffffu, q, 16);
                 __syncthreads();
-                if (lane == 0) rsum[warp] = q;
+                if (lane < 8) rsum[warp * 8 + lane] = q;
                 __syncthreads();
-                const float rstd = rsqrtf((rsum[rr * 2] + rsum[rr * 2 + 1]) * (1.0f / DG_D) + p.eps);
                 if (live) {
-                    const float4 gm = *reinterpret_cast<const float4*>(ly.g3 + c0), bt = *reinterpret_cast<const float4*>(ly.be3 + c0);
+                    float var = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 16; ++w) var += rsum[w * 8 + rr];
+                    const float rstd = rsqrtf(var * (1.0f / DG_D) + p.eps);
+                    const float4 gm = *reinterpret_cast<const float4*>(ly.g3 + c4 * 4), bt = *reinterpret_cast<const float4*>(ly.be3 + c4 * 4);
                     uint2 o;
                     o.x = pack_bf16(a * rstd * gm.x + bt.x, b * rstd * gm.y + bt.y);
                     o.y = pack_bf16(cc * rstd * gm.z + bt.z, d * rstd * gm.w + bt.w);
-                    *reinterpret_cast<uint2*>(p.xbuf + (size_t)(row0 + r) * DG_D + c0) = o;
+                    *reinterpret_cast<uint2*>(p.xbuf + (size_t)(row0 + r) * DG_D + c4 * 4) = o;
                 }
             }
             gsync(nop);
@@ -866,53 +857,62 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         {
             int my_chunks = 0;
             for (int c = j; c < n_vchunks; c += DG_P) ++my_chunks;
+            const uint32_t idesc = umma_idesc_bf16(128);
+            auto issue_chunk = [&](int i) {      // MMA thread: chunk i -> TMEM columns [128 (i & 1), +128)
+                const int s = i & 1;
+                mbar_wait(&ms.st_full[s], ((par_stf >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sST + s * DG_STAGE + kb * 16384);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem + s * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                }
+                umma_commit(&ms.st_empty[s]);
+                umma_commit(&ms.acc_full[s]);
+            };
             if (is_tma) {
                 load_a(map_x);
-                for (int i = 2; i < my_chunks; ++i) {        // chunks 0 and 1 were prefetched
-                    const int s = i & 1;
-                    mbar_wait(&ms.st_empty[s], ((par_ste >> s) & 1) ^ (uint32_t)(((i - 2) >> 1) & 1));
-                    load_wout(j + i * DG_P, s);
-                }
             } else if (is_mma) {
-                const uint32_t idesc = umma_idesc_bf16(128);
                 for (int kb = 0; kb < 4; ++kb) mbar_wait(&ms.a_full[kb], (par_a >> kb) & 1);
-                for (int i = 0; i < my_chunks; ++i) {
-                    const int s = i & 1;
-                    const uint32_t use = (uint32_t)((i >> 1) & 1);
-                    if (i >= 2) {
-                        mbar_wait(&ms.acc_empty[s], ((par_acce >> s) & 1) ^ (uint32_t)(((i - 2) >> 1) & 1));
-                        tc_fence_after();
-                    }
-                    mbar_wait(&ms.st_full[s], ((par_stf >> s) & 1) ^ use);
-                    tc_fence_after();
-                    for (int kb = 0; kb < 4; ++kb) {
-                        const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sST + s * DG_STAGE + kb * 16384);
+                if (my_chunks > 0) issue_chunk(0);
+            }
+            // All 16 warps drain a chunk: warp w stores rows [32 (w & 3), +32) x columns [32 (w >> 2), +32) as eight 16-byte pieces
+            // per row in the [column group][row] order (512 contiguous bytes per warp instruction).  The MMAs of chunk i + 1 are
+            // issued before chunk i is drained (other TMEM half); the CTA barrier at the end of an iteration is what frees a half.
+            for (int i = 0; i < my_chunks; ++i) {
+                const int s = i & 1;
+                const int col0 = (j + i * DG_P) * 128;
+                if (tid < 128) ms.bias[s * 128 + tid] = (p.bout != nullptr && col0 + tid < V) ? p.bout[col0 + tid] : 0.f;
+                if (is_mma && i + 1 < my_chunks) issue_chunk(i + 1);
+                if (is_tma && i + 2 < my_chunks) {        // chunks 0 and 1 were prefetched; stage s is free once chunk i has been multiplied
+                    mbar_wait(&ms.st_empty[s], ((par_ste >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
+                    load_wout(j + (i + 2) * DG_P, s);
+                }
+                __syncthreads();
+                mbar_wait(&ms.acc_full[s], ((par_accf >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                const int cc0 = col0 + ecg * 32;
+                if (cc0 < p.ldv) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + s * 128 + ecg * 32, r);
+                    tmem_ld_wait();
+                    if (erow < nrows) {
+                        const float* bs = ms.bias + s * 128 + ecg * 32;
+                        uint4* dst = lg4 + (size_t)(cc0 >> 2) * 128 + erow;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem + s * 128, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                        for (int q = 0; q < 8; ++q) {
+                            uint4 o;
+                            o.x = __float_as_uint(__uint_as_float(r[4 * q]) + bs[4 * q]);
+                            o.y = __float_as_uint(__uint_as_float(r[4 * q + 1]) + bs[4 * q + 1]);
+                            o.z = __float_as_uint(__uint_as_float(r[4 * q + 2]) + bs[4 * q + 2]);
+                            o.w = __float_as_uint(__uint_as_float(r[4 * q + 3]) + bs[4 * q + 3]);
+                            dst[(size_t)q * 128] = o;
+                        }
                     }
-                    umma_commit(&ms.st_empty[s]);
-                    umma_commit(&ms.acc_full[s]);
                 }
-            } else if (is_epi) {
-                float* biasw = reinterpret_cast<float*>(sSB) + 4 * 32 * 33 + equad * 32;     // this warp's 32 bias values
-                for (int i = 0; i < my_chunks; ++i) {
-                    const int s = i & 1;
-                    const int col0 = (j + i * DG_P) * 128;
-                    mbar_wait(&ms.acc_full[s], ((par_accf >> s) & 1) ^ (uint32_t)((i >> 1) & 1));
-                    tc_fence_after();
-#pragma unroll 1
-                    for (int c = 0; c < 128; c += 32) {
-                        const int cc0 = col0 + c;
-                        if (cc0 >= V) break;      // warp-uniform
-                        __syncwarp();
-                        biasw[lane] = (p.bout != nullptr && cc0 + lane < V) ? p.bout[cc0 + lane] : 0.f;
-                        __syncwarp();
-                        store_tile32(t_row + s * 128 + c, p.logits + (size_t)row0 * p.ldv + cc0, p.ldv, biasw, min(32, V - cc0));
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&ms.acc_empty[s]);
-                }
+                tc_fence_before();
+                __syncthreads();
             }
             // parity bookkeeping: barrier pair s was used ceil((my_chunks - s) / 2) times
             const uint32_t u0n = (uint32_t)((my_chunks + 1) >> 1), u1n = (uint32_t)(my_chunks >> 1);
@@ -920,7 +920,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             par_stf ^= (u0n & 1) | ((u1n & 1) << 1);
             par_ste ^= (u0n & 1) | ((u1n & 1) << 1);
             par_accf ^= (u0n & 1) | ((u1n & 1) << 1);
-            par_acce ^= (u0n & 1) | ((u1n & 1) << 1);
         }
         gsync(nop);
         DG_STAMP();
@@ -936,27 +935,36 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             //           typically 10-20); the list is ranked by (log-prob, lower token id) exactly like the reference path.
             // A flat row (more than 128 elements >= T) takes the exact fallback: `beam` ordered arg-max scans of the row.
             // (v3 staged each row in shared memory with scalar loads behind dependent stores and spent 30 k cycles per row.)
+            // The rows of the utterance are gathered from the [column group][row] logits into row-major shared memory (the A
+            // tile and both weight stages are idle: 192 KB) by all 16 warps with cp.async -- every 16-byte piece in flight at
+            // once, `beam` consecutive rows = one contiguous run per column group; the two passes below then run on shared
+            // memory.  A vocabulary x beam that does not fit is read in place (element stride 128 x 16 bytes).
+            const bool staged = (size_t)beam * p.ldv * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
+            const int lr0 = ul * beam;                               // first row of the utterance inside the group tile
+            if (staged) {
+                const int npieces = ldv4 * beam;
+                for (int i = tid; i < npieces; i += DG_THREADS) {
+                    const int c4 = i / beam, rr = i - c4 * beam;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + ((size_t)rr * p.ldv + c4 * 4) * 4)),
+                                 "l"(lg4 + (size_t)c4 * 128 + lr0 + rr) : "memory");
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();
+            }
+            if (ul == j) DG_STAMP();      // rows gathered
             if (warp < beam) {
                 const int r = warp, n = u * beam + r;
-                const float4* x4 = reinterpret_cast<const float4*>(p.logits + (size_t)n * p.ldv);
+                const float4* x4 = staged ? reinterpret_cast<const float4*>(smem + (size_t)r * p.ldv * 4) : reinterpret_cast<const float4*>(lg4 + lr0 + r);
+                const int xs4 = staged ? 1 : 128;                    // float4 stride between consecutive column groups
+                auto xel = [&](int c) { return reinterpret_cast<const float*>(x4 + (size_t)(c >> 2) * xs4)[c & 3]; };
                 const int nv4 = (V + 3) >> 2;
-                if ((size_t)beam * p.ldv * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE)) {
-                    // the A tile and both weight stages are idle here: each warp copies ITS row with cp.async (every 16-byte piece
-                    // in flight at once: one L2 round trip) and makes its two passes over shared memory
-                    float4* srow4 = reinterpret_cast<float4*>(smem + (size_t)warp * p.ldv * 4);
-                    for (int i = lane; i < nv4; i += 32)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(srow4 + i)), "l"(x4 + i) : "memory");
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    __syncwarp();
-                    x4 = srow4;
-                }
                 float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
                 float lmax = -INFINITY;
                 for (int base = 0; base < nv4; base += 32 * 8) {
                     const int i0 = base + lane;
                     float4 v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[i0 + 32 * q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int c0 = (i0 + 32 * q) * 4;
@@ -982,7 +990,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     const int i0 = base + lane;
                     float4 v[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[i0 + 32 * q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int c0 = (i0 + 32 * q) * 4;
@@ -1005,8 +1013,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const float lse = rowmax + logf(sum);
                 if (p.dbg_logp) {
                     float* dump = p.dbg_logp + ((size_t)step * N + n) * V;
-                    const float* xs = p.logits + (size_t)n * p.ldv;
-                    for (int c = lane; c < V; c += 32) dump[c] = xs[c] - lse;
+                    for (int c = lane; c < V; c += 32) dump[c] = xel(c) - lse;
                 }
                 __syncwarp();
                 if (ncand <= 128) {
@@ -1042,14 +1049,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     }
                 } else {
                     // exact fallback: the next element after (pv, pi) in the order (log-prob descending, token id ascending)
-                    const float* xs = p.logits + (size_t)n * p.ldv;
                     float pv = INFINITY;
                     int pi = -1;
                     for (int k = 0; k < beam; ++k) {
                         float bv = -INFINITY;
                         int bi = 0x7fffffff;
                         for (int c = lane; c < V; c += 32) {
-                            const float v = xs[c] - lse;
+                            const float v = xel(c) - lse;
                             const bool after = (v < pv) || (v == pv && c > pi);
                             if (after && better(v, c, bv, bi)) { bv = v; bi = c; }
                         }
@@ -1066,6 +1072,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
             }
             __syncthreads();
+            if (ul == j) DG_STAMP();      // per-row log-softmax statistics + top-`beam`
             for (int r = warp; r < beam; r += 16) {
                 const int n = u * beam + r;
                 if (p.st.flag[n]) {                      // mask_finished_scores / mask_finished_preds (speech2text.py:156-192)
@@ -1110,6 +1117,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             }
             __syncthreads();
         }
+        if (j >= nutt) { DG_STAMP(); DG_STAMP(); }      // keep the stamp count of a CTA without an utterance
         if (tid == 0) {
             ended_here = ms.flag;
             ms.flag = 0;
@@ -1168,8 +1176,8 @@ size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int be
     take((size_t)N * DG_D * 2);                                // x2buf
     take((size_t)N * DG_D * 4);                                // pre
     take((size_t)N * DG_D * 2);                                // q2
-    take((size_t)DG_P * N * DG_D * 2);                         // part (fp16)
-    take((size_t)N * dg_ldv(V) * 4);                           // logits
+    take((size_t)DG_P * G * 128 * DG_D * 4);                   // part (fp32, 128 rows per group)
+    take((size_t)G * 128 * dg_ldv(V) * 4);                     // logits (128 rows per group)
     take((size_t)G * 128);                                     // bar
     take((size_t)G * Lmax * 4);                                // gstate
     return b + 1024;
@@ -1201,9 +1209,9 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.x2buf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.pre = reinterpret_cast<float*>(take((size_t)N * DG_D * 4));
     p.q2 = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
-    p.part = reinterpret_cast<__half*>(take((size_t)DG_P * N * DG_D * 2));
+    p.part = reinterpret_cast<float*>(take((size_t)DG_P * G * 128 * DG_D * 4));
     p.ldv = dg_ldv(mp.V);
-    p.logits = reinterpret_cast<float*>(take((size_t)N * p.ldv * 4));
+    p.logits = reinterpret_cast<float*>(take((size_t)G * 128 * p.ldv * 4));
     p.bar = reinterpret_cast<int*>(take((size_t)G * 128));
     p.gstate = reinterpret_cast<int*>(take((size_t)G * mp.st.Lmax * 4));
 

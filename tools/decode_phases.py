@@ -22,7 +22,7 @@ for l in range(6):
     names += [f'L{l} ' + n for n in ('qkv gemm', 'barrier', 'self-attn', 'barrier', 'out-proj', 'barrier', 'LN1 build', 'q-proj', 'barrier',
                                      'cross-attn', 'barrier', 'out-proj2', 'barrier', 'LN2 build', 'w1+glu', 'w2 partial', 'barrier',
                                      'reduce+LN3', 'barrier')]
-names += ['logits', 'barrier', 'lsm+topk+beam', 'barrier']
+names += ['logits', 'barrier', 'gather rows', 'row top-k', 'beam step', 'barrier']
 with torch.no_grad():
     mem, lens, B, T2 = model.encode_bf16(x, mask)
     bd = BeamDecoder(model.decoder, B, 10, T2, 60, dev, use_graph=False, persistent=True)
@@ -50,4 +50,4 @@ with torch.no_grad():
         d = (allt[:, 1:n] - allt[:, :n - 1])                      # [cta, phase] durations of every CTA of group 0
         print('    layer 2, per phase (min / max over the 16 CTAs):',
               [(names[i].split(' ', 1)[1], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(2 + 2 * 19, 2 + 3 * 19)])
-        print('    tail, per phase (min / max over CTAs):', [(names[i], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(n - 4, n)])
+        print('    tail, per phase (min / max over CTAs):', [(names[i], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(n - 6, n)])
