@@ -63,10 +63,12 @@ struct DgMisc {
     uint64_t st_full[2];      // big stage landed
     uint64_t st_empty[2];     // big stage consumed (tcgen05.commit)
     uint64_t acc_full[2];     // accumulator complete (tcgen05.commit)
-    uint64_t acc_empty[2];    // accumulator drained by the 128 epilogue threads
+    uint64_t acc_empty[2];    // (unused since v6: the CTA barrier behind a drained chunk frees the accumulator half)
+    uint64_t pw_full[4];      // k-blocks of the out-projection weights (self-attention W_o, then cross-attention W_o) landed
+    uint64_t pq_full[4];      // k-blocks of the cross-attention query projection landed
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
-    alignas(16) uint32_t rs[128 * 8];     // residual slice of this CTA: rows x 16 columns, bf16 pairs
+    alignas(16) uint32_t zero16[4];       // the (zero) rows 8..15 of the m16 A fragments of the row-block projections
     alignas(16) float bias[256];          // per-phase bias slice
     float c_val[KMAX * KMAX];
     int c_tok[KMAX * KMAX];
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const CUtensorMap* map_ctx = maps + nl * 6 + 1;
     const CUtensorMap* map_kvx = maps + nl * 6 + 2;
     const CUtensorMap* map_x = maps + nl * 6 + 3;
+    const CUtensorMap* map_x2 = maps + nl * 6 + 4;
     int* bar = p.bar + g * 32;                        // 128-byte separated counters
     const bool is_tma = (warp == 0 && lane == 0), is_mma = (warp == 1 && lane == 0);
     const int equad = warp & 3;                       // TMEM lane quadrant this warp may read
@@ -147,6 +150,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             mbar_init(&ms.kb_full[i], 1);
             mbar_init(&ms.a_full[i], 1);
             mbar_init(&ms.w1_full[i], 1);
+            mbar_init(&ms.pw_full[i], 1);
+            mbar_init(&ms.pq_full[i], 1);
+            ms.zero16[i] = 0;
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&ms.st_full[i], 1);
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
@@ -225,14 +231,19 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             tma_load_2d(sA + kb * 16384, ma, &ms.a_full[kb], kb * 64, row0);
         }
     };
-    auto load_w1 = [&](int l) {   // both stages: k-block kb -> stage kb/2, [value rows | gate rows] of this CTA's 128 hidden features
+    auto load_w1 = [&](int l, int kb0) {   // k-blocks kb0, kb0 + 1 -> stage kb0 / 2: [value rows | gate rows] of this CTA's 128 hidden features
         const CUtensorMap* m = maps + l * 6 + 4;
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = kb0; kb < kb0 + 2; ++kb) {
             uint8_t* dst = sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768;
             mbar_arrive_expect_tx(&ms.w1_full[kb], 32768);
             tma_load_2d_hint(dst, m, &ms.w1_full[kb], kb * 64, j * 128, TMA_EVICT_LAST);
             tma_load_2d_hint(dst + 16384, m, &ms.w1_full[kb], kb * 64, DG_DFF + j * 128, TMA_EVICT_LAST);
         }
+    };
+    // one k-block (all 256 output features x 64 input features, 32 KB, SWIZZLE_128B) of a d x d projection
+    auto load_proj_kb = [&](const CUtensorMap* m, uint64_t* full, int kb, uint8_t* dst) {
+        mbar_arrive_expect_tx(&full[kb], 32768);
+        tma_load_2d_hint(dst, m, &full[kb], kb * 64, 0, TMA_EVICT_LAST);
     };
     auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
         const int u = u0 + task / DG_H, h = task % DG_H;
@@ -275,58 +286,87 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         fence_proxy_async_smem();
         __syncthreads();
     };
-    // LayerNorm of the gathered pre-norm rows (fp32: residual + projection + bias) -> bf16 A tile (transformer.py:54-56 ...).
-    // 8 lanes per row (4 rows per warp instruction; lane c of a row owns columns 32 k + 4 c .. + 3, k = 0..7: every load
-    // instruction reads 128 contiguous bytes per row), statistics through 3 shuffles.  v2 gave a row to a whole warp (5-level
-    // shuffles, 16-byte swizzled stores): 7.5 k cycles per build, three per layer.  The 16 columns of this CTA go to the
-    // residual stash rs; with x2_out the rows [8 j, 8 j + 8) are also written to global memory (residual of the w_2 reduction).
-    auto build_a_ln = [&](const float* gamma, const float* beta, bf16* x_out) {
-        const int g4 = lane >> 3, c = lane & 7;
+    // ---- row-block projections (v7) ------------------------------------------------------------------------------
+    // The three d x d projections between the attention cores (self-attention W_o, the cross-attention query projection and
+    // the cross-attention W_o) are computed by the OWNER of the rows: CTA j holds rows [8 j, 8 j + 8) of the tile and
+    // multiplies them by the WHOLE weight matrix (128 KB, streamed by TMA through the idle A tile / stages one phase ahead)
+    // with mma.sync m16n8k16 (rows 8..15 of the fragment are zero).  A complete row in one CTA means bias + residual +
+    // LayerNorm finish right there: v6 split these projections by output column over the 16 CTAs, which cost a group
+    // barrier in front of every LayerNorm plus a 128 KB fp32 gather of ALL rows by EVERY CTA (6 k cycles, twice per layer).
+    // Activations: [8 rows][256] bf16 in shared memory, 16-byte chunks XOR-swizzled by the row (conflict-free ldmatrix).
+    uint8_t* sA0 = sSB + 16384;                       // attention output rows (A operand of W_o)
+    uint8_t* sA1 = sSB + 20480;                       // LayerNorm-1 output rows: A operand of the query projection, residual of W_o #2
+    auto a_off = [](int r, int chunk) { return (uint32_t)(r * 512 + ((chunk ^ (r & 7)) << 4)); };
+    const int er = lane >> 2;                         // row of the block held by this thread's accumulator fragment
+    const int ec = warp * 16 + 2 * (lane & 3);        // its columns: ec + 8 nt + {0, 1}, nt = 0, 1
+    const bool elive = j * 8 + er < nrows;
+    const size_t erow_g = (size_t)(row0 + j * 8 + er) * DG_D;
+    auto load_rows = [&](const bf16* src, uint8_t* dstA) {    // this CTA's 8 rows of a [N, 256] bf16 buffer -> swizzled smem
+        if (tid < 256) {
+            const int r = tid >> 5, ch = tid & 31;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (j * 8 + r < nrows) v = *reinterpret_cast<const uint4*>(src + (size_t)(row0 + j * 8 + r) * DG_D + ch * 8);
+            *reinterpret_cast<uint4*>(dstA + a_off(r, ch)) = v;
+        }
+    };
+    // acc[nt][0..1] = sum_k A[er][k] * W[ec + 8 nt + {0,1}][k]; warp w owns output features [16 w, 16 w + 16)
+    auto rowgemm = [&](const uint8_t* A, uint64_t* full, uint32_t par, auto kb_addr, float (&acc)[2][4]) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+        const int m = lane >> 3, rr = lane & 7;
+        const uint32_t zaddr = smem_u32(ms.zero16), abase = smem_u32(A);
 #pragma unroll 1
-        for (int it = 0; it < 2; ++it) {      // (unrolling the two row groups was tried: +200 B of spills in the attention loops)
-            const int r = warp * 8 + it * 4 + g4;
-            float4 v[8];
-            if (r < nrows) {
-                const float* src = p.pre + (size_t)(row0 + r) * DG_D + 4 * c;
+        for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&full[kb], (par >> kb) & 1);
+            const uint32_t wb = smem_u32(kb_addr(kb));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(src + 32 * k);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            const float mean = s * (1.0f / DG_D);
-            float q = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float a = v[k].x - mean, b = v[k].y - mean, cc = v[k].z - mean, d = v[k].w - mean;
-                q += (a * a + b * b) + (cc * cc + d * d);
-            }
-            q += __shfl_xor_sync(0xffffffffu, q, 1);
-            q += __shfl_xor_sync(0xffffffffu, q, 2);
-            q += __shfl_xor_sync(0xffffffffu, q, 4);
-            const float rstd = rsqrtf(q * (1.0f / DG_D) + p.eps);
-            const bool live = r < nrows;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + 32 * k + 4 * c));     // L1-resident after the first row
-                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + 32 * k + 4 * c));
-                uint2 o;
-                o.x = live ? pack_bf16((v[k].x - mean) * rstd * gm.x + bt.x, (v[k].y - mean) * rstd * gm.y + bt.y) : 0u;
-                o.y = live ? pack_bf16((v[k].z - mean) * rstd * gm.z + bt.z, (v[k].w - mean) * rstd * gm.w + bt.w) : 0u;
-                const int col = 32 * k + 4 * c;           // 4 consecutive columns = half of a 16-byte chunk
-                *reinterpret_cast<uint2*>(sA + (col >> 6) * 16384 + sw128(r, (col & 63) >> 3) + (col & 4) * 2) = o;
-                if ((col >> 4) == j) *reinterpret_cast<uint2*>(&ms.rs[r * 8 + ((col & 15) >> 1)]) = o;
-                if (x_out != nullptr && live && (r >> 3) == j) *reinterpret_cast<uint2*>(x_out + (size_t)(row0 + r) * DG_D + col) = o;
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+                // A matrices: (rows 0-7, k lo) (rows 8-15, k lo) (rows 0-7, k hi) (rows 8-15, k hi); rows 8-15 read the zero chunk
+                ldmatrix_x4((m & 1) ? zaddr : abase + a_off(rr, kb * 8 + ks * 2 + (m >> 1)), a0, a1, a2, a3);
+                ldmatrix_x4(wb + sw128(warp * 16 + (m >> 1) * 8 + rr, 2 * ks + (m & 1)), b0, b1, b2, b3);
+                dg_mma16816(acc[0], a0, a1, a2, a3, b0, b1);
+                dg_mma16816(acc[1], a0, a1, a2, a3, b2, b3);
             }
         }
-        fence_proxy_async_smem();
+    };
+    // LayerNorm of the 8 rows held as v[nt][e] (fp32: projection + bias + residual), statistics across the 16 warps
+    auto row_ln = [&](float (&v)[2][2], const float* gamma, const float* beta) {
+        float* rsum = ms.c_val;                       // [16 warps][8 rows]
+        float s = (v[0][0] + v[0][1]) + (v[1][0] + v[1][1]);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if ((lane & 3) == 0) rsum[warp * 8 + er] = s;
         __syncthreads();
+        float mean = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) mean += rsum[w * 8 + er];
+        mean *= (1.0f / DG_D);
+        float q = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                v[nt][e] -= mean;
+                q += v[nt][e] * v[nt][e];
+            }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        __syncthreads();
+        if ((lane & 3) == 0) rsum[warp * 8 + er] = q;
+        __syncthreads();
+        float var = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) var += rsum[w * 8 + er];
+        const float rstd = rsqrtf(var * (1.0f / DG_D) + p.eps);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const float2 gm = *reinterpret_cast<const float2*>(gamma + ec + 8 * nt), bt = *reinterpret_cast<const float2*>(beta + ec + 8 * nt);
+            v[nt][0] = v[nt][0] * rstd * gm.x + bt.x;
+            v[nt][1] = v[nt][1] * rstd * gm.y + bt.y;
+        }
     };
 
     // ---- small GEMM: acc[128 x nB] = A[128 x 256] * Bslice^T, B slice prefetched into sSB (kb_full).  a_map != null: A is fetched
@@ -406,7 +446,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 reinterpret_cast<uint4*>(dst)[0] = o[0];
                 reinterpret_cast<uint4*>(dst)[1] = o[1];
             });
-            gsync([&] { load_small_b(maps + l * 6 + 1, j * 16, 16); });      // out-projection weights arrive during the barrier
+            gsync([&] {      // W_o (whole) and the first half of the query projection stream in behind the self-attention
+                for (int kb = 0; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 1, ms.pw_full, kb, kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768);
+                for (int kb = 0; kb < 2; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sST + DG_STAGE + kb * 32768);
+            });
             DG_STAMP();
             // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
             // One warp per (hypothesis, head); 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V
@@ -415,7 +458,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
-                int* an_s = reinterpret_cast<int*>(sST) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
                 const int g4 = lane >> 3, c8 = lane & 7;
                 for (int task = j * 16 + warp; task < nrows * DG_H; task += DG_P * 16) {
                     const int r = task / DG_H, h = task % DG_H;
@@ -504,41 +547,46 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             }
             gsync(nop);
             DG_STAMP();
-            // ---------------- out-projection + residual (the layer input, xbuf) -> pre-norm rows (attention.py:44, transformer.py:54)
-            uint4 res_a = make_uint4(0, 0, 0, 0), res_b = res_a;
-            gemm_small(16, map_ctx, ly.bo, j * 16, [&] {
-                if (erow < nrows) {
-                    const uint4* rsrc = reinterpret_cast<const uint4*>(p.xbuf + (size_t)(row0 + erow) * DG_D + j * 16);
-                    res_a = rsrc[0];
-                    res_b = rsrc[1];
+            // ---------------- rows [8 j, 8 j + 8): W_o + bias + residual (the layer input) -> LayerNorm 1 -> query projection
+            // (attention.py:44, transformer.py:54-56, attention.py:128), all inside the owning CTA
+            {
+                load_rows(p.ctx, sA0);
+                uint32_t xres[2] = {0u, 0u};
+                if (elive) {
+                    xres[0] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec);
+                    xres[1] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec + 8);
                 }
-            }, [&](int c, const uint32_t (&r)[16]) {
-                if (erow >= nrows) return;
-                const uint32_t rw[8] = {res_a.x, res_a.y, res_a.z, res_a.w, res_b.x, res_b.y, res_b.z, res_b.w};
-                float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
+                __syncthreads();
+                float acc[2][4];
+                rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
+                par_pw ^= 0xF;
+                __syncthreads();      // every warp is done with W_o: its first half makes room for the second half of W_q
+                if (is_tma)
+                    for (int kb = 2; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sA + (kb - 2) * 32768);
+                float v[2][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 r0 = unpack_bf16(rw[2 * i]), r1 = unpack_bf16(rw[2 * i + 1]);
-                    dst[i] = make_float4(__uint_as_float(r[4 * i]) + ms.bias[4 * i] + r0.x, __uint_as_float(r[4 * i + 1]) + ms.bias[4 * i + 1] + r0.y,
-                                         __uint_as_float(r[4 * i + 2]) + ms.bias[4 * i + 2] + r1.x, __uint_as_float(r[4 * i + 3]) + ms.bias[4 * i + 3] + r1.y);
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float2 bb = *reinterpret_cast<const float2*>(ly.bo + ec + 8 * nt);
+                    const float2 xr = unpack_bf16(xres[nt]);
+                    v[nt][0] = acc[nt][0] + bb.x + xr.x;
+                    v[nt][1] = acc[nt][1] + bb.y + xr.y;
                 }
-            });
-            gsync([&] { load_small_b(maps + l * 6 + 2, j * 16, 16); });      // q-projection weights
-            DG_STAMP();
-            // ---------------- LayerNorm 1 + cross-attention query projection (attention.py:128)
-            build_a_ln(ly.g1, ly.be1, nullptr);
-            DG_STAMP();   // LN1
-            gemm_small(16, nullptr, ly.bq, j * 16, nop, [&](int c, const uint32_t (&r)[16]) {
-                if (erow >= nrows) return;
-                uint4 o[2];
-                uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+                row_ln(v, ly.g1, ly.be1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    ow[i] = pack_bf16(__uint_as_float(r[2 * i]) + ms.bias[2 * i], __uint_as_float(r[2 * i + 1]) + ms.bias[2 * i + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(p.q2 + (size_t)(row0 + erow) * DG_D + j * 16);
-                dst[0] = o[0];
-                dst[1] = o[1];
-            });
+                for (int nt = 0; nt < 2; ++nt)
+                    *reinterpret_cast<uint32_t*>(sA1 + a_off(er, (ec + 8 * nt) >> 3) + ((ec + 8 * nt) & 7) * 2) = pack_bf16(v[nt][0], v[nt][1]);
+                __syncthreads();
+                DG_STAMP();   // W_o + LN1
+                rowgemm(sA1, ms.pq_full, par_pq, [&](int kb) { return kb < 2 ? sST + DG_STAGE + kb * 32768 : sA + (kb - 2) * 32768; }, acc);
+                par_pq ^= 0xF;
+                if (elive) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const float2 bb = *reinterpret_cast<const float2*>(ly.bq + ec + 8 * nt);
+                        *reinterpret_cast<uint32_t*>(p.q2 + erow_g + ec + 8 * nt) = pack_bf16(acc[nt][0] + bb.x, acc[nt][1] + bb.y);
+                    }
+                }
+            }
             gsync([&] {   // encoder K / V tiles of this CTA's first two (utterance, head) problems arrive during the barrier
                 if (j < n_tasks) load_kv(l, j, 0);
                 if (j + DG_P < n_tasks) load_kv(l, j + DG_P, 1);
@@ -676,33 +724,46 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     __syncthreads();
                 }
             }
-            gsync([&] {    // W1 slice (128 KB) and the out-projection weights stream in while the other CTAs finish
-                load_w1(l);
-                load_small_b(maps + l * 6 + 3, j * 16, 16);
+            gsync([&] {    // cross-attention W_o (whole) and the second half of this CTA's W1 slice stream in while the other CTAs finish
+                for (int kb = 0; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 3, ms.pw_full, kb, kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768);
+                load_w1(l, 2);
             });
             DG_STAMP();
-            // ---------------- cross-attention out-projection + residual (x1, the stash of LayerNorm 1) -> pre-norm rows
-            gemm_small(16, map_ctx, ly.bo2, j * 16, nop, [&](int c, const uint32_t (&r)[16]) {
-                if (erow >= nrows) return;
-                float4* dst = reinterpret_cast<float4*>(p.pre + (size_t)(row0 + erow) * DG_D + j * 16);
+            // ---------------- rows [8 j, 8 j + 8): cross-attention W_o + bias + residual (x1, still in shared memory) -> LayerNorm 2
+            // -> x2 (bf16, global: A operand of the feed-forward of every CTA and residual of its reduction)
+            {
+                load_rows(p.ctx, sA0);
+                __syncthreads();
+                float acc[2][4];
+                rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
+                par_pw ^= 0xF;
+                __syncthreads();      // stage 0 (second half of W_o) is free: first half of W1
+                if (is_tma) load_w1(l, 0);
+                float v[2][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 r0 = unpack_bf16(ms.rs[erow * 8 + 2 * i]), r1 = unpack_bf16(ms.rs[erow * 8 + 2 * i + 1]);
-                    dst[i] = make_float4(__uint_as_float(r[4 * i]) + ms.bias[4 * i] + r0.x, __uint_as_float(r[4 * i + 1]) + ms.bias[4 * i + 1] + r0.y,
-                                         __uint_as_float(r[4 * i + 2]) + ms.bias[4 * i + 2] + r1.x, __uint_as_float(r[4 * i + 3]) + ms.bias[4 * i + 3] + r1.y);
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float2 bb = *reinterpret_cast<const float2*>(ly.bo2 + ec + 8 * nt);
+                    const float2 xr = unpack_bf16(*reinterpret_cast<const uint32_t*>(sA1 + a_off(er, (ec + 8 * nt) >> 3) + ((ec + 8 * nt) & 7) * 2));
+                    v[nt][0] = acc[nt][0] + bb.x + xr.x;
+                    v[nt][1] = acc[nt][1] + bb.y + xr.y;
                 }
-            });
+                row_ln(v, ly.g2, ly.be2);
+                if (elive) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) *reinterpret_cast<uint32_t*>(p.x2buf + erow_g + ec + 8 * nt) = pack_bf16(v[nt][0], v[nt][1]);
+                }
+            }
             gsync(nop);
             DG_STAMP();
-            // ---------------- LayerNorm 2 + GLU feed-forward: hidden features [128 j, 128 j + 128) (ffn.py:18,39-41)
-            build_a_ln(ly.g2, ly.be2, p.x2buf);
-            DG_STAMP();   // LN2
+            // ---------------- GLU feed-forward: hidden features [128 j, 128 j + 128) (ffn.py:18,39-41); A = x2 of all rows by TMA
+            if (is_tma) load_a(map_x2);
             {
                 if (tid < 256) ms.bias[tid] = ly.b1[(tid < 128 ? 0 : DG_DFF - 128) + j * 128 + tid];
                 if (is_mma) {
                     const uint32_t idesc = umma_idesc_bf16(256);
                     for (int kb = 0; kb < 4; ++kb) {
                         mbar_wait(&ms.w1_full[kb], (par_w1 >> kb) & 1);
+                        mbar_wait(&ms.a_full[kb], (par_a >> kb) & 1);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(sA + kb * 16384);
                         const uint32_t b_addr = smem_u32(sST + (kb >> 1) * DG_STAGE + (kb & 1) * 32768);
@@ -724,8 +785,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     tc_fence_after();
                     // h = (a + b_a) * sigmoid(g + b_g) -> bf16, written over the (dead) A tile as a [128 x 128] K-major operand;
                     // all 16 warps: warp w takes rows [32 (w & 3), +32) and hidden features [32 (w >> 2), +32)
+                    const bool glu4 = (p.flags & 1) != 0;      // A/B switch (OTB_DG_FLAGS=1): the v5 epilogue on warps 4-7 only
+                    const int gc0 = glu4 ? (ecg == 1 ? 0 : 128) : ecg * 32, gc1 = glu4 ? 128 : ecg * 32 + 32;
 #pragma unroll 1
-                    for (int c = ecg * 32; c < ecg * 32 + 32; c += 16) {
+                    for (int c = gc0; c < gc1; c += 16) {
                         uint32_t ra[16], rg[16];
                         tmem_ld16(t_row + c, ra);
                         tmem_ld16(t_row + 128 + c, rg);
@@ -746,6 +809,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     fence_proxy_async_smem();
                 }
                 par_w1 ^= 0xF;
+                par_a ^= 0xF;
                 par_accf ^= 1;
                 __syncthreads();
                 DG_STAMP();   // W1 + GLU
@@ -1169,12 +1233,11 @@ size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int be
     const int G = (B + upg - 1) / upg;
     size_t b = 0;
     auto take = [&](size_t n) { b += (n + 255) & ~(size_t)255; };
-    take((size_t)(n_layers * 6 + 4) * sizeof(CUtensorMap));   // maps
+    take((size_t)(n_layers * 6 + 5) * sizeof(CUtensorMap));   // maps
     take((size_t)N * DG_D * 2);                                // qbuf
     take((size_t)(N + 128) * DG_D * 2);                        // ctx (+ one tile of slack rows for the last group's TMA box)
     take((size_t)(N + 128) * DG_D * 2);                        // xbuf
-    take((size_t)N * DG_D * 2);                                // x2buf
-    take((size_t)N * DG_D * 4);                                // pre
+    take((size_t)(N + 128) * DG_D * 2);                        // x2buf
     take((size_t)N * DG_D * 2);                                // q2
     take((size_t)DG_P * G * 128 * DG_D * 4);                   // part (fp32, 128 rows per group)
     take((size_t)G * 128 * dg_ldv(V) * 4);                     // logits (128 rows per group)
@@ -1202,12 +1265,11 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     memset(&p, 0, sizeof(p));
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
     auto take = [&](size_t n) { uint8_t* r = w; w += (n + 255) & ~(size_t)255; return r; };
-    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 4) * sizeof(CUtensorMap)));
+    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 5) * sizeof(CUtensorMap)));
     p.qbuf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.ctx = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
     p.xbuf = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
-    p.x2buf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
-    p.pre = reinterpret_cast<float*>(take((size_t)N * DG_D * 4));
+    p.x2buf = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
     p.q2 = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.part = reinterpret_cast<float*>(take((size_t)DG_P * G * 128 * DG_D * 4));
     p.ldv = dg_ldv(mp.V);
@@ -1216,14 +1278,14 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.gstate = reinterpret_cast<int*>(take((size_t)G * mp.st.Lmax * 4));
 
     // tensor maps (host encode -> device array).  Weights [rows, K] bf16 row-major, box = (64 columns) x (rows of one slice).
-    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 4];
+    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 5];
     const char* err;
     for (int l = 0; l < mp.n_layers; ++l) {
         const MegaLayer& ly = mp.layers[l];
         if ((err = encode_tmap_2d(&h_maps[l * 6 + 0], ly.wqkv, DG_D, 3 * DG_D, DG_D, 64, 48))) return err;
-        if ((err = encode_tmap_2d(&h_maps[l * 6 + 1], ly.wo, DG_D, DG_D, DG_D, 64, 16))) return err;
-        if ((err = encode_tmap_2d(&h_maps[l * 6 + 2], ly.wq, DG_D, DG_D, DG_D, 64, 16))) return err;
-        if ((err = encode_tmap_2d(&h_maps[l * 6 + 3], ly.wo2, DG_D, DG_D, DG_D, 64, 16))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 1], ly.wo, DG_D, DG_D, DG_D, 64, 256))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 2], ly.wq, DG_D, DG_D, DG_D, 64, 256))) return err;
+        if ((err = encode_tmap_2d(&h_maps[l * 6 + 3], ly.wo2, DG_D, DG_D, DG_D, 64, 256))) return err;
         if ((err = encode_tmap_2d(&h_maps[l * 6 + 4], ly.w1, DG_D, 2 * DG_DFF, DG_D, 64, 128))) return err;
         if ((err = encode_tmap_2d(&h_maps[l * 6 + 5], ly.w2, DG_DFF, DG_D, DG_DFF, 64, 256))) return err;
         DgLayer& d = p.layers[l];
@@ -1235,7 +1297,8 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     if ((err = encode_tmap_2d(&h_maps[nm + 1], p.ctx, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 2], mp.kvx, 2 * DG_D, (uint64_t)mp.n_layers * mp.B * mp.T, 2 * DG_D, 64, 256))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 3], p.xbuf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
-    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 4) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+    if ((err = encode_tmap_2d(&h_maps[nm + 4], p.x2buf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
+    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 5) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.bar, 0, (size_t)G * 128, st)) != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.gstate, 0, (size_t)G * mp.st.Lmax * 4, st)) != cudaSuccess) return cudaGetErrorString(e);
@@ -1247,6 +1310,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.st = mp.st; p.B = mp.B; p.T = mp.T; p.max_steps = mp.max_steps; p.eps = mp.eps;
     p.dbg_logp = mp.dbg_logp; p.dbg_scores = mp.dbg_scores;
     p.dbg_clk = g_dg_dbg; p.dbg_step = g_dg_dbg_step;
+    { const char* f_ = getenv("OTB_DG_FLAGS"); p.flags = f_ ? atoi(f_) : 0; }
 
     static bool attr_set = false;
     static int cluster_ok = -1;     // -1 unknown, 0 clusters of 16 unavailable, 1 available

@@ -183,6 +183,7 @@ struct DgParams {
     bf16* x2buf;               // [N, d]   LayerNorm 2 output (residual of the feed-forward)
     float* pre;                // [N, d]   pre-LayerNorm rows (residual + projection + bias), fp32
     bf16* q2;                  // [N, d]   cross-attention queries
+    int flags;                 // experiment switches (OTB_DG_FLAGS)
     float* part;               // [16 slices][groups][64 column groups][128 rows][4] w_2 partial products (fp32)
     float* logits;             // [N, ldv] output-layer logits of the step
     int ldv;

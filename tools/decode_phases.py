@@ -17,11 +17,12 @@ with torch.no_grad():
 x, mask = bench.synthetic_batch(32, 0)
 x, mask = x.to(dev), mask.to(dev)
 L = _lib.lib()
+PH = ('qkv gemm', 'barrier', 'self-attn', 'barrier', 'W_o+LN1', 'q-proj', 'barrier', 'cross-attn', 'barrier', 'W_o2+LN2', 'barrier',
+      'w1+glu', 'w2 partial', 'barrier', 'reduce+LN3', 'barrier')
+NP = len(PH)
 names = ['start', 'embed']
 for l in range(6):
-    names += [f'L{l} ' + n for n in ('qkv gemm', 'barrier', 'self-attn', 'barrier', 'out-proj', 'barrier', 'LN1 build', 'q-proj', 'barrier',
-                                     'cross-attn', 'barrier', 'out-proj2', 'barrier', 'LN2 build', 'w1+glu', 'w2 partial', 'barrier',
-                                     'reduce+LN3', 'barrier')]
+    names += [f'L{l} ' + n for n in PH]
 names += ['logits', 'barrier', 'gather rows', 'row top-k', 'beam step', 'barrier']
 with torch.no_grad():
     mem, lens, B, T2 = model.encode_bf16(x, mask)
@@ -46,8 +47,8 @@ with torch.no_grad():
             agg[key] = agg.get(key, 0) + dt
         for k, v in agg.items():
             print(f'    {k:14s} {v:9d} cycles  {100.0 * v / (t[n-1]-t[0]):5.1f}%')
-        print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 21)])
+        print('    layer 0 detail:', [(names[i].split(' ', 1)[1], t[i] - t[i - 1]) for i in range(2, 2 + NP)])
         d = (allt[:, 1:n] - allt[:, :n - 1])                      # [cta, phase] durations of every CTA of group 0
         print('    layer 2, per phase (min / max over the 16 CTAs):',
-              [(names[i].split(' ', 1)[1], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(2 + 2 * 19, 2 + 3 * 19)])
+              [(names[i].split(' ', 1)[1], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(2 + 2 * NP, 2 + 3 * NP)])
         print('    tail, per phase (min / max over CTAs):', [(names[i], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(n - 6, n)])

@@ -17,3 +17,4 @@ for L in ${LANES:-3}; do timeout 600 python bench.py --steps 12 --min-ms 300 --n
 import json; d=json.loads(open('gpurun_out/r2_bench_${TAG}_l$L.json').read().strip().splitlines()[-1]); print('lanes $L', round(d['value']), round(d['e2e']['value']), d['config']['decode_path'], d['config']['persistent_probe'][:120], d['breakdown']['single_lane_step_ms'], d['breakdown']['persistent_decode_kernel_ms'], d['validation']['ids_sha1'])"; done
 OTB_DG_CLUSTER=0 timeout 600 python bench.py --steps 12 --min-ms 300 --no-extras --no-cpu-baseline --lanes 3 > gpurun_out/r2_bench_${TAG}_sw3.json 2> gpurun_out/r2_bench_${TAG}_sw3.err; python -c "
 import json; d=json.loads(open('gpurun_out/r2_bench_${TAG}_sw3.json').read().strip().splitlines()[-1]); print('software barrier, lanes 3', round(d['value']), round(d['e2e']['value']), d['breakdown']['single_lane_step_ms'])"
+if [ -n "$FLAGS_AB" ]; then for F in $FLAGS_AB; do OTB_DG_FLAGS=$F timeout 300 python tools/decode_phases.py 5 > gpurun_out/r2_decode_phases_${TAG}_f$F.txt 2>&1; echo "flags $F"; grep -E "whole|layer 2" gpurun_out/r2_decode_phases_${TAG}_f$F.txt | cut -c1-900; done; fi
