@@ -104,6 +104,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                  : "r"(addr));
 }
+// 16-byte global load with an L2 eviction-priority descriptor
+__device__ __forceinline__ uint4 ldg_v4_hint(const void* ptr, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ float dg_sigmoid(float x) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
@@ -215,6 +223,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         __syncthreads();
     };
     auto nop = [] {};
+    // L2 eviction priorities (OTB_DG_FLAGS experiments: 2 = encoder K/V normal, 4 = encoder K/V evict-last, 8 = self-attention K/V evict-first)
+    const uint64_t kvx_policy = (p.flags & 2) ? TMA_EVICT_NORMAL : (p.flags & 4) ? TMA_EVICT_LAST : TMA_EVICT_FIRST;
+    const uint64_t kv_policy = (p.flags & 8) ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
 
     // ---- operand loads issued by the TMA thread ------------------------------------------------------------------
     // small B operand: nB weight rows [b_row0, b_row0 + nB) x 256, k-block kb at sSB + kb * nB * 128 (prefetched at the
@@ -250,8 +261,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         mbar_arrive_expect_tx(&ms.st_full[s], 65536);
         // the encoder K / V tiles are streamed once per step (49 MB per batch): evict-first, so that they do not push the
         // decoder weights (re-read by every group, every step) out of L2
-        tma_load_2d_hint(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T, TMA_EVICT_FIRST);
-        tma_load_2d_hint(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T, TMA_EVICT_FIRST);
+        tma_load_2d_hint(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T, kvx_policy);
+        tma_load_2d_hint(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T, kvx_policy);
     };
     const int n_vchunks = (V + 127) / 128;
     auto load_wout = [&](int chunk, int s) {
@@ -486,8 +497,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             if (sidx < nkeys) {
                                 const int slot = (sidx < step) ? an_s[sidx] : n;
                                 const size_t off = (((size_t)l * Lmax + sidx) * N + slot) * DG_D + col;
-                                ku[u] = *reinterpret_cast<const uint4*>(p.kc + off);
-                                vu[u] = *reinterpret_cast<const uint4*>(p.vc + off);
+                                ku[u] = ldg_v4_hint(p.kc + off, kv_policy);
+                                vu[u] = ldg_v4_hint(p.vc + off, kv_policy);
                             } else {
                                 ku[u] = make_uint4(0, 0, 0, 0);
                                 vu[u] = ku[u];
@@ -964,13 +975,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     if (erow < nrows) {
                         const float* bs = ms.bias + s * 128 + ecg * 32;
                         uint4* dst = lg4 + (size_t)(cc0 >> 2) * 128 + erow;
+                        const bool full32 = cc0 + 32 <= V;     // warp-uniform; columns [V, ldv) are stored as -inf (no bounds checks in the readers)
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             uint4 o;
-                            o.x = __float_as_uint(__uint_as_float(r[4 * q]) + bs[4 * q]);
-                            o.y = __float_as_uint(__uint_as_float(r[4 * q + 1]) + bs[4 * q + 1]);
-                            o.z = __float_as_uint(__uint_as_float(r[4 * q + 2]) + bs[4 * q + 2]);
-                            o.w = __float_as_uint(__uint_as_float(r[4 * q + 3]) + bs[4 * q + 3]);
+                            o.x = (full32 || cc0 + 4 * q < V) ? __float_as_uint(__uint_as_float(r[4 * q]) + bs[4 * q]) : 0xff800000u;
+                            o.y = (full32 || cc0 + 4 * q + 1 < V) ? __float_as_uint(__uint_as_float(r[4 * q + 1]) + bs[4 * q + 1]) : 0xff800000u;
+                            o.z = (full32 || cc0 + 4 * q + 2 < V) ? __float_as_uint(__uint_as_float(r[4 * q + 2]) + bs[4 * q + 2]) : 0xff800000u;
+                            o.w = (full32 || cc0 + 4 * q + 3 < V) ? __float_as_uint(__uint_as_float(r[4 * q + 3]) + bs[4 * q + 3]) : 0xff800000u;
                             dst[(size_t)q * 128] = o;
                         }
                     }
@@ -1003,13 +1015,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // tile and both weight stages are idle: 192 KB) by all 16 warps with cp.async -- every 16-byte piece in flight at
             // once, `beam` consecutive rows = one contiguous run per column group; the two passes below then run on shared
             // memory.  A vocabulary x beam that does not fit is read in place (element stride 128 x 16 bytes).
-            const bool staged = (size_t)beam * p.ldv * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
+            const int lds = p.ldv + 4;                               // shared-memory row stride (floats): rows 16 bytes apart in the banks
+            const bool staged = (size_t)beam * lds * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
             const int lr0 = ul * beam;                               // first row of the utterance inside the group tile
             if (staged) {
                 const int npieces = ldv4 * beam;
                 for (int i = tid; i < npieces; i += DG_THREADS) {
                     const int c4 = i / beam, rr = i - c4 * beam;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + ((size_t)rr * p.ldv + c4 * 4) * 4)),
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + ((size_t)rr * lds + c4 * 4) * 4)),
                                  "l"(lg4 + (size_t)c4 * 128 + lr0 + rr) : "memory");
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1018,23 +1031,19 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             if (ul == j) DG_STAMP();      // rows gathered
             if (warp < beam) {
                 const int r = warp, n = u * beam + r;
-                const float4* x4 = staged ? reinterpret_cast<const float4*>(smem + (size_t)r * p.ldv * 4) : reinterpret_cast<const float4*>(lg4 + lr0 + r);
+                const float4* x4 = staged ? reinterpret_cast<const float4*>(smem + (size_t)r * lds * 4) : reinterpret_cast<const float4*>(lg4 + lr0 + r);
                 const int xs4 = staged ? 1 : 128;                    // float4 stride between consecutive column groups
                 auto xel = [&](int c) { return reinterpret_cast<const float*>(x4 + (size_t)(c >> 2) * xs4)[c & 3]; };
-                const int nv4 = (V + 3) >> 2;
+                const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                 float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
                 float lmax = -INFINITY;
-                for (int base = 0; base < nv4; base += 32 * 8) {
+                for (int base = 0; base < ldv4; base += 32 * 8) {
                     const int i0 = base + lane;
                     float4 v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < ldv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : ninf4;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int c0 = (i0 + 32 * q) * 4;
-                        lmax = fmaxf(lmax, fmaxf(fmaxf(c0 < V ? v[q].x : -INFINITY, c0 + 1 < V ? v[q].y : -INFINITY),
-                                                 fmaxf(c0 + 2 < V ? v[q].z : -INFINITY, c0 + 3 < V ? v[q].w : -INFINITY)));
-                    }
+                    for (int q = 0; q < 8; ++q) lmax = fmaxf(lmax, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
                 }
                 const float rowmax = warp_max(lmax);
                 float T = -INFINITY;
@@ -1048,31 +1057,36 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         if (lane == __ffs(who) - 1) t = -INFINITY;
                     }
                 }
-                float sum = 0.f;
+                // pass 2: sum of exp(x - max) (ex2.approx on a pre-scaled argument: 2 instructions per element, relative error
+                // 2^-22 -- the log-sum-exp moves by ~1e-7) and the candidates >= T; one ballot per 128 elements decides whether
+                // any lane has to look at its four values at all
+                const float l2e = 1.4426950408889634f, nm = -rowmax * l2e;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 int ncand = 0;
-                for (int base = 0; base < nv4; base += 32 * 4) {      // warp-uniform trip count: whole warps take part in the ballots
+                for (int base = 0; base < ldv4; base += 32) {        // warp-uniform trip count: whole warps take part in the ballots
                     const int i0 = base + lane;
-                    float4 v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < nv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c0 = (i0 + 32 * q) * 4;
-                        const float xv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+                    const float4 v = (i0 < ldv4) ? x4[(size_t)i0 * xs4] : ninf4;
+                    s0 += ex2f(fmaf(v.x, l2e, nm));                  // ex2(-inf) = 0: padding and masked lanes add nothing
+                    s1 += ex2f(fmaf(v.y, l2e, nm));
+                    s2 += ex2f(fmaf(v.z, l2e, nm));
+                    s3 += ex2f(fmaf(v.w, l2e, nm));
+                    const bool any4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= T && T != -INFINITY;
+                    const bool all4 = T == -INFINITY && i0 < ldv4;   // degenerate threshold: every real element is a candidate
+                    if (__ballot_sync(0xffffffffu, any4 || all4)) {
+                        const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const bool in = (i0 + 32 * q < nv4) && (c0 + e < V);
-                            if (in) sum += expf(xv[e] - rowmax);
-                            const bool hit = in && xv[e] >= T;
+                            const bool hit = (any4 && xv[e] >= T) || (all4 && xv[e] != -INFINITY);
                             const unsigned bm = __ballot_sync(0xffffffffu, hit);
                             if (bm) {
                                 const int pos = ncand + __popc(bm & ((1u << lane) - 1));
-                                if (hit && pos < 128) cand[pos] = make_float2(xv[e], __int_as_float(c0 + e));
+                                if (hit && pos < 128) cand[pos] = make_float2(xv[e], __int_as_float(i0 * 4 + e));
                                 ncand += __popc(bm);
                             }
                         }
                     }
                 }
+                float sum = (s0 + s1) + (s2 + s3);
                 sum = warp_sum(sum);
                 const float lse = rowmax + logf(sum);
                 if (p.dbg_logp) {
