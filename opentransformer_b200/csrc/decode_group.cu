@@ -66,6 +66,7 @@ struct DgMisc {
     uint64_t acc_empty[2];    // (unused since v6: the CTA barrier behind a drained chunk frees the accumulator half)
     uint64_t pw_full[4];      // k-blocks of the out-projection weights (self-attention W_o, then cross-attention W_o) landed
     uint64_t pq_full[4];      // k-blocks of the cross-attention query projection landed
+    uint64_t lg_full;         // logits rows of an utterance landed (TMA gather of the beam phase)
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
     alignas(16) uint32_t zero16[4];       // the (zero) rows 8..15 of the m16 A fragments of the row-block projections
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const CUtensorMap* map_kvx = maps + nl * 6 + 2;
     const CUtensorMap* map_x = maps + nl * 6 + 3;
     const CUtensorMap* map_x2 = maps + nl * 6 + 4;
+    const CUtensorMap* map_lg = maps + nl * 6 + 5;
     int* bar = p.bar + g * 32;                        // 128-byte separated counters
     const bool is_tma = (warp == 0 && lane == 0), is_mma = (warp == 1 && lane == 0);
     const int equad = warp & 3;                       // TMEM lane quadrant this warp may read
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             mbar_init(&ms.acc_full[i], 1);
             mbar_init(&ms.acc_empty[i], 128);
         }
+        mbar_init(&ms.lg_full, 1);
         ms.flag = 0;
         fence_barrier_init();
     }
@@ -179,13 +182,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0, par_lg = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
     int dbg_n = 0;
     bool dbg_on = false;
 #define DG_STAMP() do { if (dbg_on) p.dbg_clk[blockIdx.x * 256 + dbg_n++] = clock64(); } while (0)
+    // sub-phase stamps of layer 2 in slots 200.. (tools/decode_phases.py prints them)
+#define DG_STAMP2(k) do { if (dbg_on && l == 2) p.dbg_clk[blockIdx.x * 256 + 200 + (k)] = clock64(); } while (0)
 
     // Group barrier: every CTA of the group has finished the phase (its global writes are visible).  `pre` runs on the TMA
     // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles); the
@@ -226,6 +231,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     // L2 eviction priorities (OTB_DG_FLAGS experiments: 2 = encoder K/V normal, 4 = encoder K/V evict-last, 8 = self-attention K/V evict-first)
     const uint64_t kvx_policy = (p.flags & 2) ? TMA_EVICT_NORMAL : (p.flags & 4) ? TMA_EVICT_LAST : TMA_EVICT_FIRST;
     const uint64_t kv_policy = (p.flags & 8) ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+    // element offset of (layer l, position s, hypothesis row n) in the self-attention K / V cache.  flags & 16: an utterance's
+    // beam is contiguous per position and its positions are contiguous ([layer][utterance][position][beam][d]): the prefix
+    // gather of a hypothesis walks one 0.6 MB region instead of one 512-byte piece per 180 KB.
+    const bool kv_by_utt = (p.flags & 16) != 0;
+    auto kv_off = [&](int l, int s, int n) -> size_t {
+        if (!kv_by_utt) return (((size_t)l * Lmax + s) * N + n) * DG_D;
+        const int uu = n / beam;
+        return ((((size_t)l * p.B + uu) * Lmax + s) * beam + (n - uu * beam)) * DG_D;
+    };
 
     // ---- operand loads issued by the TMA thread ------------------------------------------------------------------
     // small B operand: nB weight rows [b_row0, b_row0 + nB) x 256, k-block kb at sSB + kb * nB * 128 (prefetched at the
@@ -452,8 +466,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     ow[i] = pack_bf16(__uint_as_float(r[2 * i]) + ms.bias[c + 2 * i], __uint_as_float(r[2 * i + 1]) + ms.bias[c + 2 * i + 1]);
                 bf16* dst;
                 if (col < DG_D) dst = p.qbuf + (size_t)(row0 + erow) * DG_D + col;
-                else if (col < 2 * DG_D) dst = p.kc + (((size_t)l * Lmax + step) * N + row0 + erow) * DG_D + (col - DG_D);
-                else dst = p.vc + (((size_t)l * Lmax + step) * N + row0 + erow) * DG_D + (col - 2 * DG_D);
+                else if (col < 2 * DG_D) dst = p.kc + kv_off(l, step, row0 + erow) + (col - DG_D);
+                else dst = p.vc + kv_off(l, step, row0 + erow) + (col - 2 * DG_D);
                 reinterpret_cast<uint4*>(dst)[0] = o[0];
                 reinterpret_cast<uint4*>(dst)[1] = o[1];
             });
@@ -471,11 +485,21 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
                 int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
                 const int g4 = lane >> 3, c8 = lane & 7;
-                for (int task = j * 16 + warp; task < nrows * DG_H; task += DG_P * 16) {
-                    const int r = task / DG_H, h = task % DG_H;
-                    const int n = row0 + r;
-                    __syncwarp();
+                // v9: the hypotheses [8 j, 8 j + 8) of the tile are attended by their OWNER (the CTA that multiplies them by W_o
+                // next): warp w takes row w / 2 and two of its four heads -- every warp exactly two problems (v8 dealt the 480
+                // problems round-robin: some warps two, some one, then a group barrier and a trip through global memory for the
+                // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
+                // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
+                const int r = j * 8 + (warp >> 1);
+                const int n = row0 + r;
+                if (r < nrows)
                     for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
+                for (int t2 = 0; t2 < 2; ++t2) {
+                    const int h = (warp & 1) * 2 + t2;
+                    if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
+                        if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(warp >> 1, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
+                        continue;
+                    }
                     float qf[8];
                     {
                         const uint4 qu = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n * DG_D + h * 64 + c8 * 8);
@@ -496,7 +520,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             const int sidx = k0 + 4 * u + g4;
                             if (sidx < nkeys) {
                                 const int slot = (sidx < step) ? an_s[sidx] : n;
-                                const size_t off = (((size_t)l * Lmax + sidx) * N + slot) * DG_D + col;
+                                const size_t off = kv_off(l, sidx, slot) + col;
                                 ku[u] = ldg_v4_hint(p.kc + off, kv_policy);
                                 vu[u] = ldg_v4_hint(p.vc + off, kv_policy);
                             } else {
@@ -552,26 +576,29 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         ou.y = pack_bf16(o[2] * inv, o[3] * inv);
                         ou.z = pack_bf16(o[4] * inv, o[5] * inv);
                         ou.w = pack_bf16(o[6] * inv, o[7] * inv);
-                        *reinterpret_cast<uint4*>(p.ctx + (size_t)n * DG_D + h * 64 + c8 * 8) = ou;
+                        *reinterpret_cast<uint4*>(sA0 + a_off(warp >> 1, h * 8 + c8)) = ou;      // context row -> A operand of W_o
                     }
                 }
             }
-            gsync(nop);
+            __syncthreads();
             DG_STAMP();
+            DG_STAMP();      // (the group barrier that used to stand here)
             // ---------------- rows [8 j, 8 j + 8): W_o + bias + residual (the layer input) -> LayerNorm 1 -> query projection
             // (attention.py:44, transformer.py:54-56, attention.py:128), all inside the owning CTA
             {
-                load_rows(p.ctx, sA0);
+                DG_STAMP2(9);
                 uint32_t xres[2] = {0u, 0u};
                 if (elive) {
                     xres[0] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec);
                     xres[1] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec + 8);
                 }
                 __syncthreads();
+                DG_STAMP2(10);
                 float acc[2][4];
                 rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
                 par_pw ^= 0xF;
                 __syncthreads();      // every warp is done with W_o: its first half makes room for the second half of W_q
+                DG_STAMP2(11);
                 if (is_tma)
                     for (int kb = 2; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sA + (kb - 2) * 32768);
                 float v[2][2];
@@ -611,6 +638,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
                 const int gq = lane >> 2, tq = lane & 3;
                 int it = 0;
+                DG_STAMP2(0);
                 for (int task = j; task < n_tasks; task += DG_P, ++it) {
                     const int s = it & 1;
                     const int u = u0 + task / DG_H, h = task % DG_H;
@@ -632,6 +660,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     }
                     mbar_wait(&ms.st_full[s], (par_stf >> s) & 1);
                     par_stf ^= (1u << s);
+                    if (it < 4) DG_STAMP2(1 + 2 * it);
                     // S = Q K^T for this warp's 16 keys
                     float sc[2][4];
 #pragma unroll
@@ -733,6 +762,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         }
                     }
                     __syncthreads();
+                    if (it < 4) DG_STAMP2(2 + 2 * it);
                 }
             }
             gsync([&] {    // cross-attention W_o (whole) and the second half of this CTA's W1 slice stream in while the other CTAs finish
@@ -1015,24 +1045,30 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // tile and both weight stages are idle: 192 KB) by all 16 warps with cp.async -- every 16-byte piece in flight at
             // once, `beam` consecutive rows = one contiguous run per column group; the two passes below then run on shared
             // memory.  A vocabulary x beam that does not fit is read in place (element stride 128 x 16 bytes).
-            const int lds = p.ldv + 4;                               // shared-memory row stride (floats): rows 16 bytes apart in the banks
-            const bool staged = (size_t)beam * lds * 4 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
+            // The rows of the utterance are gathered from the [column group][row] logits by TMA: box = (the `beam` consecutive
+            // 16-byte pieces of one column group) x 64 column groups, ~17 boxes per utterance, issued by one thread (v8 used
+            // 10 k 16-byte cp.async: 11.7 k cycles; the A tile and both weight stages are idle: 192 KB).  In shared memory the
+            // piece of (column group c, row r) sits at float4 index c * beam + r.  A vocabulary x beam that does not fit is read
+            // in place (element stride 128 x 16 bytes).
+            const int nbox = (ldv4 + 63) >> 6;
+            const bool staged = (size_t)nbox * 64 * beam * 16 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
             const int lr0 = ul * beam;                               // first row of the utterance inside the group tile
             if (staged) {
-                const int npieces = ldv4 * beam;
-                for (int i = tid; i < npieces; i += DG_THREADS) {
-                    const int c4 = i / beam, rr = i - c4 * beam;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem + ((size_t)rr * lds + c4 * 4) * 4)),
-                                 "l"(lg4 + (size_t)c4 * 128 + lr0 + rr) : "memory");
+                if (is_tma) {
+                    mbar_arrive_expect_tx(&ms.lg_full, (uint32_t)(nbox * 64 * beam * 16));
+                    for (int bx = 0; bx < nbox; ++bx)
+                        tma_load_2d(smem + (size_t)bx * 64 * beam * 16, map_lg, &ms.lg_full, lr0 * 4, g * ldv4 + bx * 64);
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncthreads();
+                mbar_wait(&ms.lg_full, par_lg);
+                par_lg ^= 1;
             }
             if (ul == j) DG_STAMP();      // rows gathered
             if (warp < beam) {
                 const int r = warp, n = u * beam + r;
-                const float4* x4 = staged ? reinterpret_cast<const float4*>(smem + (size_t)r * lds * 4) : reinterpret_cast<const float4*>(lg4 + lr0 + r);
-                const int xs4 = staged ? 1 : 128;                    // float4 stride between consecutive column groups
+                const int pf_flag = p.st.flag[n];                    // needed after the ranking: their L2 round trips overlap the passes
+                const float pf_score = p.st.scores[n];
+                const float4* x4 = staged ? reinterpret_cast<const float4*>(smem) + r : reinterpret_cast<const float4*>(lg4 + lr0 + r);
+                const int xs4 = staged ? beam : 128;                 // float4 stride between consecutive column groups
                 auto xel = [&](int c) { return reinterpret_cast<const float*>(x4 + (size_t)(c >> 2) * xs4)[c & 3]; };
                 const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                 float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
@@ -1148,25 +1184,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         if (lane == 0) { ms.row_v[r][k] = bv; ms.row_i[r][k] = bi; }
                     }
                 }
+                // finished hypotheses keep emitting EOS at no cost (mask_finished_scores / mask_finished_preds, speech2text.py:156-192);
+                // candidate scores = scores + last_k_scores (:118)
+                __syncwarp();
+                if (lane < beam) {
+                    const float rv = pf_flag ? ((lane == 0) ? 0.f : -INFINITY) : ms.row_v[r][lane];
+                    const int ri = pf_flag ? (int)EOS_ID : ms.row_i[r][lane];
+                    ms.c_val[r * beam + lane] = pf_score + rv;
+                    ms.c_tok[r * beam + lane] = ri;
+                }
             }
             __syncthreads();
             if (ul == j) DG_STAMP();      // per-row log-softmax statistics + top-`beam`
-            for (int r = warp; r < beam; r += 16) {
-                const int n = u * beam + r;
-                if (p.st.flag[n]) {                      // mask_finished_scores / mask_finished_preds (speech2text.py:156-192)
-                    if (lane < beam) {
-                        ms.row_v[r][lane] = (lane == 0) ? 0.f : -INFINITY;
-                        ms.row_i[r][lane] = (int)EOS_ID;
-                    }
-                }
-                __syncwarp();
-                const float base = p.st.scores[n];
-                if (lane < beam) {
-                    ms.c_val[r * beam + lane] = base + ms.row_v[r][lane];      // scores + last_k_scores (:118)
-                    ms.c_tok[r * beam + lane] = ms.row_i[r][lane];
-                }
-            }
-            __syncthreads();
             if (warp == 0) warp_topk([&](int idx) { return ms.c_val[idx]; }, beam * beam, beam, ms.sel_v, ms.sel_i);   // (:119-122)
             __syncthreads();
             const int cur = step & 1, nxt = cur ^ 1;
@@ -1176,7 +1205,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int nn = u * beam + r;
                 const int* a_old = p.st.anc + ((size_t)cur * N + parent) * Lmax;
                 int* a_new = p.st.anc + ((size_t)nxt * N + nn) * Lmax;
-                for (int s = lane; s < step; s += 32) a_new[s] = a_old[s];
+                int av[4];                                           // Lmax <= 128: all loads in flight before the first store
+#pragma unroll
+                for (int q = 0; q < 4; ++q) av[q] = (lane + 32 * q < step) ? a_old[lane + 32 * q] : 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (lane + 32 * q < step) a_new[lane + 32 * q] = av[q];
                 if (lane == 0) {
                     a_new[step] = parent;
                     p.st.tok_hist[(size_t)step * N + nn] = ms.c_tok[off];
@@ -1237,6 +1271,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         tmem_dealloc(tmem, 512);
     }
 #undef DG_STAMP
+#undef DG_STAMP2
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -1247,7 +1282,7 @@ size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int be
     const int G = (B + upg - 1) / upg;
     size_t b = 0;
     auto take = [&](size_t n) { b += (n + 255) & ~(size_t)255; };
-    take((size_t)(n_layers * 6 + 5) * sizeof(CUtensorMap));   // maps
+    take((size_t)(n_layers * 6 + 6) * sizeof(CUtensorMap));   // maps
     take((size_t)N * DG_D * 2);                                // qbuf
     take((size_t)(N + 128) * DG_D * 2);                        // ctx (+ one tile of slack rows for the last group's TMA box)
     take((size_t)(N + 128) * DG_D * 2);                        // xbuf
@@ -1279,7 +1314,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     memset(&p, 0, sizeof(p));
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
     auto take = [&](size_t n) { uint8_t* r = w; w += (n + 255) & ~(size_t)255; return r; };
-    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 5) * sizeof(CUtensorMap)));
+    CUtensorMap* d_maps = reinterpret_cast<CUtensorMap*>(take((size_t)(mp.n_layers * 6 + 6) * sizeof(CUtensorMap)));
     p.qbuf = reinterpret_cast<bf16*>(take((size_t)N * DG_D * 2));
     p.ctx = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
     p.xbuf = reinterpret_cast<bf16*>(take((size_t)(N + 128) * DG_D * 2));
@@ -1292,7 +1327,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     p.gstate = reinterpret_cast<int*>(take((size_t)G * mp.st.Lmax * 4));
 
     // tensor maps (host encode -> device array).  Weights [rows, K] bf16 row-major, box = (64 columns) x (rows of one slice).
-    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 5];
+    CUtensorMap h_maps[OTB_MEGA_MAX_LAYERS_INT * 6 + 6];
     const char* err;
     for (int l = 0; l < mp.n_layers; ++l) {
         const MegaLayer& ly = mp.layers[l];
@@ -1312,7 +1347,8 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     if ((err = encode_tmap_2d(&h_maps[nm + 2], mp.kvx, 2 * DG_D, (uint64_t)mp.n_layers * mp.B * mp.T, 2 * DG_D, 64, 256))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 3], p.xbuf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 4], p.x2buf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
-    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 5) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
+    if ((err = encode_tmap_2d_f32(&h_maps[nm + 5], p.logits, 512, (uint64_t)G * (p.ldv / 4), 512, (uint32_t)beam * 4, 64))) return err;
+    cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 6) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.bar, 0, (size_t)G * 128, st)) != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.gstate, 0, (size_t)G * mp.st.Lmax * 4, st)) != cudaSuccess) return cudaGetErrorString(e);

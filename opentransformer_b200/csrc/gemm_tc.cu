@@ -633,6 +633,23 @@ const char* encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint
     return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
 }
 
+// fp32, no swizzle: box_cols consecutive floats (a multiple of 4) of box_rows consecutive rows land densely in shared memory
+const char* encode_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+                               uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled unavailable (no CUDA driver?)";
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 3) || (box_cols & 3) || box_cols > 256 || box_rows > 256)
+        return "fp32 TMA operand must be 16-byte aligned with ld % 4 == 0 and a box of <= 256 x 256";
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d, fp32) failed";
+}
+
 // conv1 output buffer [B, 2*T1h, 2*F1h, C] bf16 viewed as (c, f-parity, f/2, t-parity, b*T1h + t/2)
 const char* encode_tmap_conv5d(CUtensorMap* m, const void* base, int C, int F1h, int T1h_total, uint32_t boxF,
                                uint32_t boxR) {

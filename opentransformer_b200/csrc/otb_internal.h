@@ -66,6 +66,8 @@ const char* gemm_wgrad_launch(cudaStream_t st, const void* dY, int lddy, const v
 // encode helpers (driver entry point fetched at runtime; libcuda is not a link-time dependency)
 const char* encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
                            uint32_t box_cols, uint32_t box_rows);
+const char* encode_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+                               uint32_t box_cols, uint32_t box_rows);
 const char* encode_tmap_conv5d(CUtensorMap* m, const void* base, int C, int F1h, int T1h_total, uint32_t boxF,
                                uint32_t boxR);
 

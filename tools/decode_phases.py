@@ -52,3 +52,9 @@ with torch.no_grad():
         print('    layer 2, per phase (min / max over the 16 CTAs):',
               [(names[i].split(' ', 1)[1], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(2 + 2 * NP, 2 + 3 * NP)])
         print('    tail, per phase (min / max over CTAs):', [(names[i], int(d[:, i - 1].min()), int(d[:, i - 1].max())) for i in range(n - 6, n)])
+        sub = allt[:, 200:216]
+        def dd(a, b):
+            return [int(x) for x in (sub[:, b] - sub[:, a]).tolist()]
+        print('    layer 2 cross-attention, per CTA: wait K/V 1st', dd(0, 1), 'task 1', dd(1, 2), 'wait 2nd', dd(2, 3), 'task 2', dd(3, 4),
+              'wait 3rd', dd(4, 5), 'task 3', dd(5, 6))
+        print('    layer 2 W_o block, per CTA: rows in', dd(9, 10), 'GEMM', dd(10, 11))
