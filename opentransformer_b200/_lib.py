@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libotb200.so')
+LIB_PATH = os.environ.get('OTB_LIB_PATH') or os.path.join(_HERE, 'libotb200.so')   # OTB_LIB_PATH: A/B runs of two builds (tools/)
 
 _lib = None
 

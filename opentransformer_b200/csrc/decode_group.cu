@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #define DG_STAMP() do { if (dbg_on) p.dbg_clk[blockIdx.x * 256 + dbg_n++] = clock64(); } while (0)
     // sub-phase stamps of layer 2 in slots 200.. (tools/decode_phases.py prints them)
 #define DG_STAMP2(k) do { if (dbg_on && l == 2) p.dbg_clk[blockIdx.x * 256 + 200 + (k)] = clock64(); } while (0)
+#define DG_STAMP3(k) do { if (dbg_on) p.dbg_clk[blockIdx.x * 256 + 200 + (k)] = clock64(); } while (0)
 
     // Group barrier: every CTA of the group has finished the phase (its global writes are visible).  `pre` runs on the TMA
     // thread between arrive and wait -- prefetches that do not depend on the other CTAs (weights, encoder K/V tiles); the
@@ -486,20 +487,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
                 const int g4 = lane >> 3, c8 = lane & 7;
                 // v9: the hypotheses [8 j, 8 j + 8) of the tile are attended by their OWNER (the CTA that multiplies them by W_o
-                // next): warp w takes row w / 2 and two of its four heads -- every warp exactly two problems (v8 dealt the 480
+                // next): 32 (row, head) problems per CTA -- every warp exactly two problems (v8 dealt the 480
                 // problems round-robin: some warps two, some one, then a group barrier and a trip through global memory for the
                 // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
                 // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
-                const int r = j * 8 + (warp >> 1);
-                const int n = row0 + r;
-                if (r < nrows)
-                    for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
                 for (int t2 = 0; t2 < 2; ++t2) {
-                    const int h = (warp & 1) * 2 + t2;
+                    // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
+                    // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
+                    const int rl = (warp >> 2) + 4 * t2, h = warp & 3;
+                    const int r = j * 8 + rl;
+                    const int n = row0 + r;
                     if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
-                        if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(warp >> 1, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
+                        if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
                         continue;
                     }
+                    __syncwarp();
+                    for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
                     float qf[8];
                     {
                         const uint4 qu = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n * DG_D + h * 64 + c8 * 8);
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         ou.y = pack_bf16(o[2] * inv, o[3] * inv);
                         ou.z = pack_bf16(o[4] * inv, o[5] * inv);
                         ou.w = pack_bf16(o[6] * inv, o[7] * inv);
-                        *reinterpret_cast<uint4*>(sA0 + a_off(warp >> 1, h * 8 + c8)) = ou;      // context row -> A operand of W_o
+                        *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = ou;      // context row -> A operand of W_o
                     }
                 }
             }
@@ -698,7 +701,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         wmax[warp * 16 + gq] = mlo;
                         wmax[warp * 16 + gq + 8] = mhi;
                     }
+                    if (it == 0) DG_STAMP2(20);
                     __syncthreads();
+                    if (it == 0) DG_STAMP2(21);
                     float Mlo = -INFINITY, Mhi = -INFINITY;
 #pragma unroll
                     for (int w = 0; w < 16; ++w) {
@@ -724,7 +729,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         wsum[warp * 16 + gq] = slo;
                         wsum[warp * 16 + gq + 8] = shi;
                     }
+                    if (it == 0) DG_STAMP2(22);
                     __syncthreads();
+                    if (it == 0) DG_STAMP2(23);
                     // O = P V: warp = (8 output dims, half of the keys)
                     const int nt8 = warp & 7, kh = warp >> 3;
                     float oc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -745,7 +752,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     red[(warp * 16 + gq) * 8 + 2 * tq + 1] = oc[1];
                     red[(warp * 16 + gq + 8) * 8 + 2 * tq] = oc[2];
                     red[(warp * 16 + gq + 8) * 8 + 2 * tq + 1] = oc[3];
+                    if (it == 0) DG_STAMP2(24);
                     __syncthreads();
+                    if (it == 0) DG_STAMP2(25);
                     // the stage is free: fetch the K / V tiles of the task after next
                     if (is_tma && task + 2 * DG_P < n_tasks) load_kv(l, task + 2 * DG_P, s);
                     {
@@ -1197,7 +1206,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             __syncthreads();
             if (ul == j) DG_STAMP();      // per-row log-softmax statistics + top-`beam`
             if (warp == 0) warp_topk([&](int idx) { return ms.c_val[idx]; }, beam * beam, beam, ms.sel_v, ms.sel_i);   // (:119-122)
+            if (ul == j) DG_STAMP3(30);
             __syncthreads();
+            if (ul == j) DG_STAMP3(31);
             const int cur = step & 1, nxt = cur ^ 1;
             for (int r = warp; r < beam; r += 16) {      // ancestry of the surviving hypotheses (:126-140)
                 const int off = ms.sel_i[r];
@@ -1217,7 +1228,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     p.st.par_hist[(size_t)step * N + nn] = parent;
                 }
             }
+            if (ul == j) DG_STAMP3(32);
             __syncthreads();   // every read of the old scores / flags of this utterance is done
+            if (ul == j) DG_STAMP3(33);
             if (tid < beam) {
                 const int nn = u * beam + tid;
                 const int tok = ms.c_tok[ms.sel_i[tid]];
@@ -1227,7 +1240,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 if (p.dbg_scores) p.dbg_scores[(size_t)step * N + nn] = ms.sel_v[tid];
                 if (tok == (int)EOS_ID) atomicAdd(&ms.flag, 1);
             }
+            if (ul == j) DG_STAMP3(34);
             __syncthreads();
+            if (ul == j) DG_STAMP3(35);
         }
         if (j >= nutt) { DG_STAMP(); DG_STAMP(); }      // keep the stamp count of a CTA without an utterance
         if (tid == 0) {
@@ -1272,6 +1287,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     }
 #undef DG_STAMP
 #undef DG_STAMP2
+#undef DG_STAMP3
 }
 
 // ---------------------------------------------------------------------------------------------- host side

@@ -18,3 +18,4 @@ import json; d=json.loads(open('gpurun_out/r2_bench_${TAG}_l$L.json').read().str
 OTB_DG_CLUSTER=0 timeout 600 python bench.py --steps 12 --min-ms 300 --no-extras --no-cpu-baseline --lanes 3 > gpurun_out/r2_bench_${TAG}_sw3.json 2> gpurun_out/r2_bench_${TAG}_sw3.err; python -c "
 import json; d=json.loads(open('gpurun_out/r2_bench_${TAG}_sw3.json').read().strip().splitlines()[-1]); print('software barrier, lanes 3', round(d['value']), round(d['e2e']['value']), d['breakdown']['single_lane_step_ms'])"
 if [ -n "$FLAGS_AB" ]; then for F in $FLAGS_AB; do OTB_DG_FLAGS=$F timeout 300 python tools/decode_phases.py 5 > gpurun_out/r2_decode_phases_${TAG}_f$F.txt 2>&1; echo "flags $F"; grep -E "whole|layer 2" gpurun_out/r2_decode_phases_${TAG}_f$F.txt | cut -c1-900; done; fi
+if [ -f opentransformer_b200/libotb200_prev.so ] && [ -n "$PREV_AB" ]; then OTB_LIB_PATH=$PWD/opentransformer_b200/libotb200_prev.so timeout 300 python tools/decode_phases.py 5 50 > gpurun_out/r2_decode_phases_${TAG}_prevlib.txt 2>&1; echo "previous build on the same box:"; grep -E "whole|layer 2, per|tail" gpurun_out/r2_decode_phases_${TAG}_prevlib.txt | cut -c1-1300; fi
