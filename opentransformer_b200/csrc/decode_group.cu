@@ -113,6 +113,11 @@ __device__ __forceinline__ uint4 ldg_v4_hint(const void* ptr, uint64_t policy) {
                  : "l"(ptr), "l"(policy));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_v4_cg(const void* ptr) {      // cache in L2 only
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
+}
 __device__ __forceinline__ float dg_sigmoid(float x) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     // beam is contiguous per position and its positions are contiguous ([layer][utterance][position][beam][d]): the prefix
     // gather of a hypothesis walks one 0.6 MB region instead of one 512-byte piece per 180 KB.
     const bool kv_by_utt = (p.flags & 16) != 0;
+    const bool kv_cg = (p.flags & 32) != 0;
     auto kv_off = [&](int l, int s, int n) -> size_t {
         if (!kv_by_utt) return (((size_t)l * Lmax + s) * N + n) * DG_D;
         const int uu = n / beam;
@@ -494,7 +500,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 for (int t2 = 0; t2 < 2; ++t2) {
                     // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
                     // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
-                    const int rl = (warp >> 2) + 4 * t2, h = warp & 3;
+                    // (flags & 64: warp w = row w / 2, heads 2 (w & 1) + t2 -- the two problems of a warp share the ancestry row)
+                    const int rl = (p.flags & 64) ? (warp >> 1) : (warp >> 2) + 4 * t2, h = (p.flags & 64) ? (warp & 1) * 2 + t2 : warp & 3;
                     const int r = j * 8 + rl;
                     const int n = row0 + r;
                     if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
@@ -524,8 +531,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             if (sidx < nkeys) {
                                 const int slot = (sidx < step) ? an_s[sidx] : n;
                                 const size_t off = kv_off(l, sidx, slot) + col;
-                                ku[u] = ldg_v4_hint(p.kc + off, kv_policy);
-                                vu[u] = ldg_v4_hint(p.vc + off, kv_policy);
+                                if (kv_cg) {      // L2 only: the 16 lines a lane keeps in flight x 512 lanes exceed the ~20 KB of L1 left beside 227 KB of shared memory
+                                    ku[u] = ldg_v4_cg(p.kc + off);
+                                    vu[u] = ldg_v4_cg(p.vc + off);
+                                } else {
+                                    ku[u] = ldg_v4_hint(p.kc + off, kv_policy);
+                                    vu[u] = ldg_v4_hint(p.vc + off, kv_policy);
+                                }
                             } else {
                                 ku[u] = make_uint4(0, 0, 0, 0);
                                 vu[u] = ku[u];
