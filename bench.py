@@ -528,6 +528,13 @@ def run_b200(args):
     # with full rounds finish sooner (K = 20 -> 2 rounds of 10)
     rounds = -(-args.steps // L)
     L_eff = min(L, -(-args.steps // rounds))
+    # group barrier of the persistent kernel: a cluster of 16 CTAs fills a GPC, so clusters cap the GPU at 8 row groups in
+    # flight; 3 batches x 3 groups want 9 -> plain CTAs + the software barrier (all 148 SMs) for the multi-lane region, the
+    # hardware cluster barrier for the lone-batch latency above (ops.set_decode_barrier, include/otb200.h)
+    groups = -(-B_PER_GPU // max(1, 128 // BEAM))
+    barrier = args.barrier if args.barrier != 'auto' else ('software' if (use_persist and L_eff * groups > 8) else 'default')
+    if use_persist:
+        ops.set_decode_barrier(barrier)
     if L > 1:
         timed(step_resident, 2 * L, L)      # untimed multi-lane pass: thread start-up, allocator growth per stream
     # The timed region is EXACTLY `steps` steps between barrier + synchronize; it is repeated until ~1 s of device time has
@@ -594,6 +601,8 @@ def run_b200(args):
         cfg['lanes'] = L_eff
         cfg['decode_path'] = 'persistent (one launch per batch)' if use_persist else 'per-step CUDA graph'
         cfg['persistent_probe'] = probe_note
+        cfg['group_barrier'] = ({'default': 'cluster (hardware)', 'cluster': 'cluster (hardware)', 'software': 'software (L2 counter)'}[barrier]
+                                if use_persist else None)
         cfg['tile_policy'] = policy
         cfg['repeats'] = repeats
         # output check: digest of the n-best ids of input batch 0 against the committed one (tools/make_bench_digest.py runs
@@ -1005,6 +1014,9 @@ def main():
                          "default is the headline workload")
     ap.add_argument('--lanes', type=int, default=0, help='utterance batches kept in flight per GPU (streams); 0 = auto: 3 for the '
                                                        'persistent decode kernel (48 SMs per batch), 16 for the per-step graph')
+    ap.add_argument('--barrier', default='auto', choices=['auto', 'cluster', 'software'],
+                    help='group barrier of the persistent decode kernel in the timed multi-lane region (auto: software when more than 8 '
+                         'row groups are in flight, else thread-block clusters)')
     ap.add_argument('--decode', default='auto', choices=['auto', 'persistent', 'graph'],
                     help='decode path: one persistent launch per batch (csrc/decode_group.cu) or one CUDA-graph replay per step')
     ap.add_argument('--min-ms', type=float, default=1000.0, help='repeat the timed K-step region until this much device time is measured')

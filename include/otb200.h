@@ -54,6 +54,11 @@ int otb_debug_gemm_mode(int mode);
 /* Profiling aid: buf (device, u64 [>= 256]) receives clock64 stamps at every phase boundary of decode step `step`
  * of the next otb_decode_persistent launches (group 0, CTA 0); NULL disables. */
 int otb_debug_decode_timing(unsigned long long* buf, int step);
+/* Serving knob of otb_decode_persistent (no counterpart in the reference): how the 16 CTAs of a row group synchronise.
+ * 1 = thread-block cluster of 16 + barrier.cluster (lowest latency; one cluster per GPC, i.e. at most 8 groups in flight),
+ * 0 = plain CTAs + a release/acquire counter in L2 (all 148 SMs usable: best throughput with 3 batches in flight),
+ * -1 = default (clusters when the device grants them, unless OTB_DG_CLUSTER=0).  Process-wide. */
+int otb_set_decode_barrier(int kind);
 
 /* Conv2dLayer output geometry, kernel 3, stride 2, padding (0,1)  (frontend/conv.py:10-11,27):
  * T1 = (T-3)/2+1, F1 = (F-1)/2+1, T2 = (T1-3)/2+1, F2 = (F1-1)/2+1.  The conv1 activation buffer is

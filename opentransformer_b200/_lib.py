@@ -44,6 +44,7 @@ _SIGS = {
     'otb_debug_gemm_mode': (c_int, [c_int]),
     'otb_set_tile_policy': (c_int, [c_int]),
     'otb_debug_decode_timing': (c_int, [_P, c_int]),
+    'otb_set_decode_barrier': (c_int, [c_int]),
     'otb_conv_geometry': (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'otb_conv1_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'otb_conv2_relu': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -67,6 +67,12 @@ int otb_debug_decode_timing(unsigned long long* buf, int step) {
     return 0;
 }
 
+int otb_set_decode_barrier(int kind) {
+    if (kind < -1 || kind > 1) return fail("otb_set_decode_barrier", "kind must be -1 (default), 0 (software) or 1 (cluster)");
+    g_dg_barrier = kind;
+    return 0;
+}
+
 int otb_conv_geometry(int T, int F, int* T1, int* F1, int* T2, int* F2) {
     if (T < 7 || F < 1) return fail("otb_conv_geometry", "need T >= 7 and F >= 1");
     const int t1 = (T - 3) / 2 + 1, f1 = (F - 1) / 2 + 1;

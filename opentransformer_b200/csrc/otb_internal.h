@@ -198,6 +198,7 @@ struct DgParams {
 };
 extern unsigned long long* g_dg_dbg;
 extern int g_dg_dbg_step;
+extern int g_dg_barrier;
 size_t decode_group_workspace_bytes(int N, int n_layers, int Lmax, int B, int beam, int V);
 const char* decode_group_launch(cudaStream_t st, const MegaParams& p, void* workspace, size_t workspace_bytes);
 

@@ -64,6 +64,11 @@ def _need(t, dtype, name):
     return t
 
 
+def set_decode_barrier(kind):
+    """'cluster', 'software' or 'default': group barrier of the persistent decode kernel (otb_set_decode_barrier)."""
+    check(_lib.lib().otb_set_decode_barrier({'default': -1, 'software': 0, 'cluster': 1}[kind]), 'otb_set_decode_barrier')
+
+
 def set_tile_policy(policy):
     """'latency' (default) or 'throughput': tiling of the small decode-step GEMMs (otb_set_tile_policy).  Takes effect for
     launches / graph captures made afterwards."""
