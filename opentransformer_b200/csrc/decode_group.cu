@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / DG_P, j = blockIdx.x % DG_P;
+    if (g >= p.G) return;      // padding groups of the grid-size experiment (OTB_DG_FLAGS & 128): whole clusters leave at once
     const int beam = p.st.beam, N = p.st.N, Lmax = p.st.Lmax, V = p.V;
     const int u0 = g * p.utts_per_group;
     const int nutt = min(p.utts_per_group, p.B - u0);
@@ -654,11 +655,17 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
                 const int gq = lane >> 2, tq = lane & 3;
                 int it = 0;
+                int kvl[4];      // memory lengths of this CTA's problems, fetched before the first one (each was an exposed L2 round trip)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int tk = j + q * DG_P;
+                    kvl[q] = (tk < n_tasks) ? min(p.mem_len[u0 + tk / DG_H], p.T) : 0;
+                }
                 DG_STAMP2(0);
                 for (int task = j; task < n_tasks; task += DG_P, ++it) {
                     const int s = it & 1;
                     const int u = u0 + task / DG_H, h = task % DG_H;
-                    const int kv_len = min(p.mem_len[u], p.T);
+                    const int kv_len = (it == 0) ? kvl[0] : (it == 1) ? kvl[1] : (it == 2) ? kvl[2] : (it == 3) ? kvl[3] : min(p.mem_len[u], p.T);
                     const uint8_t* sK = sST + s * DG_STAGE;
                     const uint8_t* sV = sK + 32768;
                     // Q fragments (rows = hypotheses of the utterance) straight from L2
@@ -1431,11 +1438,12 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
         }
     }
     const int use_cluster = (cluster_ok && g_dg_barrier != 0) ? 1 : 0;
+    const int Gpad = (p.flags & 128) ? (G > 10 ? G : 10) : G;      // experiment: a grid of >= 148 CTAs (the padding CTAs return at once)
     p.cluster = use_cluster;
     if (use_cluster) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(G * DG_P); cfg.blockDim = dim3(DG_THREADS); cfg.dynamicSmemBytes = DG_SMEM; cfg.stream = st;
+        cfg.gridDim = dim3(Gpad * DG_P); cfg.blockDim = dim3(DG_THREADS); cfg.dynamicSmemBytes = DG_SMEM; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = DG_P; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1444,7 +1452,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
         if (e != cudaSuccess) (void)cudaGetLastError();
         return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
     }
-    decode_group_kernel<<<G * DG_P, DG_THREADS, DG_SMEM, st>>>(p);
+    decode_group_kernel<<<Gpad * DG_P, DG_THREADS, DG_SMEM, st>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
