@@ -655,17 +655,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
                 const int gq = lane >> 2, tq = lane & 3;
                 int it = 0;
-                int kvl[4];      // memory lengths of this CTA's problems, fetched before the first one (each was an exposed L2 round trip)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int tk = j + q * DG_P;
-                    kvl[q] = (tk < n_tasks) ? min(p.mem_len[u0 + tk / DG_H], p.T) : 0;
-                }
                 DG_STAMP2(0);
                 for (int task = j; task < n_tasks; task += DG_P, ++it) {
                     const int s = it & 1;
                     const int u = u0 + task / DG_H, h = task % DG_H;
-                    const int kv_len = (it == 0) ? kvl[0] : (it == 1) ? kvl[1] : (it == 2) ? kvl[2] : (it == 3) ? kvl[3] : min(p.mem_len[u], p.T);
+                    const int kv_len = min(p.mem_len[u], p.T);
                     const uint8_t* sK = sST + s * DG_STAGE;
                     const uint8_t* sV = sK + 32768;
                     // Q fragments (rows = hypotheses of the utterance) straight from L2
