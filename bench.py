@@ -584,7 +584,8 @@ def run_b200(args):
                                   f'utterances on 3 row groups x 16 CTAs; {dec_kernel_ms:.2f} ms per launch (CUDA events on its stream, lone batch, '
                                   f'median of 6); algorithmic bytes per launch = {MAX_LEN} steps x ({w_bytes / 1e6:.1f} MB decoder weights + '
                                   f'{kv_bytes / 1e6:.1f} MB cross-attention K/V) = {dec_bytes / 1e9:.2f} GB (SURVEY.md 8d), {DEC_FLOP / 1e9:.0f} GFLOP; '
-                                  'latency-bound (58 dependent phases per step behind group barriers), the working set is L2-resident',
+                                  'latency-bound: 38 group barriers and ~60 dependent phases per step (profiles/r2_decode_phases_*.txt); the self-attention '
+                                  'K/V prefix (<= 133 MB per batch, read through an ancestry table) is not counted in the algorithmic bytes',
                         'alt': fr(DEC_FLOP, dec_bytes, dec_kernel_ms, peak_tf_burst),
                         'peak_source': f'MEASURED_PEAKS.json ({src}); burst bf16 figure for the lone kernel, sustained for whole steps'}
         else:

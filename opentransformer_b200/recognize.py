@@ -278,7 +278,7 @@ class SpeechToTextRecognizer(Recognizer):
     """otrans/recognize/speech2text.py:6-93 on the B200 path."""
 
     def __init__(self, model, lm=None, lm_weight=0.1, ctc_weight=0.0, beam_width=5, nbest=1, max_len=50,
-                 idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True, persistent=False):
+                 idx2unit=None, penalty=0, lamda=5, ngpu=1, apply_cache=False, use_graph=True, persistent=None):
         super().__init__(model, idx2unit, lm, lm_weight, ngpu)
         if lm is not None and getattr(lm, 'model_type', None) != 'transformer_lm':
             raise NotImplementedError('shallow fusion is implemented for the Transformer LM (opentransformer_b200.lm); '
@@ -289,7 +289,9 @@ class SpeechToTextRecognizer(Recognizer):
         self.attn_weights = {}
         self.apply_cache = False
         self.use_graph = use_graph
-        self.persistent = persistent
+        # None = automatic: the persistent decode kernel (one launch per batch, csrc/decode_group.cu) whenever the decoder,
+        # the batch geometry and the options (no LM fusion) fit it; False forces the per-step CUDA-graph path
+        self.persistent = True if persistent is None else bool(persistent)
         self._decoders = {}
 
     # ---- reference-facing seams -------------------------------------------------------------

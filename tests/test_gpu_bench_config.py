@@ -221,7 +221,7 @@ def test_graph_path_natural_eos_step_count_and_freeze(case):
         gp, gs = bd.state.finalize(0.6, 5, 2)
         assert torch.equal(gp[:, :, :steps_ref].cpu(), nb)
     # the public call: run() with its 8-step poll must report the same count and the same hypotheses
-    rec = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1)
+    rec = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=False)
     p, s, n = rec.recognize_ids(x.to(DEV), mask.to(DEV))
     print(f'natural EOS (bias {case["eos_bias"]}, beam {beam}): reference loop breaks after {steps_ref} of {max_len} steps; '
           f'graph path executed {n}')
@@ -238,7 +238,7 @@ def test_persistent_path_natural_eos_step_count(case):
     beam, max_len = case['beam'], case['max_len']
     _, _, _, steps = _lockstep_persistent(model, sd, params, x, mask, 6, beam, max_len, check_logp=False)
     assert steps < max_len, f'calibrated case must end early, ran {steps} of {max_len}'
-    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1)
+    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=False)
     rec_p = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=True)
     pg, sg, ng = rec_g.recognize_ids(x.to(DEV), mask.to(DEV))
     pp, sp, np_ = rec_p.recognize_ids(x.to(DEV), mask.to(DEV))
