@@ -532,9 +532,9 @@ def run_b200(args):
     # flight; 3 batches x 3 groups want 9 -> plain CTAs + the software barrier (all 148 SMs) for the multi-lane region, the
     # hardware cluster barrier for the lone-batch latency above (ops.set_decode_barrier, include/otb200.h)
     groups = -(-B_PER_GPU // max(1, 128 // BEAM))
-    barrier = args.barrier if args.barrier != 'auto' else ('software' if (use_persist and L_eff * groups > 8) else 'default')
+    grp_barrier = args.barrier if args.barrier != 'auto' else ('software' if (use_persist and L_eff * groups > 8) else 'default')
     if use_persist:
-        ops.set_decode_barrier(barrier)
+        ops.set_decode_barrier(grp_barrier)
     if L > 1:
         timed(step_resident, 2 * L, L)      # untimed multi-lane pass: thread start-up, allocator growth per stream
     # The timed region is EXACTLY `steps` steps between barrier + synchronize; it is repeated until ~1 s of device time has
@@ -602,7 +602,7 @@ def run_b200(args):
         cfg['lanes'] = L_eff
         cfg['decode_path'] = 'persistent (one launch per batch)' if use_persist else 'per-step CUDA graph'
         cfg['persistent_probe'] = probe_note
-        cfg['group_barrier'] = ({'default': 'cluster (hardware)', 'cluster': 'cluster (hardware)', 'software': 'software (L2 counter)'}[barrier]
+        cfg['group_barrier'] = ({'default': 'cluster (hardware)', 'cluster': 'cluster (hardware)', 'software': 'software (L2 counter)'}[grp_barrier]
                                 if use_persist else None)
         cfg['tile_policy'] = policy
         cfg['repeats'] = repeats

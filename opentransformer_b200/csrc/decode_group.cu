@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+        float acc2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int m = lane >> 3, rr = lane & 7;
         const uint32_t zaddr = smem_u32(ms.zero16), abase = smem_u32(A);
 #pragma unroll 1
@@ -361,10 +362,21 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // A matrices: (rows 0-7, k lo) (rows 8-15, k lo) (rows 0-7, k hi) (rows 8-15, k hi); rows 8-15 read the zero chunk
                 ldmatrix_x4((m & 1) ? zaddr : abase + a_off(rr, kb * 8 + ks * 2 + (m >> 1)), a0, a1, a2, a3);
                 ldmatrix_x4(wb + sw128(warp * 16 + (m >> 1) * 8 + rr, 2 * ks + (m & 1)), b0, b1, b2, b3);
-                dg_mma16816(acc[0], a0, a1, a2, a3, b0, b1);
-                dg_mma16816(acc[1], a0, a1, a2, a3, b2, b3);
+                // a dependent mma.sync costs ~125 cycles on this part (measured: 16 chained k-steps = 2.1 k cycles): even and odd
+                // k-steps accumulate separately, four independent chains of 8 instead of two of 16
+                if (ks & 1) {
+                    dg_mma16816(acc2[0], a0, a1, a2, a3, b0, b1);
+                    dg_mma16816(acc2[1], a0, a1, a2, a3, b2, b3);
+                } else {
+                    dg_mma16816(acc[0], a0, a1, a2, a3, b0, b1);
+                    dg_mma16816(acc[1], a0, a1, a2, a3, b2, b3);
+                }
             }
         }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] += acc2[nt][i];
     };
     // LayerNorm of the 8 rows held as v[nt][e] (fp32: projection + bias + residual), statistics across the 16 warps
     auto row_ln = [&](float (&v)[2][2], const float* gamma, const float* beta) {
@@ -687,13 +699,23 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     {
                         const int m = lane >> 3, rr = lane & 7;
                         const int key = warp * 16 + (m >> 1) * 8 + rr;
+                        float sc2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // odd k-steps: shorter dependent mma.sync chains
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             uint32_t b0, b1, b2, b3;
                             ldmatrix_x4(smem_u32(sK) + sw128(key, 2 * ks + (m & 1)), b0, b1, b2, b3);
-                            dg_mma16816(sc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
-                            dg_mma16816(sc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                            if (ks & 1) {
+                                dg_mma16816(sc2[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                                dg_mma16816(sc2[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                            } else {
+                                dg_mma16816(sc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                                dg_mma16816(sc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                            }
                         }
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) sc[nt][i] += sc2[nt][i];
                     }
                     const float sl2 = 0.125f * 1.4426950408889634f;
                     float mlo = -INFINITY, mhi = -INFINITY;
@@ -748,7 +770,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     if (it == 0) DG_STAMP2(23);
                     // O = P V: warp = (8 output dims, half of the keys)
                     const int nt8 = warp & 7, kh = warp >> 3;
-                    float oc[4] = {0.f, 0.f, 0.f, 0.f};
+                    float oc[4] = {0.f, 0.f, 0.f, 0.f}, oc2[4] = {0.f, 0.f, 0.f, 0.f};      // two independent mma.sync chains
                     {
                         const int m = lane >> 3, rr = lane & 7;
 #pragma unroll
@@ -759,8 +781,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + 16 + (m >> 1) * 8) * 2), c0, c1, c2, c3);
                             ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, nt8), v0, v1, v2, v3);   // keys key0 .. key0+31
                             dg_mma16816(oc, a0, a1, a2, a3, v0, v1);
-                            dg_mma16816(oc, c0, c1, c2, c3, v2, v3);
+                            dg_mma16816(oc2, c0, c1, c2, c3, v2, v3);
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oc[i] += oc2[i];
                     }
                     red[(warp * 16 + gq) * 8 + 2 * tq] = oc[0];
                     red[(warp * 16 + gq) * 8 + 2 * tq + 1] = oc[1];
