@@ -68,6 +68,7 @@ struct DgMisc {
     uint64_t pw_full[4];      // k-blocks of the out-projection weights (self-attention W_o, then cross-attention W_o) landed
     uint64_t pq_full[4];      // k-blocks of the cross-attention query projection landed
     uint64_t lg_full;         // logits rows of an utterance landed (TMA gather of the beam phase)
+    uint64_t kv_full[32];     // self-attention: [warp][half] 16 cached K rows + 16 V rows of one head landed (bulk copies)
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
     alignas(16) uint32_t zero16[4];       // the (zero) rows 8..15 of the m16 A fragments of the row-block projections
@@ -106,18 +107,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                  : "r"(addr));
 }
-// 16-byte global load with an L2 eviction-priority descriptor
-__device__ __forceinline__ uint4 ldg_v4_hint(const void* ptr, uint64_t policy) {
-    uint4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(ptr), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ uint4 ldg_v4_cg(const void* ptr) {      // cache in L2 only
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
-    return v;
+// contiguous global -> shared bulk copy (TMA engine, no tensor map); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float dg_sigmoid(float x) {
     float t;
@@ -151,7 +144,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const int nl = p.n_layers;
     const CUtensorMap* maps = p.maps;
     const CUtensorMap* map_wout = maps + nl * 6;
-    const CUtensorMap* map_ctx = maps + nl * 6 + 1;
     const CUtensorMap* map_kvx = maps + nl * 6 + 2;
     const CUtensorMap* map_x = maps + nl * 6 + 3;
     const CUtensorMap* map_x2 = maps + nl * 6 + 4;
@@ -178,6 +170,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             mbar_init(&ms.acc_empty[i], 128);
         }
         mbar_init(&ms.lg_full, 1);
+        for (int i = 0; i < 32; ++i) mbar_init(&ms.kv_full[i], 1);
         ms.flag = 0;
         fence_barrier_init();
     }
@@ -189,7 +182,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0, par_lg = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0, par_lg = 0, par_kvw = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
@@ -236,14 +229,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         __syncthreads();
     };
     auto nop = [] {};
-    // L2 eviction priorities (OTB_DG_FLAGS experiments: 2 = encoder K/V normal, 4 = encoder K/V evict-last, 8 = self-attention K/V evict-first)
+    // L2 eviction priority of the encoder K/V tiles (OTB_DG_FLAGS experiments: 2 = normal, 4 = evict-last; default evict-first)
     const uint64_t kvx_policy = (p.flags & 2) ? TMA_EVICT_NORMAL : (p.flags & 4) ? TMA_EVICT_LAST : TMA_EVICT_FIRST;
-    const uint64_t kv_policy = (p.flags & 8) ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
     // element offset of (layer l, position s, hypothesis row n) in the self-attention K / V cache.  flags & 16: an utterance's
     // beam is contiguous per position and its positions are contiguous ([layer][utterance][position][beam][d]): the prefix
     // gather of a hypothesis walks one 0.6 MB region instead of one 512-byte piece per 180 KB.
     const bool kv_by_utt = (p.flags & 16) != 0;
-    const bool kv_cg = (p.flags & 32) != 0;
     auto kv_off = [&](int l, int s, int n) -> size_t {
         if (!kv_by_utt) return (((size_t)l * Lmax + s) * N + n) * DG_D;
         const int uu = n / beam;
@@ -492,9 +483,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 reinterpret_cast<uint4*>(dst)[0] = o[0];
                 reinterpret_cast<uint4*>(dst)[1] = o[1];
             });
-            gsync([&] {      // W_o (whole) and the first half of the query projection stream in behind the self-attention
-                for (int kb = 0; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 1, ms.pw_full, kb, kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768);
-                for (int kb = 0; kb < 2; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sST + DG_STAGE + kb * 32768);
+            gsync([&] {      // first half of W_o streams in behind the self-attention (both stages are its K/V staging area)
+                for (int kb = 0; kb < 2; ++kb) load_proj_kb(maps + l * 6 + 1, ms.pw_full, kb, sA + kb * 32768);
             });
             DG_STAMP();
             // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
@@ -505,6 +495,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
                 int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                uint8_t* kvst = sST + warp * 8192;                             // this warp's K/V staging: [2 halves][K 16 x 128 B | V 16 x 128 B]
+                uint64_t* kvb = &ms.kv_full[warp * 2];
+                fence_proxy_async_all();      // K / V rows written with ordinary stores (this step's by other CTAs, behind the barrier) are read by the async proxy
                 const int g4 = lane >> 3, c8 = lane & 7;
                 // v9: the hypotheses [8 j, 8 j + 8) of the tile are attended by their OWNER (the CTA that multiplies them by W_o
                 // next): 32 (row, head) problems per CTA -- every warp exactly two problems (v8 dealt the 480
@@ -534,39 +527,48 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     __syncwarp();
                     float m = -INFINITY, lsum = 0.f;
                     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    const size_t col = (size_t)h * 64 + c8 * 8;
-                    // 32 keys per iteration: 8 K and 8 V chunks of 16 bytes in flight per lane -- a 60-token prefix costs two exposed
-                    // HBM / L2 round trips (the K/V cache of a batch is ~100 MB: these gathers mostly miss L2)
-                    for (int k0 = 0; k0 < nkeys; k0 += 32) {
-                        uint4 ku[8], vu[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int sidx = k0 + 4 * u + g4;
-                            if (sidx < nkeys) {
-                                const int slot = (sidx < step) ? an_s[sidx] : n;
-                                const size_t off = kv_off(l, sidx, slot) + col;
-                                if (kv_cg) {      // L2 only: the 16 lines a lane keeps in flight x 512 lanes exceed the ~20 KB of L1 left beside 227 KB of shared memory
-                                    ku[u] = ldg_v4_cg(p.kc + off);
-                                    vu[u] = ldg_v4_cg(p.vc + off);
-                                } else {
-                                    ku[u] = ldg_v4_hint(p.kc + off, kv_policy);
-                                    vu[u] = ldg_v4_hint(p.vc + off, kv_policy);
-                                }
-                            } else {
-                                ku[u] = make_uint4(0, 0, 0, 0);
-                                vu[u] = ku[u];
-                            }
+                    // v14: the cached K / V rows of the prefix (128 bytes per position and head, scattered by the ancestry table) are
+                    // fetched by the TMA engine -- one bulk copy per row, 16 positions per half, two halves in flight per warp --
+                    // into this warp's 8 KB of the (idle) stages, and the dot products read shared memory.  v13 gathered with
+                    // 16-byte LDGs: 16 per lane in flight, yet 9.5 B/clk per SM at step 50 (44 k cycles per layer) whatever the
+                    // cache policy -- the load/store unit tracks too few outstanding lines for 1 k of them.
+                    const int nh = (nkeys + 15) >> 4;
+                    auto issue = [&](int hh) {
+                        const int kk0 = hh * 16, buf = hh & 1;
+                        const int nk = min(16, nkeys - kk0);
+                        if (lane == 0) mbar_arrive_expect_tx(&kvb[buf], (uint32_t)(nk * 256));
+                        __syncwarp();
+                        const int key = lane & 15, isv = lane >> 4;
+                        if (key < nk) {
+                            const int sidx = kk0 + key;
+                            const int slot = (sidx < step) ? an_s[sidx] : n;
+                            const bf16* src = (isv ? p.vc : p.kc) + kv_off(l, sidx, slot) + h * 64;
+                            bulk_g2s(kvst + buf * 4096 + isv * 2048 + key * 128, src, 128, &kvb[buf]);
                         }
-                        float sc[8];
+                    };
+                    issue(0);
+                    if (nh > 1) issue(1);
+                    for (int hh = 0; hh < nh; ++hh) {
+                        const int buf = hh & 1, k0 = hh * 16;
+                        mbar_wait(&kvb[buf], (par_kvw >> buf) & 1);
+                        par_kvw ^= (1u << buf);
+                        const uint8_t* kb_ = kvst + buf * 4096;
+                        uint4 ku[4], vu[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            ku[u] = *reinterpret_cast<const uint4*>(kb_ + (4 * u + g4) * 128 + c8 * 16);
+                            vu[u] = *reinterpret_cast<const uint4*>(kb_ + 2048 + (4 * u + g4) * 128 + c8 * 16);
+                        }
+                        float sc[4];
                         float mb = m;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < 4; ++u) {
                             const float2 a = unpack_bf16(ku[u].x), b2 = unpack_bf16(ku[u].y), c2 = unpack_bf16(ku[u].z), e = unpack_bf16(ku[u].w);
                             float d = qf[0] * a.x + qf[1] * a.y + qf[2] * b2.x + qf[3] * b2.y + qf[4] * c2.x + qf[5] * c2.y + qf[6] * e.x + qf[7] * e.y;
                             d += __shfl_xor_sync(0xffffffffu, d, 1);
                             d += __shfl_xor_sync(0xffffffffu, d, 2);
                             d += __shfl_xor_sync(0xffffffffu, d, 4);
-                            sc[u] = (k0 + 4 * u + g4 < nkeys) ? d : -INFINITY;
+                            sc[u] = (k0 + 4 * u + g4 < nkeys) ? d : -INFINITY;      // rows beyond the prefix hold stale bytes: masked here
                             mb = fmaxf(mb, sc[u]);
                         }
                         if (mb != -INFINITY) {
@@ -575,15 +577,20 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #pragma unroll
                             for (int q = 0; q < 8; ++q) o[q] *= alpha;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const float pw = (sc[u] == -INFINITY) ? 0.f : __expf(sc[u] - mb);
+                            for (int u = 0; u < 4; ++u) {
+                                const bool live_k = sc[u] != -INFINITY;
+                                const float pw = live_k ? __expf(sc[u] - mb) : 0.f;
                                 lsum += pw;
                                 const float2 a = unpack_bf16(vu[u].x), b2 = unpack_bf16(vu[u].y), c2 = unpack_bf16(vu[u].z), e = unpack_bf16(vu[u].w);
-                                o[0] = fmaf(pw, a.x, o[0]); o[1] = fmaf(pw, a.y, o[1]); o[2] = fmaf(pw, b2.x, o[2]); o[3] = fmaf(pw, b2.y, o[3]);
-                                o[4] = fmaf(pw, c2.x, o[4]); o[5] = fmaf(pw, c2.y, o[5]); o[6] = fmaf(pw, e.x, o[6]); o[7] = fmaf(pw, e.y, o[7]);
+                                if (live_k) {      // stale V bytes may be NaN patterns: never multiply them, not even by zero
+                                    o[0] = fmaf(pw, a.x, o[0]); o[1] = fmaf(pw, a.y, o[1]); o[2] = fmaf(pw, b2.x, o[2]); o[3] = fmaf(pw, b2.y, o[3]);
+                                    o[4] = fmaf(pw, c2.x, o[4]); o[5] = fmaf(pw, c2.y, o[5]); o[6] = fmaf(pw, e.x, o[6]); o[7] = fmaf(pw, e.y, o[7]);
+                                }
                             }
                             m = mb;
                         }
+                        __syncwarp();      // every lane is done with this half
+                        if (hh + 2 < nh) issue(hh + 2);
                     }
                     // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
                     float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
@@ -610,6 +617,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 }
             }
             __syncthreads();
+            if (is_tma) {      // the stages are free again: second half of W_o, first half of W_q
+                for (int kb = 2; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 1, ms.pw_full, kb, sST + (kb - 2) * 32768);
+                for (int kb = 0; kb < 2; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sST + DG_STAGE + kb * 32768);
+            }
             DG_STAMP();
             DG_STAMP();      // (the group barrier that used to stand here)
             // ---------------- rows [8 j, 8 j + 8): W_o + bias + residual (the layer input) -> LayerNorm 1 -> query projection
@@ -1243,7 +1254,35 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             }
             __syncthreads();
             if (ul == j) DG_STAMP();      // per-row log-softmax statistics + top-`beam`
-            if (warp == 0) warp_topk([&](int idx) { return ms.c_val[idx]; }, beam * beam, beam, ms.sel_v, ms.sel_i);   // (:119-122)
+            if (warp == 0) {      // beam^2 -> beam (:119-122): <= 256 candidates, 8 per lane in registers, `beam` arg-max rounds (ties -> lower
+                                  // index).  The generic warp_topk (sorted per-lane insertion lists) spent 11 k cycles here.
+                float cv[8];
+                int ci[8];
+                const int nc = beam * beam;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int idx = lane + 32 * q;
+                    cv[q] = (idx < nc) ? ms.c_val[idx] : -INFINITY;
+                    ci[q] = (idx < nc) ? idx : 0x7fffffff;
+                }
+                for (int k = 0; k < beam; ++k) {
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (better(cv[q], ci[q], bv, bi)) { bv = cv[q]; bi = ci[q]; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (ci[q] == bi) { cv[q] = -INFINITY; ci[q] = 0x7fffffff; }
+                    if (lane == 0) { ms.sel_v[k] = bv; ms.sel_i[k] = bi; }
+                }
+            }
             if (ul == j) DG_STAMP3(30);
             __syncthreads();
             if (ul == j) DG_STAMP3(31);
