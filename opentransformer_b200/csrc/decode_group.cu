@@ -495,8 +495,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
                 int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
-                uint8_t* kvst = sST + warp * 8192;                             // this warp's K/V staging: [2 halves][K 16 x 128 B | V 16 x 128 B]
-                uint64_t* kvb = &ms.kv_full[warp * 2];
+                // the four warps (heads) of a row share one staging area: [2 halves][K 16 x 512 B | V 16 x 512 B] = 32 KB per row,
+                // four rows at a time = both stages; one mbarrier per (row, half), one named barrier per row
+                const int rg = warp >> 2, hw = warp & 3;
+                uint8_t* kvst = sST + rg * 32768;
+                uint64_t* kvb = &ms.kv_full[rg * 2];
+                auto row_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(rg + 1) : "memory"); };
                 fence_proxy_async_all();      // K / V rows written with ordinary stores (this step's by other CTAs, behind the barrier) are read by the async proxy
                 const int g4 = lane >> 3, c8 = lane & 7;
                 // v9: the hypotheses [8 j, 8 j + 8) of the tile are attended by their OWNER (the CTA that multiplies them by W_o
@@ -504,11 +508,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // problems round-robin: some warps two, some one, then a group barrier and a trip through global memory for the
                 // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
                 // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
+                DG_STAMP2(39);
                 for (int t2 = 0; t2 < 2; ++t2) {
                     // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
                     // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
-                    // (flags & 64: warp w = row w / 2, heads 2 (w & 1) + t2 -- the two problems of a warp share the ancestry row)
-                    const int rl = (p.flags & 64) ? (warp >> 1) : (warp >> 2) + 4 * t2, h = (p.flags & 64) ? (warp & 1) * 2 + t2 : warp & 3;
+                    const int rl = rg + 4 * t2, h = hw;
                     const int r = j * 8 + rl;
                     const int n = row0 + r;
                     if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
@@ -527,37 +531,44 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     __syncwarp();
                     float m = -INFINITY, lsum = 0.f;
                     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    // v14: the cached K / V rows of the prefix (128 bytes per position and head, scattered by the ancestry table) are
-                    // fetched by the TMA engine -- one bulk copy per row, 16 positions per half, two halves in flight per warp --
-                    // into this warp's 8 KB of the (idle) stages, and the dot products read shared memory.  v13 gathered with
-                    // 16-byte LDGs: 16 per lane in flight, yet 9.5 B/clk per SM at step 50 (44 k cycles per layer) whatever the
-                    // cache policy -- the load/store unit tracks too few outstanding lines for 1 k of them.
+                    // v15: the cached K / V rows of the prefix (512 bytes per position: all four heads; scattered by the ancestry table)
+                    // are fetched by the TMA engine -- ONE bulk copy per row and position, shared by the four warps (heads) of the
+                    // row, 16 positions per half, two halves in flight -- and the dot products read shared memory.
+                    // History: v13 gathered with 16-byte LDGs, 16 per lane in flight: 9.5 B/clk per SM at step 50 (44 k cycles per
+                    // layer) whatever the cache policy.  v14 issued one 128-byte bulk copy per (position, head): the stamps showed the
+                    // ISSUE as the limit -- 3.3 k cycles per 32 copies with 16 warps issuing, i.e. the SM starts one bulk copy per
+                    // ~6.5 cycles (41 k cycles per layer at step 50).  512-byte copies need a quarter of the operations.
                     const int nh = (nkeys + 15) >> 4;
                     auto issue = [&](int hh) {
                         const int kk0 = hh * 16, buf = hh & 1;
                         const int nk = min(16, nkeys - kk0);
-                        if (lane == 0) mbar_arrive_expect_tx(&kvb[buf], (uint32_t)(nk * 256));
-                        __syncwarp();
-                        const int key = lane & 15, isv = lane >> 4;
-                        if (key < nk) {
-                            const int sidx = kk0 + key;
-                            const int slot = (sidx < step) ? an_s[sidx] : n;
-                            const bf16* src = (isv ? p.vc : p.kc) + kv_off(l, sidx, slot) + h * 64;
-                            bulk_g2s(kvst + buf * 4096 + isv * 2048 + key * 128, src, 128, &kvb[buf]);
+                        if (hw == 0 && lane == 0) mbar_arrive_expect_tx(&kvb[buf], (uint32_t)(nk * 1024));
+                        if (lane < 8) {
+                            const int c = hw * 8 + lane;               // 32 copies per half: 16 K rows, 16 V rows; 8 per warp
+                            const int key = c & 15, isv = c >> 4;
+                            if (key < nk) {
+                                const int sidx = kk0 + key;
+                                const int slot = (sidx < step) ? an_s[sidx] : n;
+                                const bf16* src = (isv ? p.vc : p.kc) + kv_off(l, sidx, slot);
+                                bulk_g2s(kvst + buf * 16384 + isv * 8192 + key * 512, src, 512, &kvb[buf]);
+                            }
                         }
                     };
+                    row_sync();        // the four warps are done with the staging area of the previous row
                     issue(0);
                     if (nh > 1) issue(1);
+                    if (t2 == 0) DG_STAMP2(41);
                     for (int hh = 0; hh < nh; ++hh) {
                         const int buf = hh & 1, k0 = hh * 16;
                         mbar_wait(&kvb[buf], (par_kvw >> buf) & 1);
                         par_kvw ^= (1u << buf);
-                        const uint8_t* kb_ = kvst + buf * 4096;
+                        if (t2 == 0 && hh < 4) DG_STAMP2(42 + 2 * hh);
+                        const uint8_t* kb_ = kvst + buf * 16384 + h * 128 + c8 * 16;
                         uint4 ku[4], vu[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            ku[u] = *reinterpret_cast<const uint4*>(kb_ + (4 * u + g4) * 128 + c8 * 16);
-                            vu[u] = *reinterpret_cast<const uint4*>(kb_ + 2048 + (4 * u + g4) * 128 + c8 * 16);
+                            ku[u] = *reinterpret_cast<const uint4*>(kb_ + (4 * u + g4) * 512);
+                            vu[u] = *reinterpret_cast<const uint4*>(kb_ + 8192 + (4 * u + g4) * 512);
                         }
                         float sc[4];
                         float mb = m;
@@ -589,9 +600,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             }
                             m = mb;
                         }
-                        __syncwarp();      // every lane is done with this half
-                        if (hh + 2 < nh) issue(hh + 2);
+                        if (hh + 2 < nh) {
+                            row_sync();    // all four heads are done with this half
+                            issue(hh + 2);
+                        }
+                        if (t2 == 0 && hh < 4) DG_STAMP2(43 + 2 * hh);
                     }
+                    if (t2 == 0) DG_STAMP2(50);
                     // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
                     float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
                     M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
@@ -614,6 +629,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         ou.w = pack_bf16(o[6] * inv, o[7] * inv);
                         *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = ou;      // context row -> A operand of W_o
                     }
+                    if (t2 == 0) DG_STAMP2(51);
                 }
             }
             __syncthreads();
