@@ -1172,14 +1172,25 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // any lane has to look at its four values at all
                 const float l2e = 1.4426950408889634f, nm = -rowmax * l2e;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // pass 2a: sum of exp(x - max), four float4 per lane in flight (no warp-wide instruction in the loop)
+                for (int base = 0; base < ldv4; base += 32 * 4) {
+                    const int i0 = base + lane;
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < ldv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : ninf4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        s0 += ex2f(fmaf(v[q].x, l2e, nm));           // ex2(-inf) = 0: padding and masked lanes add nothing
+                        s1 += ex2f(fmaf(v[q].y, l2e, nm));
+                        s2 += ex2f(fmaf(v[q].z, l2e, nm));
+                        s3 += ex2f(fmaf(v[q].w, l2e, nm));
+                    }
+                }
+                // pass 2b: the candidates >= T; one ballot per 128 elements decides whether any lane has to look at its four values
                 int ncand = 0;
                 for (int base = 0; base < ldv4; base += 32) {        // warp-uniform trip count: whole warps take part in the ballots
                     const int i0 = base + lane;
                     const float4 v = (i0 < ldv4) ? x4[(size_t)i0 * xs4] : ninf4;
-                    s0 += ex2f(fmaf(v.x, l2e, nm));                  // ex2(-inf) = 0: padding and masked lanes add nothing
-                    s1 += ex2f(fmaf(v.y, l2e, nm));
-                    s2 += ex2f(fmaf(v.z, l2e, nm));
-                    s3 += ex2f(fmaf(v.w, l2e, nm));
                     const bool any4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= T && T != -INFINITY;
                     const bool all4 = T == -INFINITY && i0 < ldv4;   // degenerate threshold: every real element is a candidate
                     if (__ballot_sync(0xffffffffu, any4 || all4)) {
