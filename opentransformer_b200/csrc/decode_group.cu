@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
-                int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                int* an_w = reinterpret_cast<int*>(sSB) + warp * 256;          // this warp's two ancestry rows (<= 128 positions each)
                 // the four warps (heads) of a row share one staging area: [2 halves][K 16 x 512 B | V 16 x 512 B] = 32 KB per row,
                 // four rows at a time = both stages; one mbarrier per (row, half), one named barrier per row
                 const int rg = warp >> 2, hw = warp & 3;
@@ -509,7 +509,22 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
                 // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
                 DG_STAMP2(39);
+                // ancestry rows and queries of BOTH problems of the warp are requested up front: one exposed L2 round trip, not two
+                uint4 qpre[2];
+#pragma unroll
                 for (int t2 = 0; t2 < 2; ++t2) {
+                    const int r_ = j * 8 + rg + 4 * t2;
+                    qpre[t2] = make_uint4(0, 0, 0, 0);
+                    if (r_ < nrows) {
+                        const int n_ = row0 + r_;
+                        for (int s0 = lane; s0 < step; s0 += 32) an_w[t2 * 128 + s0] = an_base[(size_t)n_ * Lmax + s0];
+                        qpre[t2] = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n_ * DG_D + hw * 64 + c8 * 8);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t2 = 0; t2 < 2; ++t2) {
+                    const int* an_s = an_w + t2 * 128;
                     // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
                     // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
                     const int rl = rg + 4 * t2, h = hw;
@@ -519,11 +534,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
                         continue;
                     }
-                    __syncwarp();
-                    for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
                     float qf[8];
                     {
-                        const uint4 qu = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n * DG_D + h * 64 + c8 * 8);
+                        const uint4 qu = qpre[t2];
                         const float2 q0 = unpack_bf16(qu.x), q1 = unpack_bf16(qu.y), q2 = unpack_bf16(qu.z), q3 = unpack_bf16(qu.w);
                         qf[0] = q0.x * 0.125f; qf[1] = q0.y * 0.125f; qf[2] = q1.x * 0.125f; qf[3] = q1.y * 0.125f;
                         qf[4] = q2.x * 0.125f; qf[5] = q2.y * 0.125f; qf[6] = q3.x * 0.125f; qf[7] = q3.y * 0.125f;
@@ -694,6 +707,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
                 const int gq = lane >> 2, tq = lane & 3;
                 int it = 0;
+                uint32_t qa[4][4];
+                auto load_q = [&](int tk, uint32_t (&q)[4][4]) {
+                    const bf16* qb = p.q2 + (size_t)((u0 + tk / DG_H) * beam) * DG_D + (tk % DG_H) * 64;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const int d0 = ks * 16 + 2 * tq;
+                        q[ks][0] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0) : 0u;
+                        q[ks][1] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0) : 0u;
+                        q[ks][2] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0 + 8) : 0u;
+                        q[ks][3] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0 + 8) : 0u;
+                    }
+                };
                 DG_STAMP2(0);
                 for (int task = j; task < n_tasks; task += DG_P, ++it) {
                     const int s = it & 1;
@@ -701,19 +726,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     const int kv_len = min(p.mem_len[u], p.T);
                     const uint8_t* sK = sST + s * DG_STAGE;
                     const uint8_t* sV = sK + 32768;
-                    // Q fragments (rows = hypotheses of the utterance) straight from L2
-                    uint32_t qa[4][4];
-                    {
-                        const bf16* qb = p.q2 + (size_t)(u * beam) * DG_D + h * 64;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const int d0 = ks * 16 + 2 * tq;
-                            qa[ks][0] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0) : 0u;
-                            qa[ks][1] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0) : 0u;
-                            qa[ks][2] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0 + 8) : 0u;
-                            qa[ks][3] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0 + 8) : 0u;
-                        }
-                    }
+                    // Q fragments (rows = hypotheses of the utterance) straight from L2; those of the NEXT problem are requested
+                    // right behind the QK^T below (its L2 round trip was ~750 exposed cycles per problem)
+                    if (it == 0) load_q(task, qa);
                     mbar_wait(&ms.st_full[s], (par_stf >> s) & 1);
                     par_stf ^= (1u << s);
                     if (it < 4) DG_STAMP2(1 + 2 * it);
@@ -743,6 +758,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                             for (int i = 0; i < 4; ++i) sc[nt][i] += sc2[nt][i];
+                        if (task + DG_P < n_tasks) load_q(task + DG_P, qa);
                     }
                     const float sl2 = 0.125f * 1.4426950408889634f;
                     float mlo = -INFINITY, mhi = -INFINITY;
@@ -1172,25 +1188,15 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // any lane has to look at its four values at all
                 const float l2e = 1.4426950408889634f, nm = -rowmax * l2e;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                // pass 2a: sum of exp(x - max), four float4 per lane in flight (no warp-wide instruction in the loop)
-                for (int base = 0; base < ldv4; base += 32 * 4) {
-                    const int i0 = base + lane;
-                    float4 v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < ldv4) ? x4[(size_t)(i0 + 32 * q) * xs4] : ninf4;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        s0 += ex2f(fmaf(v[q].x, l2e, nm));           // ex2(-inf) = 0: padding and masked lanes add nothing
-                        s1 += ex2f(fmaf(v[q].y, l2e, nm));
-                        s2 += ex2f(fmaf(v[q].z, l2e, nm));
-                        s3 += ex2f(fmaf(v[q].w, l2e, nm));
-                    }
-                }
-                // pass 2b: the candidates >= T; one ballot per 128 elements decides whether any lane has to look at its four values
                 int ncand = 0;
+                // (a separate, unrolled sum pass in front of the candidate pass was tried: 22.7 k -> 25.5 k cycles)
                 for (int base = 0; base < ldv4; base += 32) {        // warp-uniform trip count: whole warps take part in the ballots
                     const int i0 = base + lane;
                     const float4 v = (i0 < ldv4) ? x4[(size_t)i0 * xs4] : ninf4;
+                    s0 += ex2f(fmaf(v.x, l2e, nm));                  // ex2(-inf) = 0: padding and masked lanes add nothing
+                    s1 += ex2f(fmaf(v.y, l2e, nm));
+                    s2 += ex2f(fmaf(v.z, l2e, nm));
+                    s3 += ex2f(fmaf(v.w, l2e, nm));
                     const bool any4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= T && T != -INFINITY;
                     const bool all4 = T == -INFINITY && i0 < ldv4;   // degenerate threshold: every real element is a candidate
                     if (__ballot_sync(0xffffffffu, any4 || all4)) {
