@@ -68,6 +68,7 @@ struct DgMisc {
     uint64_t pw_full[4];      // k-blocks of the out-projection weights (self-attention W_o, then cross-attention W_o) landed
     uint64_t pq_full[4];      // k-blocks of the cross-attention query projection landed
     uint64_t lg_full;         // logits rows of an utterance landed (TMA gather of the beam phase)
+    uint64_t kx_full[3];      // encoder K/V tile of a cross-attention problem landed in stage 0 / stage 1 / the A tile
     uint64_t kv_full[32];     // self-attention: [warp][half] 16 cached K rows + 16 V rows of one head landed (bulk copies)
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         }
         mbar_init(&ms.lg_full, 1);
         for (int i = 0; i < 32; ++i) mbar_init(&ms.kv_full[i], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&ms.kx_full[i], 1);
         ms.flag = 0;
         fence_barrier_init();
     }
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     const uint32_t t_row = tmem + ((uint32_t)(equad * 32) << 16);
 
     // parity of the NEXT completion of every mbarrier, tracked identically by all threads (every thread walks the same phases)
-    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0, par_lg = 0, par_kvw = 0;   // bit i = barrier i
+    uint32_t par_kb = 0, par_a = 0, par_w1 = 0, par_stf = 0, par_ste = 0, par_accf = 0, par_pw = 0, par_pq = 0, par_lg = 0, par_kvw = 0, par_kx = 0;   // bit i = barrier i
     int bar_target = 0;
 
     const bool dbg_cta = (p.dbg_clk != nullptr && blockIdx.x < DG_P && tid == 0);     // every CTA of group 0: [cta][256] stamps
@@ -270,13 +272,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
         mbar_arrive_expect_tx(&full[kb], 32768);
         tma_load_2d_hint(dst, m, &full[kb], kb * 64, 0, TMA_EVICT_LAST);
     };
-    auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s
+    auto load_kv = [&](int l, int task, int s) {   // K and V tile of (utterance, head) -> stage s (0, 1: the stages; 2: the A tile)
         const int u = u0 + task / DG_H, h = task % DG_H;
-        mbar_arrive_expect_tx(&ms.st_full[s], 65536);
+        uint8_t* dst = (s < 2) ? sST + s * DG_STAGE : sA;
+        mbar_arrive_expect_tx(&ms.kx_full[s], 65536);
         // the encoder K / V tiles are streamed once per step (49 MB per batch): evict-first, so that they do not push the
         // decoder weights (re-read by every group, every step) out of L2
-        tma_load_2d_hint(sST + s * DG_STAGE, map_kvx, &ms.st_full[s], h * 64, (l * p.B + u) * p.T, kvx_policy);
-        tma_load_2d_hint(sST + s * DG_STAGE + 32768, map_kvx, &ms.st_full[s], DG_D + h * 64, (l * p.B + u) * p.T, kvx_policy);
+        tma_load_2d_hint(dst, map_kvx, &ms.kx_full[s], h * 64, (l * p.B + u) * p.T, kvx_policy);
+        tma_load_2d_hint(dst + 32768, map_kvx, &ms.kx_full[s], DG_D + h * 64, (l * p.B + u) * p.T, kvx_policy);
     };
     const int n_vchunks = (V + 127) / 128;
     auto load_wout = [&](int chunk, int s) {
@@ -509,22 +512,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
                 // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
                 DG_STAMP2(39);
-                // ancestry rows and queries of BOTH problems of the warp are requested up front: one exposed L2 round trip, not two
-                uint4 qpre[2];
-#pragma unroll
                 for (int t2 = 0; t2 < 2; ++t2) {
-                    const int r_ = j * 8 + rg + 4 * t2;
-                    qpre[t2] = make_uint4(0, 0, 0, 0);
-                    if (r_ < nrows) {
-                        const int n_ = row0 + r_;
-                        for (int s0 = lane; s0 < step; s0 += 32) an_w[t2 * 128 + s0] = an_base[(size_t)n_ * Lmax + s0];
-                        qpre[t2] = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n_ * DG_D + hw * 64 + c8 * 8);
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t2 = 0; t2 < 2; ++t2) {
-                    const int* an_s = an_w + t2 * 128;
+                    int* an_s = an_w;      // (requesting the ancestry rows / queries of both problems up front was tried: no gain)
                     // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
                     // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
                     const int rl = rg + 4 * t2, h = hw;
@@ -534,9 +523,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
                         continue;
                     }
+                    __syncwarp();
+                    for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
                     float qf[8];
                     {
-                        const uint4 qu = qpre[t2];
+                        const uint4 qu = *reinterpret_cast<const uint4*>(p.qbuf + (size_t)n * DG_D + h * 64 + c8 * 8);
                         const float2 q0 = unpack_bf16(qu.x), q1 = unpack_bf16(qu.y), q2 = unpack_bf16(qu.z), q3 = unpack_bf16(qu.w);
                         qf[0] = q0.x * 0.125f; qf[1] = q0.y * 0.125f; qf[2] = q1.x * 0.125f; qf[3] = q1.y * 0.125f;
                         qf[4] = q2.x * 0.125f; qf[5] = q2.y * 0.125f; qf[6] = q3.x * 0.125f; qf[7] = q3.y * 0.125f;
@@ -694,77 +685,70 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     }
                 }
             }
-            gsync([&] {   // encoder K / V tiles of this CTA's first two (utterance, head) problems arrive during the barrier
-                if (j < n_tasks) load_kv(l, j, 0);
-                if (j + DG_P < n_tasks) load_kv(l, j + DG_P, 1);
+            gsync([&] {   // encoder K / V tiles of this CTA's first three (utterance, head) problems arrive during the barrier
+                for (int i = 0; i < 3; ++i)
+                    if (j + i * DG_P < n_tasks) load_kv(l, j + i * DG_P, i);
             });
             DG_STAMP();
-            // ---------------- cross-attention (attention.py:129-141,34-41): one m16 problem per (utterance, head)
+            // ---------------- cross-attention (attention.py:129-141,34-41): one m16 problem per (utterance, head), 3 per CTA at
+            // beam 10.  v18: the two HALVES of the CTA (8 warps each, own named barrier, own scratch) work on different problems
+            // at the same time -- a problem is a chain of short dependent stages (QK^T 1.8 k cycles, exp 1.1 k, PV 1.0 k,
+            // normalise 0.7 k with all 16 warps on it: latency, not throughput), so two chains side by side cost little more
+            // than one.  Tiles of the first three problems are prefetched (both stages + the idle A tile).
             {
-                float* wmax = reinterpret_cast<float*>(sSB);                  // [16 warps][16 rows]
-                float* wsum = wmax + 256;
-                float* red = wsum + 256;                                       // [16 warps][16 rows][8] PV partials
-                uint8_t* sP = sSB + 2048 + 8192;                               // [16 rows][DG_PP bytes] probabilities (bf16)
+                const int hf = warp >> 3, w8 = warp & 7;
+                float* wmax = reinterpret_cast<float*>(sSB + hf * 9472);       // [8 warps][16 rows]
+                float* wsum = wmax + 128;
+                uint8_t* sP = sSB + hf * 9472 + 1024;                          // [16 rows][DG_PP bytes] probabilities (bf16)
+                auto half_sync = [&] { asm volatile("bar.sync %0, 256;" ::"r"(5 + hf) : "memory"); };
                 const int gq = lane >> 2, tq = lane & 3;
-                int it = 0;
-                uint32_t qa[4][4];
-                auto load_q = [&](int tk, uint32_t (&q)[4][4]) {
-                    const bf16* qb = p.q2 + (size_t)((u0 + tk / DG_H) * beam) * DG_D + (tk % DG_H) * 64;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const int d0 = ks * 16 + 2 * tq;
-                        q[ks][0] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0) : 0u;
-                        q[ks][1] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0) : 0u;
-                        q[ks][2] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0 + 8) : 0u;
-                        q[ks][3] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0 + 8) : 0u;
-                    }
-                };
+                const int n_mine = (n_tasks > j) ? (n_tasks - j + DG_P - 1) / DG_P : 0;      // problems of this CTA
                 DG_STAMP2(0);
-                for (int task = j; task < n_tasks; task += DG_P, ++it) {
-                    const int s = it & 1;
+                for (int i = hf; i < n_mine; i += 2) {
+                    const int task = j + i * DG_P, st = i % 3;
                     const int u = u0 + task / DG_H, h = task % DG_H;
                     const int kv_len = min(p.mem_len[u], p.T);
-                    const uint8_t* sK = sST + s * DG_STAGE;
+                    const uint8_t* sK = (st < 2) ? sST + st * DG_STAGE : sA;
                     const uint8_t* sV = sK + 32768;
-                    // Q fragments (rows = hypotheses of the utterance) straight from L2; those of the NEXT problem are requested
-                    // right behind the QK^T below (its L2 round trip was ~750 exposed cycles per problem)
-                    if (it == 0) load_q(task, qa);
-                    mbar_wait(&ms.st_full[s], (par_stf >> s) & 1);
-                    par_stf ^= (1u << s);
-                    if (it < 4) DG_STAMP2(1 + 2 * it);
-                    // S = Q K^T for this warp's 16 keys
-                    float sc[2][4];
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+                    // Q fragments (rows = hypotheses of the utterance) straight from L2
+                    uint32_t qa[4][4];
                     {
-                        const int m = lane >> 3, rr = lane & 7;
-                        const int key = warp * 16 + (m >> 1) * 8 + rr;
-                        float sc2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // odd k-steps: shorter dependent mma.sync chains
+                        const bf16* qb = p.q2 + (size_t)(u * beam) * DG_D + h * 64;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            uint32_t b0, b1, b2, b3;
-                            ldmatrix_x4(smem_u32(sK) + sw128(key, 2 * ks + (m & 1)), b0, b1, b2, b3);
-                            if (ks & 1) {
-                                dg_mma16816(sc2[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
-                                dg_mma16816(sc2[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
-                            } else {
-                                dg_mma16816(sc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
-                                dg_mma16816(sc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                            const int d0 = ks * 16 + 2 * tq;
+                            qa[ks][0] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0) : 0u;
+                            qa[ks][1] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0) : 0u;
+                            qa[ks][2] = (gq < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)gq * DG_D + d0 + 8) : 0u;
+                            qa[ks][3] = (gq + 8 < beam) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)(gq + 8) * DG_D + d0 + 8) : 0u;
+                        }
+                    }
+                    mbar_wait(&ms.kx_full[st], ((par_kx >> st) & 1) ^ (uint32_t)((i / 3) & 1));
+                    // S = Q K^T for this warp's 32 keys
+                    float sc[4][4];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+                    {
+                        const int m = lane >> 3, rr = lane & 7;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                            for (int kq = 0; kq < 2; ++kq) {
+                                const int key = w8 * 32 + kq * 16 + (m >> 1) * 8 + rr;
+                                uint32_t b0, b1, b2, b3;
+                                ldmatrix_x4(smem_u32(sK) + sw128(key, 2 * ks + (m & 1)), b0, b1, b2, b3);
+                                dg_mma16816(sc[2 * kq], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                                dg_mma16816(sc[2 * kq + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
                             }
                         }
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) sc[nt][i] += sc2[nt][i];
-                        if (task + DG_P < n_tasks) load_q(task + DG_P, qa);
                     }
                     const float sl2 = 0.125f * 1.4426950408889634f;
                     float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const int k0 = warp * 16 + nt * 8 + 2 * tq;
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int k0 = w8 * 32 + nt * 8 + 2 * tq;
                         sc[nt][0] = (k0 < kv_len) ? sc[nt][0] * sl2 : -INFINITY;
                         sc[nt][1] = (k0 + 1 < kv_len) ? sc[nt][1] * sl2 : -INFINITY;
                         sc[nt][2] = (k0 < kv_len) ? sc[nt][2] * sl2 : -INFINITY;
@@ -777,26 +761,24 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
                     if (tq == 0) {
-                        wmax[warp * 16 + gq] = mlo;
-                        wmax[warp * 16 + gq + 8] = mhi;
+                        wmax[w8 * 16 + gq] = mlo;
+                        wmax[w8 * 16 + gq + 8] = mhi;
                     }
-                    if (it == 0) DG_STAMP2(20);
-                    __syncthreads();
-                    if (it == 0) DG_STAMP2(21);
+                    half_sync();
                     float Mlo = -INFINITY, Mhi = -INFINITY;
 #pragma unroll
-                    for (int w = 0; w < 16; ++w) {
+                    for (int w = 0; w < 8; ++w) {
                         Mlo = fmaxf(Mlo, wmax[w * 16 + gq]);
                         Mhi = fmaxf(Mhi, wmax[w * 16 + gq + 8]);
                     }
                     float slo = 0.f, shi = 0.f;
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
+                    for (int nt = 0; nt < 4; ++nt) {
                         const float p0 = ex2f(sc[nt][0] - Mlo), p1 = ex2f(sc[nt][1] - Mlo);     // exp2(-inf) = 0 for masked keys
                         const float p2 = ex2f(sc[nt][2] - Mhi), p3 = ex2f(sc[nt][3] - Mhi);
                         slo += p0 + p1;
                         shi += p2 + p3;
-                        const int kc = warp * 16 + nt * 8 + 2 * tq;
+                        const int kc = w8 * 32 + nt * 8 + 2 * tq;
                         *reinterpret_cast<uint32_t*>(sP + gq * DG_PP + kc * 2) = pack_bf16(p0, p1);
                         *reinterpret_cast<uint32_t*>(sP + (gq + 8) * DG_PP + kc * 2) = pack_bf16(p2, p3);
                     }
@@ -805,54 +787,45 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     shi += __shfl_xor_sync(0xffffffffu, shi, 1);
                     shi += __shfl_xor_sync(0xffffffffu, shi, 2);
                     if (tq == 0) {
-                        wsum[warp * 16 + gq] = slo;
-                        wsum[warp * 16 + gq + 8] = shi;
+                        wsum[w8 * 16 + gq] = slo;
+                        wsum[w8 * 16 + gq + 8] = shi;
                     }
-                    if (it == 0) DG_STAMP2(22);
-                    __syncthreads();
-                    if (it == 0) DG_STAMP2(23);
-                    // O = P V: warp = (8 output dims, half of the keys)
-                    const int nt8 = warp & 7, kh = warp >> 3;
-                    float oc[4] = {0.f, 0.f, 0.f, 0.f}, oc2[4] = {0.f, 0.f, 0.f, 0.f};      // two independent mma.sync chains
+                    half_sync();
+                    // O = P V: warp w8 = output dims [8 w8, 8 w8 + 8) over all 256 keys (no cross-warp reduction)
+                    float oc[4] = {0.f, 0.f, 0.f, 0.f}, oc2[4] = {0.f, 0.f, 0.f, 0.f};
                     {
                         const int m = lane >> 3, rr = lane & 7;
 #pragma unroll
-                        for (int kk = 0; kk < 8; kk += 2) {
-                            const int key0 = kh * 128 + kk * 16;
+                        for (int kk = 0; kk < 16; kk += 2) {
+                            const int key0 = kk * 16;
                             uint32_t a0, a1, a2, a3, c0, c1, c2, c3, v0, v1, v2, v3;
                             ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + (m >> 1) * 8) * 2), a0, a1, a2, a3);
                             ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + 16 + (m >> 1) * 8) * 2), c0, c1, c2, c3);
-                            ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, nt8), v0, v1, v2, v3);   // keys key0 .. key0+31
+                            ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, w8), v0, v1, v2, v3);   // keys key0 .. key0+31
                             dg_mma16816(oc, a0, a1, a2, a3, v0, v1);
                             dg_mma16816(oc2, c0, c1, c2, c3, v2, v3);
                         }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) oc[i] += oc2[i];
                     }
-                    red[(warp * 16 + gq) * 8 + 2 * tq] = oc[0];
-                    red[(warp * 16 + gq) * 8 + 2 * tq + 1] = oc[1];
-                    red[(warp * 16 + gq + 8) * 8 + 2 * tq] = oc[2];
-                    red[(warp * 16 + gq + 8) * 8 + 2 * tq + 1] = oc[3];
-                    if (it == 0) DG_STAMP2(24);
-                    __syncthreads();
-                    if (it == 0) DG_STAMP2(25);
-                    // the stage is free: fetch the K / V tiles of the task after next
-                    if (is_tma && task + 2 * DG_P < n_tasks) load_kv(l, task + 2 * DG_P, s);
+                    float Llo = 0.f, Lhi = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        Llo += wsum[w * 16 + gq];
+                        Lhi += wsum[w * 16 + gq + 8];
+                    }
                     {
-                        const int r = tid >> 5, dp = tid & 31;     // row, output dim pair
-                        if (r < beam) {
-                            const int w0 = dp >> 2, e = (dp & 3) * 2;
-                            float L = 0.f;
-#pragma unroll
-                            for (int w = 0; w < 16; ++w) L += wsum[w * 16 + r];
-                            const float inv = 1.0f / L;
-                            const float ox = red[(w0 * 16 + r) * 8 + e] + red[((w0 + 8) * 16 + r) * 8 + e];
-                            const float oy = red[(w0 * 16 + r) * 8 + e + 1] + red[((w0 + 8) * 16 + r) * 8 + e + 1];
-                            *reinterpret_cast<uint32_t*>(p.ctx + (size_t)(u * beam + r) * DG_D + h * 64 + 2 * dp) = pack_bf16(ox * inv, oy * inv);
-                        }
+                        const float ilo = 1.0f / Llo, ihi = 1.0f / Lhi;
+                        bf16* dst = p.ctx + (size_t)(u * beam) * DG_D + h * 64 + w8 * 8 + 2 * tq;
+                        if (gq < beam) *reinterpret_cast<uint32_t*>(dst + (size_t)gq * DG_D) = pack_bf16((oc[0] + oc2[0]) * ilo, (oc[1] + oc2[1]) * ilo);
+                        if (gq + 8 < beam) *reinterpret_cast<uint32_t*>(dst + (size_t)(gq + 8) * DG_D) = pack_bf16((oc[2] + oc2[2]) * ihi, (oc[3] + oc2[3]) * ihi);
                     }
-                    __syncthreads();
-                    if (it < 4) DG_STAMP2(2 + 2 * it);
+                    half_sync();      // this half is done with its tile and its scratch
+                    if (w8 == 0 && lane == 0 && i + 3 < n_mine) load_kv(l, j + (i + 3) * DG_P, st);
+                }
+                // stage s was filled once per problem i = s, s + 3, ...
+#pragma unroll
+                for (int st = 0; st < 3; ++st) {
+                    const int uses = (n_mine > st) ? (n_mine - st + 2) / 3 : 0;
+                    par_kx ^= (uint32_t)(uses & 1) << st;
                 }
             }
             gsync([&] {    // cross-attention W_o (whole) and the second half of this CTA's W1 slice stream in while the other CTAs finish

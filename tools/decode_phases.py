@@ -55,11 +55,7 @@ with torch.no_grad():
         sub = allt[:, 200:256]
         def dd(a, b):
             return [int(x) for x in (sub[:, b] - sub[:, a]).tolist()]
-        print('    layer 2 cross-attention, per CTA: wait K/V 1st', dd(0, 1), 'task 1', dd(1, 2), 'wait 2nd', dd(2, 3), 'task 2', dd(3, 4),
-              'wait 3rd', dd(4, 5), 'task 3', dd(5, 6))
         print('    layer 2 W_o block, per CTA: rows in', dd(9, 10), 'GEMM', dd(10, 11))
-        print('    layer 2 cross-attention task 1, per CTA: QK^T+max', dd(1, 20), 'sync', dd(20, 21), 'exp+P', dd(21, 22), 'sync', dd(22, 23), 'PV', dd(23, 24),
-              'sync', dd(24, 25), 'normalise+store', dd(25, 2))
         print('    beam step, per CTA: beam^2 top-k', dd(30, 31)[:12], 'ancestry', dd(31, 32)[:12], 'sync', dd(32, 33)[:12], 'state', dd(33, 35)[:12])
         print('    layer 2 self-attention, warp 0 task 1, per CTA: ancestry+q', dd(39, 40)[:6], 'issue 2 halves', dd(40, 41)[:6], 'wait half 0', dd(41, 42)[:6],
               'compute', dd(42, 43)[:6], 'wait half 1', dd(43, 44)[:6], 'compute', dd(44, 45)[:6], 'wait half 2', dd(45, 46)[:6], 'compute', dd(46, 47)[:6],
