@@ -691,25 +691,26 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             });
             DG_STAMP();
             // ---------------- cross-attention (attention.py:129-141,34-41): one m16 problem per (utterance, head), 3 per CTA at
-            // beam 10.  v18: the two HALVES of the CTA (8 warps each, own named barrier, own scratch) work on different problems
-            // at the same time -- a problem is a chain of short dependent stages (QK^T 1.8 k cycles, exp 1.1 k, PV 1.0 k,
-            // normalise 0.7 k with all 16 warps on it: latency, not throughput), so two chains side by side cost little more
-            // than one.  Tiles of the first three problems are prefetched (both stages + the idle A tile).
+            // beam 10.  A problem is a chain of short dependent stages (with all 16 warps on one problem: QK^T 1.8 k cycles,
+            // exp 1.1 k, PV 1.0 k, normalise 0.7 k -- latency, not throughput), so the CTA works on THREE problems at the same
+            // time: warp groups 0..2 (4 warps each, own named barrier and scratch; v18 ran two halves of 8 warps: 16.5 k ->
+            // 10.5 k cycles per layer) take problems g, g + 3, ...; the tiles of the first three problems are prefetched into
+            // both stages and the idle A tile.  The probabilities of a problem are written over its (dead) K tile.
             {
-                const int hf = warp >> 3, w8 = warp & 7;
-                float* wmax = reinterpret_cast<float*>(sSB + hf * 9472);       // [8 warps][16 rows]
-                float* wsum = wmax + 128;
-                uint8_t* sP = sSB + hf * 9472 + 1024;                          // [16 rows][DG_PP bytes] probabilities (bf16)
-                auto half_sync = [&] { asm volatile("bar.sync %0, 256;" ::"r"(5 + hf) : "memory"); };
+                const int grp = warp >> 2, w4 = warp & 3;
+                float* wmax = reinterpret_cast<float*>(sSB + grp * 1024);      // [4 warps][16 rows]
+                float* wsum = wmax + 64;
+                auto grp_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(5 + grp) : "memory"); };
                 const int gq = lane >> 2, tq = lane & 3;
                 const int n_mine = (n_tasks > j) ? (n_tasks - j + DG_P - 1) / DG_P : 0;      // problems of this CTA
                 DG_STAMP2(0);
-                for (int i = hf; i < n_mine; i += 2) {
+                for (int i = grp; i < n_mine && grp < 3; i += 3) {
                     const int task = j + i * DG_P, st = i % 3;
                     const int u = u0 + task / DG_H, h = task % DG_H;
                     const int kv_len = min(p.mem_len[u], p.T);
-                    const uint8_t* sK = (st < 2) ? sST + st * DG_STAGE : sA;
+                    uint8_t* sK = (st < 2) ? sST + st * DG_STAGE : sA;
                     const uint8_t* sV = sK + 32768;
+                    uint8_t* sP = sK;                                          // [16 rows][DG_PP bytes] probabilities (bf16), after QK^T
                     // Q fragments (rows = hypotheses of the utterance) straight from L2
                     uint32_t qa[4][4];
                     {
@@ -724,10 +725,10 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         }
                     }
                     mbar_wait(&ms.kx_full[st], ((par_kx >> st) & 1) ^ (uint32_t)((i / 3) & 1));
-                    // S = Q K^T for this warp's 32 keys
-                    float sc[4][4];
+                    // S = Q K^T for this warp's 64 keys
+                    float sc[8][4];
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
                     {
@@ -735,8 +736,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                            for (int kq = 0; kq < 2; ++kq) {
-                                const int key = w8 * 32 + kq * 16 + (m >> 1) * 8 + rr;
+                            for (int kq = 0; kq < 4; ++kq) {
+                                const int key = w4 * 64 + kq * 16 + (m >> 1) * 8 + rr;
                                 uint32_t b0, b1, b2, b3;
                                 ldmatrix_x4(smem_u32(sK) + sw128(key, 2 * ks + (m & 1)), b0, b1, b2, b3);
                                 dg_mma16816(sc[2 * kq], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
@@ -747,8 +748,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     const float sl2 = 0.125f * 1.4426950408889634f;
                     float mlo = -INFINITY, mhi = -INFINITY;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        const int k0 = w8 * 32 + nt * 8 + 2 * tq;
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const int k0 = w4 * 64 + nt * 8 + 2 * tq;
                         sc[nt][0] = (k0 < kv_len) ? sc[nt][0] * sl2 : -INFINITY;
                         sc[nt][1] = (k0 + 1 < kv_len) ? sc[nt][1] * sl2 : -INFINITY;
                         sc[nt][2] = (k0 < kv_len) ? sc[nt][2] * sl2 : -INFINITY;
@@ -761,24 +762,24 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                     mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
                     if (tq == 0) {
-                        wmax[w8 * 16 + gq] = mlo;
-                        wmax[w8 * 16 + gq + 8] = mhi;
+                        wmax[w4 * 16 + gq] = mlo;
+                        wmax[w4 * 16 + gq + 8] = mhi;
                     }
-                    half_sync();
+                    grp_sync();       // every warp of the group is also done reading the K tile
                     float Mlo = -INFINITY, Mhi = -INFINITY;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
+                    for (int w = 0; w < 4; ++w) {
                         Mlo = fmaxf(Mlo, wmax[w * 16 + gq]);
                         Mhi = fmaxf(Mhi, wmax[w * 16 + gq + 8]);
                     }
                     float slo = 0.f, shi = 0.f;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
+                    for (int nt = 0; nt < 8; ++nt) {
                         const float p0 = ex2f(sc[nt][0] - Mlo), p1 = ex2f(sc[nt][1] - Mlo);     // exp2(-inf) = 0 for masked keys
                         const float p2 = ex2f(sc[nt][2] - Mhi), p3 = ex2f(sc[nt][3] - Mhi);
                         slo += p0 + p1;
                         shi += p2 + p3;
-                        const int kc = w8 * 32 + nt * 8 + 2 * tq;
+                        const int kc = w4 * 64 + nt * 8 + 2 * tq;
                         *reinterpret_cast<uint32_t*>(sP + gq * DG_PP + kc * 2) = pack_bf16(p0, p1);
                         *reinterpret_cast<uint32_t*>(sP + (gq + 8) * DG_PP + kc * 2) = pack_bf16(p2, p3);
                     }
@@ -787,39 +788,52 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     shi += __shfl_xor_sync(0xffffffffu, shi, 1);
                     shi += __shfl_xor_sync(0xffffffffu, shi, 2);
                     if (tq == 0) {
-                        wsum[w8 * 16 + gq] = slo;
-                        wsum[w8 * 16 + gq + 8] = shi;
+                        wsum[w4 * 16 + gq] = slo;
+                        wsum[w4 * 16 + gq + 8] = shi;
                     }
-                    half_sync();
-                    // O = P V: warp w8 = output dims [8 w8, 8 w8 + 8) over all 256 keys (no cross-warp reduction)
-                    float oc[4] = {0.f, 0.f, 0.f, 0.f}, oc2[4] = {0.f, 0.f, 0.f, 0.f};
+                    grp_sync();
+                    // O = P V: warp w4 = output dims [16 w4, 16 w4 + 16) over all 256 keys (no cross-warp reduction)
+                    float oc[2][4], oc2[2][4];
+#pragma unroll
+                    for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) oc[dn][e] = oc2[dn][e] = 0.f;
                     {
                         const int m = lane >> 3, rr = lane & 7;
 #pragma unroll
                         for (int kk = 0; kk < 16; kk += 2) {
                             const int key0 = kk * 16;
-                            uint32_t a0, a1, a2, a3, c0, c1, c2, c3, v0, v1, v2, v3;
+                            uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
                             ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + (m >> 1) * 8) * 2), a0, a1, a2, a3);
                             ldmatrix_x4(smem_u32(sP) + (uint32_t)(((m & 1) * 8 + rr) * DG_PP + (key0 + 16 + (m >> 1) * 8) * 2), c0, c1, c2, c3);
-                            ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, w8), v0, v1, v2, v3);   // keys key0 .. key0+31
-                            dg_mma16816(oc, a0, a1, a2, a3, v0, v1);
-                            dg_mma16816(oc2, c0, c1, c2, c3, v2, v3);
+#pragma unroll
+                            for (int dn = 0; dn < 2; ++dn) {
+                                uint32_t v0, v1, v2, v3;
+                                ldmatrix_x4_trans(smem_u32(sV) + sw128(key0 + m * 8 + rr, w4 * 2 + dn), v0, v1, v2, v3);   // keys key0 .. key0+31
+                                dg_mma16816(oc[dn], a0, a1, a2, a3, v0, v1);
+                                dg_mma16816(oc2[dn], c0, c1, c2, c3, v2, v3);
+                            }
                         }
                     }
                     float Llo = 0.f, Lhi = 0.f;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
+                    for (int w = 0; w < 4; ++w) {
                         Llo += wsum[w * 16 + gq];
                         Lhi += wsum[w * 16 + gq + 8];
                     }
                     {
                         const float ilo = 1.0f / Llo, ihi = 1.0f / Lhi;
-                        bf16* dst = p.ctx + (size_t)(u * beam) * DG_D + h * 64 + w8 * 8 + 2 * tq;
-                        if (gq < beam) *reinterpret_cast<uint32_t*>(dst + (size_t)gq * DG_D) = pack_bf16((oc[0] + oc2[0]) * ilo, (oc[1] + oc2[1]) * ilo);
-                        if (gq + 8 < beam) *reinterpret_cast<uint32_t*>(dst + (size_t)(gq + 8) * DG_D) = pack_bf16((oc[2] + oc2[2]) * ihi, (oc[3] + oc2[3]) * ihi);
+#pragma unroll
+                        for (int dn = 0; dn < 2; ++dn) {
+                            bf16* dst = p.ctx + (size_t)(u * beam) * DG_D + h * 64 + (w4 * 2 + dn) * 8 + 2 * tq;
+                            if (gq < beam)
+                                *reinterpret_cast<uint32_t*>(dst + (size_t)gq * DG_D) = pack_bf16((oc[dn][0] + oc2[dn][0]) * ilo, (oc[dn][1] + oc2[dn][1]) * ilo);
+                            if (gq + 8 < beam)
+                                *reinterpret_cast<uint32_t*>(dst + (size_t)(gq + 8) * DG_D) = pack_bf16((oc[dn][2] + oc2[dn][2]) * ihi, (oc[dn][3] + oc2[dn][3]) * ihi);
+                        }
                     }
-                    half_sync();      // this half is done with its tile and its scratch
-                    if (w8 == 0 && lane == 0 && i + 3 < n_mine) load_kv(l, j + (i + 3) * DG_P, st);
+                    grp_sync();       // this group is done with its tile and its scratch
+                    if (w4 == 0 && lane == 0 && i + 3 < n_mine) load_kv(l, j + (i + 3) * DG_P, st);
                 }
                 // stage s was filled once per problem i = s, s + 3, ...
 #pragma unroll
