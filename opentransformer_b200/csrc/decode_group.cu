@@ -491,39 +491,36 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             });
             DG_STAMP();
             // ---------------- self-attention over the cached prefix (the cache the reference stubbed out, transformer.py:92-126)
-            // One warp per (hypothesis, head); 8 lanes share one key (lane c reads bytes [16 c, 16 c + 16) of the K and of the V
-            // row: one 128-byte line per 8 lanes, 4 keys per load instruction), the partial dot products meet through 3
-            // shuffles, each of the 4 lane groups keeps an online softmax (m, l, o[8]) over its keys, merged at the end.
+            // by the OWNER of the rows (the CTA that multiplies them by W_o next): all 8 rows x 4 heads of the CTA at the same
+            // time.  Warp w = row w / 2 and two of its heads, one per HALF-warp (v19 ran the 32 problems in two rounds of 16,
+            // one warp each: every round paid the whole latency chain ancestry -> copies -> wait -> softmax merge; 11 k cycles
+            // at step 5).  Within a half-warp 8 lanes share one key (lane c holds bytes [16 c, 16 c + 16) of the head's K / V
+            // slice), 2 keys per instruction, the partial dot products meet through 3 shuffles, each of the 2 lane groups keeps an
+            // online softmax (m, l, o[8]) over its keys, merged at the end.
+            // The cached K / V rows of the prefix (512 bytes per position: all four heads; scattered by the ancestry table) are
+            // fetched by the TMA engine -- ONE bulk copy per row and position, shared by the two warps of the row, 8 positions
+            // per half-buffer, two halves in flight -- and the dot products read shared memory.
+            // History: v13 gathered with 16-byte LDGs, 16 per lane in flight: 9.5 B/clk per SM at step 50 (44 k cycles per
+            // layer) whatever the cache policy.  v14 issued one 128-byte bulk copy per (position, head): the stamps showed the
+            // ISSUE as the limit -- an SM starts one bulk copy per ~6.5 cycles (41 k cycles per layer at step 50); 512-byte
+            // copies need a quarter of the operations (v15: 26 k).
             {
                 const int nkeys = step + 1;
                 const int* an_base = p.st.anc + (size_t)(step & 1) * N * Lmax;
-                int* an_w = reinterpret_cast<int*>(sSB) + warp * 256;          // this warp's two ancestry rows (<= 128 positions each)
-                // the four warps (heads) of a row share one staging area: [2 halves][K 16 x 512 B | V 16 x 512 B] = 32 KB per row,
-                // four rows at a time = both stages; one mbarrier per (row, half), one named barrier per row
-                const int rg = warp >> 2, hw = warp & 3;
-                uint8_t* kvst = sST + rg * 32768;
-                uint64_t* kvb = &ms.kv_full[rg * 2];
-                auto row_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(rg + 1) : "memory"); };
+                int* an_s = reinterpret_cast<int*>(sSB) + warp * 128;          // this warp's ancestry row (<= 128 positions)
+                const int rl = warp >> 1, wr = warp & 1;                       // row of the block, which of its two warps
+                const int hl = lane >> 4, g2 = (lane >> 3) & 1, c8 = lane & 7;
+                const int h = wr * 2 + hl;                                     // head of this half-warp
+                uint8_t* kvst = sST + rl * 16384;                              // [2 halves][K 8 x 512 B | V 8 x 512 B] per row: 8 rows = both stages
+                uint64_t* kvb = &ms.kv_full[rl * 2];
+                auto row_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(rl + 1) : "memory"); };
                 fence_proxy_async_all();      // K / V rows written with ordinary stores (this step's by other CTAs, behind the barrier) are read by the async proxy
-                const int g4 = lane >> 3, c8 = lane & 7;
-                // v9: the hypotheses [8 j, 8 j + 8) of the tile are attended by their OWNER (the CTA that multiplies them by W_o
-                // next): 32 (row, head) problems per CTA -- every warp exactly two problems (v8 dealt the 480
-                // problems round-robin: some warps two, some one, then a group barrier and a trip through global memory for the
-                // context rows).  The 8 rows belong to at most two utterances, whose hypotheses share most of their ancestors:
-                // the (position, slot) lines they have in common are fetched once and hit L1 for the other rows.
+                const int r = j * 8 + rl;
+                const int n = row0 + r;
                 DG_STAMP2(39);
-                for (int t2 = 0; t2 < 2; ++t2) {
-                    int* an_s = an_w;      // (requesting the ancestry rows / queries of both problems up front was tried: no gain)
-                    // warp w: head w & 3 of row (w >> 2) + 4 t2 -- the four heads of a row run side by side, so the four 128-byte
-                    // pieces of a cached (position, slot) row are requested together (one 512-byte DRAM burst)
-                    const int rl = rg + 4 * t2, h = hw;
-                    const int r = j * 8 + rl;
-                    const int n = row0 + r;
-                    if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
-                        if (g4 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
-                        continue;
-                    }
-                    __syncwarp();
+                if (r >= nrows) {      // dead row of the tile (warp-uniform): zeros, so that the projection below stays finite
+                    if (g2 == 0) *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = make_uint4(0, 0, 0, 0);
+                } else {
                     for (int s0 = lane; s0 < step; s0 += 32) an_s[s0] = an_base[(size_t)n * Lmax + s0];
                     float qf[8];
                     {
@@ -535,44 +532,37 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     __syncwarp();
                     float m = -INFINITY, lsum = 0.f;
                     float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    // v15: the cached K / V rows of the prefix (512 bytes per position: all four heads; scattered by the ancestry table)
-                    // are fetched by the TMA engine -- ONE bulk copy per row and position, shared by the four warps (heads) of the
-                    // row, 16 positions per half, two halves in flight -- and the dot products read shared memory.
-                    // History: v13 gathered with 16-byte LDGs, 16 per lane in flight: 9.5 B/clk per SM at step 50 (44 k cycles per
-                    // layer) whatever the cache policy.  v14 issued one 128-byte bulk copy per (position, head): the stamps showed the
-                    // ISSUE as the limit -- 3.3 k cycles per 32 copies with 16 warps issuing, i.e. the SM starts one bulk copy per
-                    // ~6.5 cycles (41 k cycles per layer at step 50).  512-byte copies need a quarter of the operations.
-                    const int nh = (nkeys + 15) >> 4;
+                    const int nh = (nkeys + 7) >> 3;
                     auto issue = [&](int hh) {
-                        const int kk0 = hh * 16, buf = hh & 1;
-                        const int nk = min(16, nkeys - kk0);
-                        if (hw == 0 && lane == 0) mbar_arrive_expect_tx(&kvb[buf], (uint32_t)(nk * 1024));
+                        const int kk0 = hh * 8, buf = hh & 1;
+                        const int nk = min(8, nkeys - kk0);
+                        if (wr == 0 && lane == 0) mbar_arrive_expect_tx(&kvb[buf], (uint32_t)(nk * 1024));
                         if (lane < 8) {
-                            const int c = hw * 8 + lane;               // 32 copies per half: 16 K rows, 16 V rows; 8 per warp
-                            const int key = c & 15, isv = c >> 4;
+                            const int c = wr * 8 + lane;               // 16 copies per half: 8 K rows, 8 V rows; 8 per warp
+                            const int key = c & 7, isv = c >> 3;
                             if (key < nk) {
                                 const int sidx = kk0 + key;
                                 const int slot = (sidx < step) ? an_s[sidx] : n;
                                 const bf16* src = (isv ? p.vc : p.kc) + kv_off(l, sidx, slot);
-                                bulk_g2s(kvst + buf * 16384 + isv * 8192 + key * 512, src, 512, &kvb[buf]);
+                                bulk_g2s(kvst + buf * 8192 + isv * 4096 + key * 512, src, 512, &kvb[buf]);
                             }
                         }
                     };
-                    row_sync();        // the four warps are done with the staging area of the previous row
+                    DG_STAMP2(40);
                     issue(0);
                     if (nh > 1) issue(1);
-                    if (t2 == 0) DG_STAMP2(41);
+                    DG_STAMP2(41);
                     for (int hh = 0; hh < nh; ++hh) {
-                        const int buf = hh & 1, k0 = hh * 16;
+                        const int buf = hh & 1, k0 = hh * 8;
                         mbar_wait(&kvb[buf], (par_kvw >> buf) & 1);
                         par_kvw ^= (1u << buf);
-                        if (t2 == 0 && hh < 4) DG_STAMP2(42 + 2 * hh);
-                        const uint8_t* kb_ = kvst + buf * 16384 + h * 128 + c8 * 16;
+                        if (hh < 4) DG_STAMP2(42 + 2 * hh);
+                        const uint8_t* kb_ = kvst + buf * 8192 + h * 128 + c8 * 16;
                         uint4 ku[4], vu[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            ku[u] = *reinterpret_cast<const uint4*>(kb_ + (4 * u + g4) * 512);
-                            vu[u] = *reinterpret_cast<const uint4*>(kb_ + 8192 + (4 * u + g4) * 512);
+                            ku[u] = *reinterpret_cast<const uint4*>(kb_ + (2 * u + g2) * 512);
+                            vu[u] = *reinterpret_cast<const uint4*>(kb_ + 4096 + (2 * u + g2) * 512);
                         }
                         float sc[4];
                         float mb = m;
@@ -583,7 +573,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             d += __shfl_xor_sync(0xffffffffu, d, 1);
                             d += __shfl_xor_sync(0xffffffffu, d, 2);
                             d += __shfl_xor_sync(0xffffffffu, d, 4);
-                            sc[u] = (k0 + 4 * u + g4 < nkeys) ? d : -INFINITY;      // rows beyond the prefix hold stale bytes: masked here
+                            sc[u] = (k0 + 2 * u + g2 < nkeys) ? d : -INFINITY;      // rows beyond the prefix hold stale bytes: masked here
                             mb = fmaxf(mb, sc[u]);
                         }
                         if (mb != -INFINITY) {
@@ -605,26 +595,23 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                             m = mb;
                         }
                         if (hh + 2 < nh) {
-                            row_sync();    // all four heads are done with this half
+                            row_sync();    // both warps (all four heads) are done with this half
                             issue(hh + 2);
                         }
-                        if (t2 == 0 && hh < 4) DG_STAMP2(43 + 2 * hh);
+                        if (hh < 4) DG_STAMP2(43 + 2 * hh);
                     }
-                    if (t2 == 0) DG_STAMP2(50);
-                    // merge the 4 lane groups (lanes c8, c8 + 8, c8 + 16, c8 + 24 hold the same output dims)
-                    float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+                    DG_STAMP2(50);
+                    // merge the 2 lane groups of the half-warp (lanes c8 and c8 + 8 hold the same output dims)
+                    const float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
                     const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
                     lsum *= w;
                     lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
-                    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         o[q] *= w;
                         o[q] += __shfl_xor_sync(0xffffffffu, o[q], 8);
-                        o[q] += __shfl_xor_sync(0xffffffffu, o[q], 16);
                     }
-                    if (g4 == 0) {
+                    if (g2 == 0) {
                         const float inv = 1.0f / lsum;
                         uint4 ou;
                         ou.x = pack_bf16(o[0] * inv, o[1] * inv);
@@ -633,7 +620,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                         ou.w = pack_bf16(o[6] * inv, o[7] * inv);
                         *reinterpret_cast<uint4*>(sA0 + a_off(rl, h * 8 + c8)) = ou;      // context row -> A operand of W_o
                     }
-                    if (t2 == 0) DG_STAMP2(51);
+                    DG_STAMP2(51);
                 }
             }
             __syncthreads();
