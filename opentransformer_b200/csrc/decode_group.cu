@@ -514,7 +514,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 uint8_t* kvst = sST + rl * 16384;                              // [2 halves][K 8 x 512 B | V 8 x 512 B] per row: 8 rows = both stages
                 uint64_t* kvb = &ms.kv_full[rl * 2];
                 auto row_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(rl + 1) : "memory"); };
-                fence_proxy_async_all();      // K / V rows written with ordinary stores (this step's by other CTAs, behind the barrier) are read by the async proxy
+                // (the K / V rows of this step were written with ordinary stores by other CTAs; the writer side of gsync executes
+                // fence.proxy.async before its release, the copies below read L2: no further proxy fence here -- it cost every warp
+                // a MEMBAR-class stall per layer)
                 const int r = j * 8 + rl;
                 const int n = row0 + r;
                 DG_STAMP2(39);
