@@ -103,6 +103,9 @@ __device__ __forceinline__ void dg_mma16816(float (&c)[4], uint32_t a0, uint32_t
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -325,10 +328,16 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     uint8_t* sA0 = sSB + 16384;                       // attention output rows (A operand of W_o)
     uint8_t* sA1 = sSB + 20480;                       // LayerNorm-1 output rows: A operand of the query projection, residual of W_o #2
     auto a_off = [](int r, int chunk) { return (uint32_t)(r * 512 + ((chunk ^ (r & 7)) << 4)); };
-    const int er = lane >> 2;                         // row of the block held by this thread's accumulator fragment
-    const int ec = warp * 16 + 2 * (lane & 3);        // its columns: ec + 8 nt + {0, 1}, nt = 0, 1
-    const bool elive = j * 8 + er < nrows;
-    const size_t erow_g = (size_t)(row0 + j * 8 + er) * DG_D;
+    // v22: the product is formed TRANSPOSED, out^T[256 features x 8 rows] = W[256 x 256] . X^T: the weight tile is the m16
+    // operand (16 output features per warp), the 8 activation rows are the n8 operand -- no padding rows: 256 mma.sync per
+    // projection and CTA instead of 512 (the m16n8k16 path runs at ~16 cycles per instruction and SM sub-partition, which
+    // is what bounded the projections: 2.1 k cycles each).  Accumulator fragment of a thread: features ef0 and ef0 + 8,
+    // rows era and era + 1.
+    const int ef0 = warp * 16 + (lane >> 2);          // first feature of this thread's accumulator fragment (second: + 8)
+    const int era = 2 * (lane & 3);                   // first row of the block (second: + 1)
+    const bool live_a = j * 8 + era < nrows, live_b = j * 8 + era + 1 < nrows;
+    const size_t grow_a = (size_t)(row0 + j * 8 + era) * DG_D, grow_b = grow_a + DG_D;
+    auto a_at = [&](uint8_t* A, int r, int f) { return reinterpret_cast<bf16*>(A + a_off(r, f >> 3) + (f & 7) * 2); };
     auto load_rows = [&](const bf16* src, uint8_t* dstA) {    // this CTA's 8 rows of a [N, 256] bf16 buffer -> swizzled smem
         if (tid < 256) {
             const int r = tid >> 5, ch = tid & 31;
@@ -337,76 +346,79 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             *reinterpret_cast<uint4*>(dstA + a_off(r, ch)) = v;
         }
     };
-    // acc[nt][0..1] = sum_k A[er][k] * W[ec + 8 nt + {0,1}][k]; warp w owns output features [16 w, 16 w + 16)
-    auto rowgemm = [&](const uint8_t* A, uint64_t* full, uint32_t par, auto kb_addr, float (&acc)[2][4]) {
+    // acc[0..1] = out[era + {0,1}][ef0], acc[2..3] = out[era + {0,1}][ef0 + 8]; warp w owns output features [16 w, 16 w + 16)
+    auto rowgemm = [&](const uint8_t* A, uint64_t* full, uint32_t par, auto kb_addr, float (&acc)[4]) {
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-        float acc2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int i = 0; i < 4; ++i) acc[i] = 0.f;
         const int m = lane >> 3, rr = lane & 7;
-        const uint32_t zaddr = smem_u32(ms.zero16), abase = smem_u32(A);
+        const uint32_t abase = smem_u32(A);
 #pragma unroll 1
         for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&full[kb], (par >> kb) & 1);
             const uint32_t wb = smem_u32(kb_addr(kb));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
-                // A matrices: (rows 0-7, k lo) (rows 8-15, k lo) (rows 0-7, k hi) (rows 8-15, k hi); rows 8-15 read the zero chunk
-                ldmatrix_x4((m & 1) ? zaddr : abase + a_off(rr, kb * 8 + ks * 2 + (m >> 1)), a0, a1, a2, a3);
-                ldmatrix_x4(wb + sw128(warp * 16 + (m >> 1) * 8 + rr, 2 * ks + (m & 1)), b0, b1, b2, b3);
-                // a dependent mma.sync costs ~125 cycles on this part (measured: 16 chained k-steps = 2.1 k cycles): even and odd
-                // k-steps accumulate separately, four independent chains of 8 instead of two of 16
-                if (ks & 1) {
-                    dg_mma16816(acc2[0], a0, a1, a2, a3, b0, b1);
-                    dg_mma16816(acc2[1], a0, a1, a2, a3, b2, b3);
-                } else {
-                    dg_mma16816(acc[0], a0, a1, a2, a3, b0, b1);
-                    dg_mma16816(acc[1], a0, a1, a2, a3, b2, b3);
-                }
+                uint32_t a0, a1, a2, a3, b0, b1;
+                // weight fragment (m16 x k16): (features 0-7, k lo) (features 8-15, k lo) (features 0-7, k hi) (features 8-15, k hi)
+                ldmatrix_x4(wb + sw128(warp * 16 + (m & 1) * 8 + rr, 2 * ks + (m >> 1)), a0, a1, a2, a3);
+                // activation fragment (k16 x n8): (rows 0-7, k lo) (rows 0-7, k hi); lanes 16-31 pass valid but unused addresses
+                ldmatrix_x2(abase + a_off(rr, kb * 8 + ks * 2 + (m & 1)), b0, b1);
+                if (ks & 1) dg_mma16816(acc2, a0, a1, a2, a3, b0, b1);      // two independent accumulation chains
+                else dg_mma16816(acc, a0, a1, a2, a3, b0, b1);
             }
         }
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] += acc2[nt][i];
+        for (int i = 0; i < 4; ++i) acc[i] += acc2[i];
     };
-    // LayerNorm of the 8 rows held as v[nt][e] (fp32: projection + bias + residual), statistics across the 16 warps
-    auto row_ln = [&](float (&v)[2][2], const float* gamma, const float* beta) {
+    // LayerNorm of the 8 rows held as v[0..3] = (row a, f0) (row b, f0) (row a, f0 + 8) (row b, f0 + 8) (fp32: projection + bias
+    // + residual): statistics over the 8 lane groups of a warp (shuffles) and the 16 warps (shared memory)
+    auto row_ln = [&](float (&v)[4], const float* gamma, const float* beta) {
         float* rsum = ms.c_val;                       // [16 warps][8 rows]
-        float s = (v[0][0] + v[0][1]) + (v[1][0] + v[1][1]);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) rsum[warp * 8 + er] = s;
-        __syncthreads();
-        float mean = 0.f;
+        float sa = v[0] + v[2], sb = v[1] + v[3];
 #pragma unroll
-        for (int w = 0; w < 16; ++w) mean += rsum[w * 8 + er];
-        mean *= (1.0f / DG_D);
-        float q = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                v[nt][e] -= mean;
-                q += v[nt][e] * v[nt][e];
-            }
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        __syncthreads();
-        if ((lane & 3) == 0) rsum[warp * 8 + er] = q;
-        __syncthreads();
-        float var = 0.f;
-#pragma unroll
-        for (int w = 0; w < 16; ++w) var += rsum[w * 8 + er];
-        const float rstd = rsqrtf(var * (1.0f / DG_D) + p.eps);
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const float2 gm = *reinterpret_cast<const float2*>(gamma + ec + 8 * nt), bt = *reinterpret_cast<const float2*>(beta + ec + 8 * nt);
-            v[nt][0] = v[nt][0] * rstd * gm.x + bt.x;
-            v[nt][1] = v[nt][1] * rstd * gm.y + bt.y;
+        for (int o = 4; o < 32; o <<= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
         }
+        if (lane < 4) {
+            rsum[warp * 8 + era] = sa;
+            rsum[warp * 8 + era + 1] = sb;
+        }
+        __syncthreads();
+        float ma = 0.f, mb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            ma += rsum[w * 8 + era];
+            mb += rsum[w * 8 + era + 1];
+        }
+        ma *= (1.0f / DG_D);
+        mb *= (1.0f / DG_D);
+        v[0] -= ma; v[2] -= ma; v[1] -= mb; v[3] -= mb;
+        float qa = v[0] * v[0] + v[2] * v[2], qb = v[1] * v[1] + v[3] * v[3];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            qa += __shfl_xor_sync(0xffffffffu, qa, o);
+            qb += __shfl_xor_sync(0xffffffffu, qb, o);
+        }
+        __syncthreads();
+        if (lane < 4) {
+            rsum[warp * 8 + era] = qa;
+            rsum[warp * 8 + era + 1] = qb;
+        }
+        __syncthreads();
+        float va = 0.f, vb = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+            va += rsum[w * 8 + era];
+            vb += rsum[w * 8 + era + 1];
+        }
+        const float ra = rsqrtf(va * (1.0f / DG_D) + p.eps), rb = rsqrtf(vb * (1.0f / DG_D) + p.eps);
+        const float g0 = gamma[ef0], g1 = gamma[ef0 + 8], t0 = beta[ef0], t1 = beta[ef0 + 8];
+        v[0] = v[0] * ra * g0 + t0;
+        v[1] = v[1] * rb * g0 + t0;
+        v[2] = v[2] * ra * g1 + t1;
+        v[3] = v[3] * rb * g1 + t1;
     };
 
     // ---- small GEMM: acc[128 x nB] = A[128 x 256] * Bslice^T, B slice prefetched into sSB (kb_full).  a_map != null: A is fetched
@@ -636,41 +648,50 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // (attention.py:44, transformer.py:54-56, attention.py:128), all inside the owning CTA
             {
                 DG_STAMP2(9);
-                uint32_t xres[2] = {0u, 0u};
-                if (elive) {
-                    xres[0] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec);
-                    xres[1] = *reinterpret_cast<const uint32_t*>(p.xbuf + erow_g + ec + 8);
+                float xres[4] = {0.f, 0.f, 0.f, 0.f};      // residual = the layer input (own rows, written by this CTA)
+                if (live_a) {
+                    xres[0] = __bfloat162float(p.xbuf[grow_a + ef0]);
+                    xres[2] = __bfloat162float(p.xbuf[grow_a + ef0 + 8]);
+                }
+                if (live_b) {
+                    xres[1] = __bfloat162float(p.xbuf[grow_b + ef0]);
+                    xres[3] = __bfloat162float(p.xbuf[grow_b + ef0 + 8]);
                 }
                 __syncthreads();
                 DG_STAMP2(10);
-                float acc[2][4];
+                float acc[4];
                 rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
                 par_pw ^= 0xF;
                 __syncthreads();      // every warp is done with W_o: its first half makes room for the second half of W_q
                 DG_STAMP2(11);
                 if (is_tma)
                     for (int kb = 2; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sA + (kb - 2) * 32768);
-                float v[2][2];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const float2 bb = *reinterpret_cast<const float2*>(ly.bo + ec + 8 * nt);
-                    const float2 xr = unpack_bf16(xres[nt]);
-                    v[nt][0] = acc[nt][0] + bb.x + xr.x;
-                    v[nt][1] = acc[nt][1] + bb.y + xr.y;
+                float v[4];
+                {
+                    const float b0 = ly.bo[ef0], b1 = ly.bo[ef0 + 8];
+                    v[0] = acc[0] + b0 + xres[0];
+                    v[1] = acc[1] + b0 + xres[1];
+                    v[2] = acc[2] + b1 + xres[2];
+                    v[3] = acc[3] + b1 + xres[3];
                 }
                 row_ln(v, ly.g1, ly.be1);
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-                    *reinterpret_cast<uint32_t*>(sA1 + a_off(er, (ec + 8 * nt) >> 3) + ((ec + 8 * nt) & 7) * 2) = pack_bf16(v[nt][0], v[nt][1]);
+                *a_at(sA1, era, ef0) = __float2bfloat16(v[0]);
+                *a_at(sA1, era + 1, ef0) = __float2bfloat16(v[1]);
+                *a_at(sA1, era, ef0 + 8) = __float2bfloat16(v[2]);
+                *a_at(sA1, era + 1, ef0 + 8) = __float2bfloat16(v[3]);
                 __syncthreads();
                 DG_STAMP();   // W_o + LN1
                 rowgemm(sA1, ms.pq_full, par_pq, [&](int kb) { return kb < 2 ? sST + DG_STAGE + kb * 32768 : sA + (kb - 2) * 32768; }, acc);
                 par_pq ^= 0xF;
-                if (elive) {
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const float2 bb = *reinterpret_cast<const float2*>(ly.bq + ec + 8 * nt);
-                        *reinterpret_cast<uint32_t*>(p.q2 + erow_g + ec + 8 * nt) = pack_bf16(acc[nt][0] + bb.x, acc[nt][1] + bb.y);
+                {
+                    const float b0 = ly.bq[ef0], b1 = ly.bq[ef0 + 8];
+                    if (live_a) {
+                        p.q2[grow_a + ef0] = __float2bfloat16(acc[0] + b0);
+                        p.q2[grow_a + ef0 + 8] = __float2bfloat16(acc[2] + b1);
+                    }
+                    if (live_b) {
+                        p.q2[grow_b + ef0] = __float2bfloat16(acc[1] + b0);
+                        p.q2[grow_b + ef0 + 8] = __float2bfloat16(acc[3] + b1);
                     }
                 }
             }
@@ -841,23 +862,27 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             {
                 load_rows(p.ctx, sA0);
                 __syncthreads();
-                float acc[2][4];
+                float acc[4];
                 rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
                 par_pw ^= 0xF;
                 __syncthreads();      // stage 0 (second half of W_o) is free: first half of W1
                 if (is_tma) load_w1(l, 0);
-                float v[2][2];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    const float2 bb = *reinterpret_cast<const float2*>(ly.bo2 + ec + 8 * nt);
-                    const float2 xr = unpack_bf16(*reinterpret_cast<const uint32_t*>(sA1 + a_off(er, (ec + 8 * nt) >> 3) + ((ec + 8 * nt) & 7) * 2));
-                    v[nt][0] = acc[nt][0] + bb.x + xr.x;
-                    v[nt][1] = acc[nt][1] + bb.y + xr.y;
+                float v[4];
+                {
+                    const float b0 = ly.bo2[ef0], b1 = ly.bo2[ef0 + 8];      // residual x1 is still in shared memory
+                    v[0] = acc[0] + b0 + __bfloat162float(*a_at(sA1, era, ef0));
+                    v[1] = acc[1] + b0 + __bfloat162float(*a_at(sA1, era + 1, ef0));
+                    v[2] = acc[2] + b1 + __bfloat162float(*a_at(sA1, era, ef0 + 8));
+                    v[3] = acc[3] + b1 + __bfloat162float(*a_at(sA1, era + 1, ef0 + 8));
                 }
                 row_ln(v, ly.g2, ly.be2);
-                if (elive) {
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) *reinterpret_cast<uint32_t*>(p.x2buf + erow_g + ec + 8 * nt) = pack_bf16(v[nt][0], v[nt][1]);
+                if (live_a) {
+                    p.x2buf[grow_a + ef0] = __float2bfloat16(v[0]);
+                    p.x2buf[grow_a + ef0 + 8] = __float2bfloat16(v[2]);
+                }
+                if (live_b) {
+                    p.x2buf[grow_b + ef0] = __float2bfloat16(v[1]);
+                    p.x2buf[grow_b + ef0 + 8] = __float2bfloat16(v[3]);
                 }
             }
             gsync(nop);
