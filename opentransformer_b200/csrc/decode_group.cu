@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     };
     // LayerNorm of the 8 rows held as v[0..3] = (row a, f0) (row b, f0) (row a, f0 + 8) (row b, f0 + 8) (fp32: projection + bias
     // + residual): statistics over the 8 lane groups of a warp (shuffles) and the 16 warps (shared memory)
-    auto row_ln = [&](float (&v)[4], const float* gamma, const float* beta) {
+    auto row_ln = [&](float (&v)[4], float g0, float g1, float t0, float t1) {
         float* rsum = ms.c_val;                       // [16 warps][8 rows]
         float sa = v[0] + v[2], sb = v[1] + v[3];
 #pragma unroll
@@ -414,7 +414,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             vb += rsum[w * 8 + era + 1];
         }
         const float ra = rsqrtf(va * (1.0f / DG_D) + p.eps), rb = rsqrtf(vb * (1.0f / DG_D) + p.eps);
-        const float g0 = gamma[ef0], g1 = gamma[ef0 + 8], t0 = beta[ef0], t1 = beta[ef0 + 8];
         v[0] = v[0] * ra * g0 + t0;
         v[1] = v[1] * rb * g0 + t0;
         v[2] = v[2] * ra * g1 + t1;
@@ -648,6 +647,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // (attention.py:44, transformer.py:54-56, attention.py:128), all inside the owning CTA
             {
                 DG_STAMP2(9);
+                // parameters of this thread's two features, requested before the GEMM (behind it each was an exposed L2 round trip)
+                const float pb0 = ly.bo[ef0], pb1 = ly.bo[ef0 + 8], pg0 = ly.g1[ef0], pg1 = ly.g1[ef0 + 8], pt0 = ly.be1[ef0], pt1 = ly.be1[ef0 + 8];
+                const float qb0 = ly.bq[ef0], qb1 = ly.bq[ef0 + 8];
                 float xres[4] = {0.f, 0.f, 0.f, 0.f};      // residual = the layer input (own rows, written by this CTA)
                 if (live_a) {
                     xres[0] = __bfloat162float(p.xbuf[grow_a + ef0]);
@@ -668,13 +670,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                     for (int kb = 2; kb < 4; ++kb) load_proj_kb(maps + l * 6 + 2, ms.pq_full, kb, sA + (kb - 2) * 32768);
                 float v[4];
                 {
-                    const float b0 = ly.bo[ef0], b1 = ly.bo[ef0 + 8];
+                    const float b0 = pb0, b1 = pb1;
                     v[0] = acc[0] + b0 + xres[0];
                     v[1] = acc[1] + b0 + xres[1];
                     v[2] = acc[2] + b1 + xres[2];
                     v[3] = acc[3] + b1 + xres[3];
                 }
-                row_ln(v, ly.g1, ly.be1);
+                row_ln(v, pg0, pg1, pt0, pt1);
                 *a_at(sA1, era, ef0) = __float2bfloat16(v[0]);
                 *a_at(sA1, era + 1, ef0) = __float2bfloat16(v[1]);
                 *a_at(sA1, era, ef0 + 8) = __float2bfloat16(v[2]);
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 rowgemm(sA1, ms.pq_full, par_pq, [&](int kb) { return kb < 2 ? sST + DG_STAGE + kb * 32768 : sA + (kb - 2) * 32768; }, acc);
                 par_pq ^= 0xF;
                 {
-                    const float b0 = ly.bq[ef0], b1 = ly.bq[ef0 + 8];
+                    const float b0 = qb0, b1 = qb1;
                     if (live_a) {
                         p.q2[grow_a + ef0] = __float2bfloat16(acc[0] + b0);
                         p.q2[grow_a + ef0 + 8] = __float2bfloat16(acc[2] + b1);
@@ -861,6 +863,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // -> x2 (bf16, global: A operand of the feed-forward of every CTA and residual of its reduction)
             {
                 load_rows(p.ctx, sA0);
+                const float pb0 = ly.bo2[ef0], pb1 = ly.bo2[ef0 + 8], pg0 = ly.g2[ef0], pg1 = ly.g2[ef0 + 8], pt0 = ly.be2[ef0], pt1 = ly.be2[ef0 + 8];
                 __syncthreads();
                 float acc[4];
                 rowgemm(sA0, ms.pw_full, par_pw, [&](int kb) { return kb < 2 ? sA + kb * 32768 : sST + (kb - 2) * 32768; }, acc);
@@ -869,13 +872,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 if (is_tma) load_w1(l, 0);
                 float v[4];
                 {
-                    const float b0 = ly.bo2[ef0], b1 = ly.bo2[ef0 + 8];      // residual x1 is still in shared memory
+                    const float b0 = pb0, b1 = pb1;      // residual x1 is still in shared memory
                     v[0] = acc[0] + b0 + __bfloat162float(*a_at(sA1, era, ef0));
                     v[1] = acc[1] + b0 + __bfloat162float(*a_at(sA1, era + 1, ef0));
                     v[2] = acc[2] + b1 + __bfloat162float(*a_at(sA1, era, ef0 + 8));
                     v[3] = acc[3] + b1 + __bfloat162float(*a_at(sA1, era + 1, ef0 + 8));
                 }
-                row_ln(v, ly.g2, ly.be2);
+                row_ln(v, pg0, pg1, pt0, pt1);
                 if (live_a) {
                     p.x2buf[grow_a + ef0] = __float2bfloat16(v[0]);
                     p.x2buf[grow_a + ef0 + 8] = __float2bfloat16(v[2]);
@@ -1000,6 +1003,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int r = j * 8 + rr;
                 const bool live = r < nrows;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 gm = *reinterpret_cast<const float4*>(ly.g3 + c4 * 4), bt = *reinterpret_cast<const float4*>(ly.be3 + c4 * 4);
                 if (live) {
                     const float4* src = reinterpret_cast<const float4*>(p.part) + (size_t)g * part_slab + (size_t)c4 * 128 + r;
 #pragma unroll
@@ -1036,7 +1040,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
 #pragma unroll
                     for (int w = 0; w < 16; ++w) var += rsum[w * 8 + rr];
                     const float rstd = rsqrtf(var * (1.0f / DG_D) + p.eps);
-                    const float4 gm = *reinterpret_cast<const float4*>(ly.g3 + c4 * 4), bt = *reinterpret_cast<const float4*>(ly.be3 + c4 * 4);
                     uint2 o;
                     o.x = pack_bf16(a * rstd * gm.x + bt.x, b * rstd * gm.y + bt.y);
                     o.y = pack_bf16(cc * rstd * gm.z + bt.z, d * rstd * gm.w + bt.w);
@@ -1139,16 +1142,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             // The rows of the utterance are gathered from the [column group][row] logits by TMA: box = (the `beam` consecutive
             // 16-byte pieces of one column group) x 64 column groups, ~17 boxes per utterance, issued by one thread (v8 used
             // 10 k 16-byte cp.async: 11.7 k cycles; the A tile and both weight stages are idle: 192 KB).  In shared memory the
-            // piece of (column group c, row r) sits at float4 index c * beam + r.  A vocabulary x beam that does not fit is read
+            // piece of (column group c, row r) sits at float4 index c * (beam | 1) + r.  A vocabulary x beam that does not fit is read
             // in place (element stride 128 x 16 bytes).
             const int nbox = (ldv4 + 63) >> 6;
-            const bool staged = (size_t)nbox * 64 * beam * 16 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
+            const int bpad = beam | 1;      // rows fetched per column group: an ODD number of 16-byte pieces keeps the float4 reads of
+                                            // a warp (stride bpad x 16 bytes between lanes) free of bank conflicts; the extra row is ignored
+            const bool staged = (size_t)nbox * 64 * bpad * 16 <= (size_t)(DG_A_BYTES + 2 * DG_STAGE);
             const int lr0 = ul * beam;                               // first row of the utterance inside the group tile
             if (staged) {
                 if (is_tma) {
-                    mbar_arrive_expect_tx(&ms.lg_full, (uint32_t)(nbox * 64 * beam * 16));
+                    mbar_arrive_expect_tx(&ms.lg_full, (uint32_t)(nbox * 64 * bpad * 16));
                     for (int bx = 0; bx < nbox; ++bx)
-                        tma_load_2d(smem + (size_t)bx * 64 * beam * 16, map_lg, &ms.lg_full, lr0 * 4, g * ldv4 + bx * 64);
+                        tma_load_2d(smem + (size_t)bx * 64 * bpad * 16, map_lg, &ms.lg_full, lr0 * 4, g * ldv4 + bx * 64);
                 }
                 mbar_wait(&ms.lg_full, par_lg);
                 par_lg ^= 1;
@@ -1159,7 +1164,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
                 const int pf_flag = p.st.flag[n];                    // needed after the ranking: their L2 round trips overlap the passes
                 const float pf_score = p.st.scores[n];
                 const float4* x4 = staged ? reinterpret_cast<const float4*>(smem) + r : reinterpret_cast<const float4*>(lg4 + lr0 + r);
-                const int xs4 = staged ? beam : 128;                 // float4 stride between consecutive column groups
+                const int xs4 = staged ? bpad : 128;                 // float4 stride between consecutive column groups
                 auto xel = [&](int c) { return reinterpret_cast<const float*>(x4 + (size_t)(c >> 2) * xs4)[c & 3]; };
                 const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                 float2* cand = reinterpret_cast<float2*>(sSB) + warp * 128;      // (logit, token id as float bits) x 128 per row
@@ -1474,7 +1479,7 @@ const char* decode_group_launch(cudaStream_t st, const MegaParams& mp, void* wor
     if ((err = encode_tmap_2d(&h_maps[nm + 2], mp.kvx, 2 * DG_D, (uint64_t)mp.n_layers * mp.B * mp.T, 2 * DG_D, 64, 256))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 3], p.xbuf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
     if ((err = encode_tmap_2d(&h_maps[nm + 4], p.x2buf, DG_D, (uint64_t)N + 128, DG_D, 64, 128))) return err;
-    if ((err = encode_tmap_2d_f32(&h_maps[nm + 5], p.logits, 512, (uint64_t)G * (p.ldv / 4), 512, (uint32_t)beam * 4, 64))) return err;
+    if ((err = encode_tmap_2d_f32(&h_maps[nm + 5], p.logits, 512, (uint64_t)G * (p.ldv / 4), 512, (uint32_t)(beam | 1) * 4, 64))) return err;
     cudaError_t e = cudaMemcpyAsync(d_maps, h_maps, (size_t)(nm + 6) * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     if ((e = cudaMemsetAsync(p.bar, 0, (size_t)G * 128, st)) != cudaSuccess) return cudaGetErrorString(e);

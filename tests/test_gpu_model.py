@@ -419,6 +419,29 @@ def test_persistent_equals_per_step_graph_path():
     torch.testing.assert_close(s1, s2, rtol=3e-2, atol=0.3)    # two bf16 pipelines with different rounding points
 
 
+def test_persistent_group_barrier_kinds_give_identical_results():
+    """otb_set_decode_barrier: thread-block clusters + barrier.cluster vs plain CTAs + a release/acquire counter in L2.  The
+    barrier kind changes scheduling only: hypotheses and scores must be bit-identical."""
+    from opentransformer_b200 import ops
+    params = _params(n_enc=1, n_dec=2)
+    model, sd = _build(params)
+    B, beam, max_len = 5, 4, 9
+    x, mask = _batch(B, 200, 80, [200, 180, 150, 199, 64])
+    xd, md = x.to(DEV), mask.to(DEV)
+    rec = SpeechToTextRecognizer(model, beam_width=beam, nbest=2, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=True)
+    out = {}
+    try:
+        for kind in ('cluster', 'software'):
+            ops.set_decode_barrier(kind)
+            p_, s_, n_ = rec.recognize_ids(xd, md)
+            out[kind] = (p_.clone(), s_.clone(), n_)
+    finally:
+        ops.set_decode_barrier('default')
+    assert next(iter(rec._decoders.values())).persistent
+    assert out['cluster'][2] == out['software'][2]
+    assert torch.equal(out['cluster'][0], out['software'][0]) and torch.equal(out['cluster'][1], out['software'][1])
+
+
 def test_end_to_end_best_hypothesis_vs_fp32_oracle():
     """Whole pipeline vs the fp32 oracle: scores of the 1-best within tolerance; report id agreement."""
     params = _params(n_enc=2, n_dec=2)
