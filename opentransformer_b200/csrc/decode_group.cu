@@ -204,32 +204,45 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     // Launched as thread-block clusters of 16 (p.cluster) the group IS the cluster: hardware barrier.cluster with release /
     // acquire semantics (~1-3 k cycles measured, profiles/r2_decode_phases_*.txt); otherwise one atomic + an acquire poll on a
     // counter in L2 (~4 k cycles).
+    int dbg_b = 0;      // group barriers since the start of the step; the six of layer 2 (12..17) get inner stamps (slots 212..229)
     auto gsync = [&](auto pre) {
         __syncthreads();
         DG_STAMP();
+        const bool rec = dbg_on && dbg_b >= 12 && dbg_b < 18;
+        unsigned long long* slot = p.dbg_clk + blockIdx.x * 256 + 212 + (dbg_b - 12) * 3;
+        ++dbg_b;
         if (p.cluster) {
             if (tid == 0) fence_proxy_async_all();
             __syncwarp();
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            if (tid == 0) pre();
+            if (rec) slot[0] = clock64();
+            // the prefetch is issued by ANOTHER thread than the one that executes the proxy fence behind the wait: inner stamps
+            // showed barriers with a prefetch taking ~1.5 k cycles longer than those without -- fence.proxy.async of a thread
+            // also waits for the bulk copies that thread has in flight, i.e. for the weights it had just asked for
+            if (tid == 32) pre();
+            if (rec) slot[1] = clock64();
             __syncwarp();
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
             if (tid == 0) fence_proxy_async_all();
+            if (rec) slot[2] = clock64();
             __syncthreads();
             return;
         }
         bar_target += DG_P;
+        if (tid == 32) pre();
         if (tid == 0) {
             __threadfence();
             fence_proxy_async_all();
             red_release_gpu_add(bar, 1);
-            pre();
+            if (rec) slot[0] = clock64();
+            if (rec) slot[1] = clock64();
             const long long t0 = clock64();
             uint32_t spins = 0;
             while (ld_acquire_gpu(bar) < bar_target) {
                 if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 20000000000LL) __trap();   // a protocol bug traps instead of hanging
             }
             fence_proxy_async_all();
+            if (rec) slot[2] = clock64();
         }
         __syncthreads();
     };
@@ -476,6 +489,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
     for (int step = 0; step < p.max_steps; ++step) {
         dbg_on = dbg_cta && step == p.dbg_step;
         dbg_n = 0;
+        dbg_b = 0;
         DG_STAMP();
         build_a_embed(step);
         DG_STAMP();   // 1 embed

@@ -60,3 +60,12 @@ with torch.no_grad():
         print('    layer 2 self-attention, warp 0 task 1, per CTA: ancestry+q', dd(39, 40)[:6], 'issue 2 halves', dd(40, 41)[:6], 'wait half 0', dd(41, 42)[:6],
               'compute', dd(42, 43)[:6], 'wait half 1', dd(43, 44)[:6], 'compute', dd(44, 45)[:6], 'wait half 2', dd(45, 46)[:6], 'compute', dd(46, 47)[:6],
               'wait half 3', dd(47, 48)[:6], 'compute', dd(48, 49)[:6], 'merge+store', dd(50, 51)[:6])
+        # inner stamps of the six group barriers of layer 2: stamp index of the barrier's entry = 2 + 2*NP + position of 'barrier' - 1
+        bpos = [i for i, nme in enumerate(PH) if nme == 'barrier']
+        rows = []
+        for k, bp in enumerate(bpos):
+            entry = allt[:, 2 + 2 * NP + bp - 1]      # stamp taken after the leading __syncthreads of gsync
+            done = allt[:, 2 + 2 * NP + bp]
+            a, b, c = allt[:, 212 + 3 * k], allt[:, 213 + 3 * k], allt[:, 214 + 3 * k]
+            rows.append((PH[bp - 1], int((a - entry).median()), int((b - a).median()), int((c - b).median()), int((done - c).median())))
+        print('    layer 2 group barriers (median over CTAs): after phase, fence+arrive (release), prefetch issue, wait (acquire), trailing sync:', rows)
