@@ -229,12 +229,18 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             return;
         }
         bar_target += DG_P;
-        if (tid == 32) pre();
+        if (warp == 1) {      // the prefetch follows the arrival (issued together, the arrival queued behind 100+ KB of TMA requests)
+            asm volatile("bar.sync 15, 64;" ::: "memory");
+            if (tid == 32) pre();
+        }
         if (tid == 0) {
             __threadfence();
             fence_proxy_async_all();
             red_release_gpu_add(bar, 1);
             if (rec) slot[0] = clock64();
+        }
+        if (warp == 0) asm volatile("bar.sync 15, 64;" ::: "memory");
+        if (tid == 0) {
             if (rec) slot[1] = clock64();
             const long long t0 = clock64();
             uint32_t spins = 0;

@@ -62,6 +62,7 @@ with torch.no_grad():
               'wait half 3', dd(47, 48)[:6], 'compute', dd(48, 49)[:6], 'merge+store', dd(50, 51)[:6])
         # inner stamps of the six group barriers of layer 2: stamp index of the barrier's entry = 2 + 2*NP + position of 'barrier' - 1
         bpos = [i for i, nme in enumerate(PH) if nme == 'barrier']
+        del bpos[1]      # the entry behind the self-attention is a plain CTA barrier since v9, not a group barrier
         rows = []
         for k, bp in enumerate(bpos):
             entry = allt[:, 2 + 2 * NP + bp - 1]      # stamp taken after the leading __syncthreads of gsync
