@@ -45,8 +45,8 @@ class TrainPack:
         fe, enc, dec = model.frontend, model.encoder, model.decoder
         if not isinstance(fe, ConvFrontEnd) or not isinstance(enc, TransformerEncoder) or not isinstance(dec, TransformerDecoder):
             raise NotImplementedError('training path: conv front end + Transformer encoder / decoder only (round 1)')
-        if enc.normalize_before or dec.normalize_before or enc.relative_positional:
-            raise NotImplementedError('training path: post-norm, absolute positions only (round 1)')
+        if enc.relative_positional:
+            raise NotImplementedError('training path: absolute positions only')
         if fe.front_end_layer_norm or enc.pos_emb.scale_learnable or dec.pos_emb.scale_learnable:
             raise NotImplementedError('training path: front_end_layer_norm / learnable positional scale')
         for blk in list(enc.blocks) + list(dec.blocks):
@@ -64,6 +64,10 @@ class TrainPack:
         self.fe = self._frontend(fe)
         self.enc = [self._enc_layer(b) for b in enc.blocks]
         self.dec = [self._dec_layer(b) for b in dec.blocks]
+        # pre-norm stacks end with one more LayerNorm (encoder/transformer.py:96-97,131-132; decoder/transformer.py:151-152,178-179)
+        self.enc_pre, self.dec_pre = bool(enc.normalize_before), bool(dec.normalize_before)
+        self.enc_norm = self._ln(enc.norm) if self.enc_pre else None
+        self.dec_norm = self._ln(dec.after_norm) if self.dec_pre else None
         V, d = dec.vocab_size, dec.d_model
         self.ld_logits = dec.ld_logits
         emb = self._w(dec.embedding.weight)
@@ -201,6 +205,20 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     x = ops.linear(h2, fpk['wo'], fpk['bo'], EPI_TABLE, alpha=scale, table=table, period=T2)
     enc_tape = []
     for i, p in enumerate(pk.enc):
+        if pk.enc_pre:
+            # pre-norm as the reference writes it (encoder/transformer.py:41-63): the residual is taken AFTER the norm,
+            # x = n + sublayer(n) with n = norm(x); the stack ends with one more LayerNorm
+            xn = ops.layernorm(x, *p['ln1'])
+            qkv = ops.linear(xn, p['qkv'][0], p['qkv'][2])
+            ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
+            z1 = _resid(ctx, p['o'][0], p['o'][2], xn, e_rates[i], drop_seed, ENC_SITE + 2 * i)
+            x1 = ops.layernorm(z1, *p['ln2'])
+            u = ops.linear(x1, p['w1'][0], p['w1'][2])
+            h = ops.glu_fwd(u)
+            z2 = _resid(h, p['w2'][0], p['w2'][2], x1, e_rates[i], drop_seed, ENC_SITE + 2 * i + 1)
+            enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, xn))
+            x = z2
+            continue
         qkv = ops.linear(x, p['qkv'][0], p['qkv'][2])
         ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
         z1 = _resid(ctx, p['o'][0], p['o'][2], x, e_rates[i], drop_seed, ENC_SITE + 2 * i)
@@ -210,7 +228,8 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         z2 = _resid(h, p['w2'][0], p['w2'][2], x1, e_rates[i], drop_seed, ENC_SITE + 2 * i + 1)
         enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, z2))
         x = ops.layernorm(z2, *p['ln2'])
-    mem = x
+    enc_last = x
+    mem = ops.layernorm(x, *pk.enc_norm) if pk.enc_pre else x
 
     tgt_in = truth[:, :-1].contiguous()
     tgt_out = truth[:, 1:].contiguous()
@@ -220,6 +239,23 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     y = ops.embed_posenc(tgt_in, pk.out['emb'], dtable, B * L, d, period=L)
     dec_tape = []
     for i, p in enumerate(pk.dec):
+        if pk.dec_pre:      # decoder/transformer.py:54-90 with normalize_before: y = n + sublayer(n), n = norm(y), three times
+            yn = ops.layernorm(y, *p['ln1'])
+            qkv = ops.linear(yn, p['qkv'][0], p['qkv'][2])
+            ctx, lse = ops.attention_train(qkv, qkv, qkv, B, Hd, L, L, causal=True, q_col0=0, k_col0=d, v_col0=2 * d)
+            z1 = _resid(ctx, p['o'][0], p['o'][2], yn, d_rates[i], drop_seed, DEC_SITE + 3 * i)
+            y1 = ops.layernorm(z1, *p['ln2'])
+            q = ops.linear(y1, p['q'][0], p['q'][2])
+            kv = ops.linear(mem, p['kv'][0], p['kv'][2])
+            ctx2, lse2 = ops.attention_train(q, kv, kv, B, Hd, L, T2, kv_len=lengths, k_col0=0, v_col0=d)
+            z2 = _resid(ctx2, p['o2'][0], p['o2'][2], y1, d_rates[i], drop_seed, DEC_SITE + 3 * i + 1)
+            y2 = ops.layernorm(z2, *p['ln3'])
+            u = ops.linear(y2, p['w1'][0], p['w1'][2])
+            h = ops.glu_fwd(u)
+            z3 = _resid(h, p['w2'][0], p['w2'][2], y2, d_rates[i], drop_seed, DEC_SITE + 3 * i + 2)
+            dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, yn))
+            y = z3
+            continue
         qkv = ops.linear(y, p['qkv'][0], p['qkv'][2])
         ctx, lse = ops.attention_train(qkv, qkv, qkv, B, Hd, L, L, causal=True, q_col0=0, k_col0=d, v_col0=2 * d)
         z1 = _resid(ctx, p['o'][0], p['o'][2], y, d_rates[i], drop_seed, DEC_SITE + 3 * i)
@@ -235,6 +271,9 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3))
         y = ops.layernorm(z3, *p['ln3'])
     V = dec.vocab_size
+    dec_last = y
+    if pk.dec_pre:
+        y = ops.layernorm(y, *pk.dec_norm)
     logits = ops.linear(y, pk.out['wout'], pk.out['bout'], EPI_BIAS, out_f32=True, n_out=pk.ld_logits)
     sm = model.smoothing if smoothing is None else smoothing
     loss_ctc, dctc = None, None
@@ -264,10 +303,34 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
     g.put('decoder.output_layer.bias', ops.colsum(dlogits)[:V])
     dy = ops.linear(dlogits, pk.out['wout_t'])                                   # [B*L, d]
     dmem = None
+    if pk.dec_pre:
+        dy = _ln_bwd(dy, dec_last, pk.dec_norm[0], g, 'decoder.after_norm.weight', 'decoder.after_norm.bias')
     for i in reversed(range(len(pk.dec))):
         p, pre = pk.dec[i], f'decoder.blocks.{i}.'
-        (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3) = dec_tape[i]
         rt, st0 = d_rates[i], DEC_SITE + 3 * i
+        if pk.dec_pre:
+            (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, yn) = dec_tape[i]
+            # z3 = y2 + drop(ffn(y2)), y2 = norm3(z2): dy is the gradient of z3
+            dh = _linear_bwd(_drop_bwd(dy, rt, drop_seed, st0 + 2), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+            du = ops.glu_bwd(dh, u)
+            dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dy)
+            dz2 = _ln_bwd(dy2, z2, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
+            dctx2 = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
+            dq = torch.empty_like(q)
+            dkv = torch.empty_like(kv)
+            ops.attention_bwd(q, kv, kv, ctx2, dctx2, lse2, B, Hd, L, T2, dq, dkv, dkv, kv_len=lengths, k_col0=0, v_col0=d,
+                              dq_col0=0, dk_col0=0, dv_col0=d)
+            dmem = _linear_bwd(dkv, mem, p['kv'][1], g, pre + 'src_attn.vk_proj.weight', pre + 'src_attn.vk_proj.bias', resid=dmem)
+            dy1 = _linear_bwd(dq, y1, p['q'][1], g, pre + 'src_attn.q_proj.weight', pre + 'src_attn.q_proj.bias', resid=dz2)
+            dz1 = _ln_bwd(dy1, z1, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
+            dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+            dqkv = torch.empty_like(qkv)
+            ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, Hd, L, L, dqkv, dqkv, dqkv, causal=True, q_col0=0, k_col0=d,
+                              v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
+            dyn = _linear_bwd(dqkv, yn, p['qkv'][1], g, pre + 'slf_attn.qvk_proj.weight', pre + 'slf_attn.qvk_proj.bias', resid=dz1)
+            dy = _ln_bwd(dyn, y0, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
+            continue
+        (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3) = dec_tape[i]
         dz3 = _ln_bwd(dy, z3, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
         # the sub-layer branch sees the replayed dropout mask, the residual branch (resid= below) the plain gradient
         dh = _linear_bwd(_drop_bwd(dz3, rt, drop_seed, st0 + 2), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
@@ -307,10 +370,25 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         wc_t = torch.zeros(d, dctc.shape[1], dtype=BF16, device=dev)
         wc_t[:, :V] = wc.t()
         dx = ops.linear(dctc, wc_t, None, EPI_RESID, resid=dmem)
+    if pk.enc_pre:
+        dx = _ln_bwd(dx, enc_last, pk.enc_norm[0], g, 'encoder.norm.weight', 'encoder.norm.bias')
     for i in reversed(range(len(pk.enc))):
         p, pre = pk.enc[i], f'encoder.blocks.{i}.'
-        (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
         rt, st0 = e_rates[i], ENC_SITE + 2 * i
+        if pk.enc_pre:
+            (x0, qkv, ctx, lse, z1, x1, u, h, xn) = enc_tape[i]
+            dh = _linear_bwd(_drop_bwd(dx, rt, drop_seed, st0 + 1), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
+            du = ops.glu_bwd(dh, u)
+            dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dx)
+            dz1 = _ln_bwd(dx1, z1, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
+            dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
+            dqkv = torch.empty_like(qkv)
+            ops.attention_bwd(qkv, qkv, qkv, ctx, dctx, lse, B, H, T2, T2, dqkv, dqkv, dqkv, kv_len=lengths, q_col0=0, k_col0=d,
+                              v_col0=2 * d, dq_col0=0, dk_col0=d, dv_col0=2 * d)
+            dxn = _linear_bwd(dqkv, xn, p['qkv'][1], g, pre + 'slf_attn.qvk_proj.weight', pre + 'slf_attn.qvk_proj.bias', resid=dz1)
+            dx = _ln_bwd(dxn, x0, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
+            continue
+        (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
         dz2 = _ln_bwd(dx, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
         dh = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
         du = ops.glu_bwd(dh, u)

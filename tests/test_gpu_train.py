@@ -95,6 +95,34 @@ def test_gradients_match_oracle(tied):
     assert worst[0][0] < REL_L2_GRAD, worst[:3]
 
 
+@pytest.mark.parametrize('which', ['both', 'encoder_only', 'decoder_only'])
+def test_prenorm_gradients_match_oracle(which):
+    """normalize_before=True as the reference writes it (encoder/transformer.py:41-63, decoder/transformer.py:54-90,151-152):
+    the residual is taken AFTER the norm and the stack ends with one more LayerNorm.  Loss and every parameter gradient
+    (the extra `encoder.norm` / `decoder.after_norm` included) against the oracle's autograd."""
+    params = _params(tied=True)
+    params['encoder']['normalize_before'] = which in ('both', 'encoder_only')
+    params['decoder']['normalize_before'] = which in ('both', 'decoder_only')
+    model, sd = _build(params)
+    x, mask, tgt = _batch()
+    loss_ref, g_ref = ot.loss_and_grads(x, mask, tgt, sd, params)
+    with torch.no_grad():
+        loss, g = train.forward_backward(model.train(), x.to(DEV), mask.to(DEV), tgt.to(DEV))
+    names = [n for n, _ in model.named_parameters()]
+    assert set(names) == set(g_ref) == set(g), (set(names) ^ set(g_ref), set(names) ^ set(g))
+    if which != 'decoder_only':
+        assert 'encoder.norm.weight' in g
+    if which != 'encoder_only':
+        assert 'decoder.after_norm.weight' in g
+    worst = sorted(((_rel(g[n], g_ref[n]), n) for n in names), reverse=True)
+    r_all = _rel(torch.cat([g[n].reshape(-1).cpu() for n in names]), torch.cat([g_ref[n].reshape(-1) for n in names]))
+    print(f'pre-norm ({which}): loss gpu {float(loss):.5f} oracle {float(loss_ref):.5f}; all grads rel_l2 {r_all:.3e}; worst: '
+          + ', '.join(f'{n} {r:.2e}' for r, n in worst[:4]))
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    assert r_all < REL_L2_GRAD_ALL
+    assert worst[0][0] < REL_L2_GRAD, worst[:3]
+
+
 def test_autograd_seam_fills_param_grads():
     """model.train(); loss, _ = model(inputs, targets); loss.backward()  -- the reference's calling convention."""
     params = _params(n_enc=1, n_dec=1)
