@@ -24,7 +24,7 @@ from . import ops
 from . import modules
 from .dp import allreduce_mean_
 from .modules import TransformerDecoder, TransformerEncoder, ConvFrontEnd, _lengths
-from .ops import BF16, EPI_BIAS, EPI_RESID, EPI_TABLE
+from .ops import BF16, EPI_BIAS, EPI_RESID, EPI_TABLE, EPI_RELU
 
 
 def _bf(t):
@@ -50,8 +50,8 @@ class TrainPack:
         if fe.front_end_layer_norm or enc.pos_emb.scale_learnable or dec.pos_emb.scale_learnable:
             raise NotImplementedError('training path: front_end_layer_norm / learnable positional scale')
         for blk in list(enc.blocks) + list(dec.blocks):
-            if blk.feed_forward.activation != 'glu':
-                raise NotImplementedError('training path: GLU feed-forward only (round 1)')
+            if blk.feed_forward.activation not in ('glu', 'relu'):
+                raise NotImplementedError('training path: GLU or ReLU feed-forward only')
             rates = getattr(blk, 'dropout_rates', {})
             other = {k: v for k, v in rates.items() if k != 'residual_dropout' and float(v) > 0.0}
             if other:
@@ -97,13 +97,13 @@ class TrainPack:
     def _enc_layer(self, b):
         a, f = b.slf_attn, b.feed_forward
         return {'qkv': self._lin(a.qvk_proj), 'o': self._lin(a.output_proj), 'w1': self._lin(f.w_1), 'w2': self._lin(f.w_2),
-                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2)}
+                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2), 'act': f.activation}
 
     def _dec_layer(self, b):
         a, c, f = b.slf_attn, b.src_attn, b.feed_forward
         return {'qkv': self._lin(a.qvk_proj), 'o': self._lin(a.output_proj), 'q': self._lin(c.q_proj),
                 'kv': self._lin(c.vk_proj), 'o2': self._lin(c.output_proj), 'w1': self._lin(f.w_1), 'w2': self._lin(f.w_2),
-                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2), 'ln3': self._ln(b.norm3)}
+                'ln1': self._ln(b.norm1), 'ln2': self._ln(b.norm2), 'ln3': self._ln(b.norm3), 'act': f.activation}
 
 
 class _Grads(dict):
@@ -147,6 +147,18 @@ def _linear_bwd(dy, x, wt, grads, wname, bname, resid=None):
 
 
 ENC_SITE, DEC_SITE = 0, 1000      # dropout site ids: encoder layer i -> 2 i + {0, 1}; decoder layer i -> 1000 + 3 i + {0, 1, 2}
+
+
+def _ffn_fwd(p, x):
+    """First half of the position-wise feed-forward (ffn.py:38-41): returns (pre-activation u or None, hidden h)."""
+    if p['act'] == 'glu':
+        u = ops.linear(x, p['w1'][0], p['w1'][2])
+        return u, ops.glu_fwd(u)
+    return None, ops.linear(x, p['w1'][0], p['w1'][2], EPI_RELU)      # ReLU fused into the GEMM; its backward needs only h
+
+
+def _ffn_act_bwd(p, dh, u, h):
+    return ops.glu_bwd(dh, u) if p['act'] == 'glu' else ops.relu_bwd(dh, h)
 
 
 def dropout_sites(model):
@@ -213,8 +225,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
             ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
             z1 = _resid(ctx, p['o'][0], p['o'][2], xn, e_rates[i], drop_seed, ENC_SITE + 2 * i)
             x1 = ops.layernorm(z1, *p['ln2'])
-            u = ops.linear(x1, p['w1'][0], p['w1'][2])
-            h = ops.glu_fwd(u)
+            u, h = _ffn_fwd(p, x1)
             z2 = _resid(h, p['w2'][0], p['w2'][2], x1, e_rates[i], drop_seed, ENC_SITE + 2 * i + 1)
             enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, xn))
             x = z2
@@ -223,8 +234,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         ctx, lse = ops.attention_train(qkv, qkv, qkv, B, H, T2, T2, kv_len=lengths, q_col0=0, k_col0=d, v_col0=2 * d)
         z1 = _resid(ctx, p['o'][0], p['o'][2], x, e_rates[i], drop_seed, ENC_SITE + 2 * i)
         x1 = ops.layernorm(z1, *p['ln1'])
-        u = ops.linear(x1, p['w1'][0], p['w1'][2])
-        h = ops.glu_fwd(u)
+        u, h = _ffn_fwd(p, x1)
         z2 = _resid(h, p['w2'][0], p['w2'][2], x1, e_rates[i], drop_seed, ENC_SITE + 2 * i + 1)
         enc_tape.append((x, qkv, ctx, lse, z1, x1, u, h, z2))
         x = ops.layernorm(z2, *p['ln2'])
@@ -250,8 +260,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
             ctx2, lse2 = ops.attention_train(q, kv, kv, B, Hd, L, T2, kv_len=lengths, k_col0=0, v_col0=d)
             z2 = _resid(ctx2, p['o2'][0], p['o2'][2], y1, d_rates[i], drop_seed, DEC_SITE + 3 * i + 1)
             y2 = ops.layernorm(z2, *p['ln3'])
-            u = ops.linear(y2, p['w1'][0], p['w1'][2])
-            h = ops.glu_fwd(u)
+            u, h = _ffn_fwd(p, y2)
             z3 = _resid(h, p['w2'][0], p['w2'][2], y2, d_rates[i], drop_seed, DEC_SITE + 3 * i + 2)
             dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, yn))
             y = z3
@@ -265,8 +274,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         ctx2, lse2 = ops.attention_train(q, kv, kv, B, Hd, L, T2, kv_len=lengths, k_col0=0, v_col0=d)
         z2 = _resid(ctx2, p['o2'][0], p['o2'][2], y1, d_rates[i], drop_seed, DEC_SITE + 3 * i + 1)
         y2 = ops.layernorm(z2, *p['ln2'])
-        u = ops.linear(y2, p['w1'][0], p['w1'][2])
-        h = ops.glu_fwd(u)
+        u, h = _ffn_fwd(p, y2)
         z3 = _resid(h, p['w2'][0], p['w2'][2], y2, d_rates[i], drop_seed, DEC_SITE + 3 * i + 2)
         dec_tape.append((y, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, z3))
         y = ops.layernorm(z3, *p['ln3'])
@@ -312,7 +320,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
             (y0, qkv, ctx, lse, z1, y1, q, kv, ctx2, lse2, z2, y2, u, h, yn) = dec_tape[i]
             # z3 = y2 + drop(ffn(y2)), y2 = norm3(z2): dy is the gradient of z3
             dh = _linear_bwd(_drop_bwd(dy, rt, drop_seed, st0 + 2), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
-            du = ops.glu_bwd(dh, u)
+            du = _ffn_act_bwd(p, dh, u, h)
             dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dy)
             dz2 = _ln_bwd(dy2, z2, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
             dctx2 = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
@@ -334,7 +342,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         dz3 = _ln_bwd(dy, z3, p['ln3'][0], g, pre + 'norm3.weight', pre + 'norm3.bias')
         # the sub-layer branch sees the replayed dropout mask, the residual branch (resid= below) the plain gradient
         dh = _linear_bwd(_drop_bwd(dz3, rt, drop_seed, st0 + 2), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
-        du = ops.glu_bwd(dh, u)
+        du = _ffn_act_bwd(p, dh, u, h)
         dy2 = _linear_bwd(du, y2, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz3)
         dz2 = _ln_bwd(dy2, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
         dctx2 = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), ctx2, p['o2'][1], g, pre + 'src_attn.output_proj.weight', pre + 'src_attn.output_proj.bias')
@@ -378,7 +386,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         if pk.enc_pre:
             (x0, qkv, ctx, lse, z1, x1, u, h, xn) = enc_tape[i]
             dh = _linear_bwd(_drop_bwd(dx, rt, drop_seed, st0 + 1), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
-            du = ops.glu_bwd(dh, u)
+            du = _ffn_act_bwd(p, dh, u, h)
             dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dx)
             dz1 = _ln_bwd(dx1, z1, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
             dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')
@@ -391,7 +399,7 @@ def forward_backward(model, inputs, mask, truth, smoothing=None, want_grads=True
         (x0, qkv, ctx, lse, z1, x1, u, h, z2) = enc_tape[i]
         dz2 = _ln_bwd(dx, z2, p['ln2'][0], g, pre + 'norm2.weight', pre + 'norm2.bias')
         dh = _linear_bwd(_drop_bwd(dz2, rt, drop_seed, st0 + 1), h, p['w2'][1], g, pre + 'feed_forward.w_2.weight', pre + 'feed_forward.w_2.bias')
-        du = ops.glu_bwd(dh, u)
+        du = _ffn_act_bwd(p, dh, u, h)
         dx1 = _linear_bwd(du, x1, p['w1'][1], g, pre + 'feed_forward.w_1.weight', pre + 'feed_forward.w_1.bias', resid=dz2)
         dz1 = _ln_bwd(dx1, z1, p['ln1'][0], g, pre + 'norm1.weight', pre + 'norm1.bias')
         dctx = _linear_bwd(_drop_bwd(dz1, rt, drop_seed, st0), ctx, p['o'][1], g, pre + 'slf_attn.output_proj.weight', pre + 'slf_attn.output_proj.bias')

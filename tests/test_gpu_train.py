@@ -123,6 +123,30 @@ def test_prenorm_gradients_match_oracle(which):
     assert worst[0][0] < REL_L2_GRAD, worst[:3]
 
 
+@pytest.mark.parametrize('prenorm', [False, True])
+def test_relu_feed_forward_gradients_match_oracle(prenorm):
+    """activation='relu' (the reference's default, ffn.py:38-41): ReLU fused into the w_1 GEMM, backward from the hidden
+    activations alone; post- and pre-norm."""
+    params = _params(tied=False)
+    for part in ('encoder', 'decoder'):
+        params[part]['activation'] = 'relu'
+        params[part]['normalize_before'] = prenorm
+    model, sd = _build(params)
+    x, mask, tgt = _batch()
+    loss_ref, g_ref = ot.loss_and_grads(x, mask, tgt, sd, params)
+    with torch.no_grad():
+        loss, g = train.forward_backward(model.train(), x.to(DEV), mask.to(DEV), tgt.to(DEV))
+    names = [n for n, _ in model.named_parameters()]
+    assert set(names) == set(g_ref) == set(g)
+    worst = sorted(((_rel(g[n], g_ref[n]), n) for n in names), reverse=True)
+    r_all = _rel(torch.cat([g[n].reshape(-1).cpu() for n in names]), torch.cat([g_ref[n].reshape(-1) for n in names]))
+    print(f'relu ffn (prenorm={prenorm}): loss gpu {float(loss):.5f} oracle {float(loss_ref):.5f}; all grads rel_l2 {r_all:.3e}; '
+          f'worst: ' + ', '.join(f'{n} {r:.2e}' for r, n in worst[:3]))
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
+    assert r_all < REL_L2_GRAD_ALL
+    assert worst[0][0] < REL_L2_GRAD, worst[:3]
+
+
 def test_autograd_seam_fills_param_grads():
     """model.train(); loss, _ = model(inputs, targets); loss.backward()  -- the reference's calling convention."""
     params = _params(n_enc=1, n_dec=1)
