@@ -69,10 +69,10 @@ struct DgMisc {
     uint64_t pq_full[4];      // k-blocks of the cross-attention query projection landed
     uint64_t lg_full;         // logits rows of an utterance landed (TMA gather of the beam phase)
     uint64_t kx_full[3];      // encoder K/V tile of a cross-attention problem landed in stage 0 / stage 1 / the A tile
-    uint64_t kv_full[32];     // self-attention: [warp][half] 16 cached K rows + 16 V rows of one head landed (bulk copies)
+    uint64_t kv_full[32];     // self-attention: [row of the block][half-buffer] (16 used) -- 8 cached K rows + 8 V rows, all heads, landed (bulk copies)
     uint32_t tmem_slot;
     int flag;                 // broadcast scratch
-    alignas(16) uint32_t zero16[4];       // the (zero) rows 8..15 of the m16 A fragments of the row-block projections
+    alignas(16) uint32_t zero16[4];       // (unused since v22: the row-block projections have no padding rows any more)
     alignas(16) float bias[256];          // per-phase bias slice
     float c_val[KMAX * KMAX];
     int c_tok[KMAX * KMAX];
