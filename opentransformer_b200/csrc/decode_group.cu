@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             if (tid == 32) pre();
         }
         if (tid == 0) {
-            __threadfence();
+            // red.release.gpu orders every write this thread has observed -- those of the other warps through the CTA barrier
+            // above (cumulativity) -- before the arrival: no separate __threadfence (it cost a second MEMBAR round per barrier)
+            if (p.flags & 256) __threadfence();
             fence_proxy_async_all();
             red_release_gpu_add(bar, 1);
             if (rec) slot[0] = clock64();
