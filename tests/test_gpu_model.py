@@ -419,6 +419,32 @@ def test_persistent_equals_per_step_graph_path():
     torch.testing.assert_close(s1, s2, rtol=3e-2, atol=0.3)    # two bf16 pipelines with different rounding points
 
 
+@pytest.mark.parametrize('B,beam', [(32, 4), (16, 8), (70, 2)])
+def test_persistent_full_row_groups_with_even_beam(B, beam):
+    """A FULL row group (128 hypotheses) with an even beam: the logits gather of the group's last utterance asks TMA for
+    (beam | 1) rows, one past the 128-row tile (out-of-bounds fill), and 70 x 2 spans two groups.  Persistent kernel vs the
+    per-step graph path: same hypotheses up to bf16 near-ties, scores within tolerance, deterministic."""
+    params = _params(n_enc=1, n_dec=1)
+    model, sd = _build(params)
+    max_len = 6
+    lens = [64 - (i * 7) % 40 for i in range(B)]
+    x, mask = _batch(B, 64, 80, lens)
+    xd, md = x.to(DEV), mask.to(DEV)
+    rec_p = SpeechToTextRecognizer(model, beam_width=beam, nbest=1, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=True)
+    rec_g = SpeechToTextRecognizer(model, beam_width=beam, nbest=1, max_len=max_len, penalty=0.6, lamda=5, ngpu=1, persistent=False)
+    p1, s1, n1 = rec_p.recognize_ids(xd, md)
+    p1b, s1b, _ = rec_p.recognize_ids(xd, md)
+    p2, s2, n2 = rec_g.recognize_ids(xd, md)
+    assert next(iter(rec_p._decoders.values())).persistent
+    assert n1 == n2 == max_len
+    assert torch.equal(p1, p1b) and torch.equal(s1, s1b), 'persistent kernel must be deterministic'
+    same = int((p1 == p2).all(dim=2).sum())
+    print(f'B={B} beam={beam}: {same}/{B} 1-best identical between the persistent kernel and the graph path')
+    assert torch.isfinite(s1).all()
+    assert same >= (9 * B) // 10
+    torch.testing.assert_close(s1, s2, rtol=3e-2, atol=0.3)
+
+
 def test_persistent_group_barrier_kinds_give_identical_results():
     """otb_set_decode_barrier: thread-block clusters + barrier.cluster vs plain CTAs + a release/acquire counter in L2.  The
     barrier kind changes scheduling only: hypotheses and scores must be bit-identical."""
