@@ -7,25 +7,30 @@
 // step).  This kernel keeps the rows of up to 12 utterances (beam 10 -> 120 hypotheses) together as ONE 128-row tcgen05
 // tile and gives each such ROW GROUP to P = 16 co-operating CTAs:
 //
-//   * every projection is split over the group's CTAs by OUTPUT column (QKV 48, out / q projections 16, GLU 128 hidden
-//     features per CTA) or, for w_2, by CONTRACTION slice (the CTA's own 128 hidden features; the 16 partial products are
-//     summed by a row-partitioned pass that also applies the residual and LayerNorm 3) -- so the 25.8 MB of decoder weights
-//     are read once per group-step (3 groups for 32 utterances x beam 10), straight from L2 by TMA into the UMMA
-//     shared-memory layout, accumulators in TMEM; every weight slice is prefetched during the barrier in front of its phase;
-//   * activations move between the phases through L2 (a [rows, 256] matrix is 64 KB).  The group is launched as ONE
-//     thread-block cluster of 16 CTAs: the phase boundary is barrier.cluster (release / acquire, 1-3 k cycles measured)
-//     instead of a kernel boundary (7-13 us); groups never synchronise with each other, utterances are independent.  A
-//     software barrier (atomic + acquire poll in L2) is kept for devices that refuse the non-portable cluster size;
-//   * LayerNorm 1 / 2 are applied by the CONSUMER while it builds its A operand (fp32 pre-norm rows -> bf16 swizzled tile),
-//     so a post-norm layer costs 7 barriers: QKV | self-attention | out-proj | LN+q-proj | cross-attention | out-proj |
-//     LN+GLU+w_2 partial | reduce+LN (= input of the next layer);
-//   * self-attention over the per-hypothesis KV cache is SIMT: a warp per (hypothesis, head), 8 lanes per cached position
-//     (coalesced 128-byte rows through the ancestry table), online softmax per lane group;
-//     cross-attention of the <= 16 hypotheses of an utterance against its <= 256 encoder frames is one m16 problem per
-//     (utterance, head): mma.sync on K / V tiles that TMA prefetches during the preceding phase (tcgen05 has no M < 64 shape);
-//   * the tail -- logits (coalesced fp32 rows in L2), then per utterance log-softmax + per-row top-k + finished masking +
-//     beam^2 pruning + ancestry update -- follows beam.cu exactly (ties -> lower index), so ids / parents are bit-exact with
-//     the oracle's beam_step driven by this kernel's log-probs.
+//   * the wide projections are split over the group's CTAs by OUTPUT column (QKV: 48 columns per CTA; GLU: 128 hidden
+//     features per CTA) or, for w_2, by CONTRACTION slice (the CTA's own 128 hidden features; the 16 fp32 partial products are
+//     summed by a row-partitioned pass that also applies the residual and LayerNorm 3): tcgen05.mma 128 x N x 16, operands
+//     by TMA straight into the UMMA shared-memory layout, accumulators in TMEM, all 16 warps drain them;
+//   * the d x d projections between the attention cores (W_o, the cross-attention query projection, the second W_o) run on
+//     the OWNER of the rows: CTA j holds rows [8 j, 8 j + 8), streams the whole 128 KB weight matrix by TMA one phase ahead
+//     and forms the product transposed with mma.sync (weights = m16 operand, the 8 rows = n8 operand); bias + residual +
+//     LayerNorm finish inside that CTA (v1 split them by column too: a barrier + a 128-row fp32 gather per LayerNorm);
+//   * self-attention of the owner's 8 rows x 4 heads: one (row, head) problem per half-warp, the cached K / V rows (addressed
+//     through the ancestry table; beam reordering never moves K / V) are fetched by 512-byte bulk copies of the TMA engine
+//     into shared memory, online softmax per lane group; the context rows stay in shared memory for W_o;
+//   * cross-attention of the <= 16 hypotheses of an utterance against its <= 256 encoder frames is one m16 problem per
+//     (utterance, head), three per CTA, all three side by side on warp groups of 4: mma.sync on K / V tiles that TMA
+//     prefetches during the preceding barrier (tcgen05 has no M < 64 shape);
+//   * activations cross CTAs through L2 at 6 group barriers per layer: QKV | self-attention + W_o + LN1 + W_q |
+//     cross-attention | W_o + LN2 | GLU + w_2 partial | reduction + LN3.  The group is launched as ONE thread-block cluster
+//     of 16 CTAs (barrier.cluster, release / acquire) or as plain CTAs with a release / acquire counter in L2
+//     (otb_set_decode_barrier): ~3 k cycles either way instead of a kernel boundary (7-13 us); weight prefetches are issued
+//     between arrive and wait; groups never synchronise with each other, utterances are independent;
+//   * the tail -- logits (fp32, stored in accumulator order [column group][row]), then per utterance a TMA gather of its rows,
+//     log-softmax + per-row top-k (lane-maxima threshold), finished masking, beam^2 pruning, ancestry update -- follows
+//     beam.cu exactly (ties -> lower index), so ids / parents are bit-exact with the oracle's beam_step driven by this
+//     kernel's log-probs.
+// What each change bought, with the phase stamps behind it: profiles/r2_bench_history.md, DESIGN.md 4.4.
 //
 // Supported: post-norm decoder, GLU feed-forward with d_ff = 2048, d_model 256, 4 heads, beam <= 16, memory length <= 256
 // frames, max_len <= 128.  Anything else runs on the per-step graph path (recognize.BeamDecoder.step).
@@ -47,7 +52,7 @@ static constexpr int DG_H = 4;
 static constexpr int DG_DFF = 2048;
 static constexpr int DG_A_BYTES = 65536;   // A operand tile: 4 k-blocks of [128 rows x 64] bf16, SWIZZLE_128B
 static constexpr int DG_STAGE = 65536;     // two big stages: weight chunks / cross-attention K|V tiles / logit rows of the beam step
-static constexpr int DG_SB = 24576;        // small B operand (<= 48 weight rows x 256) | cross-attention scratch | store staging
+static constexpr int DG_SB = 24576;        // QKV B operand (48 weight rows x 256) | ancestry rows | row-block activations | cross-attention scratch | top-k candidates
 static constexpr int DG_MISC = 9728;
 static constexpr int DG_SMEM = DG_A_BYTES + 2 * DG_STAGE + DG_SB + DG_MISC + 1024;
 static_assert(DG_SMEM <= 227 * 1024, "decode_group_kernel: shared-memory budget (227 KB per CTA)");
