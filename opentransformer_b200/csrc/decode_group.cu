@@ -251,8 +251,17 @@ __global__ void __launch_bounds__(DG_THREADS, 1) decode_group_kernel(const __gri
             if (rec) slot[1] = clock64();
             const long long t0 = clock64();
             uint32_t spins = 0;
-            while (ld_acquire_gpu(bar) < bar_target) {
-                if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 20000000000LL) __trap();   // a protocol bug traps instead of hanging
+            if (p.flags & 512) {      // experiment: relaxed polls + one acquire fence behind the successful one
+                int v;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                    if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 20000000000LL) __trap();
+                } while (v < bar_target);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            } else {
+                while (ld_acquire_gpu(bar) < bar_target) {
+                    if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 20000000000LL) __trap();   // a protocol bug traps instead of hanging
+                }
             }
             fence_proxy_async_all();
             if (rec) slot[2] = clock64();
