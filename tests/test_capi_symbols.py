@@ -52,6 +52,25 @@ def test_conv_geometry_matches_reference_formula(libpath):
         assert f1 == (F + 2 - 3) // 2 + 1 and f2 == (f1 + 2 - 3) // 2 + 1  # pad 1
 
 
+def test_persistent_decode_host_arithmetic(libpath):
+    """Host-only parts of the persistent decode entry points: workspace size (no GPU needed) and argument checks."""
+    from opentransformer_b200 import _lib
+    lib = _lib.lib()
+    ws = lib.otb_decode_persistent_workspace
+    base = ws(320, 6, 60, 32, 10, 4234)                 # benchmark geometry: 32 utterances x beam 10, 3 row groups
+    assert base > 0
+    groups, ldv = 3, (4234 + 31) // 32 * 32
+    # dominated by the fp32 logits (128 rows per group) and the 16 fp32 feed-forward partial products per group
+    assert base >= groups * 128 * ldv * 4 + 16 * groups * 128 * 256 * 4
+    assert ws(640, 6, 60, 64, 10, 4234) > base          # more utterances -> more row groups
+    assert ws(320, 6, 60, 32, 10, 8000) > base          # larger vocabulary -> larger logits buffer
+    assert ws(320, 6, 60, 32, 17, 4234) == -1           # beam > 16 is not supported by the kernel
+    assert ws(0, 6, 60, 32, 10, 4234) == -1
+    assert lib.otb_set_decode_barrier(2) != 0 and b'otb_set_decode_barrier' in lib.otb_last_error()
+    for kind in (1, 0, -1):
+        assert lib.otb_set_decode_barrier(kind) == 0
+
+
 def test_product_refuses_cpu_tensors(libpath):
     import torch
     from opentransformer_b200 import ops
