@@ -251,6 +251,37 @@ def cpu_reference_pass(sd, params, x, mask):
         return obs.recognize(x, mask, sd, params, beam=BEAM, nbest=1, max_len=MAX_LEN, penalty=PENALTY, lamda=LAMDA)
 
 
+def reference_recognizer(model):
+    """The reference's OWN SpeechToTextRecognizer on the CPU with the weights of `model`, from the byte-compiled package
+    under oracle/_ref (oracle/build_ref.py; built by __graft_entry__.build() where /root/reference exists, travels with
+    gpurun).  None when oracle/_ref is absent: the caller then times the oracle port instead."""
+    try:
+        from oracle import build_ref
+        if build_ref.load() is None:
+            return None
+        from otrans.model import End2EndModel
+        from otrans.recognize.speech2text import SpeechToTextRecognizer as RefRecognizer
+        ref = End2EndModel['speech2text'](model_params()).eval()
+        for part in ('frontend', 'encoder', 'decoder'):          # identical state_dict keys (tests/test_capi_symbols.py)
+            getattr(ref, part).load_state_dict({k: v.detach().float().cpu() for k, v in getattr(model, part).state_dict().items()})
+        idx2unit = {i: str(i) for i in range(model_params()['decoder']['vocab_size'])}
+        return RefRecognizer(ref, beam_width=BEAM, nbest=1, max_len=MAX_LEN, idx2unit=idx2unit, penalty=PENALTY, lamda=LAMDA, ngpu=0)
+    except Exception as e:      # an unusable _ref must not cost the line: fall back to the port and say so
+        sys.stderr.write(f'bench.py: oracle/_ref unusable ({type(e).__name__}: {e}); timing the oracle port\n')
+        return None
+
+
+def reference_ids(rec, x, mask):
+    """1-best token ids [B, <= max_len] of the reference recogniser (it returns strings of unit names = the ids here)."""
+    with torch.no_grad():
+        hyps, _ = rec.recognize(x, mask)
+    rows = []
+    for h in hyps:
+        toks = [int(t) for t in h[0].split()] if h and h[0] else []
+        rows.append(toks)
+    return rows
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -261,21 +292,30 @@ def run_reference(args):
     model = build_model()
     sd, params = flat_state_dict(model), model_params()
     x, mask = synthetic_batch(sample, 0)
+    rec = reference_recognizer(model)
+    kind = 'reference' if rec is not None else 'port'
+
+    def one_pass():
+        if rec is not None:
+            with torch.no_grad():
+                return rec.recognize(x, mask)
+        return cpu_reference_pass(sd, params, x, mask)
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_pass(sd, params, x, mask)
+        one_pass()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(sd, params, x, mask)
+        one_pass()
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {'impl': 'reference', 'metric': 'utterances/sec (encoder-fwd + beam-10 decode, 60 steps)', 'value': val,
             'unit': 'utt/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1),
             'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, sample),
-            'cpu_baseline': {'value': val, 'unit': 'utt/s', 'cores': threads, 'visible_cores': cores, 'kind': 'port',
+            'cpu_baseline': {'value': val, 'unit': 'utt/s', 'cores': threads, 'visible_cores': cores, 'kind': kind,
                              'sample': f'{sample} utterances x {args.steps} passes of the full workload '
-                                       '(oracle/ = torch-CPU fp32 restatement of the reference; the Python reference '
-                                       'itself cannot travel to the GPU box)'},
+                                       + ('(the reference\'s own SpeechToTextRecognizer.recognize, byte-compiled into oracle/_ref '
+                                          'by oracle/build_ref.py, fp32 on the host cores)' if kind == 'reference' else
+                                          '(oracle/ = torch-CPU fp32 restatement of the reference; oracle/_ref is absent here)')},
             'e2e': {'value': val, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
@@ -649,17 +689,31 @@ def run_b200(args):
             threads, cores = pick_cpu_threads()
             sd, params = flat_state_dict(model), model_params()
             xs, ms_ = ring_cpu[0][0][:args.ref_sample], ring_cpu[0][1][:args.ref_sample]
+            rec_ref = reference_recognizer(model)
             t0 = time.perf_counter()
-            nb_ref, _, _, _ = cpu_reference_pass(sd, params, xs, ms_)
-            dt = time.perf_counter() - t0
+            if rec_ref is not None:      # the reference itself (oracle/_ref); the port runs afterwards, untimed, as the cross-check
+                ref_rows = reference_ids(rec_ref, xs, ms_)
+                dt = time.perf_counter() - t0
+                nb_ref, _, _, _ = cpu_reference_pass(sd, params, xs, ms_)
+                port_rows = [[int(t) for t in nb_ref[b, 0].tolist() if int(t) != 1] for b in range(args.ref_sample)]
+                port_equal = sum(int(ref_rows[b] == port_rows[b]) for b in range(args.ref_sample))
+            else:
+                nb_ref, _, _, _ = cpu_reference_pass(sd, params, xs, ms_)
+                dt = time.perf_counter() - t0
+                port_equal = None
             same = sum(int(torch.equal(ids0[b, 0].cpu(), nb_ref[b, 0])) for b in range(args.ref_sample)) \
                 if nb_ref.shape[2] == ids0.shape[2] else 0
+            kind = 'reference' if rec_ref is not None else 'port'
             line['cpu_baseline'] = {'value': args.ref_sample / dt, 'unit': 'utt/s', 'cores': threads,
-                                    'visible_cores': cores, 'kind': 'port',
+                                    'visible_cores': cores, 'kind': kind,
                                     'sample': f'{args.ref_sample} utterances (the first of input batch 0), one full pass '
-                                              f'(encoder-fwd + 60-step beam-10 decode) of the oracle port in {dt:.1f} s'}
+                                              f'(encoder-fwd + 60-step beam-10 decode) of '
+                                              + ('the reference\'s own recogniser (oracle/_ref)' if kind == 'reference' else 'the oracle port')
+                                              + f' in {dt:.1f} s'}
             line['validation']['oracle_check'] = {'utterances': args.ref_sample, 'one_best_ids_equal': same,
-                                                  'note': 'fp32 oracle port vs the CUDA path on the same utterances'}
+                                                  'port_equals_reference': port_equal,
+                                                  'note': 'fp32 oracle port vs the CUDA path on the same utterances; '
+                                                          'port_equals_reference: 1-best of the port vs the reference itself (oracle/_ref)'}
     del lanes, rec_graph, rec_pers, probe
     torch.cuda.empty_cache()
     if args.extras:
