@@ -68,3 +68,42 @@ def test_port_equals_live_reference(normalize_before, activation):
             want = [int(t) for t in hyps[b][r].split()] if hyps[b][r] else []
             assert port == want, (b, r, port, want)
     torch.testing.assert_close(ns, scores_ref.float(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('normalize_before,activation', [(False, 'glu'), (True, 'glu'), (False, 'relu'), (True, 'relu')])
+def test_port_gradients_equal_live_reference_autograd(normalize_before, activation):
+    """model.train(); loss, _ = model(inputs, targets); loss.backward() through the REFERENCE's own modules (trainer.py:206-217)
+    vs oracle/train_step.loss_and_grads: the loss and every parameter gradient -- in particular for the pre-norm and ReLU
+    stacks whose hand-written CUDA backward is tested against this port (tests/test_gpu_train.py)."""
+    from otrans.model import End2EndModel
+    from oracle import train_step as ot
+    params = _params(normalize_before, activation)
+    torch.manual_seed(99)
+    ref = End2EndModel['speech2text'](params)
+    ref.train()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if 'norm' in n:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith('.bias'):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        ref.decoder.embedding.weight.mul_(0.12)
+    sd = {k: v.detach().clone().float() for k, v in ref.state_dict().items() if k.split('.')[0] in ('frontend', 'encoder', 'decoder')}
+    B, T, L = 3, 70, 8
+    lens = torch.tensor([70, 55, 41])
+    mask = torch.arange(T)[None] < lens[:, None]
+    x = torch.randn(B, T, 20, generator=g) * mask.unsqueeze(2)
+    tgt = torch.randint(3, 40, (B, L), generator=g)
+    tgt[:, 0] = 1
+    tgt[0, L - 2:] = torch.tensor([1, 0])
+    tgt[1, L - 1] = 1
+    tgt[2, 4:] = torch.tensor([1, 0, 0, 0])
+    loss_ref, _ = ref({'inputs': x, 'mask': mask}, {'targets': tgt, 'targets_length': None})
+    loss_ref.backward()
+    g_ref = {n: p.grad.clone() for n, p in ref.named_parameters() if p.grad is not None}
+    loss, grads = ot.loss_and_grads(x, mask, tgt, sd, params)
+    torch.testing.assert_close(loss, loss_ref.detach(), rtol=1e-5, atol=1e-5)
+    assert set(grads) == set(g_ref), set(grads) ^ set(g_ref)
+    for n in grads:
+        torch.testing.assert_close(grads[n], g_ref[n], rtol=2e-4, atol=2e-6, msg=lambda m, n=n: f'{n}: {m}')
