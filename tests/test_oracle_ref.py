@@ -107,3 +107,51 @@ def test_port_gradients_equal_live_reference_autograd(normalize_before, activati
     assert set(grads) == set(g_ref), set(grads) ^ set(g_ref)
     for n in grads:
         torch.testing.assert_close(grads[n], g_ref[n], rtol=2e-4, atol=2e-6, msg=lambda m, n=n: f'{n}: {m}')
+
+
+@pytest.mark.parametrize('kind', ['conformer', 'relpos_transformer'])
+def test_port_encoder_states_equal_live_reference_for_relpos_encoders(kind):
+    """Conformer (macaron FFN, rel-pos attention without output projection, conv module with BatchNorm running statistics,
+    only post_ffn_norm applied: SURVEY.md 8a quirks) and the rel-pos Transformer encoder: valid-frame states of the port vs
+    the live reference modules, recognize() ids bit-exact."""
+    from otrans.model import End2EndModel
+    from otrans.recognize.speech2text import SpeechToTextRecognizer
+    params = _params(False, 'glu')
+    if kind == 'conformer':
+        params['encoder_type'] = 'conformer'
+        params['encoder'] = dict(d_model=32, d_ff=24, cov_kernel_size=5, n_heads=4, nblocks=2, pos_dropout=0.0, slf_attn_dropout=0.0,
+                                 ffn_dropout=0.0, residual_dropout=0.0, conv_dropout=0.0, macaron_style=True, ffn_scale=0.5,
+                                 conv_bias=True, activation='glu', positional_encoding=True, relative_positional=True)
+    else:
+        params['encoder']['relative_positional'] = True
+    torch.manual_seed(77)
+    ref = End2EndModel['speech2text'](params).eval()
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n, buf in ref.named_buffers():
+            if n.endswith('running_mean'):
+                buf.add_(0.3 * torch.randn(buf.shape, generator=g))
+            if n.endswith('running_var'):
+                buf.mul_(1.0 + 0.5 * torch.rand(buf.shape, generator=g))
+        ref.decoder.embedding.weight.mul_(0.15)
+        ref.decoder.output_layer.bias[1] = 1.5
+    sd = {k: v.detach().clone().float() for k, v in ref.state_dict().items() if k.split('.')[0] in ('frontend', 'encoder', 'decoder')}
+    B, T, beam, max_len = 3, 72, 3, 7
+    lens = torch.tensor([72, 60, 33])
+    mask = torch.arange(T)[None] < lens[:, None]
+    x = torch.randn(B, T, 20, generator=g) * mask.unsqueeze(2)
+    with torch.no_grad():
+        fx, fm = ref.frontend(x, mask)
+        mem_ref, mm_ref, _ = ref.encoder(fx, fm)
+        mem, mm = om.encode(x, mask, sd, params)
+        assert torch.equal(mm, mm_ref)
+        torch.testing.assert_close(mem[mm], mem_ref[mm_ref], rtol=1e-4, atol=2e-5)
+        rec = SpeechToTextRecognizer(ref, beam_width=beam, nbest=1, max_len=max_len, idx2unit={i: str(i) for i in range(40)},
+                                     penalty=0.6, lamda=5, ngpu=0)
+        hyps, _ = rec.recognize(x, mask)
+        nb, _, _, _ = obs.recognize(x, mask, sd, params, beam=beam, nbest=1, max_len=max_len, penalty=0.6, lamda=5)
+    for b in range(B):
+        port = [int(t) for t in nb[b, 0].tolist()]
+        port = port[:port.index(1)] if 1 in port else port
+        want = [int(t) for t in hyps[b][0].split()] if hyps[b][0] else []
+        assert port == want, (b, port, want)
