@@ -12,6 +12,7 @@ import importlib
 import os
 import py_compile
 import sys
+import warnings
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = '/root/reference'
@@ -31,8 +32,10 @@ def build(dst=DST):
                 continue
             out = os.path.join(dst, rel, f[:-3] + '.pyc')
             os.makedirs(os.path.dirname(out), exist_ok=True)
-            py_compile.compile(os.path.join(root, f), cfile=out, dfile=os.path.join(rel, f), doraise=True,
-                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            with warnings.catch_warnings():      # the reference has a docstring with an invalid escape (train/__init__.py:1)
+                warnings.simplefilter('ignore', SyntaxWarning)
+                py_compile.compile(os.path.join(root, f), cfile=out, dfile=os.path.join(rel, f), doraise=True,
+                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
             n += 1
     with open(os.path.join(dst, 'BUILD_INFO'), 'w') as fh:
         fh.write(f'{n} modules byte-compiled from {src} with python {sys.version.split()[0]} by oracle/build_ref.py\n')
